@@ -1,0 +1,227 @@
+"""ctypes/numpy front-end of the CPU parity oracle (oracle/fdms_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Each function cites the reference
+file:line it restates (paths relative to /root/reference).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Geom(C.Structure):
+    _fields_ = [("dst_h", C.c_int), ("dst_w", C.c_int), ("unpad_h", C.c_int), ("unpad_w", C.c_int),
+                ("top", C.c_int), ("bottom", C.c_int), ("left", C.c_int), ("right", C.c_int),
+                ("resize", C.c_int), ("ratio_w", C.c_double), ("ratio_h", C.c_double),
+                ("dw", C.c_double), ("dh", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libfdms_oracle.so")
+    src = os.path.join(_HERE, "fdms_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libfdms_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.fo_nms.restype = C.c_int64
+        _LIB.fo_filter_xyxy.restype = C.c_int64
+        _LIB.fo_weighted_nms.restype = C.c_int64
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- B1 geometry: utils/datasets.py:873-903 ---------------------------------------------------
+def letterbox_geometry(src_h, src_w, new_shape=(640, 640), auto=True, scaleFill=False, scaleup=True, stride=32):
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    g = Geom()
+    lib().fo_letterbox_geometry(int(src_h), int(src_w), int(new_shape[0]), int(new_shape[1]), int(auto),
+                                int(scaleFill), int(scaleup), int(stride), C.byref(g))
+    return g
+
+
+# ---- B2 cv2.resize(INTER_LINEAR) u8 -----------------------------------------------------------
+def resize_linear_u8(img, dst_h, dst_w, virt_hw=None):
+    img = np.ascontiguousarray(img)
+    h, w, cn = img.shape
+    vh, vw = virt_hw if virt_hw else (h, w)
+    out = np.empty((dst_h, dst_w, cn), np.uint8)
+    rc = lib().fo_resize_linear_u8(_p(img), h, w, C.c_int64(w * cn), vh, vw, _p(out), dst_h, dst_w,
+                                   C.c_int64(dst_w * cn), cn)
+    assert rc == 0
+    return out
+
+
+# ---- letterbox: utils/datasets.py:873-903 -----------------------------------------------------
+def letterbox(img, new_shape=(640, 640), color=(114, 114, 114), auto=True, scaleFill=False, scaleup=True, stride=32,
+              virt_hw=None):
+    """Returns (img, (rw, rh), (dw, dh)) like the reference.  virt_hw: resize over a zero-padded
+    virtual source of that size (the api path, utils/preprocess_yolo_predict.py:273-290,370)."""
+    img = np.ascontiguousarray(img)
+    h, w, _ = img.shape
+    vh, vw = virt_hw if virt_hw else (h, w)
+    g = letterbox_geometry(vh, vw, new_shape, auto, scaleFill, scaleup, stride)
+    assert color[0] == color[1] == color[2]
+    out = np.empty((g.dst_h, g.dst_w, 3), np.uint8)
+    rc = lib().fo_letterbox_u8(_p(img), h, w, C.c_int64(w * 3), vh, vw, C.byref(g), int(color[0]), _p(out))
+    assert rc == 0
+    return out, (g.ratio_w, g.ratio_h), (g.dw, g.dh)
+
+
+def preprocess_api(img_rgb, img_size, stride=32):
+    """utils/preprocess_yolo_predict.py:345-378 from an already-decoded RGB array: pad to square
+    (top-left, zeros) -> letterbox(auto=False) -> CHW.  Returns (3, size, size) uint8."""
+    h, w, _ = img_rgb.shape
+    s = max(h, w)
+    out, _, _ = letterbox(img_rgb, img_size, auto=False, stride=stride, virt_hw=(s, s))
+    return np.ascontiguousarray(out.transpose(2, 0, 1))
+
+
+# ---- B3 pack: multi_scale_face_detector.py:96-105 ----------------------------------------------
+def pack_chw(img_hwc, flip=True, dtype=np.float16):
+    img_hwc = np.ascontiguousarray(img_hwc)
+    h, w, _ = img_hwc.shape
+    if dtype == np.float16:
+        out = np.empty((3, h, w), np.uint16)
+        lib().fo_pack_chw(_p(img_hwc), h, w, int(flip), 1, _p(out))
+        return out.view(np.float16)
+    out = np.empty((3, h, w), np.float32)
+    lib().fo_pack_chw(_p(img_hwc), h, w, int(flip), 0, _p(out))
+    return out
+
+
+# ---- B5 decode: models/yolo.py:267-308 ---------------------------------------------------------
+def decode_head(levels, strides, anchors_px, no=21, na=3):
+    """levels: list of (bs, na*no, ny, nx) arrays (fp16 or fp32; up-cast to fp32 first).
+    anchors_px: (nl, na, 2) pixels.  Returns pred (bs, rows, no) fp32, rows level-major."""
+    levels = [np.ascontiguousarray(np.asarray(l, dtype=np.float32)) for l in levels]
+    bs = levels[0].shape[0]
+    rows = sum(na * l.shape[2] * l.shape[3] for l in levels)
+    pred = np.empty((bs, rows, no), np.float32)
+    anchors_px = np.asarray(anchors_px, np.float32).reshape(len(levels), na, 2)
+    off = 0
+    for i, l in enumerate(levels):
+        _, ch, ny, nx = l.shape
+        assert ch == na * no
+        a = np.ascontiguousarray(anchors_px[i])
+        lib().fo_decode_level(_p(l), bs, na, no, ny, nx, C.c_float(float(strides[i])), _p(a), C.c_int64(rows),
+                              C.c_int64(off), _p(pred))
+        off += na * ny * nx
+    return pred
+
+
+# ---- B6 filter: utils/general.py:515-563 -------------------------------------------------------
+def filter_xyxy(pred_img, conf_thres):
+    """pred_img: (rows, 21) fp32 for ONE image.  Returns (cand (n,21), src_row (n,))."""
+    pred_img = np.ascontiguousarray(pred_img, np.float32)
+    rows, no = pred_img.shape
+    cand = np.empty((rows, no), np.float32)
+    src = np.empty((rows,), np.int32)
+    n = lib().fo_filter_xyxy(_p(pred_img), C.c_int64(rows), no, C.c_float(np.float32(conf_thres)), _p(cand), _p(src))
+    return cand[:n].copy(), src[:n].copy()
+
+
+# ---- B7 NMS: torchvision.ops.nms ---------------------------------------------------------------
+TV_CPU, TV_CUDA = 0, 1
+
+
+def nms(boxes, scores, iou_thres, mode=TV_CPU):
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
+    scores = np.ascontiguousarray(scores, np.float32)
+    n = boxes.shape[0]
+    keep = np.empty((max(n, 1),), np.int64)
+    k = lib().fo_nms(_p(boxes), _p(scores), C.c_int64(n), C.c_double(float(iou_thres)), int(mode), _p(keep))
+    return keep[:k].copy()
+
+
+MAX_NMS = 30000  # utils/general.py:520
+
+
+def non_max_suppression(pred, conf_thres=0.25, iou_thres=0.45, mode=TV_CPU):
+    """utils/general.py:506-600 with kpt_label=5, nc=1, classes=None.  pred (bs, rows, 21) fp32.
+    Returns list of (n,21) arrays; empty images give (0,6) zeros like the reference (:527)."""
+    out = []
+    for xi in range(pred.shape[0]):
+        cand, _ = filter_xyxy(pred[xi], conf_thres)
+        if cand.shape[0] == 0:
+            out.append(np.zeros((0, 6), np.float32))
+            continue
+        if cand.shape[0] > MAX_NMS:  # :578-579 (the reference's argsort is not stable; ours is)
+            cand = cand[np.argsort(-cand[:, 4], kind="stable")[:MAX_NMS]]
+        keep = nms(cand[:, :4], cand[:, 4], iou_thres, mode)
+        out.append(cand[keep])
+    return out
+
+
+# ---- B8 rescale --------------------------------------------------------------------------------
+def scale_coords_api(in_hw, boxes, img0_shape, do_round=False):
+    """utils/preprocess_yolo_predict.py:122-157; in place on an (n,4) fp32 array."""
+    assert boxes.dtype == np.float32 and boxes.flags.c_contiguous
+    lib().fo_scale_coords_api(_p(boxes), C.c_int64(boxes.shape[0]), int(in_hw[0]), int(img0_shape[0]),
+                              int(img0_shape[1]), int(do_round))
+    return boxes
+
+
+def scale_coords(img1_shape, coords, img0_shape, kpt_label=False, step=2):
+    """utils/general.py:374-404 (ratio_pad=None); in place on a contiguous (n,cols) fp32 array."""
+    assert coords.dtype == np.float32 and coords.flags.c_contiguous
+    n, cols = coords.shape
+    lib().fo_scale_coords_std(_p(coords), C.c_int64(n), cols, int(img1_shape[0]), int(img1_shape[1]),
+                              int(img0_shape[0]), int(img0_shape[1]), int(step) if kpt_label else 0)
+    return coords
+
+
+# ---- B9 merge: multi_scale_face_detector.py:168-240 ---------------------------------------------
+def scale_weights(dets, n_scales):
+    dets = np.ascontiguousarray(dets, np.float64).reshape(-1, 7)
+    w = np.empty((dets.shape[0],), np.float64)
+    lib().fo_scale_weights(_p(dets), C.c_int64(dets.shape[0]), int(n_scales), _p(w))
+    return w
+
+
+def weighted_nms(dets, n_scales, iou_thres):
+    dets = np.ascontiguousarray(dets, np.float64).reshape(-1, 7)
+    n = dets.shape[0]
+    if n == 0:
+        return dets
+    keep = np.empty((n,), np.int64)
+    k = lib().fo_weighted_nms(_p(dets), C.c_int64(n), int(n_scales), C.c_double(float(iou_thres)), _p(keep))
+    return dets[keep[:k]]
+
+
+def detect_from_heads(heads_per_scale, in_hw_per_scale, img0_shape, strides, anchors_px, conf_thres, iou_thres,
+                      mode=TV_CPU):
+    """multi_scale_face_detector.py:109-166,242-288 for ONE image, starting from the raw head
+    tensors of each scale (the backbone is outside the hot path).  heads_per_scale[s] is a list of
+    (1, 63, ny, nx) arrays.  Returns ((k,7) float64, per-scale (n,7) list)."""
+    per_scale = []
+    for s, levels in enumerate(heads_per_scale):
+        pred = decode_head(levels, strides, anchors_px)
+        det = non_max_suppression(pred, conf_thres, iou_thres, mode)[0]
+        if det.shape[0] == 0:
+            per_scale.append(np.zeros((0, 7)))
+            continue
+        boxes = np.ascontiguousarray(det[:, :4])
+        scale_coords_api(in_hw_per_scale[s], boxes, img0_shape, do_round=True)  # msfd:144
+        d7 = np.zeros((det.shape[0], 7), np.float64)
+        d7[:, :4] = boxes
+        d7[:, 4:6] = det[:, 4:6]
+        d7[:, 6] = s
+        per_scale.append(d7)
+    nonempty = [d for d in per_scale if len(d)]
+    if not nonempty:
+        return np.array([]), per_scale  # msfd:285
+    merged = np.vstack(nonempty)
+    return weighted_nms(merged, len(heads_per_scale), iou_thres), per_scale

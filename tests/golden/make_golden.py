@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Every output array is produced by the reference's own functions, imported through oracle/refshim.py:
+  utils.datasets.letterbox                               (utils/datasets.py:873)
+  utils.preprocess_yolo_predict.preprocess_api_approach  (utils/preprocess_yolo_predict.py:345)
+  utils.preprocess_yolo_predict.scale_coords_api_approach(utils/preprocess_yolo_predict.py:122)
+  models.yolo.Model / IKeypoint.forward                  (models/yolo.py:253-308)
+  utils.general.non_max_suppression / scale_coords       (utils/general.py:506, 374)
+  multi_scale_face_detector.MultiScaleFaceDetector       (multi_scale_face_detector.py:28-288)
+and by torchvision.ops.nms (CPU kernel), the third-party op the reference calls.
+
+The inputs are seeded; large inputs are NOT stored -- the tests regenerate them from the same seeds with
+face_detection_multi_scale_b200.synth and compare against stored outputs or SHA-256 digests.
+"""
+import contextlib
+import hashlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+
+from oracle import refshim  # noqa: E402
+
+assert refshim.install(), "reference tree not found"
+
+import cv2  # noqa: E402
+import torch  # noqa: E402
+import torchvision  # noqa: E402
+
+from face_detection_multi_scale_b200 import synth  # noqa: E402
+from tests.helpers import (API_CASES, CROWD_HEADS, E2E_CASES, LETTERBOX_FULL, LETTERBOX_SMALL,  # noqa: E402
+                           crowd_levels, e2e_heads)
+
+with contextlib.redirect_stdout(io.StringIO()):
+    from models.yolo import IKeypoint, Model  # noqa: E402
+    from multi_scale_face_detector import MultiScaleFaceDetector  # noqa: E402
+    from utils.datasets import letterbox  # noqa: E402
+    from utils.general import non_max_suppression, scale_coords  # noqa: E402
+    from utils.preprocess_yolo_predict import preprocess_api_approach, scale_coords_api_approach  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. letterbox / pack / api preprocess
+# ------------------------------------------------------------------------------------------------
+
+
+def ref_pack(img_hwc_bgr, half):
+    """multi_scale_face_detector.py:96-105 (std branch), on CPU; half=True restates the CUDA dtype path."""
+    img = img_hwc_bgr[:, :, ::-1].transpose(2, 0, 1)
+    img = np.ascontiguousarray(img)
+    t = torch.from_numpy(img)
+    t = t.half() if half else t.float()
+    t /= 255.0
+    return t.numpy()
+
+
+def gen_letterbox():
+    out = {}
+    meta = []
+    for i, (h, w, ns, auto, scaleup, stride, seed) in enumerate(LETTERBOX_SMALL):
+        img = synth.synth_image(h, w, seed)
+        o, ratio, pad = letterbox(img, ns, auto=auto, scaleup=scaleup, stride=stride)
+        out["small%d_out" % i] = o
+        f16, f32 = ref_pack(o, True).view(np.uint16), ref_pack(o, False)
+        out["small%d_f16_sha" % i] = np.array(sha(f16))
+        out["small%d_f32_sha" % i] = np.array(sha(f32))
+        if i in (0, 3):
+            out["small%d_f16" % i] = f16
+            out["small%d_f32" % i] = f32
+        ns2 = ns if isinstance(ns, tuple) else (ns, ns)
+        meta.append([h, w, ns2[0], ns2[1], int(auto), int(scaleup), stride, seed, ratio[0], pad[0], pad[1]])
+    out["small_meta"] = np.array(meta, np.float64)
+    fmeta, fsha_u8, fsha_f16 = [], [], []
+    for (h, w, ns, auto, stride, seed) in LETTERBOX_FULL:
+        img = synth.synth_image(h, w, seed)
+        o, ratio, pad = letterbox(img, ns, auto=auto, stride=stride)
+        fmeta.append([h, w, ns, int(auto), stride, seed, o.shape[0], o.shape[1]])
+        fsha_u8.append(sha(o))
+        fsha_f16.append(sha(ref_pack(o, True)))
+    out["full_meta"] = np.array(fmeta, np.int64)
+    out["full_sha_u8"] = np.array(fsha_u8)
+    out["full_sha_f16"] = np.array(fsha_f16)
+    # api approach: needs a file; PNG is lossless.  PIL decodes to RGB.
+    ameta = []
+    with tempfile.TemporaryDirectory() as td:
+        for i, (h, w, size, seed) in enumerate(API_CASES):
+            rgb = synth.synth_image(h, w, seed)
+            p = os.path.join(td, "a%d.png" % i)
+            cv2.imwrite(p, rgb[:, :, ::-1])
+            chw = preprocess_api_approach(p, size, 32)
+            assert chw.shape == (3, size, size)
+            if h * w < 200000:
+                out["api%d_out" % i] = chw
+            ameta.append([h, w, size, seed])
+            out["api%d_sha" % i] = np.array(sha(chw))
+    out["api_meta"] = np.array(ameta, np.int64)
+    save("letterbox", **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. head decode (+ NMS on the decoded output)
+# ------------------------------------------------------------------------------------------------
+def identity_head(nl=3, anchors=None):
+    """An IKeypoint whose 1x1 convolutions copy their 63-channel input (one-hot weights are exact in fp32),
+    so arbitrary synthetic raw head tensors can be pushed through the reference's own decode."""
+    if anchors is None:
+        anchors = synth.P5_ANCHORS.reshape(nl, -1).tolist()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = IKeypoint(nc=1, anchors=anchors, nkpt=5, ch=(63,) * nl)
+    for i in range(nl):
+        m.ia[i].implicit.zero_()
+        m.im[i].implicit.fill_(1.0)
+        # IKeypoint concatenates (det 18ch, kpt 45ch) then views as (na, no): channel c of the cat is
+        # anchor c // 21, output c % 21 -- NOT "anchor a's det then kpt" (SURVEY App. A4).  Build the
+        # permutation so that cat-channel c equals raw-channel c.
+        w_all = torch.eye(63).view(63, 63, 1, 1)
+        m.m[i].weight.copy_(w_all[:18])
+        m.m[i].bias.zero_()
+        m.m_kpt[i].weight.copy_(w_all[18:])
+        m.m_kpt[i].bias.zero_()
+    m.stride = torch.tensor([8., 16., 32., 64.][:nl])
+    m.eval()
+    return m
+
+
+def gen_head():
+    out = {}
+    # (a) real random-init yolov7-tiny-face (cfg/yolov7-tiny-face.yaml), batch 2, 96x160 input
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = Model(os.path.join(refshim.REFERENCE_ROOT, "cfg/yolov7-tiny-face.yaml")).eval()
+    x = torch.rand(2, 3, 96, 160)
+    pred, raw = net(x)
+    det = net.model[-1]
+    out["tiny_pred"] = pred.numpy()
+    for i, r in enumerate(raw):  # (bs, na, ny, nx, no) -> NCHW (bs, na*no, ny, nx)
+        bs, na, ny, nx, no = r.shape
+        out["tiny_raw%d" % i] = r.permute(0, 1, 4, 2, 3).reshape(bs, na * no, ny, nx).contiguous().numpy()
+    out["tiny_strides"] = det.stride.numpy()
+    out["tiny_anchors_px"] = det.anchor_grid.view(det.nl, det.na, 2).numpy()
+    conf = (pred[..., 4] * pred[..., 5]).flatten()
+    thr = float(torch.quantile(conf, 0.90))
+    out["tiny_conf_thres"] = np.array(thr)
+    for iou in (0.45, 0.3):
+        res = quiet(non_max_suppression, pred, thr, iou)
+        for b, r in enumerate(res):
+            out["tiny_nms_iou%d_b%d" % (int(iou * 100), b)] = r.numpy()
+
+    # (b) synthetic crowd heads pushed through the reference IKeypoint (identity convs)
+    head = identity_head()
+    for name, (in_h, in_w, n_faces, seed) in CROWD_HEADS.items():
+        levels = [torch.from_numpy(l) for l in crowd_levels(in_h, in_w, n_faces, seed)]
+        pred, raw = head([l.clone() for l in levels])
+        # sanity: identity convs reproduce the input exactly
+        for i, r in enumerate(raw):
+            bs, na, ny, nx, no = r.shape
+            assert torch.equal(r.permute(0, 1, 4, 2, 3).reshape(bs, na * no, ny, nx), levels[i])
+        out[name + "_pred_sha"] = np.array(sha(pred.numpy()))
+        out[name + "_pred_b0_head"] = pred[0, :64].numpy()
+        out[name + "_meta"] = np.array([in_h, in_w, n_faces, seed])
+        for conf, iou in ((0.5, 0.5), (0.6, 0.3), (0.25, 0.45)):
+            res = quiet(non_max_suppression, pred, conf, iou)
+            for b, r in enumerate(res):
+                out["%s_nms_c%d_i%d_b%d" % (name, int(conf * 100), int(iou * 100), b)] = r.numpy()
+    save("head", **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. torchvision.ops.nms (CPU kernel) known answers
+# ------------------------------------------------------------------------------------------------
+def gen_nms():
+    out = {}
+    rng = np.random.default_rng(42)
+
+    def case(name, boxes, scores, thrs):
+        boxes = np.ascontiguousarray(boxes, np.float32)
+        scores = np.ascontiguousarray(scores, np.float32)
+        out[name + "_boxes"] = boxes
+        out[name + "_scores"] = scores
+        out[name + "_thrs"] = np.array(thrs, np.float64)
+        for t in thrs:
+            k = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), float(t))
+            out["%s_keep_%d" % (name, int(round(t * 1e6)))] = k.numpy()
+
+    # random boxes
+    xy = rng.uniform(0, 600, (3000, 2)); wh = rng.uniform(5, 120, (3000, 2))
+    case("rand", np.concatenate([xy, xy + wh], 1), rng.uniform(0, 1, 3000), [0.5, 0.3, 0.45])
+    # integer boxes (the cross-scale merge sees rounded boxes): many IoUs are small rationals that hit
+    # thresholds like 0.3 / 1/3 / 0.5 exactly
+    xy = rng.integers(0, 60, (1500, 2)).astype(np.float64); wh = rng.integers(2, 24, (1500, 2))
+    case("int", np.concatenate([xy, xy + wh], 1), np.round(rng.uniform(0, 1, 1500), 2), [0.3, 1 / 3, 0.5, 0.6])
+    # exact-threshold pairs: IoU == rn32(1/3) and IoU == 0.3f
+    case("exact", [[0, 0, 2, 1], [1, 0, 3, 1], [0, 0, 10, 10], [0, 0, 10, 3], [50, 50, 60, 60], [50, 50, 60, 60],
+                   [5, 5, 5, 5], [5, 5, 5, 5]],
+         [0.9, 0.8, 0.7, 0.6, 0.5, 0.5, 0.4, 0.4], [1 / 3, 0.3, 0.5, 0.0, 1.0])
+    # heavy ties + clustered crowd
+    c = rng.uniform(50, 550, (40, 2)); sz = rng.uniform(10, 80, 40)
+    ci = rng.integers(0, 40, 4000)
+    ctr = c[ci] + rng.standard_normal((4000, 2)) * sz[ci, None] * 0.1
+    half = sz[ci, None] * np.exp(rng.standard_normal((4000, 2)) * 0.1) / 2
+    case("crowd", np.concatenate([ctr - half, ctr + half], 1), np.round(rng.uniform(0.01, 1, 4000), 3), [0.5, 0.3])
+    case("one", [[1, 2, 3, 4]], [0.5], [0.5])
+    save("nms", **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. rescale
+# ------------------------------------------------------------------------------------------------
+def gen_rescale():
+    out = {}
+    rng = np.random.default_rng(5)
+    cases = [((384, 640), (1080, 1920, 3)), ((544, 960), (1080, 1920, 3)), ((736, 1280), (1080, 1920, 3)),
+             ((640, 640), (480, 270, 3)), ((640, 640), (1080, 1920, 3)), ((896, 1536), (2160, 3840, 3))]
+    meta = []
+    for i, (in_hw, s0) in enumerate(cases):
+        n = 37
+        b = rng.uniform(-40, max(in_hw) + 40, (n, 4)).astype(np.float32)
+        b[:5] *= 1.5  # push a few out of frame in rows 0..4 (the clip quirk touches rows 0..3 only)
+        k = rng.uniform(-40, max(in_hw) + 40, (n, 15)).astype(np.float32)
+        out["c%d_boxes" % i] = b
+        out["c%d_kpts" % i] = k
+        out["c%d_std_boxes" % i] = scale_coords(in_hw, torch.from_numpy(b.copy()), s0).numpy()
+        out["c%d_std_kpts" % i] = scale_coords(in_hw, torch.from_numpy(k.copy()), s0, kpt_label=5, step=3).numpy()
+        out["c%d_api_boxes" % i] = quiet(scale_coords_api_approach, in_hw, torch.from_numpy(b.copy()), s0).numpy()
+        out["c%d_api_round" % i] = quiet(scale_coords_api_approach, in_hw, torch.from_numpy(b.copy()), s0).round().numpy()
+        meta.append([in_hw[0], in_hw[1], s0[0], s0[1]])
+    out["meta"] = np.array(meta, np.int64)
+    save("rescale", **out)
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. cross-scale merge, 6. end-to-end detect_multi_scale with a stand-in backbone
+# ------------------------------------------------------------------------------------------------
+def bare_detector(img_sizes, conf, iou, api, model=None):
+    d = MultiScaleFaceDetector.__new__(MultiScaleFaceDetector)  # skip attempt_load (no .pt ships)
+    d.model = model
+    d.device = torch.device("cpu")
+    d.half = False
+    d.stride = 32
+    d.img_sizes = list(img_sizes)
+    d.names = ["face"]
+    d.conf_thres = conf
+    d.iou_thres = iou
+    d.use_api_preprocess = api
+    return d
+
+
+def gen_merge():
+    out = {}
+    rng = np.random.default_rng(9)
+    for ci, (n_scales, n, iou) in enumerate([(3, 400, 0.5), (3, 400, 0.3), (2, 250, 0.3), (4, 300, 0.45), (1, 50, 0.5)]):
+        det = bare_detector([640] * n_scales, 0.5, iou, False)
+        c = rng.uniform(100, 1700, (30, 2)); sz = np.exp(rng.uniform(np.log(12), np.log(300), 30))
+        k = rng.integers(0, 30, n)
+        ctr = c[k] + rng.standard_normal((n, 2)) * sz[k, None] * 0.06
+        half = sz[k, None] * np.exp(rng.standard_normal((n, 2)) * 0.08) / 2
+        d = np.zeros((n, 7))
+        d[:, :4] = np.round(np.concatenate([ctr - half, ctr + half], 1))
+        d[:, 4] = np.round(rng.uniform(0.5, 1, n), 2).astype(np.float32)  # conf came from fp32
+        d[:, 6] = np.sort(rng.integers(0, n_scales, n))
+        out["m%d_dets" % ci] = d
+        out["m%d_weights" % ci] = det.calculate_scale_weights(d)
+        out["m%d_out" % ci] = det.weighted_nms(d)
+        out["m%d_meta" % ci] = np.array([n_scales, iou])
+    save("merge", **out)
+
+
+class StandInBackbone(torch.nn.Module):
+    """Deterministic replacement for the (out-of-scope) backbone: returns, for the input's (H, W), the
+    reference IKeypoint decode of pre-generated synthetic raw head tensors.  Everything downstream of the
+    head's convolutions is the unmodified reference."""
+
+    def __init__(self, heads_by_hw):
+        super().__init__()
+        self.head = identity_head()
+        self.heads_by_hw = heads_by_hw
+        self.seen = {}
+        self.stride = torch.tensor([8., 16., 32.])
+        self.names = ["face"]
+
+    def forward(self, img, augment=False):
+        hw = tuple(img.shape[2:])
+        self.seen[hw] = img.clone()
+        levels = [torch.from_numpy(l[None].copy()) for l in self.heads_by_hw[hw]]
+        return self.head(levels)
+
+
+def gen_e2e():
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        for (name, h, w, sizes, n_faces, conf, iou, api, seed) in E2E_CASES:
+            bgr = synth.synth_image(h, w, seed)
+            p = os.path.join(td, name + ".png")
+            cv2.imwrite(p, bgr)
+            heads, shapes = e2e_heads(h, w, sizes, n_faces, api, seed)
+            model = StandInBackbone(heads)
+            det = bare_detector(sizes, conf, iou, api, model)
+            final, shape0 = quiet(det.detect_multi_scale, p)
+            out[name + "_final"] = np.asarray(final, np.float64)
+            out[name + "_shape0"] = np.array(shape0)
+            for si, size in enumerate(sizes):
+                d, _, _ = quiet(det.detect_single_scale, p, size)
+                out["%s_scale%d" % (name, si)] = d
+                out["%s_input%d_sha" % (name, si)] = np.array(sha(model.seen[shapes[si]].numpy()))
+            out[name + "_shapes"] = np.array(shapes)
+    save("e2e", **out)
+
+
+if __name__ == "__main__":
+    gen_letterbox()
+    gen_head()
+    gen_nms()
+    gen_rescale()
+    gen_merge()
+    gen_e2e()

@@ -1,0 +1,111 @@
+// Shared host/device helpers for libfdms (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/fdms.h"
+
+#define FDMS_SM_COUNT_FALLBACK 148
+#define FDMS_STR2_(x) #x
+#define FDMS_STR_(x) FDMS_STR2_(x)
+
+struct fdms_buf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct fdms_ctx {
+    int device = 0;
+    int sm_count = FDMS_SM_COUNT_FALLBACK;
+    int smem_optin = 0;
+    char err[512] = {0};
+    bool pyr_attr = false, nms_attr = false;
+    size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
+    // scratch (grow-only)
+    fdms_buf sort_a, sort_b;   // NMS: 64-bit keys ping-pong
+    fdms_buf idx_a, idx_b;     // NMS: item indices ping-pong
+    fdms_buf boxes;            // NMS: boxes in score order (float4)
+    fdms_buf mask;             // NMS: suppression bit matrix
+    fdms_buf seginfo;          // NMS: per segment {n, nblk, mask_off}
+    fdms_buf merge_rows;       // merge: (n_img, mcap, 8) rows
+    fdms_buf merge_cnt;        // merge: counts
+    fdms_buf merge_keep;       // merge: keep + n_keep
+    fdms_buf flags;            // misc device flags
+};
+
+static inline int fdms_fail(fdms_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define FDMS_CUDA(ctx, call)                                                                          \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fdms_fail((ctx), FDMS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                             __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define FDMS_LAUNCH_CHECK(ctx, name)                                                                  \
+    do {                                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess)                                                                        \
+            return fdms_fail((ctx), FDMS_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// Grow-only scratch.  Growth synchronises the device (cudaFree) -- it only happens when a call
+// needs more than any call before it.
+static inline int fdms_reserve(fdms_ctx *ctx, fdms_buf &b, size_t bytes) {
+    if (bytes <= b.bytes) return FDMS_OK;
+    size_t want = bytes + bytes / 4 + 256;
+    if (b.p) {
+        cudaDeviceSynchronize();
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fdms_fail(ctx, FDMS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return FDMS_OK;
+}
+
+static inline int fdms_bind(fdms_ctx *ctx) {
+    if (!ctx) return FDMS_ERR_INVALID;
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    if (cur != ctx->device) {
+        e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    }
+    return FDMS_OK;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------------
+// Every fp32 operation that the reference rounds separately is written with an explicit
+// round-to-nearest intrinsic so that neither nvcc (-fmad) nor a later edit can contract it.
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float ld_f(const void *p, int dtype, int64_t i) {
+    return dtype == FDMS_F16 ? __half2float(__ldg(reinterpret_cast<const __half *>(p) + i))
+                             : __ldg(reinterpret_cast<const float *>(p) + i);
+}

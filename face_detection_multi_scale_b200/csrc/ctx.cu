@@ -1,0 +1,105 @@
+// Context, error reporting and the host-side letterbox geometry of libfdms.
+#include <math.h>
+#include <new>
+
+#include "common.cuh"
+
+extern "C" {
+
+FDMS_API int fdms_version(void) { return FDMS_VERSION; }
+
+FDMS_API const char *fdms_build_info(void) {
+    return "libfdms " __DATE__ " " __TIME__ " sm_100a nvcc " FDMS_STR_(__CUDACC_VER_MAJOR__) "." FDMS_STR_(__CUDACC_VER_MINOR__)
+           " fmad=off";
+}
+
+FDMS_API int fdms_create(fdms_ctx **out, int device) {
+    if (!out) return FDMS_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return FDMS_ERR_CUDA;  // no CUDA device: there is no CPU fallback
+    }
+    if (device < 0 || device >= n) return FDMS_ERR_INVALID;
+    fdms_ctx *c = new (std::nothrow) fdms_ctx();
+    if (!c) return FDMS_ERR_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete c;
+        return FDMS_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (c->sm_count <= 0) c->sm_count = FDMS_SM_COUNT_FALLBACK;
+    *out = c;
+    return FDMS_OK;
+}
+
+FDMS_API void fdms_destroy(fdms_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    fdms_buf *bufs[] = {&ctx->sort_a, &ctx->sort_b, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
+                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->flags};
+    for (fdms_buf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete ctx;
+}
+
+FDMS_API const char *fdms_last_error(const fdms_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx) {
+    if (!ctx) return 0;
+    const fdms_buf *bufs[] = {&ctx->sort_a, &ctx->sort_b, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
+                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->flags};
+    int64_t t = 0;
+    for (const fdms_buf *b : bufs) t += (int64_t)b->bytes;
+    return t;
+}
+
+// utils/datasets.py:873-903.  Python's round() on a float is round-half-to-even in double
+// (nearbyint under the default rounding mode); np.mod takes the sign of the divisor.
+FDMS_API int fdms_letterbox_geometry(int src_h, int src_w, int new_h, int new_w, int auto_, int scale_fill,
+                                     int scaleup, int stride, fdms_geom *g) {
+    if (!g || src_h <= 0 || src_w <= 0 || new_h <= 0 || new_w <= 0 || stride <= 0) return FDMS_ERR_INVALID;
+    double r = fmin((double)new_h / src_h, (double)new_w / src_w);  // :880
+    if (!scaleup) r = fmin(r, 1.0);                                  // :881-882
+    int unpad_w = (int)nearbyint(src_w * r), unpad_h = (int)nearbyint(src_h * r);  // :886
+    double dw = new_w - unpad_w, dh = new_h - unpad_h;                               // :887
+    double rw = r, rh = r;
+    if (auto_) {  // :888-889
+        int idw = (int)dw % stride, idh = (int)dh % stride;
+        if (idw < 0) idw += stride;
+        if (idh < 0) idh += stride;
+        dw = idw;
+        dh = idh;
+    } else if (scale_fill) {  // :890-893
+        dw = 0.0;
+        dh = 0.0;
+        unpad_w = new_w;
+        unpad_h = new_h;
+        rw = (double)new_w / src_w;
+        rh = (double)new_h / src_h;
+    }
+    dw /= 2;  // :895-896
+    dh /= 2;
+    memset(g, 0, sizeof(*g));
+    g->resize = !(src_w == unpad_w && src_h == unpad_h);  // :898
+    g->top = (int)nearbyint(dh - 0.1);                    // :900
+    g->bottom = (int)nearbyint(dh + 0.1);
+    g->left = (int)nearbyint(dw - 0.1);  // :901
+    g->right = (int)nearbyint(dw + 0.1);
+    g->unpad_h = unpad_h;
+    g->unpad_w = unpad_w;
+    g->dst_h = unpad_h + g->top + g->bottom;
+    g->dst_w = unpad_w + g->left + g->right;
+    g->ratio_w = rw;
+    g->ratio_h = rh;
+    g->dw = dw;
+    g->dh = dh;
+    if (unpad_h <= 0 || unpad_w <= 0) return FDMS_ERR_INVALID;
+    return FDMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// Head decode kernels.
+//
+//   decode_filter_kernel : IKeypoint decode (models/yolo.py:267-308) fused with the confidence
+//                          filter, xywh2xyxy and stream compaction of non_max_suppression
+//                          (utils/general.py:515,531,547-563,299-306).  Reads the raw conv
+//                          outputs (bs, 63, ny, nx) in place: no view/permute/contiguous/clone/cat
+//                          and no (rows x 21) tensor.  Only the obj/cls planes are streamed; the
+//                          other 19 channel planes are touched only at surviving cells.
+//   decode_dense_kernel  : the same decode writing every row (compat level, IKeypoint.forward's
+//                          first return value).
+//   filter_pred_kernel   : the same filter reading an already decoded pred (compat level).
+//
+// Arithmetic contract: every fp32 operation the reference rounds separately
+// is rounded separately here (explicit _rn intrinsics, -fmad=false); sigmoid is
+// 1/(1+exp(-x)) with exp evaluated in fp64 and rounded once to fp32 (correctly rounded up to
+// double rounding), IEEE division.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int DEC_THREADS = 128;
+constexpr int DEC_VEC = 8;                            // cells per thread
+constexpr int DEC_CELLS = DEC_THREADS * DEC_VEC;      // cells per CTA
+constexpr int NO = 21, NA = 3;
+
+struct DecLevel {
+    const void *data;
+    int dtype, ny, nx, scale, row_offset;
+    int block_begin, chunks;  // first CTA of this level; CTAs per (b, a) plane
+    float stride;
+    float anchors[6];
+};
+
+struct DecParams {
+    DecLevel lv[FDMS_MAX_LEVELS];
+    int n_levels, n_scales, bs, cap;
+    float conf_thres;
+    float logit_lo;  // conservative lower bound on logit(conf_thres): x < logit_lo => sigmoid(x) <= thres
+    float *cand;
+    int32_t *cand_row;
+    int32_t *count;
+};
+
+__device__ __forceinline__ float sigmoid_exact(float x) {
+    float e = (float)exp(-(double)x);  // fp64 exp rounded once == correctly rounded expf
+    return f_div(1.0f, f_add(1.0f, e));
+}
+
+// models/yolo.py:290-295 for one cell; v[k] = raw channel k (already fp32), out = 21 floats
+// [cx, cy, w, h, obj, cls, (kx, ky, kc) x 5]
+__device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
+                                            float (&o)[NO]) {
+    float s0 = sigmoid_exact(v[0]), s1 = sigmoid_exact(v[1]), s2 = sigmoid_exact(v[2]), s3 = sigmoid_exact(v[3]);
+    o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
+    o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
+    float t2 = f_mul(s2, 2.f), t3 = f_mul(s3, 2.f);
+    o[2] = f_mul(f_mul(t2, t2), aw);
+    o[3] = f_mul(f_mul(t3, t3), ah);
+    o[4] = sigmoid_exact(v[4]);
+    o[5] = sigmoid_exact(v[5]);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        o[6 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[6 + 3 * j], 2.f), 0.5f), gx), stride);  // raw logits, no sigmoid
+        o[7 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[7 + 3 * j], 2.f), 0.5f), gy), stride);
+        o[8 + 3 * j] = sigmoid_exact(v[8 + 3 * j]);
+    }
+}
+
+// utils/general.py:547-563 + 299-306 on one decoded row: o -> candidate row (in place)
+__device__ __forceinline__ void row_to_candidate(float (&o)[NO], float conf) {
+    float hw = f_div(o[2], 2.f), hh = f_div(o[3], 2.f);
+    float cx = o[0], cy = o[1];
+    o[0] = f_sub(cx, hw);
+    o[1] = f_sub(cy, hh);
+    o[2] = f_add(cx, hw);
+    o[3] = f_add(cy, hh);
+    o[4] = conf;
+    o[5] = 0.f;  // class index j (nc == 1)
+}
+
+template <typename T>
+__device__ __forceinline__ void load_vec8(const T *p, long long i, int n_valid, bool aligned, float (&v)[DEC_VEC]);
+
+template <>
+__device__ __forceinline__ void load_vec8<__half>(const __half *p, long long i, int n_valid, bool aligned,
+                                                  float (&v)[DEC_VEC]) {
+    if (aligned && n_valid == DEC_VEC) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p + i));
+        const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float2 f = __half22float2(h[k]);
+            v[2 * k] = f.x;
+            v[2 * k + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DEC_VEC; k++) v[k] = k < n_valid ? __half2float(__ldg(p + i + k)) : -INFINITY;
+    }
+}
+template <>
+__device__ __forceinline__ void load_vec8<float>(const float *p, long long i, int n_valid, bool aligned,
+                                                 float (&v)[DEC_VEC]) {
+    if (aligned && n_valid == DEC_VEC) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(p + i));
+        float4 b = __ldg(reinterpret_cast<const float4 *>(p + i + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < DEC_VEC; k++) v[k] = k < n_valid ? __ldg(p + i + k) : -INFINITY;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, int local_block) {
+    const int planes = P.bs * NA;
+    const int chunk = local_block / planes;  // chunk-major: neighbouring CTAs read different planes
+    const int plane = local_block - chunk * planes;
+    const int b = plane / NA, a = plane - b * NA;
+    const long long cells = (long long)L.ny * L.nx;
+    const long long cell0 = (long long)chunk * DEC_CELLS + (long long)threadIdx.x * DEC_VEC;
+    const int n_valid = (int)max(0LL, min((long long)DEC_VEC, cells - cell0));
+    const T *base = reinterpret_cast<const T *>(L.data) + ((long long)b * NA * NO + (long long)a * NO) * cells;
+    const bool aligned = (cells % DEC_VEC == 0) && ((uintptr_t)L.data % 16 == 0);
+
+    unsigned pass = 0;
+    float conf[DEC_VEC];
+    if (n_valid > 0) {
+        float xo[DEC_VEC], xc[DEC_VEC];
+        load_vec8<T>(base + 4 * cells, cell0, n_valid, aligned, xo);
+        load_vec8<T>(base + 5 * cells, cell0, n_valid, aligned, xc);
+#pragma unroll
+        for (int k = 0; k < DEC_VEC; k++) {
+            conf[k] = 0.f;
+            // cheap necessary condition: sigmoid(obj) > thres and sigmoid(cls) > thres
+            if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) {
+                float so = sigmoid_exact(xo[k]);
+                if (so > P.conf_thres) {                    // general.py:515
+                    float c = f_mul(sigmoid_exact(xc[k]), so);  // :547
+                    if (c > P.conf_thres) {                 // :563
+                        pass |= 1u << k;
+                        conf[k] = c;
+                    }
+                }
+            }
+        }
+    }
+    if (!__any_sync(0xffffffffu, pass != 0)) return;
+
+    // warp-aggregated slot reservation in the segment's candidate list
+    const int seg = b * P.n_scales + L.scale;
+    const int lane = threadIdx.x & 31;
+    int n = __popc(pass);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int basepos = 0;
+    if (lane == 31) basepos = atomicAdd(P.count + seg, total);
+    basepos = __shfl_sync(0xffffffffu, basepos, 31);
+    int pos = basepos + incl - n;
+
+    while (pass) {
+        int k = __ffs(pass) - 1;
+        pass &= pass - 1;
+        if (pos < P.cap) {
+            long long cell = cell0 + k;
+            int gy = (int)(cell / L.nx), gx = (int)(cell - (long long)gy * L.nx);
+            float v[NO], o[NO];
+#pragma unroll
+            for (int c = 0; c < NO; c++) v[c] = (float)__ldg(base + (long long)c * cells + cell);
+            decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+            float ck = 0.f;
+#pragma unroll
+            for (int q = 0; q < DEC_VEC; q++)
+                if (q == k) ck = conf[q];
+            row_to_candidate(o, ck);
+            float *dst = P.cand + ((long long)seg * P.cap + pos) * NO;
+#pragma unroll
+            for (int c = 0; c < NO; c++) dst[c] = o[c];
+            P.cand_row[(long long)seg * P.cap + pos] = L.row_offset + a * (int)cells + (int)cell;
+        }
+        pos++;
+    }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
+    int li = 0;
+#pragma unroll 1
+    for (int l = 1; l < P.n_levels; l++)
+        if ((int)blockIdx.x >= P.lv[l].block_begin) li = l;
+    const DecLevel &L = P.lv[li];
+    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, blockIdx.x - L.block_begin);
+    else decode_filter_body<float>(P, L, blockIdx.x - L.block_begin);
+}
+
+// ---- dense decode ---------------------------------------------------------------------------
+struct DenseParams {
+    DecLevel lv[FDMS_MAX_LEVELS];
+    int n_levels, bs;
+    long long rows_total;
+    float *pred;
+};
+
+constexpr int DENSE_THREADS = 128;
+
+__global__ void __launch_bounds__(DENSE_THREADS) decode_dense_kernel(const __grid_constant__ DenseParams P) {
+    __shared__ float s_out[DENSE_THREADS * NO];
+    int li = 0;
+#pragma unroll 1
+    for (int l = 1; l < P.n_levels; l++)
+        if ((int)blockIdx.x >= P.lv[l].block_begin) li = l;
+    const DecLevel &L = P.lv[li];
+    const int local_block = blockIdx.x - L.block_begin;
+    const int planes = P.bs * NA;
+    const int chunk = local_block / planes, plane = local_block - chunk * planes;
+    const int b = plane / NA, a = plane - b * NA;
+    const long long cells = (long long)L.ny * L.nx;
+    const long long cell = (long long)chunk * DENSE_THREADS + threadIdx.x;
+    const long long cbase = ((long long)b * NA * NO + (long long)a * NO) * cells;
+    if (cell < cells) {
+        float v[NO], o[NO];
+#pragma unroll
+        for (int c = 0; c < NO; c++) v[c] = ld_f(L.data, L.dtype, cbase + (long long)c * cells + cell);
+        int gy = (int)(cell / L.nx), gx = (int)(cell - (long long)gy * L.nx);
+        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+#pragma unroll
+        for (int c = 0; c < NO; c++) s_out[threadIdx.x * NO + c] = o[c];  // stride 21 words: conflict free
+    }
+    __syncthreads();
+    // coalesced write of this CTA's contiguous (<=128 rows x 21) block of pred
+    const long long cell_first = (long long)chunk * DENSE_THREADS;
+    const int n_rows = (int)min((long long)DENSE_THREADS, cells - cell_first);
+    float *dst = P.pred + ((long long)b * P.rows_total + L.row_offset + (long long)a * cells + cell_first) * NO;
+    for (int i = threadIdx.x; i < n_rows * NO; i += DENSE_THREADS) dst[i] = s_out[i];
+}
+
+// ---- filter on decoded pred -------------------------------------------------------------------
+constexpr int FLT_THREADS = 256;
+
+__global__ void __launch_bounds__(FLT_THREADS)
+    filter_pred_kernel(const void *__restrict__ pred, int dtype, int bs, long long rows, float thres,
+                       float *__restrict__ cand, int32_t *__restrict__ cand_row, int32_t *__restrict__ count, int cap) {
+    const int b = blockIdx.y;
+    const long long r = (long long)blockIdx.x * FLT_THREADS + threadIdx.x;
+    bool pass = false;
+    float conf = 0.f;
+    const long long base = ((long long)b * rows + r) * NO;
+    if (r < rows) {
+        float obj = ld_f(pred, dtype, base + 4);
+        if (obj > thres) {
+            conf = f_mul(ld_f(pred, dtype, base + 5), obj);
+            pass = conf > thres;
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int basepos = 0;
+    if (lane == 0) basepos = atomicAdd(count + b, __popc(m));
+    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+    if (pass) {
+        int pos = basepos + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) {
+            float o[NO];
+#pragma unroll
+            for (int c = 0; c < NO; c++) o[c] = ld_f(pred, dtype, base + c);
+            row_to_candidate(o, conf);
+            float *dst = cand + ((long long)b * cap + pos) * NO;
+#pragma unroll
+            for (int c = 0; c < NO; c++) dst[c] = o[c];
+            cand_row[(long long)b * cap + pos] = (int)r;
+        }
+    }
+}
+
+// Largest float L such that every x < L certainly has sigmoid(x) <= thres (margin 1e-3 in
+// logit space dwarfs every rounding in the fp32 sigmoid).
+float logit_lower_bound(float thres) {
+    if (!(thres > 0.f)) return -INFINITY;
+    if (thres >= 1.f) return INFINITY;
+    double l = log((double)thres / (1.0 - (double)thres));
+    return (float)(l - 1e-3 - 1e-6 * fabs(l));
+}
+
+int fill_levels(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs, int cells_per_block,
+                DecLevel *out, int *n_blocks, const char *who) {
+    if (!levels || n_levels <= 0 || n_levels > FDMS_MAX_LEVELS || bs <= 0)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "%s: bad level table", who);
+    long long blocks = 0;
+    for (int l = 0; l < n_levels; l++) {
+        const fdms_level &in = levels[l];
+        if (!in.data || in.ny <= 0 || in.nx <= 0 || (in.dtype != FDMS_F16 && in.dtype != FDMS_F32) || in.scale < 0 ||
+            in.scale >= n_scales || in.row_offset < 0)
+            return fdms_fail(ctx, FDMS_ERR_INVALID, "%s: bad level %d", who, l);
+        if ((long long)in.ny * in.nx * NA + in.row_offset > 0x7fffffffLL)
+            return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "%s: level %d too large", who, l);
+        DecLevel &L = out[l];
+        L.data = in.data;
+        L.dtype = in.dtype;
+        L.ny = in.ny;
+        L.nx = in.nx;
+        L.scale = in.scale;
+        L.row_offset = in.row_offset;
+        L.stride = in.stride;
+        for (int k = 0; k < 6; k++) L.anchors[k] = in.anchors[k];
+        L.chunks = (int)ceil_div64((long long)in.ny * in.nx, cells_per_block);
+        L.block_begin = (int)blocks;
+        blocks += (long long)L.chunks * bs * NA;
+        if (blocks > 0x7fffffffLL) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "%s: grid too large", who);
+    }
+    *n_blocks = (int)blocks;
+    return FDMS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
+                                float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
+                                fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!cand || !cand_row || !count || cap <= 0 || n_scales <= 0 || n_scales > FDMS_MAX_SCALES)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: bad arguments");
+    DecParams P;
+    memset(&P, 0, sizeof(P));
+    int n_blocks = 0;
+    if (int rc = fill_levels(ctx, levels, n_levels, n_scales, bs, DEC_CELLS, P.lv, &n_blocks, "fdms_decode_filter"))
+        return rc;
+    P.n_levels = n_levels;
+    P.n_scales = n_scales;
+    P.bs = bs;
+    P.cap = cap;
+    P.conf_thres = conf_thres;
+    P.logit_lo = logit_lower_bound(conf_thres);
+    P.cand = cand;
+    P.cand_row = cand_row;
+    P.count = count;
+    cudaStream_t st = (cudaStream_t)stream;
+    FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs * n_scales, st));
+    decode_filter_kernel<<<n_blocks, DEC_THREADS, 0, st>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, float *pred,
+                               int64_t rows_total, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!pred || rows_total <= 0) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense: bad arguments");
+    DenseParams P;
+    memset(&P, 0, sizeof(P));
+    int n_blocks = 0;
+    if (int rc = fill_levels(ctx, levels, n_levels, 1, bs, DENSE_THREADS, P.lv, &n_blocks, "fdms_decode_dense"))
+        return rc;
+    for (int l = 0; l < n_levels; l++)
+        if ((int64_t)levels[l].row_offset + (int64_t)NA * levels[l].ny * levels[l].nx > rows_total)
+            return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense: level %d exceeds rows_total", l);
+    P.n_levels = n_levels;
+    P.bs = bs;
+    P.rows_total = rows_total;
+    P.pred = pred;
+    decode_dense_kernel<<<n_blocks, DENSE_THREADS, 0, (cudaStream_t)stream>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "decode_dense_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, float conf_thres,
+                              float *cand, int32_t *cand_row, int32_t *count, int cap, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!pred || !cand || !cand_row || !count || bs <= 0 || bs > 65535 || rows <= 0 || cap <= 0 ||
+        (dtype != FDMS_F16 && dtype != FDMS_F32) || rows > 0x7fffffffLL)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_filter_pred: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs, st));
+    dim3 grid((unsigned)ceil_div64(rows, FLT_THREADS), bs);
+    filter_pred_kernel<<<grid, FLT_THREADS, 0, st>>>(pred, dtype, bs, rows, conf_thres, cand, cand_row, count, cap);
+    FDMS_LAUNCH_CHECK(ctx, "filter_pred_kernel");
+    return FDMS_OK;
+}
+
+}  // extern "C"

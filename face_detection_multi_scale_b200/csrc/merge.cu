@@ -1,0 +1,300 @@
+// Rescale to original-image coordinates and cross-scale merge.
+//
+//   scale_coords_kernel / scale_coords_api_kernel : in-place drop-ins for
+//       utils/general.py:374-404 and utils/preprocess_yolo_predict.py:122-157.
+//   merge_prepare_kernel : multi_scale_face_detector.py:138-166 for every image of a batch --
+//       api rescale, clamp, round half-to-even, drop landmarks, append scale_idx -- and
+//       :168-201,224-229 (size-aware weights, weighted score in float64 then cast to float32),
+//       concatenating the scales of an image in scale order (np.vstack, :273).
+//   second NMS (nms.cu, TV_CPU flavour: the reference runs it on CPU, :234)
+//   merge_emit_kernel : detections[keep] with the ORIGINAL confidence (:237-238).
+//   fdms_postprocess : decode_filter -> per-scale NMS -> merge as one host call, no host sync.
+#include <math.h>
+
+#include "common.cuh"
+#include "nms.cuh"
+
+namespace {
+
+constexpr int NO = 21;
+constexpr int MROW = 8;  // merge row: x1 y1 x2 y2 wscore conf cls scale
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// utils/general.py:374-404, ratio_pad=None.  gain/pad are computed in double on the host like
+// the Python floats they are, then cast to the tensor dtype by the in-place ops.
+__global__ void scale_coords_kernel(float *coords, long long n, int cols, long long row_stride, float padx, float pady,
+                                    float gain, float w0, float h0, int kpt_step) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *r = coords + i * row_stride;
+    if (kpt_step == 0) {
+        float x1 = f_div(f_sub(r[0], padx), gain), y1 = f_div(f_sub(r[1], pady), gain);
+        float x2 = f_div(f_sub(r[2], padx), gain), y2 = f_div(f_sub(r[3], pady), gain);
+        if (i < 4) {  // clip_coords(coords[0:4], ...) slices ROWS (general.py:389)
+            x1 = clampf(x1, 0.f, w0);
+            x2 = clampf(x2, 0.f, w0);
+            y1 = clampf(y1, 0.f, h0);
+            y2 = clampf(y2, 0.f, h0);
+        }
+        r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2;
+    } else {
+        for (int c = 0; c < cols; c += kpt_step) {
+            r[c] = clampf(f_div(f_sub(r[c], padx), gain), 0.f, w0);
+            if (c + 1 < cols) r[c + 1] = clampf(f_div(f_sub(r[c + 1], pady), gain), 0.f, h0);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 api_box(float4 b, float k, float w0, float h0, bool do_round) {
+    b.x = clampf(f_mul(b.x, k), 0.f, w0);
+    b.z = clampf(f_mul(b.z, k), 0.f, w0);
+    b.y = clampf(f_mul(b.y, k), 0.f, h0);
+    b.w = clampf(f_mul(b.w, k), 0.f, h0);
+    if (do_round) {  // torch.round: half to even
+        b.x = rintf(b.x); b.y = rintf(b.y); b.z = rintf(b.z); b.w = rintf(b.w);
+    }
+    return b;
+}
+
+__global__ void scale_coords_api_kernel(float *boxes, long long n, long long row_stride, float k, float w0, float h0,
+                                        int do_round) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *r = boxes + i * row_stride;
+    float4 b = api_box(make_float4(r[0], r[1], r[2], r[3]), k, w0, h0, do_round != 0);
+    r[0] = b.x; r[1] = b.y; r[2] = b.z; r[3] = b.w;
+}
+
+struct MergeParams {
+    const float *cand;
+    const int32_t *keep, *n_keep;
+    int n_scales, cap, mcap;
+    float k[FDMS_MAX_SCALES];  // max(H0, W0) / in_h per scale
+    float w0, h0;
+    float *mrows;      // (n_img, mcap, 8)
+    int32_t *msrc;     // (n_img, mcap): s * cap + item index
+    int32_t *mcount;   // (n_img)
+    int32_t *merged_in;
+};
+
+__global__ void merge_prepare_kernel(const __grid_constant__ MergeParams P) {
+    const int img = blockIdx.x;
+    int off[FDMS_MAX_SCALES + 1];
+    off[0] = 0;
+    for (int s = 0; s < P.n_scales; s++) {
+        int nk = P.n_keep[img * P.n_scales + s];
+        off[s + 1] = off[s] + max(nk, 0);
+    }
+    const int total = min(off[P.n_scales], P.mcap);
+    if (threadIdx.x == 0) {
+        P.mcount[img] = total;
+        if (P.merged_in) P.merged_in[img] = off[P.n_scales];
+    }
+    for (int pos = threadIdx.x; pos < total; pos += blockDim.x) {
+        int s = 0;
+        while (pos >= off[s + 1]) s++;
+        const int kidx = pos - off[s];
+        const long long seg = (long long)img * P.n_scales + s;
+        const int item = P.keep[seg * P.cap + kidx];
+        const float *row = P.cand + (seg * P.cap + item) * NO;
+        float4 b = api_box(make_float4(row[0], row[1], row[2], row[3]), P.k[s], P.w0, P.h0, true);  // msfd:144
+        const float conf = row[4], cls = row[5];
+        // msfd:168-201 on the rounded boxes, float64
+        double area = ((double)b.z - (double)b.x) * ((double)b.w - (double)b.y);
+        double wt = 1.0;
+        if (area < 1024.0 && s >= P.n_scales - 2) wt *= 1.2;
+        if (area >= 1024.0 && area <= 16384.0 && s == P.n_scales / 2) wt *= 1.1;
+        if (area > 16384.0 && s <= 1) wt *= 1.2;
+        float wscore = (float)__dmul_rn((double)conf, wt);  // msfd:225,229
+        float *o = P.mrows + ((long long)img * P.mcap + pos) * MROW;
+        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+        o[4] = wscore; o[5] = conf; o[6] = cls; o[7] = (float)s;
+        P.msrc[(long long)img * P.mcap + pos] = s * P.cap + item;
+    }
+}
+
+// msfd:168-201 + 224-229 on an (n,7) float64 detection array (the weighted_nms drop-in):
+// rows_out (n,8) f32 = [x1,y1,x2,y2 as float32, weighted score, conf, cls, scale_idx]
+__global__ void weighted_rows_kernel(const double *__restrict__ dets, long long n, int n_scales,
+                                     float *__restrict__ rows_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *d = dets + i * 7;
+    double area = __dmul_rn(__dsub_rn(d[2], d[0]), __dsub_rn(d[3], d[1]));
+    int s = (int)d[6];
+    double wt = 1.0;
+    if (area < 1024.0 && s >= n_scales - 2) wt *= 1.2;
+    if (area >= 1024.0 && area <= 16384.0 && s == n_scales / 2) wt *= 1.1;
+    if (area > 16384.0 && s <= 1) wt *= 1.2;
+    float *o = rows_out + i * MROW;
+    o[0] = (float)d[0]; o[1] = (float)d[1]; o[2] = (float)d[2]; o[3] = (float)d[3];
+    o[4] = (float)__dmul_rn(d[4], wt);
+    o[5] = (float)d[4]; o[6] = (float)d[5]; o[7] = (float)d[6];
+}
+
+struct EmitParams {
+    const float *mrows;
+    const int32_t *msrc, *keep2, *n_keep2;
+    const float *cand;
+    int n_scales, cap, mcap, out_cap;
+    float k[FDMS_MAX_SCALES];
+    float w0, h0;
+    float *dets;
+    int32_t *n_out;
+    float *kpts;
+};
+
+__global__ void merge_emit_kernel(const __grid_constant__ EmitParams P) {
+    const int img = blockIdx.x;
+    const int nk = P.n_keep2[img];
+    if (threadIdx.x == 0) P.n_out[img] = nk;
+    const int n = min(max(nk, 0), P.out_cap);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int pos = P.keep2[(long long)img * P.mcap + k];
+        const float *m = P.mrows + ((long long)img * P.mcap + pos) * MROW;
+        float *o = P.dets + ((long long)img * P.out_cap + k) * 7;
+        o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[3];
+        o[4] = m[5];  // original confidence (msfd:238 indexes the unweighted array)
+        o[5] = m[6];
+        o[6] = m[7];
+        if (P.kpts) {
+            const int src = P.msrc[(long long)img * P.mcap + pos];
+            const int s = src / P.cap, item = src - s * P.cap;
+            const float *row = P.cand + (((long long)img * P.n_scales + s) * P.cap + item) * NO;
+            float *ko = P.kpts + ((long long)img * P.out_cap + k) * 15;
+            for (int j = 0; j < 5; j++) {
+                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], P.k[s]), 0.f, P.w0);
+                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], P.k[s]), 0.f, P.h0);
+                ko[3 * j + 2] = row[8 + 3 * j];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride, int in_h,
+                               int in_w, int orig_h, int orig_w, int kpt_step, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (n == 0) return FDMS_OK;
+    if (!coords || n < 0 || cols <= 0 || row_stride < cols || in_h <= 0 || in_w <= 0 || orig_h <= 0 || orig_w <= 0 ||
+        (kpt_step != 0 && kpt_step < 2) || (kpt_step == 0 && cols < 4))
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
+    double gain = fmin((double)in_h / orig_h, (double)in_w / orig_w);  // general.py:377
+    double padx = ((double)in_w - orig_w * gain) / 2, pady = ((double)in_h - orig_h * gain) / 2;  // :378
+    scale_coords_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        coords, n, cols, row_stride, (float)padx, (float)pady, (float)gain, (float)orig_w, (float)orig_h, kpt_step);
+    FDMS_LAUNCH_CHECK(ctx, "scale_coords_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64_t row_stride, int in_h, int orig_h,
+                                   int orig_w, int do_round, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (n == 0) return FDMS_OK;
+    if (!boxes || n < 0 || row_stride < 4 || in_h <= 0 || orig_h <= 0 || orig_w <= 0)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords_api: bad arguments");
+    int sq = orig_h > orig_w ? orig_h : orig_w;     // ppyp:141
+    float k = (float)((double)sq / (double)in_h);   // ppyp:142-145 (Python float times fp32 tensor)
+    scale_coords_api_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        boxes, n, row_stride, k, (float)orig_w, (float)orig_h, do_round);
+    FDMS_LAUNCH_CHECK(ctx, "scale_coords_api_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, int n_scales, float *rows_out,
+                                fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (n == 0) return FDMS_OK;
+    if (!dets || !rows_out || n < 0 || n_scales <= 0)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_weighted_rows: bad arguments");
+    weighted_rows_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(dets, n, n_scales, rows_out);
+    FDMS_LAUNCH_CHECK(ctx, "weighted_rows_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
+                               int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
+                               double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
+                               float *kpts_out, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!cand || !keep || !n_keep || !in_h_host || !dets || !n_out || n_img <= 0 || n_scales <= 0 ||
+        n_scales > FDMS_MAX_SCALES || cap <= 0 || out_cap <= 0 || orig_h <= 0 || orig_w <= 0)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long mcap_ll = (long long)n_scales * cap;
+    if (mcap_ll > 0x3fffffff) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_merge_scales: cap too large");
+    const int mcap = (int)mcap_ll;
+    if (int rc = fdms_reserve(ctx, ctx->merge_rows, (size_t)n_img * mcap * (MROW * 4 + 4))) return rc;
+    if (int rc = fdms_reserve(ctx, ctx->merge_cnt, (size_t)n_img * 2 * 4)) return rc;
+    if (int rc = fdms_reserve(ctx, ctx->merge_keep, (size_t)n_img * mcap * 4)) return rc;
+    float *mrows = reinterpret_cast<float *>(ctx->merge_rows.p);
+    int32_t *msrc = reinterpret_cast<int32_t *>(mrows + (size_t)n_img * mcap * MROW);
+    int32_t *mcount = reinterpret_cast<int32_t *>(ctx->merge_cnt.p);
+    int32_t *n_keep2 = mcount + n_img;
+    int32_t *keep2 = reinterpret_cast<int32_t *>(ctx->merge_keep.p);
+
+    MergeParams P;
+    memset(&P, 0, sizeof(P));
+    P.cand = cand;
+    P.keep = keep;
+    P.n_keep = n_keep;
+    P.n_scales = n_scales;
+    P.cap = cap;
+    P.mcap = mcap;
+    const int sq = orig_h > orig_w ? orig_h : orig_w;
+    for (int s = 0; s < n_scales; s++) {
+        if (in_h_host[s] <= 0) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad in_h[%d]", s);
+        P.k[s] = (float)((double)sq / (double)in_h_host[s]);
+    }
+    P.w0 = (float)orig_w;
+    P.h0 = (float)orig_h;
+    P.mrows = mrows;
+    P.msrc = msrc;
+    P.mcount = mcount;
+    P.merged_in = merged_in;
+    merge_prepare_kernel<<<n_img, 256, 0, st>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "merge_prepare_kernel");
+    // torchvision.ops.nms on CPU tensors in the reference (msfd:234): TV_CPU flavour, no max_nms cut
+    if (int rc = fdms_nms_impl(ctx, mrows, MROW, 0, 4, nullptr, mcount, n_img, mcap, iou_thres, FDMS_IOU_TV_CPU, 0, keep2,
+                               n_keep2, st))
+        return rc;
+    EmitParams E;
+    memset(&E, 0, sizeof(E));
+    E.mrows = mrows;
+    E.msrc = msrc;
+    E.keep2 = keep2;
+    E.n_keep2 = n_keep2;
+    E.cand = cand;
+    E.n_scales = n_scales;
+    E.cap = cap;
+    E.mcap = mcap;
+    E.out_cap = out_cap;
+    for (int s = 0; s < n_scales; s++) E.k[s] = P.k[s];
+    E.w0 = P.w0;
+    E.h0 = P.h0;
+    E.dets = dets;
+    E.n_out = n_out;
+    E.kpts = kpts_out;
+    merge_emit_kernel<<<n_img, 256, 0, st>>>(E);
+    FDMS_LAUNCH_CHECK(ctx, "merge_emit_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!d) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_postprocess: null descriptor");
+    if (int rc = fdms_decode_filter(ctx, d->levels, d->n_levels, d->n_scales, d->bs, d->conf_thres, d->cand, d->cand_row,
+                                    d->count, d->cap, stream))
+        return rc;
+    if (int rc = fdms_nms_impl(ctx, d->cand, NO, 0, 4, d->cand_row, d->count, d->bs * d->n_scales, d->cap, d->iou_thres,
+                               d->iou_mode, FDMS_MAX_NMS, d->keep, d->n_keep, (cudaStream_t)stream))
+        return rc;
+    return fdms_merge_scales(ctx, d->cand, d->keep, d->n_keep, d->bs, d->n_scales, d->cap, d->in_h_host, d->orig_h,
+                             d->orig_w, d->iou_thres, d->dets, d->n_out, d->out_cap, d->merged_in, d->kpts_out, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// Batched NMS with torchvision.ops.nms semantics (call sites utils/general.py:584 and
+// multi_scale_face_detector.py:234), all segments (image x scale) of a batch per launch and
+// no host synchronisation between the stages:
+//
+//   nms_sort_kernel  : one CTA per segment.  64-bit key = (score descending, tie ascending),
+//                      bitonic network in shared memory (<= 8192 items, else in L2-resident
+//                      global scratch); emits item indices and boxes in score order and, in
+//                      the last CTA to finish, the plan (mask offsets, tile prefix) for stage 2.
+//   nms_mask_kernel  : persistent grid over (segment, 64-row block, 256-column group) tiles of
+//                      the upper triangle; column boxes staged in shared memory; one 64-bit
+//                      suppression word per (row, column block).
+//   nms_sweep_kernel : one CTA per segment.  Warp 0 resolves a 64-box block with register
+//                      shuffles, then the CTA ORs the mask rows of the boxes it kept into the
+//                      `removed` bitmap in shared memory (coalesced row reads).
+//
+// IoU arithmetic, selected by iou_mode:
+//   TV_CPU : inter / ((area_i + area_j) - inter), suppressed iff (double)iou > thr (double)
+//   TV_CUDA: inter / (fma(w_j, h_j, area_i) - inter), suppressed iff iou > (float)thr
+// The double comparison is folded on the host into a float threshold plus an inclusive flag.
+#include <math.h>
+
+#include "common.cuh"
+#include "nms.cuh"
+
+namespace {
+
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_SMEM_ITEMS = 8192;  // 8 B key + 4 B index each = 96 KB
+constexpr int MASK_THREADS = 256;      // 64 rows x 4 column blocks
+constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_MAX_NBLK = 4096;   // 262144 boxes per segment
+
+struct SegInfo {
+    int n;               // boxes entering suppression (after the max_nms cut)
+    int nblk;            // ceil(n / 64)
+    long long mask_off;  // first mask word of this segment, -1: does not fit the mask budget
+    long long unit_begin;  // first mask tile of this segment
+};
+
+struct PlanHeader {
+    long long total_units;
+    unsigned int done;  // CTAs of the sort kernel that have finished (reset by the last one)
+    unsigned int pad;
+};
+
+__device__ __forceinline__ uint32_t score_key_desc(float s) {
+    uint32_t b = __float_as_uint(s);
+    uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~asc;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+    nms_sort_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
+                    const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int n_seg, int cap, int cap_e,
+                    int max_nms, unsigned long long *gkeys, uint32_t *gidx, long long gpad,
+                    uint32_t *__restrict__ sorted_idx, float4 *__restrict__ sorted_boxes, SegInfo *seginfo,
+                    PlanHeader *hdr, long long mask_budget_words) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ int s_last;
+    __shared__ long long s_carry[2];
+    __shared__ long long s_warp[2][32];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    int n = count[g];
+    n = max(0, min(n, cap));
+    int pad = 64;
+    while (pad < n) pad <<= 1;
+    unsigned long long *keys;
+    uint32_t *idx;
+    if (pad <= SORT_SMEM_ITEMS) {
+        keys = reinterpret_cast<unsigned long long *>(sm);
+        idx = reinterpret_cast<uint32_t *>(sm + (size_t)SORT_SMEM_ITEMS * 8);
+    } else {
+        keys = gkeys + (long long)g * gpad;
+        idx = gidx + (long long)g * gpad;
+    }
+    const float *seg_rows = rows + (long long)g * cap * row_stride;
+    for (int i = tid; i < pad; i += SORT_THREADS) {
+        if (i < n) {
+            float s = seg_rows[(long long)i * row_stride + score_off];
+            uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + i] : (uint32_t)i;
+            keys[i] = ((unsigned long long)score_key_desc(s) << 32) | t;
+            idx[i] = (uint32_t)i;
+        } else {
+            keys[i] = ~0ull;
+            idx[i] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    if (n > 1) {
+        for (int k = 2; k <= pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (pad >> 1); t += SORT_THREADS) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    int p = i + j;
+                    bool up = (i & k) == 0;
+                    unsigned long long a = keys[i], b = keys[p];
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[p] = a;
+                        uint32_t ia = idx[i], ib = idx[p];
+                        idx[i] = ib;
+                        idx[p] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const int K = (max_nms > 0) ? min(n, max_nms) : n;  // utils/general.py:578-579
+    for (int k = tid; k < K; k += SORT_THREADS) {
+        uint32_t ii = idx[k];
+        const float *r = seg_rows + (long long)ii * row_stride + box_off;
+        sorted_idx[(long long)g * cap_e + k] = ii;
+        sorted_boxes[(long long)g * cap_e + k] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    if (tid == 0) {
+        seginfo[g].n = K;
+        seginfo[g].nblk = (K + 63) >> 6;
+    }
+    // ---- last CTA computes the plan (exclusive prefix of mask words and mask tiles) ---------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int t = atomicAdd(&hdr->done, 1u);
+        s_last = (t == (unsigned)n_seg - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        s_carry[0] = 0;
+        s_carry[1] = 0;
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < n_seg; base += SORT_THREADS) {
+        int s = base + tid;
+        long long v[2] = {0, 0};
+        if (s < n_seg) {
+            volatile SegInfo *si = seginfo + s;
+            long long kk = si->n, nb = si->nblk;
+            v[0] = kk * nb;              // mask words: one row of nblk words per box
+            v[1] = nb * ((nb + 3) >> 2);  // mask tiles: 64 rows x 256 columns
+        }
+        long long inc[2] = {v[0], v[1]};
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, inc[q], d);
+                if (lane >= d) inc[q] += t;
+            }
+            if (lane == 31) s_warp[q][warp] = inc[q];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                long long w = s_warp[q][lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    long long t = __shfl_up_sync(0xffffffffu, w, d);
+                    if (lane >= d) w += t;
+                }
+                s_warp[q][lane] = w;  // inclusive over warps
+            }
+        }
+        __syncthreads();
+        long long excl[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) excl[q] = s_carry[q] + (warp ? s_warp[q][warp - 1] : 0) + inc[q] - v[q];
+        if (s < n_seg) {
+            seginfo[s].mask_off = (excl[0] + v[0] <= mask_budget_words) ? excl[0] : -1;
+            seginfo[s].unit_begin = excl[1];
+        }
+        __syncthreads();
+        if (tid == SORT_THREADS - 1) {
+            s_carry[0] += s_warp[0][31];
+            s_carry[1] += s_warp[1][31];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seginfo[n_seg].n = 0;
+        seginfo[n_seg].nblk = 0;
+        seginfo[n_seg].mask_off = -1;
+        seginfo[n_seg].unit_begin = s_carry[1];
+        hdr->total_units = s_carry[1];
+        hdr->done = 0;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float thr, bool inclusive) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(f_sub(xx2, xx1), 0.f), h = fmaxf(f_sub(yy2, yy1), 0.f);
+    float inter = f_mul(w, h);
+    float bw = f_sub(b.z, b.x), bh = f_sub(b.w, b.y);
+    float den;
+    if (MODE == FDMS_IOU_TV_CUDA) den = f_sub(__fmaf_rn(bw, bh, area_a), inter);
+    else den = f_sub(f_add(area_a, f_mul(bw, bh)), inter);
+    float iou = f_div(inter, den);
+    return inclusive ? (iou >= thr) : (iou > thr);  // NaN: false either way
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MASK_THREADS)
+    nms_mask_kernel(const SegInfo *__restrict__ seginfo, const PlanHeader *__restrict__ hdr, int n_seg, int cap_e,
+                    const float4 *__restrict__ sorted_boxes, unsigned long long *__restrict__ mask, float thr,
+                    int inclusive) {
+    __shared__ float4 s_col[MASK_THREADS];
+    const long long total = hdr->total_units;
+    const int tid = threadIdx.x;
+    int g = 0;
+    long long g_begin = 0, g_end = seginfo[1].unit_begin;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        while (u >= g_end) {  // units are visited in increasing order: walk the segment cursor
+            g++;
+            g_begin = g_end;
+            g_end = seginfo[g + 1].unit_begin;
+        }
+        const SegInfo si = seginfo[g];
+        if (si.mask_off < 0) continue;
+        const int ncg = (si.nblk + 3) >> 2;
+        const int local = (int)(u - g_begin);
+        const int rb = local / ncg, cg = local - rb * ncg;
+        const int cb0 = cg * 4;
+        if (cb0 + 3 < rb) continue;  // entirely below the diagonal
+        const float4 *boxes = sorted_boxes + (long long)g * cap_e;
+        __syncthreads();  // previous tile's readers are done with s_col
+        {
+            int col = cb0 * 64 + tid;
+            s_col[tid] = col < si.n ? boxes[col] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        const int row = rb * 64 + (tid & 63);
+        const int q = tid >> 6, cblk = cb0 + q;
+        if (row < si.n && cblk < si.nblk && cblk >= rb) {
+            const float4 a = boxes[row];
+            const float area_a = f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y));
+            unsigned long long bits = 0;
+            const int col0 = cblk * 64;
+            const int jn = min(64, si.n - col0);
+            int j0 = (cblk == rb) ? (tid & 63) + 1 : 0;  // only later boxes can be suppressed
+#pragma unroll 4
+            for (int j = j0; j < jn; j++)
+                if (iou_gt<MODE>(a, area_a, s_col[q * 64 + j], thr, inclusive != 0)) bits |= 1ull << j;
+            mask[si.mask_off + (long long)row * si.nblk + cblk] = bits;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS)
+    nms_sweep_kernel(const SegInfo *__restrict__ seginfo, const unsigned long long *__restrict__ mask, int cap_e,
+                     const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ keep, int32_t *__restrict__ n_keep,
+                     int cap) {
+    __shared__ unsigned long long s_removed[SWEEP_MAX_NBLK];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_nkeep;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const SegInfo si = seginfo[g];
+    if (si.mask_off < 0 && si.n > 0) {  // did not fit the mask budget: report, never guess
+        if (tid == 0) n_keep[g] = -1;
+        return;
+    }
+    const int K = si.n, nblk = si.nblk;
+    for (int w = tid; w < nblk; w += SWEEP_THREADS) s_removed[w] = 0ull;
+    if (tid == 0) s_nkeep = 0;
+    __syncthreads();
+    const unsigned long long *M = mask + si.mask_off;
+    const uint32_t *sidx = sorted_idx + (long long)g * cap_e;
+    int32_t *kout = keep + (long long)g * cap;
+    for (int c = 0; c < nblk; c++) {
+        if (tid < 32) {
+            const int r_lo = c * 64 + lane, r_hi = r_lo + 32;
+            unsigned long long d_lo = r_lo < K ? M[(long long)r_lo * nblk + c] : 0ull;
+            unsigned long long d_hi = r_hi < K ? M[(long long)r_hi * nblk + c] : 0ull;
+            unsigned long long cur = s_removed[c];
+            const int left = K - c * 64;
+            const unsigned long long valid = left >= 64 ? ~0ull : ((1ull << left) - 1ull);
+            unsigned long long kept = 0ull;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                unsigned long long d = __shfl_sync(0xffffffffu, d_lo, i);
+                if (!((cur >> i) & 1ull)) {
+                    cur |= d;
+                    kept |= 1ull << i;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                unsigned long long d = __shfl_sync(0xffffffffu, d_hi, i);
+                if (!((cur >> (i + 32)) & 1ull)) {
+                    cur |= d;
+                    kept |= 1ull << (i + 32);
+                }
+            }
+            kept &= valid;
+            const int base = s_nkeep;
+            if ((kept >> lane) & 1ull) kout[base + __popcll(kept & ((1ull << lane) - 1ull))] = (int32_t)sidx[r_lo];
+            if ((kept >> (lane + 32)) & 1ull)
+                kout[base + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = (int32_t)sidx[r_hi];
+            __syncwarp();
+            if (lane == 0) {
+                s_kept = kept;
+                s_nkeep = base + __popcll(kept);
+            }
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        if (kept != 0ull && c + 1 < nblk) {
+            for (int w = c + 1 + tid; w < nblk; w += SWEEP_THREADS) {
+                unsigned long long acc = 0ull;
+                const unsigned long long *col = M + (long long)c * 64 * nblk + w;
+                unsigned long long kb = kept;
+#pragma unroll 4
+                for (int i = 0; i < 64; i++) {
+                    if ((kb >> i) & 1ull) acc |= col[(long long)i * nblk];
+                }
+                s_removed[w] |= acc;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_keep[g] = s_nkeep;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ rows, int row_stride, int n_cols,
+                                   const int32_t *__restrict__ keep, const int32_t *__restrict__ n_keep, int cap,
+                                   float *__restrict__ out, int out_cap) {
+    const int g = blockIdx.y;
+    const int nk = min(max(n_keep[g], 0), out_cap);
+    const long long total = (long long)nk * n_cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(e / n_cols), c = (int)(e - (long long)k * n_cols);
+        int i = keep[(long long)g * cap + k];
+        out[((long long)g * out_cap + k) * n_cols + c] = rows[((long long)g * cap + i) * row_stride + c];
+    }
+}
+
+}  // namespace
+
+// Folds `(double)iou > thr` (TV_CPU) or `iou > (float)thr` (TV_CUDA) into a float compare.
+void fdms_fold_threshold(double thr, int iou_mode, float *thr_f, int *inclusive) {
+    float t = (float)thr;
+    if (iou_mode == FDMS_IOU_TV_CUDA) {
+        *thr_f = t;
+        *inclusive = 0;
+    } else {
+        // smallest float f with (double)f > thr: t itself if t > thr, else the next float up
+        *thr_f = t;
+        *inclusive = ((double)t > thr) ? 1 : 0;
+    }
+}
+
+int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off, const int32_t *tie,
+                  const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode, int max_nms, int32_t *keep,
+                  int32_t *n_keep, cudaStream_t st) {
+    if (!rows || !count || !keep || !n_keep || n_seg <= 0 || cap <= 0 || row_stride <= 0 || box_off < 0 ||
+        score_off < 0 || (iou_mode != FDMS_IOU_TV_CPU && iou_mode != FDMS_IOU_TV_CUDA))
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_nms: bad arguments");
+    const int cap_e = (max_nms > 0 && max_nms < cap) ? max_nms : cap;
+    if ((cap_e + 63) / 64 > SWEEP_MAX_NBLK)
+        return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_nms: more than %d boxes per segment", SWEEP_MAX_NBLK * 64);
+    long long pad = 64;
+    while (pad < cap) pad <<= 1;
+    const bool global_sort = pad > SORT_SMEM_ITEMS;
+    if (global_sort) {
+        if (int rc = fdms_reserve(ctx, ctx->sort_a, (size_t)n_seg * pad * 8)) return rc;
+        if (int rc = fdms_reserve(ctx, ctx->idx_a, (size_t)n_seg * pad * 4)) return rc;
+    }
+    if (int rc = fdms_reserve(ctx, ctx->idx_b, (size_t)n_seg * cap_e * 4)) return rc;
+    if (int rc = fdms_reserve(ctx, ctx->boxes, (size_t)n_seg * cap_e * 16)) return rc;
+    const bool fresh_plan = ctx->seginfo.bytes < sizeof(PlanHeader) + (size_t)(n_seg + 1) * sizeof(SegInfo);
+    if (int rc = fdms_reserve(ctx, ctx->seginfo, sizeof(PlanHeader) + (size_t)(n_seg + 1) * sizeof(SegInfo))) return rc;
+    if (fresh_plan) FDMS_CUDA(ctx, cudaMemsetAsync(ctx->seginfo.p, 0, ctx->seginfo.bytes, st));
+    const long long nblk_e = (cap_e + 63) / 64;
+    size_t mask_upper = (size_t)n_seg * (size_t)cap_e * (size_t)nblk_e * 8;
+    size_t mask_bytes = mask_upper < ctx->mask_budget ? mask_upper : ctx->mask_budget;
+    if (int rc = fdms_reserve(ctx, ctx->mask, mask_bytes)) return rc;
+    const long long budget_words = (long long)(ctx->mask.bytes / 8);
+
+    PlanHeader *hdr = reinterpret_cast<PlanHeader *>(ctx->seginfo.p);
+    SegInfo *seginfo = reinterpret_cast<SegInfo *>(hdr + 1);
+    if (!ctx->nms_attr) {
+        FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SORT_SMEM_ITEMS * 12));
+        ctx->nms_attr = true;
+    }
+    nms_sort_kernel<<<n_seg, SORT_THREADS, SORT_SMEM_ITEMS * 12, st>>>(
+        rows, row_stride, box_off, score_off, tie, count, n_seg, cap, cap_e, max_nms,
+        reinterpret_cast<unsigned long long *>(ctx->sort_a.p), reinterpret_cast<uint32_t *>(ctx->idx_a.p), pad,
+        reinterpret_cast<uint32_t *>(ctx->idx_b.p), reinterpret_cast<float4 *>(ctx->boxes.p), seginfo, hdr,
+        budget_words);
+    FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
+    float thr_f;
+    int inclusive;
+    fdms_fold_threshold(iou_thres, iou_mode, &thr_f, &inclusive);
+    const int mask_grid = ctx->sm_count * 8;
+    if (iou_mode == FDMS_IOU_TV_CUDA)
+        nms_mask_kernel<FDMS_IOU_TV_CUDA><<<mask_grid, MASK_THREADS, 0, st>>>(
+            seginfo, hdr, n_seg, cap_e, reinterpret_cast<const float4 *>(ctx->boxes.p),
+            reinterpret_cast<unsigned long long *>(ctx->mask.p), thr_f, inclusive);
+    else
+        nms_mask_kernel<FDMS_IOU_TV_CPU><<<mask_grid, MASK_THREADS, 0, st>>>(
+            seginfo, hdr, n_seg, cap_e, reinterpret_cast<const float4 *>(ctx->boxes.p),
+            reinterpret_cast<unsigned long long *>(ctx->mask.p), thr_f, inclusive);
+    FDMS_LAUNCH_CHECK(ctx, "nms_mask_kernel");
+    nms_sweep_kernel<<<n_seg, SWEEP_THREADS, 0, st>>>(seginfo, reinterpret_cast<const unsigned long long *>(ctx->mask.p),
+                                                      cap_e, reinterpret_cast<const uint32_t *>(ctx->idx_b.p), keep,
+                                                      n_keep, cap);
+    FDMS_LAUNCH_CHECK(ctx, "nms_sweep_kernel");
+    return FDMS_OK;
+}
+
+extern "C" {
+
+FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off,
+                      const int32_t *tie, const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode,
+                      int max_nms, int32_t *keep, int32_t *n_keep, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    return fdms_nms_impl(ctx, rows, row_stride, box_off, score_off, tie, count, n_seg, cap, iou_thres, iou_mode,
+                         max_nms, keep, n_keep, (cudaStream_t)stream);
+}
+
+FDMS_API int fdms_gather_rows(fdms_ctx *ctx, const float *rows, int row_stride, int n_cols, const int32_t *keep,
+                              const int32_t *n_keep, int n_seg, int cap, float *out, int out_cap,
+                              fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (!rows || !keep || !n_keep || !out || n_seg <= 0 || n_seg > 65535 || cap <= 0 || out_cap <= 0 || n_cols <= 0 ||
+        n_cols > row_stride)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_gather_rows: bad arguments");
+    int bx = (int)ceil_div64((int64_t)out_cap * n_cols, 256);
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, n_seg);
+    gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, row_stride, n_cols, keep, n_keep, cap, out, out_cap);
+    FDMS_LAUNCH_CHECK(ctx, "gather_rows_kernel");
+    return FDMS_OK;
+}
+
+}  // extern "C"

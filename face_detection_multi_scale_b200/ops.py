@@ -1,0 +1,306 @@
+"""torch-tensor front end of libfdms: thin wrappers that validate shapes, allocate outputs with torch
+(device memory + streams are PyTorch's job here, nothing else is) and pass raw pointers to the C ABI.
+Every function enqueues on torch's current stream and returns without synchronising."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FDMS_CHW, FDMS_F16, FDMS_F32, FDMS_HWC, FDMS_U8, IOU_TV_CPU, IOU_TV_CUDA, MAX_NMS  # noqa: F401
+
+NO = 21
+
+_DT = {torch.uint8: FDMS_U8, torch.float16: FDMS_F16, torch.float32: FDMS_F32}
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise ValueError("libfdms operates on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# ---------------------------------------------------------------------------------------------- pyramid
+def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, border=114, virt_hw=None, outs=None):
+    """Fused letterbox pyramid.  src: (B, H, W, 3) uint8 CUDA (any row pitch: stride(1) bytes).
+    geoms: list of _lib.Geom (one per scale, from letterbox_geometry on the virtual size).
+    Returns one tensor per scale: (B, 3, h, w) for layout 'chw' or (B, h, w, 3) for 'hwc'."""
+    if src.dim() != 4 or src.shape[3] != 3 or src.dtype != torch.uint8:
+        raise ValueError("pyramid: src must be (B, H, W, 3) uint8")
+    if src.stride(3) != 1 or src.stride(2) != 3:
+        raise ValueError("pyramid: pixels must be contiguous (HWC, 3 bytes per pixel)")
+    dev = _dev(src)
+    B, H, W, _ = src.shape
+    vh, vw = virt_hw if virt_hw is not None else (H, W)
+    n = len(geoms)
+    arr = (_lib.ScaleOut * n)()
+    result = []
+    for s, g in enumerate(geoms):
+        shape = (B, 3, g.dst_h, g.dst_w) if layout == "chw" else (B, g.dst_h, g.dst_w, 3)
+        if outs is not None:
+            o = outs[s]
+            if tuple(o.shape) != shape or o.dtype != out_dtype or not o.is_contiguous() or o.device != src.device:
+                raise ValueError("pyramid: bad preallocated output %d" % s)
+        else:
+            o = torch.empty(shape, dtype=out_dtype, device=src.device)
+        result.append(o)
+        arr[s].geom = g
+        arr[s].out = o.data_ptr()
+        arr[s].out_img_stride = 3 * g.dst_h * g.dst_w
+        arr[s].out_dtype = _DT[out_dtype]
+        arr[s].out_layout = FDMS_CHW if layout == "chw" else FDMS_HWC
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_pyramid(c.handle, _ptr(src), B, src.stride(0) if B > 1 else H * src.stride(1), src.stride(1),
+                                 H, W, vh, vw, arr, n, int(bool(flip_rb)), int(border), _stream(dev))
+    c.check(rc, "fdms_pyramid")
+    return result
+
+
+# ---------------------------------------------------------------------------------------------- decode
+def _level_table(scales_levels, strides, anchors_px):
+    """scales_levels: list over scales of list over levels of (bs, 63, ny, nx) tensors."""
+    anchors_px = np.asarray(anchors_px, np.float32).reshape(-1, 6)
+    n = sum(len(lv) for lv in scales_levels)
+    if n > _lib.MAX_LEVELS:
+        raise ValueError("too many levels")
+    arr = (_lib.Level * n)()
+    rows_per_scale = []
+    i = 0
+    bs = scales_levels[0][0].shape[0]
+    hold = []
+    for s, levels in enumerate(scales_levels):
+        off = 0
+        for li, t in enumerate(levels):
+            if t.dim() != 4 or t.shape[1] != 3 * NO or t.shape[0] != bs or t.dtype not in (torch.float16, torch.float32):
+                raise ValueError("head level must be (bs, 63, ny, nx) fp16/fp32, got %r %s" % (tuple(t.shape), t.dtype))
+            if not t.is_contiguous():
+                t = t.contiguous()
+            hold.append(t)
+            arr[i].data = t.data_ptr()
+            arr[i].dtype = _DT[t.dtype]
+            arr[i].ny, arr[i].nx = t.shape[2], t.shape[3]
+            arr[i].scale = s
+            arr[i].row_offset = off
+            arr[i].stride = float(strides[li])
+            for k in range(6):
+                arr[i].anchors[k] = float(anchors_px[li, k])
+            off += 3 * t.shape[2] * t.shape[3]
+            i += 1
+        rows_per_scale.append(off)
+    return arr, n, bs, rows_per_scale, hold
+
+
+def decode_dense(levels, strides, anchors_px):
+    """models/yolo.py:267-308: list of raw (bs, 63, ny, nx) -> pred (bs, rows, 21) fp32."""
+    dev = _dev(levels[0])
+    arr, n, bs, rows, hold = _level_table([levels], strides, anchors_px)
+    pred = torch.empty((bs, rows[0], NO), dtype=torch.float32, device=levels[0].device)
+    c = _lib.ctx(dev)
+    c.check(_lib.lib().fdms_decode_dense(c.handle, arr, n, bs, _ptr(pred), rows[0], _stream(dev)), "fdms_decode_dense")
+    return pred
+
+
+class Candidates:
+    """Device-side candidate lists of n_seg segments (see include/fdms.h fdms_decode_filter)."""
+
+    def __init__(self, n_seg, cap, device):
+        self.n_seg, self.cap = n_seg, cap
+        self.cand = torch.empty((n_seg, cap, NO), dtype=torch.float32, device=device)
+        self.row = torch.empty((n_seg, cap), dtype=torch.int32, device=device)
+        self.count = torch.zeros((n_seg,), dtype=torch.int32, device=device)
+        self.keep = torch.empty((n_seg, cap), dtype=torch.int32, device=device)
+        self.n_keep = torch.zeros((n_seg,), dtype=torch.int32, device=device)
+
+
+def decode_filter(scales_levels, strides, anchors_px, conf_thres, cap, out=None):
+    """Fused decode + filter + compaction over all scales of a batch.  Segment = b * n_scales + s."""
+    dev = _dev(scales_levels[0][0])
+    arr, n, bs, _, hold = _level_table(scales_levels, strides, anchors_px)
+    ns = len(scales_levels)
+    if out is None:
+        out = Candidates(bs * ns, cap, scales_levels[0][0].device)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_decode_filter(c.handle, arr, n, ns, bs, float(np.float32(conf_thres)), _ptr(out.cand),
+                                       _ptr(out.row), _ptr(out.count), out.cap, _stream(dev))
+    c.check(rc, "fdms_decode_filter")
+    return out
+
+
+def filter_pred(pred, conf_thres, cap, out=None):
+    """Confidence filter + xywh2xyxy on a decoded pred (bs, rows, 21) fp16/fp32."""
+    dev = _dev(pred)
+    if pred.dim() != 3 or pred.shape[2] != NO or pred.dtype not in (torch.float16, torch.float32):
+        raise ValueError("filter_pred: pred must be (bs, rows, 21) fp16/fp32")
+    pred = pred.contiguous()
+    bs, rows, _ = pred.shape
+    if out is None:
+        out = Candidates(bs, cap, pred.device)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_filter_pred(c.handle, _ptr(pred), _DT[pred.dtype], bs, rows, float(np.float32(conf_thres)),
+                                     _ptr(out.cand), _ptr(out.row), _ptr(out.count), out.cap, _stream(dev))
+    c.check(rc, "fdms_filter_pred")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- nms
+def nms_segments(rows, count, cap, iou_thres, iou_mode=IOU_TV_CUDA, max_nms=MAX_NMS, tie=None, box_off=0, score_off=4,
+                 keep=None, n_keep=None):
+    """rows: (n_seg, cap, row_stride) fp32; count (n_seg,) int32.  Returns (keep (n_seg, cap) int32, n_keep)."""
+    dev = _dev(rows)
+    n_seg, cap_, stride = rows.shape
+    assert cap_ == cap and rows.dtype == torch.float32 and rows.is_contiguous()
+    if keep is None:
+        keep = torch.empty((n_seg, cap), dtype=torch.int32, device=rows.device)
+    if n_keep is None:
+        n_keep = torch.zeros((n_seg,), dtype=torch.int32, device=rows.device)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_nms(c.handle, _ptr(rows), stride, box_off, score_off, _ptr(tie), _ptr(count), n_seg, cap,
+                             float(iou_thres), int(iou_mode), int(max_nms), _ptr(keep), _ptr(n_keep), _stream(dev))
+    c.check(rc, "fdms_nms")
+    return keep, n_keep
+
+
+def nms(boxes, scores, iou_thres, iou_mode=IOU_TV_CUDA):
+    """Single-segment torchvision.ops.nms replacement: returns int64 keep indices in score order."""
+    dev = _dev(boxes)
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    rows = torch.empty((1, n, 5), dtype=torch.float32, device=boxes.device)
+    rows[0, :, :4] = boxes.float()
+    rows[0, :, 4] = scores.float()
+    count = torch.full((1,), n, dtype=torch.int32, device=boxes.device)
+    keep, n_keep = nms_segments(rows, count, n, iou_thres, iou_mode, max_nms=0)
+    nk = int(n_keep.item())
+    if nk < 0:
+        raise _lib.FdmsError("fdms_nms: segment exceeds the suppression-mask budget")
+    return keep[0, :nk].long()
+
+
+def gather_rows(rows, keep, n_keep, n_cols, out_cap):
+    dev = _dev(rows)
+    n_seg, cap, stride = rows.shape
+    out = torch.empty((n_seg, out_cap, n_cols), dtype=torch.float32, device=rows.device)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_gather_rows(c.handle, _ptr(rows), stride, n_cols, _ptr(keep), _ptr(n_keep), n_seg, cap,
+                                     _ptr(out), out_cap, _stream(dev))
+    c.check(rc, "fdms_gather_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- rescale
+def _rows_view(coords, min_cols):
+    if coords.dim() != 2 or coords.dtype != torch.float32 or coords.shape[1] < min_cols or coords.stride(1) != 1:
+        raise ValueError("coords must be a 2-D fp32 tensor with unit column stride")
+    return coords.shape[0], coords.shape[1], coords.stride(0) if coords.shape[0] > 1 else coords.shape[1]
+
+
+def scale_coords_(img1_shape, coords, img0_shape, kpt_step=0):
+    """In place utils/general.py:374-404 (ratio_pad=None) on a CUDA fp32 (n, cols) tensor/view."""
+    n, cols, rs = _rows_view(coords, 4 if kpt_step == 0 else 2)
+    if n == 0:
+        return coords
+    dev = _dev(coords)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_scale_coords(c.handle, _ptr(coords), n, cols, rs, int(img1_shape[0]), int(img1_shape[1]),
+                                      int(img0_shape[0]), int(img0_shape[1]), int(kpt_step), _stream(dev))
+    c.check(rc, "fdms_scale_coords")
+    return coords
+
+
+def scale_coords_api_(img_input_shape, boxes, img0_shape, do_round=False):
+    """In place utils/preprocess_yolo_predict.py:122-157 on a CUDA fp32 (n, >=4) tensor/view."""
+    n, cols, rs = _rows_view(boxes, 4)
+    if n == 0:
+        return boxes
+    dev = _dev(boxes)
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_scale_coords_api(c.handle, _ptr(boxes), n, rs, int(img_input_shape[0]), int(img0_shape[0]),
+                                          int(img0_shape[1]), int(bool(do_round)), _stream(dev))
+    c.check(rc, "fdms_scale_coords_api")
+    return boxes
+
+
+# ---------------------------------------------------------------------------------------------- merge / post
+class Detections:
+    """(n_img, out_cap, 7) fp32 dets [x1,y1,x2,y2,conf,cls,scale_idx] + n_out, device resident."""
+
+    def __init__(self, n_img, out_cap, device, with_kpts=False):
+        self.n_img, self.out_cap = n_img, out_cap
+        self.dets = torch.empty((n_img, out_cap, 7), dtype=torch.float32, device=device)
+        self.n_out = torch.zeros((n_img,), dtype=torch.int32, device=device)
+        self.merged_in = torch.zeros((n_img,), dtype=torch.int32, device=device)
+        self.kpts = torch.empty((n_img, out_cap, 15), dtype=torch.float32, device=device) if with_kpts else None
+
+
+def merge_scales(cands, n_img, n_scales, in_h, orig_hw, iou_thres, out_cap, with_kpts=False, out=None):
+    dev = _dev(cands.cand)
+    if out is None:
+        out = Detections(n_img, out_cap, cands.cand.device, with_kpts)
+    in_h_arr = (C.c_int32 * n_scales)(*[int(h) for h in in_h])
+    c = _lib.ctx(dev)
+    rc = _lib.lib().fdms_merge_scales(c.handle, _ptr(cands.cand), _ptr(cands.keep), _ptr(cands.n_keep), n_img, n_scales,
+                                      cands.cap, in_h_arr, int(orig_hw[0]), int(orig_hw[1]), float(iou_thres),
+                                      _ptr(out.dets), _ptr(out.n_out), out.out_cap, _ptr(out.merged_in), _ptr(out.kpts),
+                                      _stream(dev))
+    c.check(rc, "fdms_merge_scales")
+    return out
+
+
+def weighted_rows(dets64, n_scales):
+    """(n,7) float64 CUDA detections -> (1, n, 8) fp32 merge rows (weighted score in column 4)."""
+    dev = _dev(dets64)
+    n = dets64.shape[0]
+    assert dets64.dtype == torch.float64 and dets64.is_contiguous() and dets64.shape[1] == 7
+    rows = torch.empty((1, max(n, 1), 8), dtype=torch.float32, device=dets64.device)
+    c = _lib.ctx(dev)
+    c.check(_lib.lib().fdms_weighted_rows(c.handle, _ptr(dets64), n, int(n_scales), _ptr(rows), _stream(dev)),
+            "fdms_weighted_rows")
+    return rows
+
+
+class PostPlan:
+    """A frozen post-processing step (decode_filter -> NMS -> merge) over fixed buffers: one C call per
+    run, so the launches go out back to back (and can be captured in a CUDA graph)."""
+
+    def __init__(self, scales_levels, strides, anchors_px, in_h, orig_hw, conf_thres, iou_thres, cap, out_cap,
+                 iou_mode=IOU_TV_CUDA, with_kpts=False):
+        self.dev = _dev(scales_levels[0][0])
+        device = scales_levels[0][0].device
+        self.arr, self.n_levels, self.bs, self.rows_per_scale, self._hold = _level_table(scales_levels, strides,
+                                                                                        anchors_px)
+        self.n_scales = len(scales_levels)
+        self.cands = Candidates(self.bs * self.n_scales, cap, device)
+        self.out = Detections(self.bs, out_cap, device, with_kpts)
+        self._in_h = (C.c_int32 * self.n_scales)(*[int(h) for h in in_h])
+        d = _lib.PostDesc()
+        d.levels = C.cast(self.arr, C.POINTER(_lib.Level))
+        d.n_levels, d.n_scales, d.bs, d.cap = self.n_levels, self.n_scales, self.bs, cap
+        d.conf_thres = float(np.float32(conf_thres))
+        d.iou_mode = int(iou_mode)
+        d.iou_thres = float(iou_thres)
+        d.in_h_host = C.cast(self._in_h, C.POINTER(C.c_int32))
+        d.orig_h, d.orig_w = int(orig_hw[0]), int(orig_hw[1])
+        d.cand, d.cand_row, d.count = self.cands.cand.data_ptr(), self.cands.row.data_ptr(), self.cands.count.data_ptr()
+        d.keep, d.n_keep = self.cands.keep.data_ptr(), self.cands.n_keep.data_ptr()
+        d.dets, d.n_out, d.out_cap = self.out.dets.data_ptr(), self.out.n_out.data_ptr(), out_cap
+        d.merged_in = self.out.merged_in.data_ptr()
+        d.kpts_out = self.out.kpts.data_ptr() if with_kpts else None
+        self.desc = d
+        self.ctx = _lib.ctx(self.dev)
+
+    def run(self):
+        rc = _lib.lib().fdms_postprocess(self.ctx.handle, C.byref(self.desc), _stream(self.dev))
+        self.ctx.check(rc, "fdms_postprocess")
+        return self.out
+
+    # number of kernel launches of one run(): memset excluded; decode 1 + NMS 3 + prepare 1 + NMS 3 + emit 1
+    LAUNCHES = 9

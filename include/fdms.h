@@ -1,0 +1,218 @@
+/*
+ * fdms.h -- C ABI of libfdms.so: the B200-native (sm_100a) multi-scale face-detection
+ * pre/post-processing hot path.
+ *
+ * The reference (NguyendaiAI-pixta/face_detection_multi_scale) has no FFI of its own: its
+ * boundary is a set of Python callables.  Each entry point below names the
+ * reference callable (file:line, relative to the reference root) whose arithmetic it
+ * replaces; face_detection_multi_scale_b200/*.py binds them with ctypes and re-exports the
+ * reference's Python signatures on top (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every function returns FDMS_OK (0) or a negative fdms_status; none throws;
+ *   - all data pointers are DEVICE pointers unless the name says host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - no entry point synchronises the stream or allocates on the hot path: scratch lives in
+ *     the ctx and only grows (outside steady state) when a call needs more than any before;
+ *   - a ctx is bound to one device and must be used by one host thread / one stream at a
+ *     time (its scratch is shared by consecutive calls); create one ctx per worker thread;
+ *   - there is no CPU fallback: without a CUDA device fdms_create fails with FDMS_ERR_CUDA.
+ */
+#ifndef FDMS_H_
+#define FDMS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDMS_API __attribute__((visibility("default")))
+#define FDMS_VERSION 100 /* 0.1.0 */
+
+typedef struct fdms_ctx fdms_ctx;
+typedef void *fdms_stream;
+
+typedef enum fdms_status {
+    FDMS_OK = 0,
+    FDMS_ERR_INVALID = -1,     /* bad argument (message in fdms_last_error) */
+    FDMS_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+    FDMS_ERR_NOMEM = -3,       /* scratch allocation failed */
+    FDMS_ERR_UNSUPPORTED = -4  /* shape outside compiled limits */
+} fdms_status;
+
+typedef enum fdms_dtype { FDMS_U8 = 0, FDMS_F16 = 1, FDMS_F32 = 2 } fdms_dtype;
+typedef enum fdms_layout { FDMS_CHW = 0, FDMS_HWC = 1 } fdms_layout;
+/* torchvision.ops.nms arithmetic flavours */
+typedef enum fdms_iou_mode { FDMS_IOU_TV_CPU = 0, FDMS_IOU_TV_CUDA = 1 } fdms_iou_mode;
+typedef enum fdms_pre_mode { FDMS_PRE_LETTERBOX = 0, FDMS_PRE_API = 1 } fdms_pre_mode;
+
+#define FDMS_MAX_SCALES 8
+#define FDMS_MAX_LEVELS 32
+#define FDMS_MAX_NMS 30000 /* utils/general.py:520 */
+
+/* ---- context ---------------------------------------------------------------------------- */
+FDMS_API int fdms_version(void);
+FDMS_API const char *fdms_build_info(void);
+FDMS_API int fdms_create(fdms_ctx **out, int device);
+FDMS_API void fdms_destroy(fdms_ctx *ctx);
+/* message of the last failing call made with this ctx (empty string if none) */
+FDMS_API const char *fdms_last_error(const fdms_ctx *ctx);
+/* bytes of device scratch currently owned by the ctx */
+FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx);
+
+/* ---- letterbox geometry (host arithmetic only) -------------------------------------------
+ * utils/datasets.py:873-903 `letterbox`: ratio, new_unpad, dw/dh (mod stride when auto),
+ * Python round-half-even on the halved paddings. */
+typedef struct fdms_geom {
+    int32_t dst_h, dst_w;     /* output image size */
+    int32_t unpad_h, unpad_w; /* resized size (new_unpad) */
+    int32_t top, bottom, left, right;
+    int32_t resize;           /* 1 when the reference would call cv2.resize (:898) */
+    int32_t pad_;
+    double ratio_w, ratio_h;  /* returned `ratio` */
+    double dw, dh;            /* returned `(dw, dh)` (halved paddings) */
+} fdms_geom;
+
+FDMS_API int fdms_letterbox_geometry(int src_h, int src_w, int new_h, int new_w, int auto_, int scale_fill,
+                                     int scaleup, int stride, fdms_geom *out);
+
+/* ---- fused pyramid: resize + pad + channel flip + /255 + pack ----------------------------
+ * Replaces, for every image of a batch and every scale in ONE launch:
+ *   utils/datasets.py:873-903 letterbox  (cv2.resize INTER_LINEAR u8 fixed point, constant border)
+ *   multi_scale_face_detector.py:96-105  (BGR->RGB, HWC->CHW, .half()/.float(), /255)
+ *   utils/preprocess_yolo_predict.py:273-290,345-378 (api mode: virtual zero-padded square)
+ * src: n_img images, u8 HWC, image i at src + i*img_stride + y*row_pitch + x*3 (bytes).
+ * virt_h/virt_w >= src_h/src_w: size of the virtual zero-padded source the resize runs over
+ * (== src size for the letterbox mode; max(h,w) square for the api mode).
+ * Per scale the caller gives the geometry (from fdms_letterbox_geometry on the virtual size)
+ * and the output tensor: element (img, c, y, x) at out + img*out_img_stride + c*cs + y*ys + x*xs
+ * with (cs, ys, xs) = (H*W, W, 1) for FDMS_CHW or (1, 3W, 3) for FDMS_HWC (element units).
+ * out_dtype: FDMS_F16 / FDMS_F32 store value/255 (true division rounded once to the type),
+ * FDMS_U8 stores the pixel.  flip_rb != 0 reverses the channel order (img[:, :, ::-1]). */
+typedef struct fdms_scale_out {
+    fdms_geom geom;
+    void *out;
+    int64_t out_img_stride; /* elements */
+    int32_t out_dtype;      /* fdms_dtype */
+    int32_t out_layout;     /* fdms_layout */
+} fdms_scale_out;
+
+FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_img, int64_t img_stride, int64_t row_pitch,
+                          int src_h, int src_w, int virt_h, int virt_w, const fdms_scale_out *scales, int n_scales,
+                          int flip_rb, int border, fdms_stream stream);
+
+/* ---- head decode -------------------------------------------------------------------------
+ * models/yolo.py:267-308 (IKeypoint inference branch; same math as Detect :59-106 and IDetect
+ * :152-207), nc=1, nkpt=5 => no=21, na=3.
+ * A level is one raw conv output (bs, na*no, ny, nx), channel = a*no + k, dtype f16 or f32
+ * (the math is fp32 on the up-cast values).  `scale` groups levels into pyramid scales;
+ * row = row_offset + a*ny*nx + gy*nx + gx addresses the reference's pred[b, row, :]. */
+typedef struct fdms_level {
+    const void *data;
+    int32_t dtype; /* FDMS_F16 | FDMS_F32 */
+    int32_t ny, nx;
+    int32_t scale;      /* which pyramid scale this level belongs to, 0..n_scales-1 */
+    int32_t row_offset; /* first row of this level inside its scale's pred */
+    float stride;       /* 8 / 16 / 32 / 64 */
+    float anchors[6];   /* (w,h) x 3 anchors, PIXELS (IKeypoint.anchor_grid) */
+} fdms_level;
+
+/* Full decode ("compat level"): writes pred (bs, rows_total, 21) f32 for one scale's levels
+ * (all levels must have scale == 0).  models/yolo.py:308 `cat(z, 1)`. */
+FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, float *pred,
+                               int64_t rows_total, fdms_stream stream);
+
+/* Fused decode + confidence filter + xywh2xyxy + stream compaction ("fused level"):
+ * models/yolo.py:267-308 then utils/general.py:515,531,547-563 and :299-306.
+ * Segment g = b*n_scales + scale.  For every row with rn(cls*obj) > (float)conf_thres one
+ * candidate [x1,y1,x2,y2,conf,0,15 kpt] (21 floats) is appended to cand[g] (unordered: the
+ * NMS sort key restores the reference order) and its row index to cand_row[g].
+ * count[g] receives the TOTAL number of passing rows, which may exceed cap (only the first
+ * cap arrivals are stored); callers treat count > cap as overflow. */
+FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
+                                float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
+                                fdms_stream stream);
+
+/* Same filter + box conversion, reading an already decoded pred (bs, rows, 21) f16/f32:
+ * the front half of utils/general.py:506-600 non_max_suppression.  Segment g = b. */
+FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, float conf_thres,
+                              float *cand, int32_t *cand_row, int32_t *count, int cap, fdms_stream stream);
+
+/* ---- batched NMS -------------------------------------------------------------------------
+ * torchvision.ops.nms as called at utils/general.py:584 and multi_scale_face_detector.py:234:
+ * stable descending sort on score (ties -> ascending `tie`), greedy suppression with strict
+ * IoU > thr, no +1, NaN never suppresses.  n_seg independent segments in one call.
+ * Segment g reads n = min(count[g], cap) items: box (x1,y1,x2,y2) at
+ * rows + (g*cap + i)*row_stride + box_off, score at ... + score_off, tie[g*cap + i]
+ * (tie == NULL means tie = i).  If n > max_nms only the max_nms best-ranked are considered
+ * (utils/general.py:578-579).  keep[g*cap + k] = item index i of the k-th kept box in score
+ * order; n_keep[g] = number kept. */
+FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off,
+                      const int32_t *tie, const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode,
+                      int max_nms, int32_t *keep, int32_t *n_keep, fdms_stream stream);
+
+/* out[g, k, :] = rows[g, keep[g,k], 0:n_cols] for k < n_keep[g]  (utils/general.py:595 x[i]) */
+FDMS_API int fdms_gather_rows(fdms_ctx *ctx, const float *rows, int row_stride, int n_cols, const int32_t *keep,
+                              const int32_t *n_keep, int n_seg, int cap, float *out, int out_cap,
+                              fdms_stream stream);
+
+/* ---- rescale -----------------------------------------------------------------------------
+ * utils/general.py:374-404 scale_coords (+clip_coords) with ratio_pad=None, in place on
+ * coords (n, cols) f32 with row stride `row_stride` floats.  kpt_step == 0: box path on
+ * columns 0..3 (the reference clips ROWS 0..3 only, :389); kpt_step == 3: keypoint path over
+ * `cols` columns, every row clipped. */
+FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride, int in_h,
+                               int in_w, int orig_h, int orig_w, int kpt_step, fdms_stream stream);
+/* utils/preprocess_yolo_predict.py:122-157 scale_coords_api_approach on (n,4) boxes;
+ * do_round applies torch.round (half to even) as multi_scale_face_detector.py:144 does. */
+FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64_t row_stride, int in_h,
+                                   int orig_h, int orig_w, int do_round, fdms_stream stream);
+
+/* ---- cross-scale rescale + merge -----------------------------------------------------------
+ * multi_scale_face_detector.py:138-166 (rescale, round, drop landmarks, append scale_idx),
+ * :168-201 calculate_scale_weights, :203-240 weighted_nms, :242-288 detect_multi_scale.
+ * Input: per-scale NMS survivors of n_img images (segment g = img*n_scales + s) given as
+ * cand/keep/n_keep from fdms_decode_filter + fdms_nms.  in_h[s] is the model-input height of
+ * scale s; every image has original size (orig_h, orig_w).  The rescale is ALWAYS the api
+ * transform, as in the reference (:144).
+ * Output: dets (n_img, out_cap, 7) f32 [x1,y1,x2,y2,conf,cls,scale_idx] in weighted-score
+ * order and n_out[img]; merged_in (n_img) optionally receives sum_s n_keep (may be NULL).
+ * If kpts_out != NULL it receives (n_img, out_cap, 15) landmarks of the kept detections
+ * rescaled with the same transform (extension: the reference drops them, :151-153). */
+FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
+                               int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
+                               double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
+                               float *kpts_out, fdms_stream stream);
+
+/* multi_scale_face_detector.py:168-201,224-229 for the standalone weighted_nms(detections) call:
+ * dets (n,7) float64 [x1,y1,x2,y2,conf,cls,scale_idx] -> rows_out (n,8) f32
+ * [x1,y1,x2,y2, (float)(conf*weight), conf, cls, scale_idx]; feed rows_out to fdms_nms
+ * (row_stride 8, box_off 0, score_off 4, tie NULL, TV_CPU) to get the keep list of :234. */
+FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, int n_scales, float *rows_out,
+                                fdms_stream stream);
+
+/* ---- whole post-processing step in one host call ---------------------------------------------
+ * decode_filter -> per-scale NMS -> merge, back to back on `stream` without host sync.
+ * cand/cand_row/count/keep/n_keep are caller-owned scratch with the shapes given above
+ * (n_seg = bs*n_scales).  Counts can be read back afterwards for overflow checks. */
+typedef struct fdms_post_desc {
+    const fdms_level *levels; /* host array */
+    int32_t n_levels, n_scales, bs, cap;
+    float conf_thres;
+    int32_t iou_mode; /* per-scale NMS flavour; the merge NMS is always TV_CPU (:234 runs on CPU) */
+    double iou_thres;
+    const int32_t *in_h_host; /* [n_scales] */
+    int32_t orig_h, orig_w;
+    float *cand; int32_t *cand_row; int32_t *count; int32_t *keep; int32_t *n_keep;
+    float *dets; int32_t *n_out; int32_t out_cap; int32_t pad_;
+    int32_t *merged_in; /* may be NULL */
+    float *kpts_out;    /* may be NULL */
+} fdms_post_desc;
+
+FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDMS_H_ */

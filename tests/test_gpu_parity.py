@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (libfdms through its C ABI) against the CPU oracle and the reference golden
+fixtures.  GPU only (`-m gpu`).  Tolerances (BASELINE.json north_star):
+  pyramid pixels        bit-exact here (north_star allows 1 LSB vs cv2 INTER_LINEAR)
+  candidate counts/sets bit-exact
+  decoded values        <= 1e-4 px absolute
+  NMS keep lists        bit-exact
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from face_detection_multi_scale_b200 import _lib, ops, synth
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_PX = 1e-4
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# =============================================================================== pyramid
+def _pyr(img, geoms, dtype, layout="chw", flip=True, virt=None):
+    src = gpu(img[None])
+    outs = ops.pyramid(src, geoms, out_dtype=dtype, layout=layout, flip_rb=flip, virt_hw=virt)
+    torch.cuda.synchronize()
+    return [o[0].cpu().numpy() for o in outs]
+
+
+@pytest.mark.parametrize("i", range(len(H.LETTERBOX_SMALL)))
+def test_letterbox_small_u8_and_pack(golden, i):
+    g = golden("letterbox")
+    h, w, ns, auto, scaleup, stride, seed = H.LETTERBOX_SMALL[i]
+    img = synth.synth_image(h, w, seed)
+    geom = _lib.letterbox_geometry(h, w, ns, auto=auto, scaleup=scaleup, stride=stride)
+    ref = g["small%d_out" % i]
+    assert (geom.dst_h, geom.dst_w) == ref.shape[:2]
+    (u8,) = _pyr(img, [geom], torch.uint8, layout="hwc", flip=False)
+    assert np.array_equal(u8, ref)  # == cv2.resize + copyMakeBorder of the reference letterbox
+    (f16,) = _pyr(img, [geom], torch.float16)
+    (f32,) = _pyr(img, [geom], torch.float32)
+    assert sha(f16.view(np.uint16)) == str(g["small%d_f16_sha" % i])
+    assert sha(f32) == str(g["small%d_f32_sha" % i])
+
+
+@pytest.mark.parametrize("i", range(len(H.LETTERBOX_FULL)))
+def test_letterbox_full_digest(golden, i):
+    g = golden("letterbox")
+    h, w, ns, auto, stride, seed = H.LETTERBOX_FULL[i]
+    img = synth.synth_image(h, w, seed)
+    geom = _lib.letterbox_geometry(h, w, ns, auto=auto, stride=stride)
+    (u8,) = _pyr(img, [geom], torch.uint8, layout="hwc", flip=False)
+    assert u8.shape[:2] == tuple(g["full_meta"][i][6:8])
+    assert sha(u8) == str(g["full_sha_u8"][i])
+    (f16,) = _pyr(img, [geom], torch.float16)
+    assert sha(f16) == str(g["full_sha_f16"][i])
+
+
+def test_pyramid_three_scales_batch_one_launch(golden):
+    """cfg2 shape: all scales x a batch in ONE launch equals the per-scale reference letterbox."""
+    g = golden("letterbox")
+    h, w, seed = 1080, 1920, 100
+    imgs = np.stack([synth.synth_image(h, w, seed), synth.synth_image(h, w, seed + 1)])
+    geoms = [_lib.letterbox_geometry(h, w, s, auto=True, stride=32) for s in (640, 960, 1280)]
+    outs = ops.pyramid(gpu(imgs), geoms, out_dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert [tuple(o.shape) for o in outs] == [(2, 3, 384, 640), (2, 3, 544, 960), (2, 3, 736, 1280)]
+    for s in range(3):
+        assert sha(outs[s][0].cpu().numpy()) == str(g["full_sha_f16"][s])  # LETTERBOX_FULL[0..2] share seed 100
+        lb, _, _ = O.letterbox(imgs[1], (640, 960, 1280)[s], auto=True, stride=32)
+        assert np.array_equal(outs[s][1].cpu().numpy().view(np.uint16), O.pack_chw(lb, True, np.float16).view(np.uint16))
+
+
+@pytest.mark.parametrize("i", range(len(H.API_CASES)))
+def test_api_preprocess(golden, i):
+    g = golden("letterbox")
+    h, w, size, seed = H.API_CASES[i]
+    rgb = synth.synth_image(h, w, seed)
+    s = max(h, w)
+    geom = _lib.letterbox_geometry(s, s, size, auto=False, stride=32)
+    (chw,) = _pyr(rgb, [geom], torch.uint8, layout="chw", flip=False, virt=(s, s))
+    assert sha(chw) == str(g["api%d_sha" % i])
+
+
+@pytest.mark.parametrize("shape", [((211, 173), (64, 53)), ((53, 37), (143, 100)), ((480, 640), (960, 1280)),
+                                   ((1, 9), (4, 31)), ((300, 300), (300, 300)), ((719, 1279), (360, 640)),
+                                   ((2160, 3840), (360, 640)), ((33, 2000), (17, 40))])
+def test_resize_ragged_shapes_vs_oracle(shape):
+    """Arbitrary (mis-aligned pitch, up- and down-scale, huge ratio) sources through the scalar staging path."""
+    (sh, sw), (dh, dw) = shape
+    img = np.random.default_rng(sh * 7 + dw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    geom = _lib.Geom()
+    geom.dst_h, geom.dst_w, geom.unpad_h, geom.unpad_w = dh, dw, dh, dw
+    geom.resize = 1
+    (u8,) = _pyr(img, [geom], torch.uint8, layout="hwc", flip=False)
+    assert np.array_equal(u8, O.resize_linear_u8(img, dh, dw))
+
+
+def test_pyramid_strided_rows():
+    """Source given as a view with a padded row pitch (16-byte aligned and not)."""
+    for pad in (16, 5):
+        full = np.random.default_rng(pad).integers(0, 256, (120, 200 + pad, 3), dtype=np.uint8)
+        t = gpu(full)[None][:, :, :200, :]
+        geom = _lib.letterbox_geometry(120, 200, 96, auto=True, stride=32)
+        (out,) = ops.pyramid(t, [geom], out_dtype=torch.uint8, layout="hwc", flip_rb=False)
+        ref, _, _ = O.letterbox(full[:, :200], 96, auto=True, stride=32)
+        assert np.array_equal(out[0].cpu().numpy(), ref)
+
+
+# =============================================================================== decode
+def _crowd(name, dtype=np.float32):
+    in_h, in_w, n_faces, seed = H.CROWD_HEADS[name]
+    return [l.astype(dtype) for l in H.crowd_levels(in_h, in_w, n_faces, seed)]
+
+
+@pytest.mark.parametrize("name", list(H.CROWD_HEADS))
+def test_decode_dense_vs_oracle_and_reference(golden, name):
+    g = golden("head")
+    levels = _crowd(name)
+    pred = ops.decode_dense([gpu(l) for l in levels], synth.P5_STRIDES, synth.P5_ANCHORS).cpu().numpy()
+    ref = O.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    assert pred.shape == ref.shape
+    assert np.max(np.abs(pred - ref)) <= TOL_PX
+    assert np.mean(pred == ref) > 0.999  # same correctly-rounded sigmoid: essentially bit identical
+    assert np.max(np.abs(pred[0, :64] - g[name + "_pred_b0_head"])) <= TOL_PX  # reference IKeypoint.forward
+
+
+def test_decode_dense_tiny_model_fp16_and_fp32(golden):
+    g = golden("head")
+    levels = [g["tiny_raw%d" % i] for i in range(3)]
+    pred = ops.decode_dense([gpu(l) for l in levels], g["tiny_strides"], g["tiny_anchors_px"]).cpu().numpy()
+    assert np.max(np.abs(pred - g["tiny_pred"])) <= TOL_PX
+    lv16 = [l.astype(np.float16) for l in levels]
+    p16 = ops.decode_dense([gpu(l) for l in lv16], g["tiny_strides"], g["tiny_anchors_px"]).cpu().numpy()
+    ref16 = O.decode_head(lv16, g["tiny_strides"], g["tiny_anchors_px"])
+    assert np.max(np.abs(p16 - ref16)) <= TOL_PX
+
+
+def _sorted_cands(c, seg):
+    n = int(c.count[seg].item())
+    rows = c.row[seg, :n].cpu().numpy()
+    cand = c.cand[seg, :n].cpu().numpy()
+    o = np.argsort(rows, kind="stable")
+    return cand[o], rows[o]
+
+
+@pytest.mark.parametrize("name", list(H.CROWD_HEADS))
+@pytest.mark.parametrize("conf", [0.5, 0.25, 0.6, 0.01])
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_decode_filter_counts_and_sets(name, conf, dtype):
+    levels = _crowd(name, dtype)
+    ref_pred = O.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    c = ops.decode_filter([[gpu(l) for l in levels]], synth.P5_STRIDES, synth.P5_ANCHORS, conf, cap=ref_pred.shape[1])
+    torch.cuda.synchronize()
+    for b in range(ref_pred.shape[0]):
+        rc, rr = O.filter_xyxy(ref_pred[b], conf)
+        cand, rows = _sorted_cands(c, b)
+        assert len(rows) == len(rr)          # candidate count: bit exact
+        assert np.array_equal(rows, rr)      # candidate set: bit exact
+        assert np.max(np.abs(cand - rc), initial=0) <= TOL_PX
+        assert np.array_equal(cand[:, 4], rc[:, 4])  # conf drives the NMS order: must be identical
+
+
+def test_decode_filter_multi_scale_segments():
+    """Three scales x batch 2 in one launch: segment g = b * n_scales + s."""
+    shapes = [(96, 160), (128, 224), (192, 320)]
+    sl = []
+    for si, (ih, iw) in enumerate(shapes):
+        sl.append(H.crowd_levels(ih, iw, 10 + 5 * si, 40 + si))
+    c = ops.decode_filter([[gpu(l) for l in lv] for lv in sl], synth.P5_STRIDES, synth.P5_ANCHORS, 0.4, cap=2048)
+    torch.cuda.synchronize()
+    for si, lv in enumerate(sl):
+        pred = O.decode_head(lv, synth.P5_STRIDES, synth.P5_ANCHORS)
+        for b in range(2):
+            rc, rr = O.filter_xyxy(pred[b], 0.4)
+            cand, rows = _sorted_cands(c, b * 3 + si)
+            assert np.array_equal(rows, rr) and len(rr) > 0
+            assert np.max(np.abs(cand - rc)) <= TOL_PX
+
+
+def test_decode_filter_overflow_is_reported():
+    levels = _crowd("crowdA")
+    c = ops.decode_filter([[gpu(l) for l in levels]], synth.P5_STRIDES, synth.P5_ANCHORS, 0.01, cap=16)
+    cnt = c.count.cpu().numpy()
+    pred = O.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    assert cnt[0] == len(O.filter_xyxy(pred[0], 0.01)[1]) > 16  # total is still exact; caller sees count > cap
+
+
+def test_filter_pred_matches_oracle(golden):
+    g = golden("head")
+    pred = g["tiny_pred"]
+    thr = float(g["tiny_conf_thres"])
+    c = ops.filter_pred(gpu(pred), thr, cap=pred.shape[1])
+    for b in range(2):
+        rc, rr = O.filter_xyxy(pred[b], thr)
+        cand, rows = _sorted_cands(c, b)
+        assert np.array_equal(rows, rr)
+        assert np.array_equal(cand, rc)  # same fp32 inputs: bit exact
+
+
+# =============================================================================== NMS
+@pytest.mark.parametrize("name", ["rand", "int", "exact", "crowd", "one"])
+def test_nms_golden_torchvision_cpu(golden, name):
+    g = golden("nms")
+    boxes, scores = gpu(g[name + "_boxes"]), gpu(g[name + "_scores"])
+    for t in g[name + "_thrs"]:
+        ref = g["%s_keep_%d" % (name, int(round(t * 1e6)))]
+        got = ops.nms(boxes, scores, float(t), ops.IOU_TV_CPU).cpu().numpy()
+        assert np.array_equal(got, ref), (name, t)
+
+
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 257, 2000, 5000, 9000])
+def test_nms_vs_oracle_sizes(mode, n):
+    rng = np.random.default_rng(n)
+    xy = rng.integers(0, 120, (n, 2)).astype(np.float32)
+    wh = rng.integers(1, 40, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = np.round(rng.uniform(0, 1, n), 2).astype(np.float32)  # many exact ties
+    for t in (0.3, 0.5, 1 / 3):
+        ref = O.nms(boxes, scores, t, mode)
+        got = ops.nms(gpu(boxes), gpu(scores), t, mode).cpu().numpy()
+        assert np.array_equal(got, ref), (n, t)
+
+
+def test_nms_matches_torchvision_cuda_kernel():
+    """The TV_CUDA flavour against the real torchvision sm_100 kernel on the same box."""
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(77)
+    for n in (300, 4000):
+        xy = rng.uniform(0, 400, (n, 2)); wh = rng.uniform(4, 90, (n, 2))
+        boxes = gpu(np.concatenate([xy, xy + wh], 1).astype(np.float32))
+        scores = gpu(rng.uniform(0, 1, n).astype(np.float32))
+        for t in (0.3, 0.45, 0.5):
+            ref = tv.ops.nms(boxes, scores, t).cpu().numpy()
+            got = ops.nms(boxes, scores, t, ops.IOU_TV_CUDA).cpu().numpy()
+            assert np.array_equal(got, ref), (n, t)
+
+
+def test_nms_batched_segments_with_ties_and_empty():
+    """Many segments of different sizes (0, 1, ragged) in one call; tie order follows `tie`."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 5, 64, 200, 0, 777, 1500]
+    cap = 1600
+    rows = np.zeros((len(sizes), cap, 21), np.float32)
+    tie = np.zeros((len(sizes), cap), np.int32)
+    refs = []
+    for gi, n in enumerate(sizes):
+        p = synth.synth_pred(max(n, 1), 12, 30, 100 + gi, tie_decimals=1)[:n]
+        cand, src = O.filter_xyxy(p, -1.0)  # everything passes; xyxy conversion
+        perm = rng.permutation(n)         # scramble storage order like the atomic compaction does
+        rows[gi, :n] = cand[perm]
+        tie[gi, :n] = src[perm]
+        keep = O.nms(cand[:, :4], cand[:, 4], 0.45, O.TV_CUDA)
+        refs.append(cand[keep])
+    count = torch.tensor(sizes, dtype=torch.int32, device=DEV)
+    rows_d = gpu(rows)
+    keep, n_keep = ops.nms_segments(rows_d, count, cap, 0.45, ops.IOU_TV_CUDA, tie=gpu(tie))
+    out = ops.gather_rows(rows_d, keep, n_keep, 21, cap).cpu().numpy()
+    nk = n_keep.cpu().numpy()
+    for gi, n in enumerate(sizes):
+        assert nk[gi] == len(refs[gi])
+        assert np.array_equal(out[gi, :nk[gi]], refs[gi])
+
+
+def test_nms_max_nms_cut():
+    """utils/general.py:578-579: more than max_nms candidates -> only the best max_nms enter NMS."""
+    n, cut = 3000, 1000
+    p = synth.synth_pred(n, 40, 60, 9)
+    cand, _ = O.filter_xyxy(p, -1.0)
+    order = np.argsort(-cand[:, 4], kind="stable")[:cut]
+    ref = order[O.nms(cand[order, :4], cand[order, 4], 0.5, O.TV_CUDA)]
+    rows = gpu(cand[None])
+    count = torch.tensor([n], dtype=torch.int32, device=DEV)
+    keep, n_keep = ops.nms_segments(rows, count, n, 0.5, ops.IOU_TV_CUDA, max_nms=cut)
+    assert np.array_equal(keep[0, :int(n_keep[0])].cpu().numpy(), ref)
+
+
+def test_nms_large_segment_global_sort_path():
+    """> 8192 candidates: sort runs out of the global scratch; dense crowd, heavy ties."""
+    n = 20000
+    p = synth.synth_pred(n, 300, 70, 21, extent=(1280.0, 1280.0), tie_decimals=2)
+    cand, src = O.filter_xyxy(p, -1.0)
+    ref = O.nms(cand[:, :4], cand[:, 4], 0.5, O.TV_CUDA)
+    rows = gpu(cand[None])
+    count = torch.tensor([n], dtype=torch.int32, device=DEV)
+    keep, n_keep = ops.nms_segments(rows, count, n, 0.5, ops.IOU_TV_CUDA)
+    assert int(n_keep[0]) == len(ref)
+    assert np.array_equal(keep[0, :len(ref)].cpu().numpy(), ref)
+
+
+# =============================================================================== rescale / merge
+def test_rescale_golden(golden):
+    g = golden("rescale")
+    for i, (ih, iw, h0, w0) in enumerate(g["meta"]):
+        b = g["c%d_boxes" % i]; k = g["c%d_kpts" % i]
+        assert np.array_equal(ops.scale_coords_((ih, iw), gpu(b), (h0, w0)).cpu().numpy(), g["c%d_std_boxes" % i])
+        assert np.array_equal(ops.scale_coords_((ih, iw), gpu(k), (h0, w0), kpt_step=3).cpu().numpy(),
+                              g["c%d_std_kpts" % i])
+        assert np.array_equal(ops.scale_coords_api_((ih, iw), gpu(b), (h0, w0)).cpu().numpy(), g["c%d_api_boxes" % i])
+        assert np.array_equal(ops.scale_coords_api_((ih, iw), gpu(b), (h0, w0), True).cpu().numpy(),
+                              g["c%d_api_round" % i])
+
+
+def test_weighted_nms_golden(golden):
+    g = golden("merge")
+    for ci in range(5):
+        dets = g["m%d_dets" % ci]
+        n_scales, iou = g["m%d_meta" % ci]
+        rows = ops.weighted_rows(gpu(dets), int(n_scales))
+        w = rows[0, :, 4].cpu().numpy().astype(np.float64) / dets[:, 4]
+        assert np.allclose(w, g["m%d_weights" % ci], rtol=1e-6)
+        count = torch.tensor([dets.shape[0]], dtype=torch.int32, device=DEV)
+        keep, n_keep = ops.nms_segments(rows, count, dets.shape[0], float(iou), ops.IOU_TV_CPU, max_nms=0)
+        k = keep[0, :int(n_keep[0])].cpu().numpy()
+        assert np.array_equal(dets[k], g["m%d_out" % ci])
+
+
+# =============================================================================== end to end
+@pytest.mark.parametrize("case", H.E2E_CASES, ids=[c[0] for c in H.E2E_CASES])
+def test_e2e_postprocess_golden(golden, case):
+    """Raw heads of every scale -> fdms_postprocess (one C call) == the reference's detect_multi_scale."""
+    g = golden("e2e")
+    name, h, w, sizes, n_faces, conf, iou, api, seed = case
+    heads, shapes = H.e2e_heads(h, w, sizes, n_faces, api, seed)
+    sl = [[gpu(l[None]) for l in heads[s]] for s in shapes]
+    plan = ops.PostPlan(sl, synth.P5_STRIDES, synth.P5_ANCHORS, [s[0] for s in shapes], (h, w), conf, iou, cap=4096,
+                        out_cap=4096, iou_mode=ops.IOU_TV_CPU)  # the golden run was on CPU
+    out = plan.run()
+    torch.cuda.synchronize()
+    n = int(out.n_out[0])
+    ref = g[name + "_final"]
+    got = out.dets[0, :n].cpu().numpy().astype(np.float64)
+    assert got.shape[0] == ref.shape[0]
+    if ref.size:
+        assert np.array_equal(got, ref)
+    # per-scale survivors as well
+    nk = plan.cands.n_keep.cpu().numpy()
+    for si in range(len(sizes)):
+        assert nk[si] == g["%s_scale%d" % (name, si)].shape[0]

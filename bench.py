@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-scale face-detection pre/post-processing hot path on B200 (libfdms).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg5] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: the fused pyramid kernel over
+B source images (all scales, one launch) followed by the post-processing of the B x scales raw head
+tensors (decode+filter, batched NMS, rescale, cross-scale weighted NMS).  The PyTorch backbone between the
+two halves is out of scope (BASELINE.json north_star: it stays unchanged) and is NOT in the timed region; its
+outputs are synthetic raw head maps with planted faces (random-init weights yield no candidates).
+
+Prints ONE JSON line (rank 0).  `value` = images/s with all inputs resident in HBM; `e2e` = the same metric
+through the public API (MultiScaleFaceDetector.detect_multi_scale_batch) with pinned HOST inputs, H2D of the
+images and of the head maps and D2H of the detections inside the timed region.
+"""
+import argparse
+import concurrent.futures
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(desc="cfg2: yolov7s-face head, 3-scale pyramid (640/960/1280), batch 32 synthetic 1920x1080 images",
+                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=60, conf=0.5, iou=0.5, radius=1, cap=4096),
+    # configs[2]: dense crowd, ~20k pre-NMS candidates per image
+    "cfg3": dict(desc="cfg3: dense-crowd stress, ~20k pre-NMS candidates/image, 3-scale pyramid, batch 32 1920x1080",
+                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=420, conf=0.5, iou=0.5, radius=2, cap=16384),
+    # configs[4]: single-scale high throughput (per-GPU shard of the batch-512 job)
+    "cfg5": dict(desc="cfg5: lite-t head, single scale 640, batch 64/GPU synthetic 1920x1080 images",
+                 h=1080, w=1920, sizes=[640], batch=64, faces=40, conf=0.5, iou=0.5, radius=1, cap=4096),
+}
+METRIC = "images/sec (3-scale pyramid, device-timed)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="fdms", choices=["fdms", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: no CPU baseline, no e2e, no clocks")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_image(oracle, synth, img, heads_s, shapes, sizes, conf, iou):
+    """The whole reference path for ONE image on the host (oracle port of the reference's CPU path):
+    per scale letterbox + pack (utils/datasets.py:873, msfd:96-105), then decode + NMS + rescale + merge
+    (models/yolo.py:267-308, utils/general.py:506, ppyp:122, msfd:168-240)."""
+    for size in sizes:
+        lb, _, _ = oracle.letterbox(img, size, auto=True, stride=32)
+        oracle.pack_chw(lb, flip=True, dtype=np.float16)
+    final, _ = oracle.detect_from_heads([[l[None] for l in hs] for hs in heads_s], shapes, img.shape, synth.P5_STRIDES,
+                                        synth.P5_ANCHORS, conf, iou, oracle.TV_CPU)
+    return len(final)
+
+
+def cpu_run(images, heads, shapes, wl, n_images, threads):
+    """Process images[0:n_images] on `threads` host threads (the C oracle releases the GIL). Returns seconds."""
+    from face_detection_multi_scale_b200 import synth
+    from oracle import oracle
+    oracle.lib()
+    per = [[[heads[s][l][b] for l in range(len(heads[s]))] for s in range(len(heads))] for b in range(n_images)]
+    t0 = time.perf_counter()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda b: cpu_image(oracle, synth, images[b], per[b], shapes, wl["sizes"], wl["conf"], wl["iou"]),
+                    range(n_images)))
+    return time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B, sizes = wl["batch"], wl["sizes"]
+
+    if args.impl == "reference":
+        return reference_arm(args, wl, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from face_detection_multi_scale_b200 import _lib, ops, standin, synth
+    from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libfdms has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic workload (per-rank seed: every GPU processes its own shard of the image batch) ----
+    images, heads, shapes = standin.make_batch(wl["h"], wl["w"], sizes, B, wl["faces"], seed=17 + rank,
+                                               radius=wl["radius"])
+    geoms = [_lib.letterbox_geometry(wl["h"], wl["w"], s, auto=True, stride=32) for s in sizes]
+    assert [(g.dst_h, g.dst_w) for g in geoms] == [tuple(s) for s in shapes]
+    n_sets = 2  # rotate two input sets: nothing of step i is still in L2 for step i+1 (each set >> 126 MB L2 anyway)
+    sets = []
+    for k in range(n_sets):
+        img_d = torch.from_numpy(images if k == 0 else np.roll(images, k, axis=0)).to(dev)
+        heads_d = [[torch.from_numpy(l if k == 0 else np.roll(l, k, axis=0)).to(dev) for l in hs] for hs in heads]
+        outs = [torch.empty((B, 3, g.dst_h, g.dst_w), dtype=torch.float16, device=dev) for g in geoms]
+        plan = ops.PostPlan(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, [g.dst_h for g in geoms], (wl["h"], wl["w"]),
+                            wl["conf"], wl["iou"], cap=wl["cap"], out_cap=wl["cap"], iou_mode=ops.IOU_TV_CUDA)
+        sets.append((img_d, heads_d, outs, plan))
+
+    def step(i):
+        img_d, _, outs, plan = sets[i % n_sets]
+        ops.pyramid(img_d, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, outs=outs)
+        plan.run()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    # capacities / counts of the workload (checked once, outside the timed region)
+    plan0 = sets[0][3]
+    cnt = plan0.cands.count.cpu().numpy()
+    nkeep = plan0.cands.n_keep.cpu().numpy()
+    nout = plan0.out.n_out.cpu().numpy()
+    if cnt.max() > wl["cap"] or nkeep.min() < 0 or nout.max() > wl["cap"]:
+        raise SystemExit("bench.py: workload exceeds capacities (count max %d)" % cnt.max())
+    cand_per_step = int(cnt.sum())
+
+    # ---- timed region: EXACTLY K steps, device-timed, max over ranks ----
+    sampler = ClockSampler(physical_gpu_index(local)) if not args.profile else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- per-stage breakdown + roofline of the dominant kernel (same steps, CUDA events per stage) ----
+    stage_names = ["pyramid", "decode_filter", "nms", "merge"]
+    K2 = min(args.steps, 50) if not args.profile else 2
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(K2)]
+    for i in range(K2):
+        img_d, heads_d, outs, plan = sets[i % n_sets]
+        c = plan.cands
+        evs[i][0].record()
+        ops.pyramid(img_d, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, outs=outs)
+        evs[i][1].record()
+        ops.decode_filter(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, wl["conf"], wl["cap"], out=c)
+        evs[i][2].record()
+        ops.nms_segments(c.cand, c.count, c.cap, wl["iou"], ops.IOU_TV_CUDA, tie=c.row, keep=c.keep, n_keep=c.n_keep)
+        evs[i][3].record()
+        ops.merge_scales(c, B, len(sizes), [g.dst_h for g in geoms], (wl["h"], wl["w"]), wl["iou"], wl["cap"], out=plan.out)
+        evs[i][4].record()
+    torch.cuda.synchronize()
+    stage_ms = {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K2)]))
+                for j, n in enumerate(stage_names)}
+    clocks = sampler.stop() if sampler else None
+
+    src_bytes = wl["h"] * wl["w"] * 3
+    out_bytes = sum(3 * g.dst_h * g.dst_w * 2 for g in geoms)
+    pyr_bytes = B * (src_bytes + out_bytes)  # source read once + every scale written once (fp16)
+    head_bytes = B * sum(int(np.prod(l.shape[1:])) * 2 for hs in heads for l in hs)
+    peaks, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("pyramid_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved = pyr_bytes / (stage_ms["pyramid"] * 1e-3) / 1e9
+    roofline = {"kernel": "pyramid_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s",
+                "unit": "GB/s", "frac": round(achieved / peaks, 4), "traffic": traffic,
+                "algorithmic_bytes_per_launch": pyr_bytes, "launch_ms": round(stage_ms["pyramid"], 4),
+                "share_of_step": round(stage_ms["pyramid"] / sum(stage_ms.values()), 3)}
+    decode_gbs = head_bytes / (stage_ms["decode_filter"] * 1e-3) / 1e9
+
+    # ---- end to end through the public API, host buffers in, host arrays out ----
+    e2e = None
+    if not args.no_e2e and not args.profile:
+        model = standin.SyntheticHeadModel()
+        for s, hw in enumerate(shapes):
+            model.set_heads(hw, heads[s], pin=True)
+        det = MultiScaleFaceDetector(model, device=dev, img_sizes=sizes, conf_thres=wl["conf"], iou_thres=wl["iou"],
+                                     cap=wl["cap"], out_cap=wl["cap"])
+        pinned = torch.from_numpy(images).pin_memory()
+        res = None
+        for _ in range(3):
+            res = det.detect_multi_scale_batch(pinned)
+        model.h2d_bytes = 0
+        Ke = min(args.steps, 100)
+        d2h = sum(r.size for r in res) * 4 + 4 * (B + 3)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        x0.record()
+        for _ in range(Ke):
+            res = det.detect_multi_scale_batch(pinned)  # ends with the D2H read of the results
+        x1.record()
+        barrier()
+        dt = x0.elapsed_time(x1) / 1e3
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(world * B * Ke / dt, 1), "unit": "images/s", "steps": Ke,
+               "h2d_bytes_per_step": int(pinned.numel() + model.h2d_bytes // Ke), "d2h_bytes_per_step": int(d2h),
+               "api": "MultiScaleFaceDetector.detect_multi_scale_batch(pinned host uint8 batch) -> list of ndarray",
+               "final_detections_per_step": int(sum(len(r) for r in res))}
+
+    # ---- CPU baseline: the oracle port of the reference's CPU path on this box's host cores (rank 0) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and not args.profile:
+        thr = host_threads()
+        n = args.cpu_sample or min(B, max(4, min(thr, 32)))
+        cpu_run(images, heads, shapes, wl, min(2, n), min(2, thr))  # warm the library / page in
+        secs = cpu_run(images, heads, shapes, wl, n, thr)
+        cpu = {"value": round(n / secs, 2), "unit": "images/s", "cores": min(thr, n), "kind": "port",
+               "sample": "%d of the %d images of one batch, all stages (3x letterbox+pack, decode, NMS, rescale, merge), "
+                         "one image per thread, %.1f s" % (n, B, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "batch_per_gpu": B, "scales": sizes,
+                       "letterboxed_hw": [list(s) for s in shapes], "conf_thres": wl["conf"], "iou_thres": wl["iou"],
+                       "planted_faces_per_image": wl["faces"], "candidates_per_step": cand_per_step,
+                       "backbone": "excluded (unchanged PyTorch, out of scope); raw head maps are synthetic fp16",
+                       "l2": "inputs larger than L2 (340 MB/step) and two input sets rotated",
+                       "parallelism": "image-sharded, no collective" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + ops.PostPlan.LAUNCHES),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+            "nms_candidates_per_sec": round(world * cand_per_step / (stage_ms["nms"] * 1e-3), 0),
+            "decode_algorithmic_gbs": round(decode_gbs, 1),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args, wl, rank, world):
+    """`--impl reference`: the reference's CPU path (oracle port -- the Python reference cannot travel to the GPU
+    box) on all host threads, same metric/config; rank 0 only."""
+    if rank != 0:
+        return
+    from face_detection_multi_scale_b200 import standin
+    thr = host_threads()
+    n = args.cpu_sample or max(4, min(thr, 32))
+    images, heads, shapes = standin.make_batch(wl["h"], wl["w"], wl["sizes"], n, wl["faces"], seed=17, radius=wl["radius"])
+    steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(images, heads, shapes, wl, n, thr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_run(images, heads, shapes, wl, n, thr)
+    dt = time.perf_counter() - t0
+    v = round(n * steps / dt, 2)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": world, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample_images_per_step": n, "scales": wl["sizes"]},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": min(thr, n), "kind": "port",
+                         "sample": "%d images per step x %d steps on %d host threads" % (n, steps, min(thr, n))},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+if __name__ == "__main__":
+    main()

@@ -117,7 +117,7 @@ __global__ void merge_prepare_kernel(const __grid_constant__ MergeParams P) {
 // msfd:168-201 + 224-229 on an (n,7) float64 detection array (the weighted_nms drop-in):
 // rows_out (n,8) f32 = [x1,y1,x2,y2 as float32, weighted score, conf, cls, scale_idx]
 __global__ void weighted_rows_kernel(const double *__restrict__ dets, long long n, int n_scales,
-                                     float *__restrict__ rows_out) {
+                                     float *__restrict__ rows_out, double *__restrict__ weights_out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double *d = dets + i * 7;
@@ -131,6 +131,7 @@ __global__ void weighted_rows_kernel(const double *__restrict__ dets, long long 
     o[0] = (float)d[0]; o[1] = (float)d[1]; o[2] = (float)d[2]; o[3] = (float)d[3];
     o[4] = (float)__dmul_rn(d[4], wt);
     o[5] = (float)d[4]; o[6] = (float)d[5]; o[7] = (float)d[6];
+    if (weights_out) weights_out[i] = wt;
 }
 
 struct EmitParams {
@@ -206,12 +207,13 @@ FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64
 }
 
 FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, int n_scales, float *rows_out,
-                                fdms_stream stream) {
+                                double *weights_out, fdms_stream stream) {
     if (int rc = fdms_bind(ctx)) return rc;
     if (n == 0) return FDMS_OK;
     if (!dets || !rows_out || n < 0 || n_scales <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_weighted_rows: bad arguments");
-    weighted_rows_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(dets, n, n_scales, rows_out);
+    weighted_rows_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(dets, n, n_scales, rows_out,
+                                                                                           weights_out);
     FDMS_LAUNCH_CHECK(ctx, "weighted_rows_kernel");
     return FDMS_OK;
 }

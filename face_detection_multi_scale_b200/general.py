@@ -1,0 +1,125 @@
+"""Drop-ins for the hot-path functions of the reference's `utils/general.py`, running on libfdms:
+
+    non_max_suppression   utils/general.py:506-600   (kpt_label=5, nc=1 -- every cfg/*.yaml of the reference)
+    scale_coords          utils/general.py:374-399   (in place, returns coords)
+    clip_coords           utils/general.py:401-404
+    xywh2xyxy             utils/general.py:299-306
+    check_img_size        utils/general.py:130-135
+    make_divisible        utils/general.py:210-212
+
+Same names, argument meaning and return types as the reference.  Tensors that live on the CPU are
+moved to the current CUDA device and back (there is no CPU implementation in this package).
+"""
+import math
+
+import torch
+
+from . import _lib, ops
+
+# torchvision.ops.nms flavour reproduced by non_max_suppression: the reference calls it
+# on whatever device the prediction lives on -- the CUDA kernel in production.
+IOU_MODE = ops.IOU_TV_CUDA
+MAX_NMS = 30000         # utils/general.py:520
+_DEFAULT_CAP = 4096     # first-try candidate capacity per image; grown on overflow
+
+
+def make_divisible(x, divisor):  # utils/general.py:210
+    return math.ceil(x / divisor) * divisor
+
+
+def check_img_size(img_size, s=32):  # utils/general.py:130
+    new_size = make_divisible(img_size, int(s))
+    if new_size != img_size:
+        print('WARNING: --img-size %g must be multiple of max stride %g, updating to %g' % (img_size, s, new_size))
+    return new_size
+
+
+def _cuda(t):
+    return t if t.is_cuda else t.to(torch.device("cuda", torch.cuda.current_device()))
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                        labels=(), kpt_label=5, nc=None, iou_mode=None):
+    """utils/general.py:506.  prediction (bs, rows, 21) -> list of (n, 21) tensors
+    [x1, y1, x2, y2, conf, cls, 15 kpt] per image, (0, 6) zeros for images without detections (:527).
+    One filter launch + one batched NMS (3 launches) + one gather for the whole batch; a single
+    device->host read of the per-image counts."""
+    if prediction.dim() != 3:
+        raise ValueError("non_max_suppression: prediction must be (bs, rows, no)")
+    if nc is None:
+        nc = prediction.shape[2] - 5 if not kpt_label else prediction.shape[2] - 5 - kpt_label * 3
+    if prediction.shape[2] != ops.NO or kpt_label != 5 or nc != 1:
+        raise NotImplementedError("non_max_suppression on libfdms covers the face head (no=21: nc=1, kpt_label=5); got "
+                                  "no=%d kpt_label=%r nc=%r" % (prediction.shape[2], kpt_label, nc))
+    if labels:
+        raise NotImplementedError("non_max_suppression: autolabelling `labels` is not on the hot path")
+    # multi_label &= nc > 1 (:522) -> always False here; agnostic only changes the class offset, 0 for nc == 1
+    src_device, src_dtype = prediction.device, prediction.dtype
+    pred = _cuda(prediction)
+    if pred.dtype not in (torch.float16, torch.float32):
+        pred = pred.float()
+    bs, rows, _ = pred.shape
+    empty = torch.zeros((0, 6), device=src_device)
+    if bs == 0:
+        return []
+    if classes is not None and 0 not in [int(c) for c in (classes if hasattr(classes, "__iter__") else [classes])]:
+        return [empty] * bs  # every detection has class 0 (:566-567)
+    mode = IOU_MODE if iou_mode is None else iou_mode
+    cap = min(rows, _DEFAULT_CAP)
+    while True:
+        c = ops.filter_pred(pred, conf_thres, cap)
+        ops.nms_segments(c.cand, c.count, cap, iou_thres, mode, max_nms=MAX_NMS, tie=c.row, keep=c.keep, n_keep=c.n_keep)
+        counts = torch.stack((c.count, c.n_keep)).cpu()  # the one synchronisation of this call
+        n_cand, n_keep = counts[0], counts[1]
+        if int(n_cand.max()) > cap:  # more candidates than capacity: redo with room for all of them
+            cap = min(rows, int(n_cand.max()))
+            continue
+        break
+    if int(n_keep.min()) < 0:
+        raise _lib.FdmsError("non_max_suppression: a segment exceeded the suppression-mask budget "
+                             "(raise FDMS_MASK_BUDGET_MB)")
+    kmax = int(n_keep.max())
+    if kmax == 0:
+        return [empty] * bs
+    out = ops.gather_rows(c.cand, c.keep, c.n_keep, ops.NO, kmax)
+    if out.dtype != src_dtype:
+        out = out.to(src_dtype)
+    if out.device != src_device:
+        out = out.to(src_device)
+    return [out[b, :int(n_keep[b])] if int(n_keep[b]) else empty for b in range(bs)]
+
+
+def xywh2xyxy(x):  # utils/general.py:299 (plain tensor arithmetic; the fused kernels do this inside the filter)
+    y = x.clone() if isinstance(x, torch.Tensor) else x.copy()
+    y[:, 0] = x[:, 0] - x[:, 2] / 2
+    y[:, 1] = x[:, 1] - x[:, 3] / 2
+    y[:, 2] = x[:, 0] + x[:, 2] / 2
+    y[:, 3] = x[:, 1] + x[:, 3] / 2
+    return y
+
+
+def _inplace_on_device(coords, fn):
+    """Run fn on a CUDA fp32 tensor that aliases `coords` when possible, else copy there and back."""
+    if coords.is_cuda and coords.dtype == torch.float32 and coords.dim() == 2 and coords.stride(1) == 1:
+        fn(coords)
+        return coords
+    tmp = _cuda(coords).float().contiguous()
+    fn(tmp)
+    coords.copy_(tmp.to(coords.dtype))
+    return coords
+
+
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, kpt_label=False, step=2):
+    """utils/general.py:374.  Mutates `coords` in place and returns it, including the reference's
+    clip quirk (boxes: only ROWS 0..3 are clipped, :389)."""
+    if ratio_pad is not None:
+        raise NotImplementedError("scale_coords: explicit ratio_pad is only used by test.py (out of the hot path)")
+    if coords.shape[0] == 0:
+        return coords
+    kstep = int(step) if kpt_label else 0
+    return _inplace_on_device(coords, lambda t: ops.scale_coords_(img1_shape, t, img0_shape, kstep))
+
+
+def clip_coords(boxes, img_shape, step=2):  # utils/general.py:401
+    boxes[:, 0::step].clamp_(0, img_shape[1])
+    boxes[:, 1::step].clamp_(0, img_shape[0])

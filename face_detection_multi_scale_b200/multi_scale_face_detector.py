@@ -1,0 +1,275 @@
+"""B200-native drop-in for the reference's `multi_scale_face_detector.py::MultiScaleFaceDetector` (:28-288).
+
+Same constructor arguments, same methods and return types (`preprocess_image`, `detect_single_scale`,
+`calculate_scale_weights`, `weighted_nms`, `detect_multi_scale`), plus the batched entry point the
+reference lacks (`detect_multi_scale_batch`): all images x all scales go through ONE pyramid launch,
+one backbone forward per scale (unchanged PyTorch), and ONE post-processing call (decode+filter,
+batched NMS, rescale, cross-scale weighted NMS) with a single device->host read at the end.
+No prints on the hot path, no per-image host synchronisation, no CPU fallback.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, ops, yolo_head
+from .general import check_img_size
+
+
+def _resolve_device(device):
+    if isinstance(device, torch.device):
+        d = device
+    else:
+        s = str(device).strip().lower()
+        if s in ("", "cuda"):
+            d = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        elif s == "cpu":
+            raise RuntimeError("MultiScaleFaceDetector (libfdms) has no CPU path; use the reference on CPU")
+        elif s.isdigit():
+            d = torch.device("cuda", int(s))
+        else:
+            d = torch.device(s)
+    if d is None or d.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("MultiScaleFaceDetector (libfdms) needs a CUDA device; none is available")
+    return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
+def _load_model(model_path, device):
+    """multi_scale_face_detector.py:48 -> utils/preprocess_yolo_predict.py:381 load_yolo_model.  A built
+    nn.Module is used as is; a checkpoint path needs the reference's own model classes importable."""
+    if isinstance(model_path, torch.nn.Module):
+        return model_path.to(device).eval()
+    try:
+        from models.experimental import attempt_load  # the user's reference checkout (unchanged backbone)
+    except Exception as e:  # pragma: no cover - depends on the deployment
+        raise RuntimeError("loading a checkpoint path needs the reference's `models` package on sys.path "
+                           "(the backbone stays the reference's PyTorch code); pass a built nn.Module instead") from e
+    return attempt_load(model_path, map_location=device).eval()
+
+
+class MultiScaleFaceDetector:
+    """Multi-scale test-time-augmentation face detector (multi_scale_face_detector.py:28)."""
+
+    def __init__(self, model_path, device='', img_sizes=[640, 3840], conf_thres=0.5, iou_thres=0.5,
+                 use_api_preprocess=False, *, cap=4096, out_cap=None, iou_mode=ops.IOU_TV_CUDA, half=True,
+                 with_landmarks=False):
+        self.device = _resolve_device(device)
+        torch.cuda.set_device(self.device)
+        self.model = _load_model(model_path, self.device)
+        self.half = bool(half)  # msfd:49: half precision on CUDA
+        if self.half:
+            self.model.half()
+        self.stride = int(self.model.stride.max())                                    # msfd:51
+        self.img_sizes = [check_img_size(size, s=self.stride) for size in img_sizes]  # msfd:52
+        m = self.model.module if hasattr(self.model, 'module') else self.model
+        self.names = getattr(m, 'names', ['face'])
+        self.conf_thres = conf_thres
+        self.iou_thres = iou_thres
+        self.use_api_preprocess = use_api_preprocess
+        # libfdms specifics
+        self.cap = int(cap)                    # candidate capacity per (image, scale); grown on overflow
+        self.out_cap = int(out_cap) if out_cap else None
+        self.iou_mode = iou_mode               # per-scale NMS flavour; the merge NMS is always TV_CPU (msfd:234)
+        self.with_landmarks = bool(with_landmarks)
+        self.head = yolo_head.patch_head(yolo_head.find_head(self.model))
+        self.strides, self.anchors_px = yolo_head.head_geometry(self.head)
+        self._plans = {}
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------ geometry / preprocessing
+    def _geoms(self, h, w, sizes=None):
+        sizes = self.img_sizes if sizes is None else sizes
+        if self.use_api_preprocess:  # ppyp:345-378: zero-padded square, letterbox(auto=False)
+            s = max(h, w)
+            return [_lib.letterbox_geometry(s, s, size, auto=False, stride=self.stride) for size in sizes], (s, s)
+        return [_lib.letterbox_geometry(h, w, size, auto=True, stride=self.stride) for size in sizes], (h, w)
+
+    @staticmethod
+    def _read(img):
+        if isinstance(img, (str, bytes)) or hasattr(img, "__fspath__"):
+            import cv2
+            img0 = cv2.imread(str(img))  # msfd:84 (BGR)
+            if img0 is None:
+                raise ValueError(f"Could not read image: {img}")  # msfd:86
+            return img0
+        return img
+
+    def _pyramid(self, batch_dev, sizes=None):
+        """(B, H, W, 3) uint8 BGR on the device -> one (B, 3, Hs, Ws) model input per scale, one launch."""
+        _, h, w, _ = batch_dev.shape
+        geoms, virt = self._geoms(h, w, sizes)
+        dtype = torch.float16 if self.half else torch.float32
+        # cv2 decodes BGR; both branches of the reference feed RGB to the model (msfd:96 / ppyp:363)
+        outs = ops.pyramid(batch_dev, geoms, out_dtype=dtype, layout="chw", flip_rb=True, virt_hw=virt)
+        return outs, geoms
+
+    def preprocess_image(self, img_path, img_size):
+        """msfd:69.  Returns (img_tensor (1,3,H,W) on the device, img0 BGR ndarray, img0.shape)."""
+        img0 = self._read(img_path)
+        dev = torch.from_numpy(np.ascontiguousarray(img0)).to(self.device)[None]
+        outs, _ = self._pyramid(dev, [img_size])
+        return outs[0], img0, img0.shape
+
+    # ------------------------------------------------------------------ model
+    def _raw_heads(self, x):
+        """Backbone forward (unchanged PyTorch) returning the head's raw NCHW conv maps."""
+        self.head.fdms_fused = True
+        try:
+            with torch.no_grad():
+                raw = self.model(x, augment=False) if self._accepts_augment() else self.model(x)
+        finally:
+            self.head.fdms_fused = False
+        return list(raw)
+
+    def _accepts_augment(self):
+        a = getattr(self, "_aug", None)
+        if a is None:
+            import inspect
+            try:
+                a = "augment" in inspect.signature(self.model.forward).parameters
+            except (TypeError, ValueError):
+                a = False
+            self._aug = a
+        return a
+
+    # ------------------------------------------------------------------ fused batch path
+    def _plan(self, scales_levels, in_h, orig_hw):
+        bs = scales_levels[0][0].shape[0]
+        key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), tuple(orig_hw),
+               self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode)
+        plan = self._plans.get(key)
+        if plan is None:
+            out_cap = self.out_cap or min(self.cap * len(scales_levels), 4 * self.cap)
+            plan = ops.PostPlan(scales_levels, self.strides, self.anchors_px, in_h, orig_hw, self.conf_thres,
+                                self.iou_thres, self.cap, out_cap, iou_mode=self.iou_mode,
+                                with_kpts=self.with_landmarks)
+            if len(self._plans) > 8:
+                self._plans.clear()
+            self._plans[key] = plan
+        else:
+            plan.rebind(scales_levels)
+        return plan
+
+    def detect_batch_device(self, batch_dev):
+        """Enqueue the whole multi-scale path for a (B, H, W, 3) uint8 BGR device batch.  Returns the plan whose
+        `.out` (dets, n_out) and `.cands` (count, n_keep) stay on the device -- no synchronisation here."""
+        _, h, w, _ = batch_dev.shape
+        xs, geoms = self._pyramid(batch_dev)
+        scales_levels = [self._raw_heads(x) for x in xs]
+        plan = self._plan(scales_levels, [g.dst_h for g in geoms], (h, w))
+        plan.run()
+        return plan
+
+    def _collect(self, plan):
+        """One device->host read of the results of `plan`; raises if a capacity was exceeded."""
+        o, c = plan.out, plan.cands
+        both = torch.cat((o.n_out, torch.stack((c.count.max(), c.n_keep.min(), o.n_out.max())))).cpu().numpy()
+        n_out, head = both[:-3], both[-3:]  # one read, synchronises
+        if head[0] > c.cap or head[2] > o.out_cap:
+            return None, head
+        if head[1] < 0:
+            raise _lib.FdmsError("a segment exceeded the NMS suppression-mask budget")
+        kmax = int(n_out.max()) if n_out.size else 0
+        dets = o.dets[:, :kmax].cpu().numpy().astype(np.float64) if kmax else np.zeros((len(n_out), 0, 7))
+        kpts = o.kpts[:, :kmax].cpu().numpy() if (o.kpts is not None and kmax) else None
+        return (dets, n_out, kpts), head
+
+    def detect_multi_scale_batch(self, images):
+        """images: (B, H, W, 3) uint8 BGR ndarray / tensor (pinned host or device), or a list of same-shape
+        images / paths.  Returns a list of (k, 7) float64 arrays [x1,y1,x2,y2,conf,cls,scale_idx] per image, rows
+        in weighted-score order (msfd:242-288); images without detections give np.array([]) (msfd:285)."""
+        if isinstance(images, (list, tuple)):
+            images = np.stack([self._read(i) for i in images])
+        t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+        if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
+            raise ValueError("detect_multi_scale_batch: expected (B, H, W, 3) uint8 images")
+        batch_dev = t.to(self.device, non_blocking=True)
+        t0 = time.perf_counter()
+        while True:
+            plan = self.detect_batch_device(batch_dev)
+            res, head = self._collect(plan)
+            if res is not None:
+                break
+            # capacity exceeded: grow to what this batch needs and redo (counts are exact even on overflow)
+            self.cap = max(self.cap * 2, int(head[0]))
+            if self.out_cap:
+                self.out_cap = max(self.out_cap * 2, int(head[2]))
+            self._plans.clear()
+        dets, n_out, kpts = res
+        self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(plan.cands.count.sum()),
+                           "kept_per_scale": int(plan.cands.n_keep.sum()), "final": int(n_out.sum())}
+        self.last_landmarks = [kpts[b, :n_out[b]] for b in range(len(n_out))] if kpts is not None else None
+        return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
+
+    # ------------------------------------------------------------------ reference-shaped methods
+    @torch.no_grad()
+    def detect_single_scale(self, img_path, img_size):
+        """msfd:110.  Returns (detections (n,7) float64 [x1,y1,x2,y2,conf,cls,scale_idx], img0_shape, seconds)."""
+        img0 = self._read(img_path)
+        img0_shape = img0.shape
+        dev = torch.from_numpy(np.ascontiguousarray(img0)).to(self.device)[None]
+        xs, geoms = self._pyramid(dev, [img_size])
+        torch.cuda.synchronize(self.device)  # time_synchronized (msfd:126)
+        t1 = time.time()
+        levels = self._raw_heads(xs[0])
+        cap = self.cap
+        while True:
+            c = ops.decode_filter([levels], self.strides, self.anchors_px, self.conf_thres, cap)
+            ops.nms_segments(c.cand, c.count, cap, self.iou_thres, self.iou_mode, tie=c.row, keep=c.keep, n_keep=c.n_keep)
+            n_cand, nk = int(c.count[0]), int(c.n_keep[0])
+            if n_cand <= cap:
+                break
+            cap = n_cand
+        t2 = time.time()
+        if nk < 0:
+            raise _lib.FdmsError("a segment exceeded the NMS suppression-mask budget")
+        if nk == 0:
+            return np.zeros((0, 7)), img0_shape, t2 - t1  # msfd:164
+        det = ops.gather_rows(c.cand, c.keep, c.n_keep, 6, nk)[0]
+        ops.scale_coords_api_((geoms[0].dst_h, geoms[0].dst_w), det, img0_shape, do_round=True)  # msfd:144
+        det_numpy = det.cpu().numpy().astype(np.float64)
+        scale_idx = np.ones((det_numpy.shape[0], 1)) * self.img_sizes.index(img_size)  # msfd:156
+        return np.hstack((det_numpy, scale_idx)), img0_shape, t2 - t1
+
+    def calculate_scale_weights(self, detections):
+        """msfd:168.  (n,7) -> (n,) float64 weights (1.0 / 1.1 / 1.2 by face area and scale index)."""
+        detections = np.asarray(detections, np.float64)
+        if len(detections) == 0:
+            return np.array([])
+        d = torch.from_numpy(np.ascontiguousarray(detections.reshape(-1, 7))).to(self.device)
+        _, w = ops.weighted_rows(d, len(self.img_sizes), want_weights=True)
+        return w.cpu().numpy()
+
+    def weighted_nms(self, detections, iou_thresh=None):
+        """msfd:203.  Size-aware score re-weighting then NMS; returns detections[keep] (original confidences,
+        weighted-score order)."""
+        detections = np.asarray(detections)
+        if len(detections) == 0:
+            return detections
+        if iou_thresh is None:
+            iou_thresh = self.iou_thres
+        d = torch.from_numpy(np.ascontiguousarray(detections, dtype=np.float64)).to(self.device)
+        n = d.shape[0]
+        rows = ops.weighted_rows(d, len(self.img_sizes))
+        count = torch.full((1,), n, dtype=torch.int32, device=self.device)
+        keep, n_keep = ops.nms_segments(rows, count, n, float(iou_thresh), ops.IOU_TV_CPU, max_nms=0)
+        nk = int(n_keep[0])
+        if nk < 0:
+            raise _lib.FdmsError("weighted_nms: the NMS suppression-mask budget was exceeded")
+        return detections[keep[0, :nk].cpu().numpy()]
+
+    def detect_multi_scale(self, img_path):
+        """msfd:242.  Returns (final_detections (k,7) float64 or np.array([]), img0_shape)."""
+        img0 = self._read(img_path)
+        out = self.detect_multi_scale_batch(img0[None])
+        return out[0], img0.shape
+
+    def get_detection_statistics(self, detections):
+        """Subset of the reference's statistics helper used by detect_multi_scale's log line (msfd:281-282)."""
+        detections = np.asarray(detections)
+        if detections.size == 0:
+            return {"total_faces": 0, "avg_confidence": 0.0}
+        return {"total_faces": int(detections.shape[0]), "avg_confidence": float(detections[:, 4].mean())}
+
+
+MultiScaleFaceDetectorB200 = MultiScaleFaceDetector

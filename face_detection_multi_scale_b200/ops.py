@@ -255,16 +255,18 @@ def merge_scales(cands, n_img, n_scales, in_h, orig_hw, iou_thres, out_cap, with
     return out
 
 
-def weighted_rows(dets64, n_scales):
-    """(n,7) float64 CUDA detections -> (1, n, 8) fp32 merge rows (weighted score in column 4)."""
+def weighted_rows(dets64, n_scales, want_weights=False):
+    """(n,7) float64 CUDA detections -> (1, n, 8) fp32 merge rows (weighted score in column 4)
+    [and the (n,) float64 weights of calculate_scale_weights]."""
     dev = _dev(dets64)
     n = dets64.shape[0]
     assert dets64.dtype == torch.float64 and dets64.is_contiguous() and dets64.shape[1] == 7
     rows = torch.empty((1, max(n, 1), 8), dtype=torch.float32, device=dets64.device)
     c = _lib.ctx(dev)
-    c.check(_lib.lib().fdms_weighted_rows(c.handle, _ptr(dets64), n, int(n_scales), _ptr(rows), _stream(dev)),
+    w = torch.empty((n,), dtype=torch.float64, device=dets64.device) if want_weights else None
+    c.check(_lib.lib().fdms_weighted_rows(c.handle, _ptr(dets64), n, int(n_scales), _ptr(rows), _ptr(w), _stream(dev)),
             "fdms_weighted_rows")
-    return rows
+    return (rows, w) if want_weights else rows
 
 
 class PostPlan:
@@ -275,6 +277,7 @@ class PostPlan:
                  iou_mode=IOU_TV_CUDA, with_kpts=False):
         self.dev = _dev(scales_levels[0][0])
         device = scales_levels[0][0].device
+        self._strides, self._anchors = list(strides), np.asarray(anchors_px, np.float32)
         self.arr, self.n_levels, self.bs, self.rows_per_scale, self._hold = _level_table(scales_levels, strides,
                                                                                         anchors_px)
         self.n_scales = len(scales_levels)
@@ -296,6 +299,14 @@ class PostPlan:
         d.kpts_out = self.out.kpts.data_ptr() if with_kpts else None
         self.desc = d
         self.ctx = _lib.ctx(self.dev)
+
+    def rebind(self, scales_levels):
+        """Point the plan at a new set of raw head tensors of the same shapes (buffers are reused)."""
+        arr, n, bs, rows, hold = _level_table(scales_levels, self._strides,
+                                              self._anchors)
+        assert n == self.n_levels and bs == self.bs
+        self.arr, self._hold = arr, hold
+        self.desc.levels = C.cast(self.arr, C.POINTER(_lib.Level))
 
     def run(self):
         rc = _lib.lib().fdms_postprocess(self.ctx.handle, C.byref(self.desc), _stream(self.dev))

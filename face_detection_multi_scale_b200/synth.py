@@ -142,3 +142,27 @@ def synth_pred(rows, n_clusters, per_cluster, seed, extent=(640.0, 640.0), conf_
         p[:, 4] = np.round(p[:, 4], tie_decimals)
         p[:, 5] = np.round(p[:, 5], tie_decimals)
     return p.astype(np.float32)
+
+
+def letterbox_hw(h, w, size, stride=32):
+    """Output (H, W) of utils/datasets.py:letterbox(auto=True) -- integer restatement used to size synthetic heads."""
+    r = min(size / h, size / w)
+    uw, uh = int(round(w * r)), int(round(h * r))
+    dw, dh = (size - uw) % stride, (size - uh) % stride
+    dw, dh = dw / 2, dh / 2
+    return (uh + int(round(dh - 0.1)) + int(round(dh + 0.1)), uw + int(round(dw - 0.1)) + int(round(dw + 0.1)))
+
+
+def multi_scale_heads(h, w, img_sizes, n_faces, seed, api=False, strides=P5_STRIDES, anchors_px=P5_ANCHORS,
+                      dtype=np.float16, stride_max=32, min_size=10.0, max_size=220.0, radius=1):
+    """Raw head tensors of ONE image at every pyramid scale, with the same faces planted at each scale.
+    Returns (list over scales of list over levels of (63, ny, nx) arrays, list of model-input (H, W))."""
+    faces0 = synth_faces(n_faces, h, w, seed, min_size=min_size, max_size=max_size) if n_faces else np.zeros((0, 4))
+    heads, shapes = [], []
+    for si, size in enumerate(img_sizes):
+        in_hw = (size, size) if api else letterbox_hw(h, w, size, stride_max)
+        f_in = faces_to_input(faces0, (h, w), in_hw, api=api)
+        heads.append(synth_head(in_hw[0], in_hw[1], f_in, seed * 16 + si, strides=strides, anchors_px=anchors_px,
+                                dtype=dtype, radius=radius))
+        shapes.append(in_hw)
+    return heads, shapes

@@ -188,9 +188,10 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
 /* multi_scale_face_detector.py:168-201,224-229 for the standalone weighted_nms(detections) call:
  * dets (n,7) float64 [x1,y1,x2,y2,conf,cls,scale_idx] -> rows_out (n,8) f32
  * [x1,y1,x2,y2, (float)(conf*weight), conf, cls, scale_idx]; feed rows_out to fdms_nms
- * (row_stride 8, box_off 0, score_off 4, tie NULL, TV_CPU) to get the keep list of :234. */
+ * (row_stride 8, box_off 0, score_off 4, tie NULL, TV_CPU) to get the keep list of :234.
+ * weights_out (n) f64, optional: the weights calculate_scale_weights returns. */
 FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, int n_scales, float *rows_out,
-                                fdms_stream stream);
+                                double *weights_out, fdms_stream stream);
 
 /* ---- whole post-processing step in one host call ---------------------------------------------
  * decode_filter -> per-scale NMS -> merge, back to back on `stream` without host sync.

@@ -1,0 +1,229 @@
+"""The reference-facing Python surface (drop-in signatures of utils/datasets.py, utils/general.py,
+utils/preprocess_yolo_predict.py, models/yolo.py head, multi_scale_face_detector.py) on the CUDA path, against
+golden outputs of the UNMODIFIED reference and against the oracle.  GPU only."""
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from face_detection_multi_scale_b200 import general, ops, standin, synth, yolo_head
+from face_detection_multi_scale_b200.datasets import letterbox
+from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
+from face_detection_multi_scale_b200.preprocess_yolo_predict import preprocess_api_approach, scale_coords_api_approach
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------ letterbox (utils/datasets.py:873)
+@pytest.mark.parametrize("i", range(len(H.LETTERBOX_SMALL)))
+def test_letterbox_signature_and_values(golden, i):
+    g = golden("letterbox")
+    h, w, ns, auto, scaleup, stride, seed = H.LETTERBOX_SMALL[i]
+    img = synth.synth_image(h, w, seed)
+    out, ratio, pad = letterbox(img, ns, auto=auto, scaleup=scaleup, stride=stride)
+    assert isinstance(out, np.ndarray) and out.dtype == np.uint8
+    assert np.array_equal(out, g["small%d_out" % i])
+    meta = g["small_meta"][i]
+    assert ratio == (meta[8], meta[8]) and pad == (meta[9], meta[10])
+
+
+def test_letterbox_scalefill_and_color_and_errors():
+    img = synth.synth_image(90, 160, 3)
+    out, ratio, pad = letterbox(img, (64, 96), auto=False, scaleFill=True)
+    ref, rr, rp = O.letterbox(img, (64, 96), auto=False, scaleFill=True)
+    assert np.array_equal(out, ref) and ratio == rr and pad == rp
+    out, _, _ = letterbox(img, 128, color=(0, 0, 0), auto=False)
+    ref, _, _ = O.letterbox(img, 128, color=(0, 0, 0), auto=False)
+    assert np.array_equal(out, ref)
+    with pytest.raises(NotImplementedError):
+        letterbox(img, 128, color=(1, 2, 3))
+    with pytest.raises(ValueError):
+        letterbox(img.astype(np.float32), 128)
+
+
+@pytest.mark.parametrize("i", range(len(H.API_CASES)))
+def test_preprocess_api_approach_from_file(golden, i):
+    cv2 = pytest.importorskip("cv2")
+    g = golden("letterbox")
+    h, w, size, seed = H.API_CASES[i]
+    rgb = synth.synth_image(h, w, seed)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "a.png")
+        cv2.imwrite(p, rgb[:, :, ::-1])
+        chw = preprocess_api_approach(p, size, 32)
+    assert chw.shape == (3, size, size) and chw.dtype == np.uint8
+    assert sha(chw) == str(g["api%d_sha" % i])
+
+
+# ------------------------------------------------------------------ head (models/yolo.py:253-308)
+def test_patched_head_returns_reference_tuple(golden):
+    g = golden("head")
+    levels = [torch.from_numpy(g["tiny_raw%d" % i]).to(DEV) for i in range(3)]
+    model = standin.SyntheticHeadModel(strides=[float(s) for s in g["tiny_strides"]], anchors_px=g["tiny_anchors_px"])
+    model.to(DEV)
+    head = yolo_head.patch_head(yolo_head.find_head(model))
+    pred, xs = head([l.clone() for l in levels])
+    assert pred.shape == g["tiny_pred"].shape
+    assert np.max(np.abs(pred.cpu().numpy() - g["tiny_pred"])) <= 1e-4
+    for x, l in zip(xs, levels):  # (bs, na, ny, nx, no) raw maps, like the reference's second output
+        bs, _, ny, nx = l.shape
+        assert x.shape == (bs, 3, ny, nx, 21)
+        assert torch.equal(x.permute(0, 1, 4, 2, 3).reshape(bs, 63, ny, nx), l)
+
+
+# ------------------------------------------------------------------ non_max_suppression (utils/general.py:506)
+def test_nms_reference_pred_bit_exact(golden):
+    g = golden("head")
+    pred = torch.from_numpy(g["tiny_pred"]).to(DEV)
+    thr = float(g["tiny_conf_thres"])
+    before = pred.clone()
+    for iou in (0.45, 0.3):
+        res = general.non_max_suppression(pred, thr, iou, iou_mode=ops.IOU_TV_CPU)
+        assert len(res) == 2
+        for b in range(2):
+            ref = g["tiny_nms_iou%d_b%d" % (int(iou * 100), b)]
+            assert res[b].is_cuda and res[b].shape == ref.shape
+            assert np.array_equal(res[b].cpu().numpy(), ref)
+    assert torch.equal(pred, before)  # does not mutate prediction
+
+
+@pytest.mark.parametrize("name", list(H.CROWD_HEADS))
+def test_nms_crowd_golden_through_decode(golden, name):
+    g = golden("head")
+    in_h, in_w, n_faces, seed = H.CROWD_HEADS[name]
+    levels = [torch.from_numpy(l).to(DEV) for l in H.crowd_levels(in_h, in_w, n_faces, seed)]
+    pred = yolo_head.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    for conf, iou in ((0.5, 0.5), (0.6, 0.3), (0.25, 0.45)):
+        res = general.non_max_suppression(pred, conf, iou, iou_mode=ops.IOU_TV_CPU)
+        for b in range(2):
+            ref = g["%s_nms_c%d_i%d_b%d" % (name, int(conf * 100), int(iou * 100), b)]
+            assert res[b].shape == ref.shape
+            if ref.size:
+                assert np.max(np.abs(res[b].cpu().numpy() - ref)) <= 1e-4
+
+
+def test_nms_empty_cpu_input_and_errors():
+    pred = torch.zeros((2, 100, 21))
+    res = general.non_max_suppression(pred, 0.5, 0.5)
+    assert len(res) == 2 and all(r.shape == (0, 6) and not r.is_cuda for r in res)  # (0,6), general.py:527
+    p = torch.from_numpy(synth.synth_pred(3000, 20, 40, 4)[None])
+    r_cpu = general.non_max_suppression(p, 0.3, 0.45)[0]
+    r_gpu = general.non_max_suppression(p.to(DEV), 0.3, 0.45)[0]
+    assert not r_cpu.is_cuda and torch.equal(r_cpu, r_gpu.cpu()) and r_cpu.shape[0] > 5
+    assert general.non_max_suppression(p.to(DEV), 0.3, 0.45, classes=[1])[0].shape == (0, 6)
+    assert general.non_max_suppression(p.to(DEV), 0.3, 0.45, classes=[0])[0].shape == r_gpu.shape
+    with pytest.raises(NotImplementedError):
+        general.non_max_suppression(torch.zeros((1, 10, 85), device=DEV), kpt_label=0)
+
+
+def test_nms_capacity_regrow_and_max_nms():
+    """More candidates than the first-try capacity (4096) and than max_nms (30000)."""
+    n = 33000
+    p = synth.synth_pred(n, 500, 80, 13, extent=(2000.0, 2000.0))
+    p[:, 4] = np.maximum(p[:, 4], 0.9)
+    p[:, 5] = np.maximum(p[:, 5], 0.9)
+    res = general.non_max_suppression(torch.from_numpy(p[None]).to(DEV), 0.5, 0.5, iou_mode=ops.IOU_TV_CPU)[0]
+    ref = O.non_max_suppression(p[None], 0.5, 0.5, O.TV_CPU)[0]
+    assert res.shape == ref.shape and np.array_equal(res.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ scale_coords (general.py:374, ppyp:122)
+def test_scale_coords_views_in_place(golden):
+    g = golden("rescale")
+    ih, iw, h0, w0 = g["meta"][0]
+    det = torch.zeros((37, 21), device=DEV)
+    det[:, :4] = torch.from_numpy(g["c0_boxes"]).to(DEV)
+    det[:, 6:] = torch.from_numpy(g["c0_kpts"]).to(DEV)
+    r = general.scale_coords((ih, iw), det[:, :4], (h0, w0, 3))  # detect.py:100
+    assert r.data_ptr() == det.data_ptr()
+    general.scale_coords((ih, iw), det[:, 6:], (h0, w0, 3), kpt_label=5, step=3)  # detect.py:101
+    assert np.array_equal(det[:, :4].cpu().numpy(), g["c0_std_boxes"])
+    assert np.array_equal(det[:, 6:].cpu().numpy(), g["c0_std_kpts"])
+    cpu = torch.from_numpy(g["c0_boxes"].copy())
+    out = scale_coords_api_approach((ih, iw), cpu, (h0, w0, 3))
+    assert out is cpu and np.array_equal(cpu.numpy(), g["c0_api_boxes"])
+    empty = torch.zeros((0, 4), device=DEV)
+    assert general.scale_coords((ih, iw), empty, (h0, w0)).shape == (0, 4)
+
+
+# ------------------------------------------------------------------ MultiScaleFaceDetector (msfd:28-288)
+def _detector(case, iou_mode=ops.IOU_TV_CPU, **kw):
+    name, h, w, sizes, n_faces, conf, iou, api, seed = case
+    heads, shapes = H.e2e_heads(h, w, sizes, n_faces, api, seed)
+    model = standin.SyntheticHeadModel()
+    for s in shapes:
+        model.set_heads(s, [l[None] for l in heads[s]], pin=False)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, conf_thres=conf, iou_thres=iou,
+                                 use_api_preprocess=api, half=False, iou_mode=iou_mode, **kw)
+    return det, shapes
+
+
+@pytest.mark.parametrize("case", H.E2E_CASES, ids=[c[0] for c in H.E2E_CASES])
+def test_detector_matches_reference_golden(golden, case):
+    cv2 = pytest.importorskip("cv2")
+    g = golden("e2e")
+    name, h, w, sizes, n_faces, conf, iou, api, seed = case
+    det, shapes = _detector(case)
+    bgr = synth.synth_image(h, w, seed)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, name + ".png")
+        cv2.imwrite(p, bgr)
+        # model inputs (fp32, as the golden CPU run): digest of the reference's tensors
+        for si, size in enumerate(sizes):
+            x, img0, shape0 = det.preprocess_image(p, size)
+            assert tuple(x.shape[2:]) == tuple(shapes[si]) and shape0 == (h, w, 3)
+            assert sha(x.cpu().numpy()) == str(g["%s_input%d_sha" % (name, si)])
+            d, shape0, dt = det.detect_single_scale(p, size)
+            ref = g["%s_scale%d" % (name, si)]
+            assert d.dtype == np.float64 and d.shape == ref.shape
+            assert np.array_equal(d, ref)
+        final, shape0 = det.detect_multi_scale(p)
+    ref = g[name + "_final"]
+    assert tuple(shape0) == tuple(g[name + "_shape0"])
+    assert final.shape == ref.shape  # np.array([]) when nothing was found (msfd:285)
+    if ref.size:
+        assert np.array_equal(final, ref)
+    with pytest.raises(ValueError):
+        det.detect_multi_scale("/nonexistent/image.jpg")  # msfd:86
+
+
+def test_detector_weighted_nms_and_weights(golden):
+    g = golden("merge")
+    for ci in range(5):
+        n_scales, iou = g["m%d_meta" % ci]
+        det = MultiScaleFaceDetector(standin.SyntheticHeadModel(), device=DEV, img_sizes=[640] * int(n_scales),
+                                     iou_thres=float(iou))
+        dets = g["m%d_dets" % ci]
+        assert np.array_equal(det.calculate_scale_weights(dets), g["m%d_weights" % ci])
+        assert np.array_equal(det.weighted_nms(dets), g["m%d_out" % ci])
+    assert det.weighted_nms(np.zeros((0, 7))).shape == (0, 7)
+
+
+def test_detector_batch_equals_single_and_capacity_growth():
+    """B images in one fused pass == each image alone; a tiny initial capacity regrows transparently."""
+    h, w, sizes, B = 270, 480, [160, 256, 320], 3
+    images, heads, shapes = standin.make_batch(h, w, sizes, B, n_faces=25, seed=3, dtype=np.float16)
+    model = standin.SyntheticHeadModel()
+    for s, hw in enumerate(shapes):
+        model.set_heads(hw, heads[s], pin=True)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, cap=32, with_landmarks=True,
+                                 iou_mode=ops.IOU_TV_CPU)
+    out = det.detect_multi_scale_batch(images)
+    assert det.cap > 32 and len(out) == B
+    for b in range(B):
+        ref, _ = O.detect_from_heads([[l[b:b + 1] for l in heads[s]] for s in range(len(sizes))], shapes, (h, w, 3),
+                                     synth.P5_STRIDES, synth.P5_ANCHORS, 0.5, 0.5, O.TV_CPU)
+        assert out[b].shape == ref.shape and np.array_equal(out[b], ref)
+        assert det.last_landmarks[b].shape == (len(ref), 15)
+    with pytest.raises(RuntimeError):
+        MultiScaleFaceDetector(model, device="cpu")

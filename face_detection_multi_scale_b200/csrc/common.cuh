@@ -23,7 +23,8 @@ struct fdms_ctx {
     int sm_count = FDMS_SM_COUNT_FALLBACK;
     int smem_optin = 0;
     char err[512] = {0};
-    bool pyr_attr = false, nms_attr = false;
+    int pyr_attr = 0;
+    bool nms_attr = false;
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
     fdms_buf sort_a, sort_b;   // NMS: 64-bit keys ping-pong

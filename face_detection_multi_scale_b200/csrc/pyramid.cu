@@ -8,30 +8,35 @@
 //   grid = (tiles of all scales of one image, image).  All scales of an image are adjacent
 //   in launch order, so the u8 source (6.2 MB at 1080p) is fetched from HBM once and the
 //   other scales re-read it from the 126 MB L2.
-//   A CTA owns a tw x th tile of one scale's output.  It stages the source row segments it
-//   needs into shared memory with one bulk async copy (TMA, cp.async.bulk -> UBLKCP) per row,
-//   completion tracked by an mbarrier; ragged/misaligned sources take a scalar staging path.
-//   Each thread then produces 2 adjacent output pixels x th rows: horizontal pass with
-//   16x8-bit dot products (IDP.2A) out of shared memory, vertical pass in registers, one
-//   32-bit store per channel row (a warp writes one full 128 B line of the fp16 plane).
+//   A CTA owns a tw x th tile of one scale's output.  Warp 0 derives the vertical taps of the
+//   tile's rows, assigns the source rows to shared-memory slots and stages every slot with ONE
+//   bulk async copy (TMA, cp.async.bulk -> UBLKCP) completing on an mbarrier; ragged /
+//   misaligned / virtual-zero sources take a scalar staging path.
+//   Each thread owns 2 adjacent output columns.  It streams over the slots in source-row
+//   order: horizontal pass of the slot for its two pixels (16x8-bit dot products, IDP.2A)
+//   into registers, then emits every output row whose lower tap is that slot (vertical pass,
+//   /255, pack, one 32-bit store per channel: a warp writes 128 contiguous bytes of a plane).
+//   Horizontal results are therefore computed once per (source row, column) even when output
+//   rows share source rows (scale < 2).
 #include "common.cuh"
 
 namespace {
 
-constexpr int PYR_THREADS = 128;
-constexpr int PYR_MAX_TH = 16;
-constexpr int PYR_SMEM_BUDGET = 64 * 1024;  // per CTA, keeps >= 3 CTAs per SM
+constexpr int PYR_THREADS = 160;  // 2 columns per thread: 320-column tiles divide 640/960/1280 evenly
+constexpr int PYR_MAX_TH = 32;    // rows per tile are handled by the lanes of warp 0
+constexpr int PYR_MAX_SLOTS = 64;
+constexpr int PYR_SMEM_BUDGET = 56 * 1024;  // per CTA: >= 4 CTAs per SM
 
 struct PyrScale {
     void *out;
     long long img_stride, cs, ys, xs;  // element strides
     int dst_h, dst_w, unpad_h, unpad_w, top, left;
-    int dtype;
     int tile_begin, tiles_x;
     int tw, th;        // output tile
     int dense_rows;    // row slots cover a contiguous source-row range (scale_y <= 2)
-    int n_slots;       // row slots per tile
     int slot_bytes;    // multiple of 16
+    int vec;           // paired stores allowed
+    int pad_;
     double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
 };
 
@@ -104,279 +109,119 @@ __device__ __forceinline__ void coeff_y(int d, double scale, int n_src, int &r0,
     b01 = pack_w(f);
 }
 
-// Horizontal pass for one output pixel out of a staged row: o = byte offset of source pixel
-// sx inside the slot; the pixel and its right neighbour are the 6 bytes at o.  Returns
-// (S[sx]*a0 + S[sx+1]*a1) >> 4 per channel (15 bits), source channel order.
-__device__ __forceinline__ void hpass(const uint8_t *slot, int o, unsigned a01, int (&r)[3]) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(slot + (o & ~3));
-    unsigned sh = (unsigned)(o & 3) * 8u;
-    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    uint32_t lo = __funnelshift_r(w0, w1, sh);  // c0 c1 c2 n0
-    uint32_t hi = __funnelshift_r(w1, w2, sh);  // n1 n2 .. ..
+// Horizontal pass of one output pixel out of a staged row.  `w` = shared-memory address of the
+// aligned word holding the first byte of source pixel sx, sh = 8 * (byte offset in that word);
+// the pixel and its right neighbour are the 6 bytes from there.  h[c] = (S[sx][c]*a0 +
+// S[sx+1][c]*a1) >> 4 (15 bits, source channel order).
+__device__ __forceinline__ void hpass(uint32_t w, unsigned sh, unsigned a01, int *h) {
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(w));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(w));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(w));
+    uint32_t lo = __funnelshift_r(w0, w1, sh);   // c0 c1 c2 n0
+    uint32_t hi = __funnelshift_r(w1, w2, sh);   // n1 n2 .. ..
     uint32_t p01 = __byte_perm(lo, hi, 0x4130);  // c0 n0 c1 n1
     uint32_t p2 = __byte_perm(lo, hi, 0x0052);   // c2 n2
-    r[0] = (int)(__dp2a_lo(a01, p01, 0u) >> 4);
-    r[1] = (int)(__dp2a_hi(a01, p01, 0u) >> 4);
-    r[2] = (int)(__dp2a_lo(a01, p2, 0u) >> 4);
+    h[0] = (int)(__dp2a_lo(a01, p01, 0u) >> 4);
+    h[1] = (int)(__dp2a_hi(a01, p01, 0u) >> 4);
+    h[2] = (int)(__dp2a_lo(a01, p2, 0u) >> 4);
 }
 
+// Vertical pass: (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  The result cannot exceed
+// 255: b0+b1 <= 2049 and R>>4 <= 32654, so the two floors sum to at most 1020.
 __device__ __forceinline__ int vpass(int r0, int r1, int b0, int b1) {
-    int v = (((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2;
-    return min(v, 255);
+    return (((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2;
 }
 
-template <typename T> struct OutCvt;
-template <> struct OutCvt<__half> {
-    // rn16(rn32(v / 255)): ATen computes half division in float and rounds once (msfd:101-102)
-    static __device__ __forceinline__ __half cvt(int v) { return __float2half_rn(__fdiv_rn((float)v, 255.0f)); }
+// ---- value conversion + paired store, per output type -------------------------------------------
+template <typename T> struct Out;
+template <> struct Out<__half> {
+    // rn16(rn32(v/255)) (ATen divides in float and rounds once, msfd:101-102) == rn16(rn32(v * rn32(1/255)))
+    // for all 256 byte values (checked exhaustively in tests/test_host_logic.py).  float(v) comes
+    // from the 2^23 magic number: fma(as_float(0x4B000000|v), c, -2^23*c) is exactly rn32(v*c).
+    static __device__ __forceinline__ float f(int v) {
+        const float c = 0.003921568859368563f;  // rn32(1/255)
+        return __fmaf_rn(__uint_as_float(0x4B000000u | (unsigned)v), c, -8388608.0f * c);
+    }
+    static __device__ __forceinline__ void store2(__half *p, long long xs, int a, int b, bool vec) {
+        if (vec) {
+            *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(f(a), f(b));
+        } else {
+            p[0] = __float2half_rn(f(a));
+            p[xs] = __float2half_rn(f(b));
+        }
+    }
+    static __device__ __forceinline__ void store1(__half *p, int a) { p[0] = __float2half_rn(f(a)); }
 };
-template <> struct OutCvt<float> {
-    static __device__ __forceinline__ float cvt(int v) { return __fdiv_rn((float)v, 255.0f); }  // true division
+template <> struct Out<float> {
+    static __device__ __forceinline__ float f(int v) { return __fdiv_rn((float)v, 255.0f); }  // true division
+    static __device__ __forceinline__ void store2(float *p, long long xs, int a, int b, bool vec) {
+        if (vec) {
+            *reinterpret_cast<float2 *>(p) = make_float2(f(a), f(b));
+        } else {
+            p[0] = f(a);
+            p[xs] = f(b);
+        }
+    }
+    static __device__ __forceinline__ void store1(float *p, int a) { p[0] = f(a); }
 };
-template <> struct OutCvt<uint8_t> {
-    static __device__ __forceinline__ uint8_t cvt(int v) { return (uint8_t)v; }
+template <> struct Out<uint8_t> {
+    static __device__ __forceinline__ void store2(uint8_t *p, long long xs, int a, int b, bool) {
+        p[0] = (uint8_t)a;
+        p[xs] = (uint8_t)b;
+    }
+    static __device__ __forceinline__ void store1(uint8_t *p, int a) { p[0] = (uint8_t)a; }
 };
 
-template <typename T>
-__device__ __forceinline__ void store_pair(T *p, long long xs, T a, T b, bool vec) {
-    p[0] = a;
-    p[xs] = b;
-}
-template <>
-__device__ __forceinline__ void store_pair<__half>(__half *p, long long xs, __half a, __half b, bool vec) {
-    if (vec) {
-        *reinterpret_cast<__half2 *>(p) = __halves2half2(a, b);
-    } else {
-        p[0] = a;
-        p[xs] = b;
+struct TileShared {
+    unsigned meta[PYR_MAX_TH];  // b0 | b1 << 12 | same-slot << 24
+    int trig[PYR_MAX_TH];       // slot after which the row is emitted; -1: border row
+    int slot_row[PYR_MAX_SLOTS];
+    int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
+    alignas(8) unsigned long long bar;
+};
+
+// One emitted output row for this thread's two pixels.  R0/R1: horizontal results of the upper /
+// lower source row, [0..2] pixel A, [3..5] pixel B.
+template <typename T, bool EDGE>
+__device__ __forceinline__ void emit_row(T *row_ptr, long long cs, long long xs, unsigned meta, const int *R0,
+                                         const int *R1, int flip, int border, bool inA, bool inB, bool two, bool vec) {
+    const int b0 = (int)(meta & 0xfffu), b1 = (int)((meta >> 12) & 0xfffu);
+    int vA[3], vB[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        vA[c] = vpass(R0[c], R1[c], b0, b1);
+        vB[c] = vpass(R0[3 + c], R1[3 + c], b0, b1);
+        if (EDGE) {
+            if (!inA) vA[c] = border;
+            if (!inB) vB[c] = border;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int a = flip ? vA[2 - c] : vA[c], b = flip ? vB[2 - c] : vB[c];
+        T *p = row_ptr + c * cs;
+        if (!EDGE || two) Out<T>::store2(p, xs, a, b, vec);
+        else Out<T>::store1(p, a);
     }
 }
-template <>
-__device__ __forceinline__ void store_pair<float>(float *p, long long xs, float a, float b, bool vec) {
-    if (vec) {
-        *reinterpret_cast<float2 *>(p) = make_float2(a, b);
-    } else {
-        p[0] = a;
-        p[xs] = b;
+
+template <typename T>
+__device__ __forceinline__ void border_row(T *row_ptr, long long cs, long long xs, int border, bool two, bool vec) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        T *p = row_ptr + c * cs;
+        if (two) Out<T>::store2(p, xs, border, border, vec);
+        else Out<T>::store1(p, border);
     }
 }
 
 template <typename T>
-__device__ __forceinline__ void run_tile(const PyrParams &P, const PyrScale &S, int tile, int img, uint8_t *smem,
-                                         const T *lut) {
-    __shared__ int s_r0[PYR_MAX_TH], s_r1[PYR_MAX_TH], s_slot0[PYR_MAX_TH], s_slot1[PYR_MAX_TH];
-    __shared__ unsigned s_b[PYR_MAX_TH];
-    __shared__ int s_slot_row[2 * PYR_MAX_TH + 4];
-    __shared__ int s_misc[4];  // n_used_slots, g0, row_bytes, n_bulk_rows
-    __shared__ __align__(8) uint64_t s_bar;
+__global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_constant__ PyrParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ TileShared sh;
 
     const int tid = threadIdx.x;
-    const int ty = tile / S.tiles_x, tx = tile - ty * S.tiles_x;
-    const int oy0 = ty * S.th, ox0 = tx * S.tw;
-    const int y_end = min(oy0 + S.th, S.dst_h), x_end = min(ox0 + S.tw, S.dst_w);
-    // interior (resized image) part of this tile, in resized-image coordinates
-    const int dya = max(oy0, S.top) - S.top, dyb = min(y_end, S.top + S.unpad_h) - S.top;      // [dya, dyb)
-    const int dxa = max(ox0, S.left) - S.left, dxb = min(x_end, S.left + S.unpad_w) - S.left;  // [dxa, dxb)
-    const bool has_interior = dya < dyb && dxa < dxb;
-
-    T *out = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride;
-    const T border = lut[P.border];
-    const bool vec = (S.xs == 1) && ((S.dst_w & 1) == 0) && ((S.cs & 1) == 0) && ((S.img_stride & 1) == 0) &&
-                     sizeof(T) > 1;
-    const int x = ox0 + 2 * tid;  // this thread's first pixel
-
-    if (has_interior) {
-        const uint8_t *src = P.src + (long long)img * P.img_stride;
-        if (tid < S.th) {
-            int dy = oy0 + tid - S.top;
-            int r0 = 0, r1 = 0;
-            unsigned b01 = 0;
-            if (dy >= 0 && dy < S.unpad_h && oy0 + tid < S.dst_h) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01);
-            s_r0[tid] = r0;
-            s_r1[tid] = r1;
-            s_b[tid] = b01;
-        }
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // slot assignment + column range
-            int ja = dya + S.top - oy0, jb = dyb + S.top - oy0;  // valid tile rows [ja, jb)
-            int n_used = 0;
-            if (S.dense_rows) {
-                int rmin = s_r0[ja], rmax = s_r1[jb - 1];
-                n_used = min(rmax - rmin + 1, S.n_slots);
-                for (int k = 0; k < n_used; k++) s_slot_row[k] = rmin + k;
-                for (int j = ja; j < jb; j++) {
-                    s_slot0[j] = s_r0[j] - rmin;
-                    s_slot1[j] = s_r1[j] - rmin;
-                }
-            } else {
-                for (int j = ja; j < jb; j++) {
-                    int b1 = (int)(s_b[j] >> 16);
-                    s_slot0[j] = n_used;
-                    s_slot_row[n_used++] = s_r0[j];
-                    if (b1 != 0) {
-                        s_slot1[j] = n_used;
-                        s_slot_row[n_used++] = s_r1[j];
-                    } else {
-                        s_slot1[j] = s_slot0[j];
-                    }
-                }
-            }
-            int sxa, sxb;
-            unsigned dummy;
-            coeff_x(dxa, S.scale_x, P.virt_w, sxa, dummy);
-            coeff_x(dxb - 1, S.scale_x, P.virt_w, sxb, dummy);
-            sxb = min(sxb + 1, P.virt_w - 1);
-            int g0 = (3 * sxa) & ~15;
-            int g1 = (3 * sxb + 3 + 15) & ~15;
-            s_misc[0] = n_used;
-            s_misc[1] = g0;
-            s_misc[2] = g1 - g0;
-        }
-        __syncthreads();
-        const int n_used = s_misc[0], g0 = s_misc[1], row_bytes = s_misc[2];
-        // ---- stage source rows ---------------------------------------------------------------
-        const int real_end = 3 * P.src_w;  // bytes of real pixels in a row; beyond: virtual zeros
-        int bulk_bytes = 0;
-        if (P.vec_ok) bulk_bytes = max(0, min(g0 + row_bytes, real_end & ~15) - g0);
-        if (tid < 32) {
-            // one bulk copy per staged row, issued by warp 0
-            int n_bulk = 0;
-            for (int k = tid; k < n_used; k += 32) {
-                int row = s_slot_row[k];
-                if (row < P.src_h && bulk_bytes > 0) {
-                    bulk_g2s(smem + (size_t)k * S.slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes,
-                             &s_bar);
-                    n_bulk++;
-                }
-            }
-            n_bulk = __reduce_add_sync(0xffffffffu, n_bulk);
-            if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)(n_bulk * bulk_bytes));
-        }
-        // scalar part: bytes not covered by the bulk copies (ragged tail, misaligned source,
-        // virtual zero rows/columns of the api mode)
-        {
-            const int rest = row_bytes - bulk_bytes;
-            for (int k = 0; k < n_used; k++) {
-                int row = s_slot_row[k];
-                uint8_t *dst = smem + (size_t)k * S.slot_bytes;
-                if (row >= P.src_h) {
-                    for (int i = tid * 4; i < row_bytes; i += PYR_THREADS * 4) *reinterpret_cast<uint32_t *>(dst + i) = 0u;
-                } else {
-                    const uint8_t *srow = src + (long long)row * P.pitch;
-                    for (int i = tid; i < rest; i += PYR_THREADS) {
-                        int pos = g0 + bulk_bytes + i;
-                        dst[bulk_bytes + i] = pos < real_end ? __ldg(srow + pos) : (uint8_t)0;
-                    }
-                }
-            }
-        }
-        mbar_wait(&s_bar, 0);
-        __syncthreads();
-
-        // ---- per-thread x coefficients ----------------------------------------------------------
-        int oA = 0, oB = 0;
-        unsigned aA = 0, aB = 0;
-        const int dxA = x - S.left, dxB = x + 1 - S.left;
-        const bool inA = x < x_end && dxA >= 0 && dxA < S.unpad_w;
-        const bool inB = x + 1 < x_end && dxB >= 0 && dxB < S.unpad_w;
-        if (inA) {
-            int sx;
-            coeff_x(dxA, S.scale_x, P.virt_w, sx, aA);
-            oA = 3 * sx - g0;
-        }
-        if (inB) {
-            int sx;
-            coeff_x(dxB, S.scale_x, P.virt_w, sx, aB);
-            oB = 3 * sx - g0;
-        }
-        // ---- rows -------------------------------------------------------------------------------
-        int c0 = -1, c1 = -1;  // cached slots
-        int A0[3] = {0, 0, 0}, A1[3] = {0, 0, 0}, B0[3] = {0, 0, 0}, B1[3] = {0, 0, 0};
-        if (x < x_end) {
-            for (int j = 0; j < S.th; j++) {
-                const int oy = oy0 + j;
-                if (oy >= S.dst_h) break;
-                T vA[3], vB[3];
-                const int dy = oy - S.top;
-                if (dy < 0 || dy >= S.unpad_h || (!inA && !inB)) {
-                    vA[0] = vA[1] = vA[2] = vB[0] = vB[1] = vB[2] = border;
-                } else {
-                    const int k0 = s_slot0[j], k1 = s_slot1[j];
-                    const unsigned b01 = s_b[j];
-                    const int b0 = (int)(b01 & 0xffffu), b1 = (int)(b01 >> 16);
-                    int nA0[3], nB0[3], nA1[3], nB1[3];
-                    // row 0 (uniform branches: k0/k1/c0/c1 are the same for the whole CTA)
-                    if (k0 == c0) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { nA0[c] = A0[c]; nB0[c] = B0[c]; }
-                    } else if (k0 == c1) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { nA0[c] = A1[c]; nB0[c] = B1[c]; }
-                    } else {
-                        const uint8_t *slot = smem + (size_t)k0 * S.slot_bytes;
-                        if (inA) hpass(slot, oA, aA, nA0);
-                        if (inB) hpass(slot, oB, aB, nB0);
-                    }
-                    if (b1 == 0 || k1 == k0) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { nA1[c] = nA0[c]; nB1[c] = nB0[c]; }
-                    } else if (k1 == c1) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { nA1[c] = A1[c]; nB1[c] = B1[c]; }
-                    } else if (k1 == c0) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { nA1[c] = A0[c]; nB1[c] = B0[c]; }
-                    } else {
-                        const uint8_t *slot = smem + (size_t)k1 * S.slot_bytes;
-                        if (inA) hpass(slot, oA, aA, nA1);
-                        if (inB) hpass(slot, oB, aB, nB1);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { A0[c] = nA0[c]; A1[c] = nA1[c]; B0[c] = nB0[c]; B1[c] = nB1[c]; }
-                    c0 = k0;
-                    c1 = (b1 == 0) ? k0 : k1;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        vA[c] = inA ? lut[vpass(A0[c], A1[c], b0, b1)] : border;
-                        vB[c] = inB ? lut[vpass(B0[c], B1[c], b0, b1)] : border;
-                    }
-                }
-                T *row = out + (long long)oy * S.ys + (long long)x * S.xs;
-                const bool two = x + 1 < x_end;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const int sc = P.flip ? 2 - c : c;
-                    T *p = row + (long long)c * S.cs;
-                    if (two) store_pair<T>(p, S.xs, vA[sc], vB[sc], vec);
-                    else p[0] = vA[sc];
-                }
-            }
-        }
-    } else {
-        // pure border tile
-        if (x < x_end) {
-            const bool two = x + 1 < x_end;
-            for (int oy = oy0; oy < y_end; oy++) {
-                T *row = out + (long long)oy * S.ys + (long long)x * S.xs;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    T *p = row + (long long)c * S.cs;
-                    if (two) store_pair<T>(p, S.xs, border, border, vec);
-                    else p[0] = border;
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(PYR_THREADS) pyramid_kernel(const __grid_constant__ PyrParams P) {
-    extern __shared__ __align__(128) uint8_t dyn_smem[];
-    __shared__ __align__(16) uint8_t s_lut_raw[256 * 4];
     int tile = blockIdx.x;
     int si = 0;
 #pragma unroll 1
@@ -384,23 +229,226 @@ __global__ void __launch_bounds__(PYR_THREADS) pyramid_kernel(const __grid_const
         if (tile >= P.sc[s].tile_begin) si = s;
     const PyrScale &S = P.sc[si];
     tile -= S.tile_begin;
-    // value LUT: out = T(v / 255) for every byte value (exact division once per CTA)
-    if (S.dtype == FDMS_F16) {
-        __half *lut = reinterpret_cast<__half *>(s_lut_raw);
-        for (int i = threadIdx.x; i < 256; i += PYR_THREADS) lut[i] = OutCvt<__half>::cvt(i);
-        __syncthreads();
-        run_tile<__half>(P, S, tile, blockIdx.y, dyn_smem, lut);
-    } else if (S.dtype == FDMS_F32) {
-        float *lut = reinterpret_cast<float *>(s_lut_raw);
-        for (int i = threadIdx.x; i < 256; i += PYR_THREADS) lut[i] = OutCvt<float>::cvt(i);
-        __syncthreads();
-        run_tile<float>(P, S, tile, blockIdx.y, dyn_smem, lut);
-    } else {
-        uint8_t *lut = s_lut_raw;
-        for (int i = threadIdx.x; i < 256; i += PYR_THREADS) lut[i] = (uint8_t)i;
-        __syncthreads();
-        run_tile<uint8_t>(P, S, tile, blockIdx.y, dyn_smem, lut);
+    const int img = blockIdx.y;
+
+    const int tw = S.tw, th = S.th;
+    const int ty = tile / S.tiles_x, tx = tile - ty * S.tiles_x;
+    const int oy0 = ty * th, ox0 = tx * tw;
+    const int dst_h = S.dst_h, dst_w = S.dst_w, top = S.top, left = S.left, unpad_h = S.unpad_h, unpad_w = S.unpad_w;
+    const int y_end = min(oy0 + th, dst_h), x_end = min(ox0 + tw, dst_w);
+    const int n_rows = y_end - oy0;
+    // interior (resized image) columns of this tile, in resized-image coordinates: [dxa, dxb)
+    const int dxa = max(ox0, left) - left, dxb = min(x_end, left + unpad_w) - left;
+    const bool has_cols = dxa < dxb;
+    const int slot_bytes = S.slot_bytes;
+    const uint8_t *src = P.src + (long long)img * P.img_stride;
+
+    // ---- warp 0: vertical taps, slot assignment, bulk copies ------------------------------------
+    if (tid < 32) {
+        const int lane = tid;
+        if (lane == 0) {
+            mbar_init(reinterpret_cast<uint64_t *>(&sh.bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        const int oy = oy0 + lane, dy = oy - top;
+        const bool valid = has_cols && lane < n_rows && dy >= 0 && dy < unpad_h;
+        int r0 = 0, r1 = 0;
+        unsigned b01 = 0;
+        if (valid) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01);
+        const int b1 = (int)(b01 >> 16);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        int slot0 = 0, slot1 = 0, n_used = 0, rmin = 0;
+        if (vmask) {
+            if (S.dense_rows) {
+                rmin = __shfl_sync(0xffffffffu, r0, __ffs(vmask) - 1);
+                const int rmax = __shfl_sync(0xffffffffu, r1, 31 - __clz(vmask));
+                n_used = min(rmax - rmin + 1, PYR_MAX_SLOTS);
+                slot0 = r0 - rmin;
+                slot1 = (b1 != 0) ? r1 - rmin : slot0;
+            } else {
+                const int cnt = valid ? (b1 != 0 ? 2 : 1) : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                n_used = __shfl_sync(0xffffffffu, incl, 31);
+                slot0 = incl - cnt;
+                slot1 = (b1 != 0) ? slot0 + 1 : slot0;
+            }
+        }
+        // source byte range of the tile's columns
+        int sx = 0;
+        unsigned dummy;
+        if (has_cols && lane < 2) coeff_x(lane == 0 ? dxa : dxb - 1, S.scale_x, P.virt_w, sx, dummy);
+        const int sxa = __shfl_sync(0xffffffffu, sx, 0);
+        const int sxb = min(__shfl_sync(0xffffffffu, sx, 1) + 1, P.virt_w - 1);
+        const int g0 = (3 * sxa) & ~15;
+        const int row_bytes = ((3 * sxb + 3 + 15) & ~15) - g0;
+        const int real_end = 3 * P.src_w;
+        const int bulk_bytes = P.vec_ok ? max(0, min(g0 + row_bytes, real_end & ~15) - g0) : 0;
+        // slot -> source row, bulk copies
+        int n_bulk = 0;
+        bool virt_row = false;
+        __syncwarp();
+        if (S.dense_rows) {
+            for (int k = lane; k < n_used; k += 32) {
+                const int row = rmin + k;
+                sh.slot_row[k] = row;
+                if (row >= P.src_h) virt_row = true;
+                else if (bulk_bytes > 0) {
+                    bulk_g2s(smem + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes,
+                             reinterpret_cast<uint64_t *>(&sh.bar));
+                    n_bulk++;
+                }
+            }
+        } else if (valid) {
+            const int nk = (b1 != 0) ? 2 : 1;
+            for (int q = 0; q < nk; q++) {
+                const int k = slot0 + q, row = q ? r1 : r0;
+                sh.slot_row[k] = row;
+                if (row >= P.src_h) virt_row = true;
+                else if (bulk_bytes > 0) {
+                    bulk_g2s(smem + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes,
+                             reinterpret_cast<uint64_t *>(&sh.bar));
+                    n_bulk++;
+                }
+            }
+        }
+        n_bulk = __reduce_add_sync(0xffffffffu, n_bulk);
+        const bool any_virt = __any_sync(0xffffffffu, virt_row);
+        if (lane == 0) {
+            mbar_expect_tx(reinterpret_cast<uint64_t *>(&sh.bar), (uint32_t)(n_bulk * bulk_bytes));
+            sh.n_used = n_used;
+            sh.g0 = g0;
+            sh.row_bytes = row_bytes;
+            sh.bulk_bytes = bulk_bytes;
+            sh.need_scalar = (bulk_bytes < row_bytes) || any_virt;
+            sh.n_rows = n_rows;
+        }
+        if (lane < n_rows) {
+            sh.trig[lane] = valid ? slot1 : -1;
+            sh.meta[lane] = (b01 & 0xfffu) | ((b01 >> 16) << 12) | ((slot0 == slot1) ? (1u << 24) : 0u);
+        }
     }
+    __syncthreads();
+    const int n_used = sh.n_used, g0 = sh.g0;
+
+    // ---- per-thread columns (overlaps the bulk copies) ---------------------------------------------
+    const int x = ox0 + 2 * tid;
+    const bool active = x < x_end && tid * 2 < tw;
+    const bool two = x + 1 < x_end;
+    const int dxA = x - left, dxB = x + 1 - left;
+    const bool inA = active && dxA >= 0 && dxA < unpad_w;
+    const bool inB = active && two && dxB >= 0 && dxB < unpad_w;
+    uint32_t wA = 0, wB = 0;
+    unsigned shA = 0, shB = 0, aA = 0, aB = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    if (inA) {
+        int sx;
+        coeff_x(dxA, S.scale_x, P.virt_w, sx, aA);
+        const int o = 3 * sx - g0;
+        wA = smem_base + (uint32_t)(o & ~3);
+        shA = (unsigned)(o & 3) * 8u;
+    } else {
+        wA = smem_base;  // reads stay in bounds; the value is replaced by the border
+    }
+    if (inB) {
+        int sx;
+        coeff_x(dxB, S.scale_x, P.virt_w, sx, aB);
+        const int o = 3 * sx - g0;
+        wB = smem_base + (uint32_t)(o & ~3);
+        shB = (unsigned)(o & 3) * 8u;
+    } else {
+        wB = smem_base;
+    }
+
+    // ---- scalar staging: whatever the bulk copies do not cover ---------------------------------------
+    if (sh.need_scalar) {
+        const int row_bytes = sh.row_bytes, bulk_bytes = sh.bulk_bytes, rest = row_bytes - bulk_bytes;
+        const int real_end = 3 * P.src_w;
+        for (int k = 0; k < n_used; k++) {
+            const int row = sh.slot_row[k];
+            uint8_t *dst = smem + (size_t)k * slot_bytes;
+            if (row >= P.src_h) {  // virtual zero rows of the api mode
+                for (int i = tid * 4; i < row_bytes; i += PYR_THREADS * 4) *reinterpret_cast<uint32_t *>(dst + i) = 0u;
+            } else {
+                const uint8_t *srow = src + (long long)row * P.pitch;
+                for (int i = tid; i < rest; i += PYR_THREADS) {
+                    const int pos = g0 + bulk_bytes + i;
+                    dst[bulk_bytes + i] = pos < real_end ? __ldg(srow + pos) : (uint8_t)0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (n_used > 0) mbar_wait(reinterpret_cast<uint64_t *>(&sh.bar), 0);
+
+    if (!active) return;
+
+    // ---- stream over the slots ------------------------------------------------------------------------
+    const bool vec = S.vec != 0;
+    const long long cs = S.cs, xs = S.xs, ys = S.ys;
+    T *out_row = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * ys + (long long)x * xs;
+    const bool edge = !(inA && inB);  // uniform per thread; interior tiles have no edge threads
+    const int flip = P.flip, border = P.border;
+    int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
+    int j = 0;
+    int trig = (j < n_rows) ? sh.trig[0] : 0x7fffffff;
+
+    auto flush = [&](int k, const int *cur, const int *other) {
+        while (trig <= k) {
+            if (trig < 0) {
+                border_row<T>(out_row, cs, xs, border, two, vec);
+            } else {
+                const unsigned meta = sh.meta[j];
+                if (meta >> 24) {  // both taps in the same slot (clamped row or zero lower weight)
+                    if (edge) emit_row<T, true>(out_row, cs, xs, meta, cur, cur, flip, border, inA, inB, two, vec);
+                    else emit_row<T, false>(out_row, cs, xs, meta, cur, cur, flip, border, true, true, true, vec);
+                } else {
+                    if (edge) emit_row<T, true>(out_row, cs, xs, meta, other, cur, flip, border, inA, inB, two, vec);
+                    else emit_row<T, false>(out_row, cs, xs, meta, other, cur, flip, border, true, true, true, vec);
+                }
+            }
+            out_row += ys;
+            j++;
+            trig = (j < n_rows) ? sh.trig[j] : 0x7fffffff;
+        }
+    };
+
+    uint32_t slot_off = 0;
+    for (int k = 0; k < n_used; k += 2) {
+        hpass(wA + slot_off, shA, aA, E);
+        hpass(wB + slot_off, shB, aB, E + 3);
+        flush(k, E, O);
+        slot_off += slot_bytes;
+        if (k + 1 < n_used) {
+            hpass(wA + slot_off, shA, aA, O);
+            hpass(wB + slot_off, shB, aB, O + 3);
+            flush(k + 1, O, E);
+        }
+        slot_off += slot_bytes;
+    }
+    // rows not tied to any slot (border rows at the end, or a tile without interior)
+    while (j < n_rows) {
+        border_row<T>(out_row, cs, xs, border, two, vec);
+        out_row += ys;
+        j++;
+    }
+}
+
+template <typename T>
+int launch_group(fdms_ctx *ctx, const PyrParams &P, int tiles, int n_img, int smem, cudaStream_t st) {
+    const int bit = 1 << (int)sizeof(T);
+    if (!(ctx->pyr_attr & bit)) {  // dynamic shared memory opt-in, once per ctx and instantiation
+        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->pyr_attr |= bit;
+    }
+    dim3 grid(tiles, n_img);
+    pyramid_kernel<T><<<grid, PYR_THREADS, smem, st>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "pyramid_kernel");
+    return FDMS_OK;
 }
 
 }  // namespace
@@ -415,20 +463,6 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
     if (n_img > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_pyramid: n_img > 65535");
     if (virt_h < src_h || virt_w < src_w || row_pitch < (int64_t)src_w * 3 || border < 0 || border > 255)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_pyramid: bad extents");
-    PyrParams P;
-    memset(&P, 0, sizeof(P));
-    P.src = src;
-    P.img_stride = img_stride;
-    P.pitch = row_pitch;
-    P.src_h = src_h;
-    P.src_w = src_w;
-    P.virt_h = virt_h;
-    P.virt_w = virt_w;
-    P.n_scales = n_scales;
-    P.flip = flip_rb ? 1 : 0;
-    P.border = border;
-    P.vec_ok = ((uintptr_t)src % 16 == 0) && (img_stride % 16 == 0) && (row_pitch % 16 == 0);
-    int tiles = 0, smem_max = 0;
     for (int s = 0; s < n_scales; s++) {
         const fdms_scale_out &in = scales[s];
         const fdms_geom &g = in.geom;
@@ -437,57 +471,78 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_pyramid: bad geometry for scale %d", s);
         if (in.out_dtype != FDMS_U8 && in.out_dtype != FDMS_F16 && in.out_dtype != FDMS_F32)
             return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_pyramid: bad out_dtype for scale %d", s);
-        PyrScale &S = P.sc[s];
-        S.out = in.out;
-        S.img_stride = in.out_img_stride;
-        if (in.out_layout == FDMS_CHW) {
-            S.cs = (long long)g.dst_h * g.dst_w;
-            S.ys = g.dst_w;
-            S.xs = 1;
-        } else {
-            S.cs = 1;
-            S.ys = 3LL * g.dst_w;
-            S.xs = 3;
-        }
-        S.dst_h = g.dst_h;
-        S.dst_w = g.dst_w;
-        S.unpad_h = g.unpad_h;
-        S.unpad_w = g.unpad_w;
-        S.top = g.top;
-        S.left = g.left;
-        S.dtype = in.out_dtype;
-        // cv2.resize: scale = 1.0 / (dsize / ssize), computed in double (inv_scale first)
-        S.scale_x = 1.0 / ((double)g.unpad_w / virt_w);
-        S.scale_y = 1.0 / ((double)g.unpad_h / virt_h);
-        // tile shape: widest tile whose staged rows fit the shared-memory budget
-        int tw = 2 * PYR_THREADS, th = 8;
-        for (;;) {
+    }
+    // one launch per output dtype present (normally one: every scale of a pyramid shares it)
+    for (int dt = FDMS_U8; dt <= FDMS_F32; dt++) {
+        PyrParams P;
+        memset(&P, 0, sizeof(P));
+        P.src = src;
+        P.img_stride = img_stride;
+        P.pitch = row_pitch;
+        P.src_h = src_h;
+        P.src_w = src_w;
+        P.virt_h = virt_h;
+        P.virt_w = virt_w;
+        P.flip = flip_rb ? 1 : 0;
+        P.border = border;
+        P.vec_ok = ((uintptr_t)src % 16 == 0) && (img_stride % 16 == 0) && (row_pitch % 16 == 0);
+        int tiles = 0, smem_max = 0, n = 0;
+        for (int s = 0; s < n_scales; s++) {
+            const fdms_scale_out &in = scales[s];
+            if (in.out_dtype != dt) continue;
+            const fdms_geom &g = in.geom;
+            PyrScale &S = P.sc[n++];
+            S.out = in.out;
+            S.img_stride = in.out_img_stride;
+            if (in.out_layout == FDMS_CHW) {
+                S.cs = (long long)g.dst_h * g.dst_w;
+                S.ys = g.dst_w;
+                S.xs = 1;
+            } else {
+                S.cs = 1;
+                S.ys = 3LL * g.dst_w;
+                S.xs = 3;
+            }
+            const size_t esz = dt == FDMS_F32 ? 4 : (dt == FDMS_F16 ? 2 : 1);
+            S.vec = (S.xs == 1) && (g.dst_w % 2 == 0) && (S.cs % 2 == 0) && (S.img_stride % 2 == 0) && esz > 1 &&
+                    ((uintptr_t)in.out % (2 * esz) == 0);
+            S.dst_h = g.dst_h;
+            S.dst_w = g.dst_w;
+            S.unpad_h = g.unpad_h;
+            S.unpad_w = g.unpad_w;
+            S.top = g.top;
+            S.left = g.left;
+            // cv2.resize: scale = 1.0 / (dsize / ssize), computed in double (inv_scale first)
+            S.scale_x = 1.0 / ((double)g.unpad_w / virt_w);
+            S.scale_y = 1.0 / ((double)g.unpad_h / virt_h);
             S.dense_rows = S.scale_y <= 2.0;
-            S.n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : 2 * th;
-            if (S.n_slots > 2 * PYR_MAX_TH + 4) S.n_slots = 2 * PYR_MAX_TH + 4;
-            int span_px = (int)(tw * S.scale_x) + 4;
-            S.slot_bytes = ((span_px * 3 + 15) & ~15) + 48;
-            if ((long long)S.n_slots * S.slot_bytes <= PYR_SMEM_BUDGET) break;
-            if (th > 1) th >>= 1;
-            else if (tw > 32) tw >>= 1;
-            else break;
+            // tile: 320 columns (fewer when the staged rows would not fit), as many rows as the slots allow
+            int tw = 2 * PYR_THREADS, th = 16;
+            for (;;) {
+                int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : 2 * th;
+                int span_px = (int)(tw * S.scale_x) + 4;
+                S.slot_bytes = ((span_px * 3 + 15) & ~15) + 48;
+                if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= PYR_SMEM_BUDGET) {
+                    if (n_slots * S.slot_bytes > smem_max) smem_max = n_slots * S.slot_bytes;
+                    break;
+                }
+                if (th > 1) th >>= 1;
+                else if (tw > 32) tw >>= 1;
+                else return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_pyramid: scale %d needs too much shared memory", s);
+            }
+            S.tw = tw;
+            S.th = th;
+            S.tiles_x = ceil_div(g.dst_w, tw);
+            S.tile_begin = tiles;
+            tiles += S.tiles_x * ceil_div(g.dst_h, th);
         }
-        if ((long long)S.n_slots * S.slot_bytes > 200 * 1024)
-            return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_pyramid: scale %d needs %lld B of shared memory", s,
-                             (long long)S.n_slots * S.slot_bytes);
-        S.tw = tw;
-        S.th = th;
-        S.tiles_x = ceil_div(g.dst_w, tw);
-        S.tile_begin = tiles;
-        tiles += S.tiles_x * ceil_div(g.dst_h, th);
-        if (S.n_slots * S.slot_bytes > smem_max) smem_max = S.n_slots * S.slot_bytes;
+        if (n == 0) continue;
+        P.n_scales = n;
+        int rc;
+        if (dt == FDMS_F16) rc = launch_group<__half>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
+        else if (dt == FDMS_F32) rc = launch_group<float>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
+        else rc = launch_group<uint8_t>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
+        if (rc) return rc;
     }
-    if (!ctx->pyr_attr) {  // dynamic shared memory opt-in, once per ctx
-        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        ctx->pyr_attr = true;
-    }
-    dim3 grid(tiles, n_img);
-    pyramid_kernel<<<grid, PYR_THREADS, smem_max, (cudaStream_t)stream>>>(P);
-    FDMS_LAUNCH_CHECK(ctx, "pyramid_kernel");
     return FDMS_OK;
 }

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: image sharding (no collective on the hot path) and the optional final gather.
+
+The reference shards inference by item over a spawn Pool, one CUDA context per worker, with no
+communication (yolov7_face_multi_scale_dataframe_predict.py:569-596,1115,1147).  Here: one process per
+GPU (torchrun), images partitioned contiguously by rank, every rank runs the whole hot path on its shard
+with its own libfdms context; the only collective is an OPTIONAL gather of the variable-length results
+(two all_gathers: counts, then max-padded rows) over NCCL / NVLink -- gloo on CPU for tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous balanced partition: item i goes to rank i * world // n_items."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    base, rem = divmod(int(n_items), world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard(items, rank=None, world=None):
+    """This rank's slice of `items` (list / array).  Defaults to the initialised process group."""
+    if rank is None or world is None:
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    a, b = shard_range(len(items), rank, world)
+    return items[a:b]
+
+
+def _comm_device(group=None):
+    backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def gather_detections(local_dets, n_total, group=None):
+    """local_dets: list of (k_i, C) float arrays for this rank's shard (in shard order; np.array([]) allowed).
+    Returns the list for ALL n_total images in global order on every rank.  Two collectives per call."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [np.asarray(d, np.float64).reshape(-1, 7) if np.size(d) else np.zeros((0, 7)) for d in local_dets]
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    a, b = shard_range(n_total, rank, world)
+    if len(local_dets) != b - a:
+        raise ValueError("rank %d holds %d results for a shard of %d images" % (rank, len(local_dets), b - a))
+    dev = _comm_device(group)
+    cols = 7
+    for d in local_dets:
+        if np.size(d):
+            cols = np.asarray(d).shape[1]
+            break
+    rows = [np.asarray(d, np.float64).reshape(-1, cols) if np.size(d) else np.zeros((0, cols)) for d in local_dets]
+    per_img = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    counts = torch.zeros((per_img + 1,), dtype=torch.int64)
+    counts[:len(rows)] = torch.tensor([r.shape[0] for r in rows], dtype=torch.int64) if rows else 0
+    counts[per_img] = cols
+    counts = counts.to(dev)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = torch.stack(all_counts).cpu().numpy()
+    cols = int(all_counts[:, per_img].max())
+    kmax = int(all_counts[:, :per_img].sum(1).max())
+    flat = np.zeros((max(kmax, 1), cols), np.float64)
+    if rows and sum(r.shape[0] for r in rows):
+        cat = np.concatenate(rows, 0)
+        flat[:cat.shape[0], :cat.shape[1]] = cat
+    buf = torch.from_numpy(flat).to(dev)
+    all_buf = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(all_buf, buf, group=group)
+    out = []
+    for r in range(world):
+        ra, rb = shard_range(n_total, r, world)
+        data = all_buf[r].cpu().numpy()
+        off = 0
+        for i in range(rb - ra):
+            k = int(all_counts[r, i])
+            out.append(data[off:off + k].copy())
+            off += k
+    return out
+
+
+def detect_sharded(detector, images, gather=True):
+    """Run `detector.detect_multi_scale_batch` on this rank's contiguous shard of `images` (B, H, W, 3) and
+    optionally gather every image's detections on every rank."""
+    n = len(images)
+    local = shard(images)
+    res = detector.detect_multi_scale_batch(local) if len(local) else []
+    return gather_detections(res, n) if gather else res

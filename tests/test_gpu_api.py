@@ -70,7 +70,7 @@ def test_patched_head_returns_reference_tuple(golden):
     g = golden("head")
     levels = [torch.from_numpy(g["tiny_raw%d" % i]).to(DEV) for i in range(3)]
     model = standin.SyntheticHeadModel(strides=[float(s) for s in g["tiny_strides"]], anchors_px=g["tiny_anchors_px"])
-    model.to(DEV)
+    model.to(DEV).eval()
     head = yolo_head.patch_head(yolo_head.find_head(model))
     pred, xs = head([l.clone() for l in levels])
     assert pred.shape == g["tiny_pred"].shape

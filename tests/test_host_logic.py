@@ -1,0 +1,162 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/fdms.h declares, host-side
+geometry, the no-fallback contract, sharding, and the world_size-2 gloo gather."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from face_detection_multi_scale_b200 import _lib, dist as fdist, general
+from oracle import oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = torch.cuda.is_available()
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "fdms.h")).read()
+    declared = re.findall(r"FDMS_API\s+[\w\s\*]+?\b(fdms_\w+)\s*\(", hdr)
+    assert len(declared) >= 18 and len(set(declared)) == len(declared)
+    h = _lib.lib()
+    for name in declared:
+        assert hasattr(h, name), "libfdms.so does not export %s" % name
+        assert name in _lib._SIGS, "no ctypes signature for %s" % name
+    assert h.fdms_version() == 100
+    assert b"sm_100a" in h.fdms_build_info() and b"fmad=off" in h.fdms_build_info()
+
+
+def test_library_has_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "face_detection_multi_scale_b200", "libfdms.so")],
+                         capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the behaviour without a CUDA device")
+def test_no_cpu_fallback():
+    h = _lib.lib()
+    p = ctypes.c_void_p()
+    assert h.fdms_create(ctypes.byref(p), 0) == -2  # FDMS_ERR_CUDA
+    with pytest.raises(_lib.FdmsError):
+        _lib.ctx(0)
+    from face_detection_multi_scale_b200 import ops
+    with pytest.raises(ValueError):
+        ops.decode_dense([torch.zeros((1, 63, 4, 4))], [8], np.ones((1, 3, 2)))
+    from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
+    with pytest.raises(RuntimeError):
+        MultiScaleFaceDetector(torch.nn.Identity(), device="")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "face_detection_multi_scale_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "fdms_oracle" not in src and "refshim" not in src, f
+
+
+def test_letterbox_geometry_matches_oracle_and_reference(golden):
+    g = golden("letterbox")
+    for i, (h, w, ns, auto, scaleup, stride, seed) in enumerate(H.LETTERBOX_SMALL):
+        a = _lib.letterbox_geometry(h, w, ns, auto=auto, scaleup=scaleup, stride=stride)
+        b = O.letterbox_geometry(h, w, ns, auto=auto, scaleup=scaleup, stride=stride)
+        for f in ("dst_h", "dst_w", "unpad_h", "unpad_w", "top", "bottom", "left", "right", "resize", "ratio_w", "dw", "dh"):
+            assert getattr(a, f) == getattr(b, f), (i, f)
+        assert (a.dst_h, a.dst_w) == g["small%d_out" % i].shape[:2]
+        meta = g["small_meta"][i]
+        assert (a.ratio_w, a.dw, a.dh) == (meta[8], meta[9], meta[10])
+    for i, (h, w, ns, auto, stride, seed) in enumerate(H.LETTERBOX_FULL):
+        a = _lib.letterbox_geometry(h, w, ns, auto=auto, stride=stride)
+        assert (a.dst_h, a.dst_w) == tuple(g["full_meta"][i][6:8])
+    with pytest.raises(ValueError):
+        _lib.letterbox_geometry(0, 10, 64)
+
+
+def test_scale_fill_geometry():
+    a = _lib.letterbox_geometry(90, 160, (64, 96), auto=False, scaleFill=True)
+    b = O.letterbox_geometry(90, 160, (64, 96), auto=False, scaleFill=True)
+    assert (a.dst_h, a.dst_w, a.ratio_w, a.ratio_h) == (b.dst_h, b.dst_w, b.ratio_w, b.ratio_h) == (64, 96, 0.6, 64 / 90)
+
+
+def test_fp16_pack_by_reciprocal_is_exact():
+    """pyramid.cu stores rn16(rn32(v * rn32(1/255))); the reference computes rn16(rn32(v / 255)) (msfd:101-102)."""
+    v = np.arange(256, dtype=np.float32)
+    a = (v / np.float32(255)).astype(np.float16)
+    c = np.float32(0.003921568859368563)
+    assert c == np.float32(1.0) / np.float32(255.0)
+    b = (v * c).astype(np.float16)
+    assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+    # and the oracle's pack agrees with torch's half division
+    t = (torch.arange(256, dtype=torch.uint8).half() / 255.0).numpy()
+    assert np.array_equal(t.view(np.uint16), a.view(np.uint16))
+
+
+def test_check_img_size(capsys):
+    assert general.make_divisible(641, 32) == 672
+    assert general.check_img_size(640, 32) == 640
+    assert general.check_img_size(3840, 64) == 3840
+    assert general.check_img_size(1000, 32) == 1024
+    assert "WARNING" in capsys.readouterr().out
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 32, 512):
+        for world in (1, 2, 3, 8):
+            spans = [fdist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        fdist.shard_range(4, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from face_detection_multi_scale_b200 import dist as fdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+n = 7
+rng = np.random.default_rng(0)
+truth = [rng.uniform(0, 100, (int(k), 7)) if k else np.array([]) for k in (3, 0, 5, 1, 0, 0, 9)]
+local = fdist.shard(truth)
+assert len(local) == (4 if rank == 0 else 3)
+out = fdist.gather_detections(local, n)
+assert len(out) == n
+for a, b in zip(out, truth):
+    b = np.asarray(b).reshape(-1, 7) if np.size(b) else np.zeros((0, 7))
+    assert a.shape == b.shape and np.array_equal(a, b)
+# all-empty shard on one rank
+out = fdist.gather_detections([np.array([])] * len(local) if rank == 1 else local, n)
+assert sum(len(o) for o in out) == sum(len(t) for t in truth[:4])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gather_world_size_2_gloo(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o

@@ -205,7 +205,7 @@ def main():
     plan0 = sets[0][3]
     cnt = plan0.cands.count.cpu().numpy()
     nkeep = plan0.cands.n_keep.cpu().numpy()
-    nout = plan0.out.n_out.cpu().numpy()
+    nout = plan0.out.merged_in.cpu().numpy()
     if cnt.max() > wl["cap"] or nkeep.min() < 0 or nout.max() > wl["cap"]:
         raise SystemExit("bench.py: workload exceeds capacities (count max %d)" % cnt.max())
     cand_per_step = int(cnt.sum())

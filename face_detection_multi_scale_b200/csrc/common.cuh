@@ -24,7 +24,9 @@ struct fdms_ctx {
     int smem_optin = 0;
     char err[512] = {0};
     int pyr_attr = 0;
-    bool nms_attr = false;
+    int pyr_smem_budget = 56 * 1024, pyr_th = 16;  // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
+    bool nms_attr = false, nms_small_attr = false;
+    int nms_small_limit = 4096;  // FDMS_NMS_SMALL_LIMIT overrides (0 forces the generic sort/mask/sweep path)
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
     fdms_buf sort_a, sort_b;   // NMS: 64-bit keys ping-pong

@@ -160,33 +160,23 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
         int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
-    int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     int basepos = 0;
     if (lane == 31) basepos = atomicAdd(P.count + seg, total);
     basepos = __shfl_sync(0xffffffffu, basepos, 31);
     int pos = basepos + incl - n;
-
-    while (pass) {
-        int k = __ffs(pass) - 1;
-        pass &= pass - 1;
-        if (pos < P.cap) {
-            long long cell = cell0 + k;
-            int gy = (int)(cell / L.nx), gx = (int)(cell - (long long)gy * L.nx);
-            float v[NO], o[NO];
+    // Survivors are only RECORDED here (row index + confidence); decode_candidates_kernel decodes them with
+    // one lane per channel.  Decoding in place would run the long exact path at 1/32 lane efficiency.
 #pragma unroll
-            for (int c = 0; c < NO; c++) v[c] = (float)__ldg(base + (long long)c * cells + cell);
-            decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
-            float ck = 0.f;
-#pragma unroll
-            for (int q = 0; q < DEC_VEC; q++)
-                if (q == k) ck = conf[q];
-            row_to_candidate(o, ck);
-            float *dst = P.cand + ((long long)seg * P.cap + pos) * NO;
-#pragma unroll
-            for (int c = 0; c < NO; c++) dst[c] = o[c];
-            P.cand_row[(long long)seg * P.cap + pos] = L.row_offset + a * (int)cells + (int)cell;
+    for (int k = 0; k < DEC_VEC; k++) {
+        if ((pass >> k) & 1u) {
+            if (pos < P.cap) {
+                const long long slot = (long long)seg * P.cap + pos;
+                P.cand_row[slot] = L.row_offset + a * (int)cells + (int)(cell0 + k);
+                P.cand[slot * NO + 4] = conf[k];
+            }
+            pos++;
         }
-        pos++;
     }
 }
 
@@ -198,6 +188,64 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid
     const DecLevel &L = P.lv[li];
     if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, blockIdx.x - L.block_begin);
     else decode_filter_body<float>(P, L, blockIdx.x - L.block_begin);
+}
+
+// Second half of the fused decode: one warp per recorded candidate, lane c < 21 owns channel c of the row
+// (one strided load, at most one exact sigmoid, one coalesced 84-byte store).  models/yolo.py:290-295 and
+// utils/general.py:299-306,547-563.
+constexpr int CAND_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ float load_ch(const void *data, long long i) {
+    return (float)__ldg(reinterpret_cast<const T *>(data) + i);
+}
+
+__global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const __grid_constant__ DecParams P) {
+    const int seg = blockIdx.y;
+    const int n = min(P.count[seg], P.cap);
+    const int warp = threadIdx.x >> 5, c = threadIdx.x & 31;
+    const int b = seg / P.n_scales, scale = seg - b * P.n_scales;
+    const bool sig = c < 4 || (c >= 8 && c < NO && (c - 8) % 3 == 0);  // obj/cls are already folded into conf
+    for (int i = blockIdx.x * (CAND_THREADS / 32) + warp; i < n; i += gridDim.x * (CAND_THREADS / 32)) {
+        const long long slot = (long long)seg * P.cap + i;
+        const int row = P.cand_row[slot];
+        // level of this row inside its scale (rows are level-major)
+        int li = -1;
+#pragma unroll 1
+        for (int l = 0; l < P.n_levels; l++) {
+            const DecLevel &Lc = P.lv[l];
+            if (Lc.scale == scale && row >= Lc.row_offset && row < Lc.row_offset + NA * Lc.ny * Lc.nx) li = l;
+        }
+        if (li < 0) continue;
+        const DecLevel &L = P.lv[li];
+        const int cells = L.ny * L.nx;
+        const int r = row - L.row_offset;
+        const int a = r / cells, cell = r - a * cells;
+        const int gy = cell / L.nx, gx = cell - gy * L.nx;
+        float val = 0.f;
+        if (c < NO) {
+            const long long idx = ((long long)b * NA * NO + (long long)a * NO + c) * cells + cell;
+            const float v = L.dtype == FDMS_F16 ? load_ch<__half>(L.data, idx) : load_ch<float>(L.data, idx);
+            const float s = sig ? sigmoid_exact(v) : 0.f;
+            const float g = (c == 0 || (c >= 6 && (c - 6) % 3 == 0)) ? (float)gx : (float)gy;
+            if (c < 2) val = f_mul(f_add(f_sub(f_mul(s, 2.f), 0.5f), g), L.stride);  // yolo.py:290
+            else if (c < 4) {
+                const float t2 = f_mul(s, 2.f);
+                val = f_mul(f_mul(t2, t2), L.anchors[2 * a + (c - 2)]);  // :291
+            } else if (c == 4) val = P.cand[slot * NO + 4];  // conf recorded by the filter (general.py:547)
+            else if (c == 5) val = 0.f;                     // class index
+            else if ((c - 6) % 3 == 2) val = s;             // yolo.py:295
+            else val = f_mul(f_add(f_sub(f_mul(v, 2.f), 0.5f), g), L.stride);  // :293-294 (raw logits)
+        }
+        // xywh2xyxy (general.py:299-306) on lanes 0..3
+        const float cx = __shfl_sync(0xffffffffu, val, 0), cy = __shfl_sync(0xffffffffu, val, 1);
+        const float bw = __shfl_sync(0xffffffffu, val, 2), bh = __shfl_sync(0xffffffffu, val, 3);
+        if (c == 0) val = f_sub(cx, f_div(bw, 2.f));
+        else if (c == 1) val = f_sub(cy, f_div(bh, 2.f));
+        else if (c == 2) val = f_add(cx, f_div(bw, 2.f));
+        else if (c == 3) val = f_add(cy, f_div(bh, 2.f));
+        if (c < NO) P.cand[slot * NO + c] = val;
+    }
 }
 
 // ---- dense decode ---------------------------------------------------------------------------
@@ -347,6 +395,12 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
     FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs * n_scales, st));
     decode_filter_kernel<<<n_blocks, DEC_THREADS, 0, st>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
+    const int n_seg = bs * n_scales;
+    if (n_seg > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_filter: more than 65535 segments");
+    int gx = ceil_div(cap, CAND_THREADS / 32);
+    if (gx > 16) gx = 16;
+    decode_candidates_kernel<<<dim3(gx, n_seg), CAND_THREADS, 0, st>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "decode_candidates_kernel");
     return FDMS_OK;
 }
 

@@ -227,8 +227,10 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
         n_scales > FDMS_MAX_SCALES || cap <= 0 || out_cap <= 0 || orig_h <= 0 || orig_w <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long mcap_ll = (long long)n_scales * cap;
-    if (mcap_ll > 0x3fffffff) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_merge_scales: cap too large");
+    // capacity of the merged (pre-NMS) list of an image: it can never need more than n_scales * cap, and the
+    // caller sizes out_cap to hold it (merged_in reports the exact demand, so overflow is detectable)
+    long long mcap_ll = (long long)n_scales * cap;
+    if (mcap_ll > out_cap) mcap_ll = out_cap;
     const int mcap = (int)mcap_ll;
     if (int rc = fdms_reserve(ctx, ctx->merge_rows, (size_t)n_img * mcap * (MROW * 4 + 4))) return rc;
     if (int rc = fdms_reserve(ctx, ctx->merge_cnt, (size_t)n_img * 2 * 4)) return rc;

@@ -29,6 +29,8 @@ constexpr int SORT_SMEM_ITEMS = 8192;  // 8 B key + 4 B index each = 96 KB
 constexpr int MASK_THREADS = 256;      // 64 rows x 4 column blocks
 constexpr int SWEEP_THREADS = 512;
 constexpr int SWEEP_MAX_NBLK = 4096;   // 262144 boxes per segment
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_LIMIT = 4096;      // largest segment the fused single-CTA kernel takes (112 KB of shared memory)
 
 struct SegInfo {
     int n;               // boxes entering suppression (after the max_nms cut)
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                     const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int n_seg, int cap, int cap_e,
                     int max_nms, unsigned long long *gkeys, uint32_t *gidx, long long gpad,
                     uint32_t *__restrict__ sorted_idx, float4 *__restrict__ sorted_boxes, SegInfo *seginfo,
-                    PlanHeader *hdr, long long mask_budget_words) {
+                    PlanHeader *hdr, long long mask_budget_words, int skip_le) {
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ int s_last;
     __shared__ long long s_carry[2];
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
     const int g = blockIdx.x, tid = threadIdx.x;
     int n = count[g];
     n = max(0, min(n, cap));
+    if (n <= skip_le) n = 0;  // handled by nms_small_kernel
     int pad = 64;
     while (pad < n) pad <<= 1;
     unsigned long long *keys;
@@ -190,10 +193,15 @@ __global__ void __launch_bounds__(SORT_THREADS)
     }
 }
 
+// IoU test of box b (later in score order) against box a.  Disjoint boxes are rejected before any
+// arithmetic: inter == 0 gives iou == 0 (or NaN when the union is empty too), which never exceeds a
+// threshold >= 0 -- exact, not an approximation.  `quick` is false for thresholds where that does not hold.
 template <int MODE>
-__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float thr, bool inclusive) {
+__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float thr, bool inclusive,
+                                       bool quick) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    if (quick && (!(xx2 > xx1) || !(yy2 > yy1))) return false;
     float w = fmaxf(f_sub(xx2, xx1), 0.f), h = fmaxf(f_sub(yy2, yy1), 0.f);
     float inter = f_mul(w, h);
     float bw = f_sub(b.z, b.x), bh = f_sub(b.w, b.y);
@@ -210,6 +218,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
                     const float4 *__restrict__ sorted_boxes, unsigned long long *__restrict__ mask, float thr,
                     int inclusive) {
     __shared__ float4 s_col[MASK_THREADS];
+    const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
     const long long total = hdr->total_units;
     const int tid = threadIdx.x;
     int g = 0;
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
             int j0 = (cblk == rb) ? (tid & 63) + 1 : 0;  // only later boxes can be suppressed
 #pragma unroll 4
             for (int j = j0; j < jn; j++)
-                if (iou_gt<MODE>(a, area_a, s_col[q * 64 + j], thr, inclusive != 0)) bits |= 1ull << j;
+                if (iou_gt<MODE>(a, area_a, s_col[q * 64 + j], thr, inclusive != 0, quick)) bits |= 1ull << j;
             mask[si.mask_off + (long long)row * si.nblk + cblk] = bits;
         }
     }
@@ -254,11 +263,13 @@ __global__ void __launch_bounds__(MASK_THREADS)
 __global__ void __launch_bounds__(SWEEP_THREADS)
     nms_sweep_kernel(const SegInfo *__restrict__ seginfo, const unsigned long long *__restrict__ mask, int cap_e,
                      const uint32_t *__restrict__ sorted_idx, int32_t *__restrict__ keep, int32_t *__restrict__ n_keep,
-                     int cap) {
+                     int cap, const int32_t *__restrict__ count, int skip_le) {
     __shared__ unsigned long long s_removed[SWEEP_MAX_NBLK];
+    __shared__ unsigned long long s_diag[64];
     __shared__ unsigned long long s_kept;
     __shared__ int s_nkeep;
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    if (max(0, min(count[g], cap)) <= skip_le) return;  // handled by nms_small_kernel
     const SegInfo si = seginfo[g];
     if (si.mask_off < 0 && si.n > 0) {  // did not fit the mask budget: report, never guess
         if (tid == 0) n_keep[g] = -1;
@@ -274,29 +285,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
     for (int c = 0; c < nblk; c++) {
         if (tid < 32) {
             const int r_lo = c * 64 + lane, r_hi = r_lo + 32;
-            unsigned long long d_lo = r_lo < K ? M[(long long)r_lo * nblk + c] : 0ull;
-            unsigned long long d_hi = r_hi < K ? M[(long long)r_hi * nblk + c] : 0ull;
-            unsigned long long cur = s_removed[c];
+            s_diag[lane] = r_lo < K ? M[(long long)r_lo * nblk + c] : 0ull;
+            s_diag[lane + 32] = r_hi < K ? M[(long long)r_hi * nblk + c] : 0ull;
+            __syncwarp();
             const int left = K - c * 64;
             const unsigned long long valid = left >= 64 ? ~0ull : ((1ull << left) - 1ull);
-            unsigned long long kept = 0ull;
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                unsigned long long d = __shfl_sync(0xffffffffu, d_lo, i);
-                if (!((cur >> i) & 1ull)) {
-                    cur |= d;
-                    kept |= 1ull << i;
-                }
+            // one step per KEPT box: the diagonal words only hold later columns
+            unsigned long long alive = ~s_removed[c] & valid, kept = 0ull;
+            while (alive) {
+                const int q = __ffsll((long long)alive) - 1;
+                kept |= 1ull << q;
+                alive &= ~(s_diag[q] | (1ull << q));
             }
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                unsigned long long d = __shfl_sync(0xffffffffu, d_hi, i);
-                if (!((cur >> (i + 32)) & 1ull)) {
-                    cur |= d;
-                    kept |= 1ull << (i + 32);
-                }
-            }
-            kept &= valid;
             const int base = s_nkeep;
             if ((kept >> lane) & 1ull) kout[base + __popcll(kept & ((1ull << lane) - 1ull))] = (int32_t)sidx[r_lo];
             if ((kept >> (lane + 32)) & 1ull)
@@ -320,6 +320,128 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
                 }
                 s_removed[w] |= acc;
             }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_keep[g] = s_nkeep;
+}
+
+// Fused single-CTA NMS for segments of at most SMALL_LIMIT boxes: bitonic sort, boxes in score
+// order and the kept list all live in shared memory; suppression is a blocked greedy sweep
+// (64 boxes per step: test against the boxes kept so far, build the 64x64 in-block mask, resolve it
+// in warp 0 with shuffles).  No global scratch, no K^2 mask, one launch.
+template <int MODE>
+__global__ void __launch_bounds__(SMALL_THREADS)
+    nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
+                     const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int cap, int max_nms,
+                     int small_cap, int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
+                     int32_t *__restrict__ n_keep) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ unsigned long long s_rowmask[64];
+    __shared__ unsigned long long s_sup;
+    __shared__ int s_nkeep;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
+    int n = max(0, min(count[g], cap));
+    if (n > small_limit) return;  // the generic three-kernel path takes it
+    if (n == 0) {
+        if (tid == 0) n_keep[g] = 0;
+        return;
+    }
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm);
+    float4 *boxes = reinterpret_cast<float4 *>(sm + (size_t)small_cap * 8);
+    uint32_t *idx = reinterpret_cast<uint32_t *>(sm + (size_t)small_cap * 24);
+    uint32_t *kept = reinterpret_cast<uint32_t *>(sm);  // aliases keys once the sort is done
+    int pad = 64;
+    while (pad < n) pad <<= 1;
+    const float *seg_rows = rows + (long long)g * cap * row_stride;
+    for (int i = tid; i < pad; i += SMALL_THREADS) {
+        if (i < n) {
+            float s = seg_rows[(long long)i * row_stride + score_off];
+            uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + i] : (uint32_t)i;
+            keys[i] = ((unsigned long long)score_key_desc(s) << 32) | t;
+            idx[i] = (uint32_t)i;
+        } else {
+            keys[i] = ~0ull;
+            idx[i] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    if (n > 1) {
+        for (int k = 2; k <= pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (pad >> 1); t += SMALL_THREADS) {
+                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    int p = i + j;
+                    bool up = (i & k) == 0;
+                    unsigned long long a = keys[i], b = keys[p];
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[p] = a;
+                        uint32_t ia = idx[i], ib = idx[p];
+                        idx[i] = ib;
+                        idx[p] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const int K = (max_nms > 0) ? min(n, max_nms) : n;
+    for (int k = tid; k < K; k += SMALL_THREADS) {
+        const float *r = seg_rows + (long long)idx[k] * row_stride + box_off;
+        boxes[k] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    if (tid == 0) s_nkeep = 0;
+    __syncthreads();  // keys are dead from here on: `kept` may overwrite them
+    int32_t *kout = keep + (long long)g * cap;
+    const int nblk = (K + 63) >> 6;
+    const int i = tid & 63, quarter = tid >> 6;
+    for (int c = 0; c < nblk; c++) {
+        const int base = c * 64, nb = min(64, K - base);
+        const int nk = s_nkeep;
+        if (tid < 64) s_rowmask[tid] = 0ull;
+        if (tid == 0) s_sup = 0ull;
+        __syncthreads();
+        if (i < nb) {
+            const float4 bi = boxes[base + i];
+            // (1) suppressed by a box kept in an earlier block?
+            bool sup = false;
+            for (int q = quarter; q < nk && !sup; q += 4) {
+                const float4 a = boxes[kept[q]];
+                sup = iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick);
+            }
+            if (sup) atomicOr(&s_sup, 1ull << i);
+            // (2) in-block mask: row i suppresses later columns j
+            const float area_i = f_mul(f_sub(bi.z, bi.x), f_sub(bi.w, bi.y));
+            unsigned long long bits = 0ull;
+            const int j0 = max(quarter * 16, i + 1), j1 = min(quarter * 16 + 16, nb);
+            for (int j = j0; j < j1; j++)
+                if (iou_gt<MODE>(bi, area_i, boxes[base + j], thr, inclusive != 0, quick)) bits |= 1ull << j;
+            if (bits) atomicOr(&s_rowmask[i], bits);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // greedy resolution of the block: visit only boxes that are still alive (one step per KEPT box)
+            const unsigned long long valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
+            unsigned long long alive = ~s_sup & valid, kb = 0ull;
+            while (alive) {
+                const int q = __ffsll((long long)alive) - 1;
+                kb |= 1ull << q;
+                alive &= ~(s_rowmask[q] | (1ull << q));  // row masks only hold later columns
+            }
+            kb &= valid;
+            if ((kb >> lane) & 1ull) {
+                const int pos = nk + __popcll(kb & ((1ull << lane) - 1ull));
+                kept[pos] = (uint32_t)(base + lane);
+                kout[pos] = (int32_t)idx[base + lane];
+            }
+            if ((kb >> (lane + 32)) & 1ull) {
+                const int pos = nk + __popcll(kb & ((1ull << (lane + 32)) - 1ull));
+                kept[pos] = (uint32_t)(base + lane + 32);
+                kout[pos] = (int32_t)idx[base + lane + 32];
+            }
+            if (lane == 0) s_nkeep = nk + __popcll(kb);
         }
         __syncthreads();
     }
@@ -362,6 +484,35 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         score_off < 0 || (iou_mode != FDMS_IOU_TV_CPU && iou_mode != FDMS_IOU_TV_CUDA))
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_nms: bad arguments");
     const int cap_e = (max_nms > 0 && max_nms < cap) ? max_nms : cap;
+    float thr_f;
+    int inclusive;
+    fdms_fold_threshold(iou_thres, iou_mode, &thr_f, &inclusive);
+    // ---- segments of at most small_limit boxes: one fused launch -------------------------------------------
+    const int small_limit = ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
+    if (small_limit > 0) {
+        int small_cap = 64;
+        while (small_cap < cap && small_cap < small_limit) small_cap <<= 1;
+        const int smem = small_cap * 28;
+        if (!ctx->nms_small_attr) {
+            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_small_kernel<FDMS_IOU_TV_CUDA>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_LIMIT * 28));
+            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_small_kernel<FDMS_IOU_TV_CPU>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_LIMIT * 28));
+            ctx->nms_small_attr = true;
+        }
+        if (iou_mode == FDMS_IOU_TV_CUDA)
+            nms_small_kernel<FDMS_IOU_TV_CUDA><<<n_seg, SMALL_THREADS, smem, st>>>(
+                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_cap, small_limit, thr_f, inclusive,
+                keep, n_keep);
+        else
+            nms_small_kernel<FDMS_IOU_TV_CPU><<<n_seg, SMALL_THREADS, smem, st>>>(
+                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_cap, small_limit, thr_f, inclusive,
+                keep, n_keep);
+        FDMS_LAUNCH_CHECK(ctx, "nms_small_kernel");
+        if (cap <= small_limit) return FDMS_OK;  // no segment can be larger
+    }
+    const int skip_le = small_limit > 0 ? small_limit : -1;
+    // ---- larger segments: sort -> mask -> sweep ----------------------------------------------------------------
     if ((cap_e + 63) / 64 > SWEEP_MAX_NBLK)
         return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_nms: more than %d boxes per segment", SWEEP_MAX_NBLK * 64);
     long long pad = 64;
@@ -393,11 +544,8 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         rows, row_stride, box_off, score_off, tie, count, n_seg, cap, cap_e, max_nms,
         reinterpret_cast<unsigned long long *>(ctx->sort_a.p), reinterpret_cast<uint32_t *>(ctx->idx_a.p), pad,
         reinterpret_cast<uint32_t *>(ctx->idx_b.p), reinterpret_cast<float4 *>(ctx->boxes.p), seginfo, hdr,
-        budget_words);
+        budget_words, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
-    float thr_f;
-    int inclusive;
-    fdms_fold_threshold(iou_thres, iou_mode, &thr_f, &inclusive);
     const int mask_grid = ctx->sm_count * 8;
     if (iou_mode == FDMS_IOU_TV_CUDA)
         nms_mask_kernel<FDMS_IOU_TV_CUDA><<<mask_grid, MASK_THREADS, 0, st>>>(
@@ -410,7 +558,7 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     FDMS_LAUNCH_CHECK(ctx, "nms_mask_kernel");
     nms_sweep_kernel<<<n_seg, SWEEP_THREADS, 0, st>>>(seginfo, reinterpret_cast<const unsigned long long *>(ctx->mask.p),
                                                       cap_e, reinterpret_cast<const uint32_t *>(ctx->idx_b.p), keep,
-                                                      n_keep, cap);
+                                                      n_keep, cap, count, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "nms_sweep_kernel");
     return FDMS_OK;
 }

@@ -127,23 +127,28 @@ __device__ __forceinline__ void hpass(uint32_t w, unsigned sh, unsigned a01, int
     h[2] = (int)(__dp2a_lo(a01, p2, 0u) >> 4);
 }
 
-// Vertical pass: (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  The result cannot exceed
-// 255: b0+b1 <= 2049 and R>>4 <= 32654, so the two floors sum to at most 1020.
-__device__ __forceinline__ int vpass(int r0, int r1, int b0, int b1) {
-    return (((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2;
+// Vertical pass.  OpenCV: (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  Returns the sum t before the
+// final shift: two full-rate IMADs, one PRMT gathering the two high halves, one IDP.2A adding them (+2).
+// t >> 2 cannot exceed 255: b0+b1 <= 2049 and R>>4 <= 32654, so the two floors sum to at most 1020.
+__device__ __forceinline__ unsigned vsum(unsigned r0, unsigned r1, unsigned b0, unsigned b1) {
+    const unsigned p0 = b0 * r0, p1 = b1 * r1;            // < 2^27
+    const unsigned hh = __byte_perm(p0, p1, 0x7632);      // (p0 >> 16) | (p1 >> 16) << 16
+    return __dp2a_lo(hh, 0x0101u, 2u);                    // (p0 >> 16) + (p1 >> 16) + 2
 }
 
-// ---- value conversion + paired store, per output type -------------------------------------------
+// ---- value conversion + paired store, per output type.  Inputs are the sums t (pixel = t >> 2). ----
 template <typename T> struct Out;
 template <> struct Out<__half> {
     // rn16(rn32(v/255)) (ATen divides in float and rounds once, msfd:101-102) == rn16(rn32(v * rn32(1/255)))
     // for all 256 byte values (checked exhaustively in tests/test_host_logic.py).  float(v) comes
-    // from the 2^23 magic number: fma(as_float(0x4B000000|v), c, -2^23*c) is exactly rn32(v*c).
-    static __device__ __forceinline__ float f(int v) {
+    // from the 2^23 magic number: (t >> 2) + 0x4B000000 is one mad.hi, and
+    // fma(as_float(0x4B000000 + v), c, -2^23*c) is exactly rn32(v*c).
+    static __device__ __forceinline__ float f(unsigned t) {
         const float c = 0.003921568859368563f;  // rn32(1/255)
-        return __fmaf_rn(__uint_as_float(0x4B000000u | (unsigned)v), c, -8388608.0f * c);
+        const unsigned bits = (t >> 2) + 0x4B000000u;  // LEA.HI
+        return __fmaf_rn(__uint_as_float(bits), c, -8388608.0f * c);
     }
-    static __device__ __forceinline__ void store2(__half *p, long long xs, int a, int b, bool vec) {
+    static __device__ __forceinline__ void store2(__half *p, long long xs, unsigned a, unsigned b, bool vec) {
         if (vec) {
             *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(f(a), f(b));
         } else {
@@ -151,11 +156,11 @@ template <> struct Out<__half> {
             p[xs] = __float2half_rn(f(b));
         }
     }
-    static __device__ __forceinline__ void store1(__half *p, int a) { p[0] = __float2half_rn(f(a)); }
+    static __device__ __forceinline__ void store1(__half *p, unsigned a) { p[0] = __float2half_rn(f(a)); }
 };
 template <> struct Out<float> {
-    static __device__ __forceinline__ float f(int v) { return __fdiv_rn((float)v, 255.0f); }  // true division
-    static __device__ __forceinline__ void store2(float *p, long long xs, int a, int b, bool vec) {
+    static __device__ __forceinline__ float f(unsigned t) { return __fdiv_rn((float)(t >> 2), 255.0f); }  // true division
+    static __device__ __forceinline__ void store2(float *p, long long xs, unsigned a, unsigned b, bool vec) {
         if (vec) {
             *reinterpret_cast<float2 *>(p) = make_float2(f(a), f(b));
         } else {
@@ -163,61 +168,62 @@ template <> struct Out<float> {
             p[xs] = f(b);
         }
     }
-    static __device__ __forceinline__ void store1(float *p, int a) { p[0] = f(a); }
+    static __device__ __forceinline__ void store1(float *p, unsigned a) { p[0] = f(a); }
 };
 template <> struct Out<uint8_t> {
-    static __device__ __forceinline__ void store2(uint8_t *p, long long xs, int a, int b, bool) {
-        p[0] = (uint8_t)a;
-        p[xs] = (uint8_t)b;
+    static __device__ __forceinline__ void store2(uint8_t *p, long long xs, unsigned a, unsigned b, bool) {
+        p[0] = (uint8_t)(a >> 2);
+        p[xs] = (uint8_t)(b >> 2);
     }
-    static __device__ __forceinline__ void store1(uint8_t *p, int a) { p[0] = (uint8_t)a; }
+    static __device__ __forceinline__ void store1(uint8_t *p, unsigned a) { p[0] = (uint8_t)(a >> 2); }
 };
 
 struct TileShared {
-    unsigned meta[PYR_MAX_TH];  // b0 | b1 << 12 | same-slot << 24
-    int trig[PYR_MAX_TH];       // slot after which the row is emitted; -1: border row
+    unsigned b01[PYR_MAX_TH];  // b0 | b1 << 16
+    int trig[PYR_MAX_TH];      // 2 * (slot after which the row is emitted) + same-slot flag; -2: border row
     int slot_row[PYR_MAX_SLOTS];
     int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
     alignas(8) unsigned long long bar;
 };
 
 // One emitted output row for this thread's two pixels.  R0/R1: horizontal results of the upper /
-// lower source row, [0..2] pixel A, [3..5] pixel B.
+// lower source row, [0..2] pixel A, [3..5] pixel B.  pc[c] + off addresses channel c of pixel A.
 template <typename T, bool EDGE>
-__device__ __forceinline__ void emit_row(T *row_ptr, long long cs, long long xs, unsigned meta, const int *R0,
-                                         const int *R1, int flip, int border, bool inA, bool inB, bool two, bool vec) {
-    const int b0 = (int)(meta & 0xfffu), b1 = (int)((meta >> 12) & 0xfffu);
-    int vA[3], vB[3];
+__device__ __forceinline__ void emit_row(T *const *pc, unsigned off, long long xs, unsigned b0s, unsigned b1s,  // plain weights
+                                         const int *R0, const int *R1, int flip, unsigned tborder, bool inA, bool inB,
+                                         bool two, bool vec) {
+    unsigned tA[3], tB[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        vA[c] = vpass(R0[c], R1[c], b0, b1);
-        vB[c] = vpass(R0[3 + c], R1[3 + c], b0, b1);
+        tA[c] = vsum((unsigned)R0[c], (unsigned)R1[c], b0s, b1s);
+        tB[c] = vsum((unsigned)R0[3 + c], (unsigned)R1[3 + c], b0s, b1s);
         if (EDGE) {
-            if (!inA) vA[c] = border;
-            if (!inB) vB[c] = border;
+            if (!inA) tA[c] = tborder;
+            if (!inB) tB[c] = tborder;
         }
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const int a = flip ? vA[2 - c] : vA[c], b = flip ? vB[2 - c] : vB[c];
-        T *p = row_ptr + c * cs;
+        const unsigned a = flip ? tA[2 - c] : tA[c], b = flip ? tB[2 - c] : tB[c];
+        T *p = pc[c] + off;
         if (!EDGE || two) Out<T>::store2(p, xs, a, b, vec);
         else Out<T>::store1(p, a);
     }
 }
 
 template <typename T>
-__device__ __forceinline__ void border_row(T *row_ptr, long long cs, long long xs, int border, bool two, bool vec) {
+__device__ __forceinline__ void border_row(T *const *pc, unsigned off, long long xs, unsigned tborder, bool two,
+                                           bool vec) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        T *p = row_ptr + c * cs;
-        if (two) Out<T>::store2(p, xs, border, border, vec);
-        else Out<T>::store1(p, border);
+        T *p = pc[c] + off;
+        if (two) Out<T>::store2(p, xs, tborder, tborder, vec);
+        else Out<T>::store1(p, tborder);
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_constant__ PyrParams P) {
+__global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_constant__ PyrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ TileShared sh;
 
@@ -242,6 +248,18 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_co
     const bool has_cols = dxa < dxb;
     const int slot_bytes = S.slot_bytes;
     const uint8_t *src = P.src + (long long)img * P.img_stride;
+
+    // ---- per-thread columns: horizontal taps (independent of warp 0's work below) -------------------
+    const int x = ox0 + 2 * tid;
+    const bool active = x < x_end && tid * 2 < tw;
+    const bool two = x + 1 < x_end;
+    const int dxA = x - left, dxB = x + 1 - left;
+    const bool inA = active && dxA >= 0 && dxA < unpad_w;
+    const bool inB = active && two && dxB >= 0 && dxB < unpad_w;
+    int sxA = 0, sxB = 0;
+    unsigned aA = 0, aB = 0;
+    if (inA) coeff_x(dxA, S.scale_x, P.virt_w, sxA, aA);
+    if (inB) coeff_x(dxB, S.scale_x, P.virt_w, sxB, aB);
 
     // ---- warp 0: vertical taps, slot assignment, bulk copies ------------------------------------
     if (tid < 32) {
@@ -328,40 +346,25 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_co
             sh.n_rows = n_rows;
         }
         if (lane < n_rows) {
-            sh.trig[lane] = valid ? slot1 : -1;
-            sh.meta[lane] = (b01 & 0xfffu) | ((b01 >> 16) << 12) | ((slot0 == slot1) ? (1u << 24) : 0u);
+            sh.trig[lane] = valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2;
+            sh.b01[lane] = b01;
         }
     }
     __syncthreads();
     const int n_used = sh.n_used, g0 = sh.g0;
 
-    // ---- per-thread columns (overlaps the bulk copies) ---------------------------------------------
-    const int x = ox0 + 2 * tid;
-    const bool active = x < x_end && tid * 2 < tw;
-    const bool two = x + 1 < x_end;
-    const int dxA = x - left, dxB = x + 1 - left;
-    const bool inA = active && dxA >= 0 && dxA < unpad_w;
-    const bool inB = active && two && dxB >= 0 && dxB < unpad_w;
-    uint32_t wA = 0, wB = 0;
-    unsigned shA = 0, shB = 0, aA = 0, aB = 0;
-    const uint32_t smem_base = smem_u32(smem);
+    // ---- per-thread byte offsets inside a slot --------------------------------------------------------
+    uint32_t wA = smem_u32(smem), wB = wA;  // out-of-image pixels read in bounds; their value is replaced
+    unsigned shA = 0, shB = 0;
     if (inA) {
-        int sx;
-        coeff_x(dxA, S.scale_x, P.virt_w, sx, aA);
-        const int o = 3 * sx - g0;
-        wA = smem_base + (uint32_t)(o & ~3);
+        const int o = 3 * sxA - g0;
+        wA += (uint32_t)(o & ~3);
         shA = (unsigned)(o & 3) * 8u;
-    } else {
-        wA = smem_base;  // reads stay in bounds; the value is replaced by the border
     }
     if (inB) {
-        int sx;
-        coeff_x(dxB, S.scale_x, P.virt_w, sx, aB);
-        const int o = 3 * sx - g0;
-        wB = smem_base + (uint32_t)(o & ~3);
+        const int o = 3 * sxB - g0;
+        wB += (uint32_t)(o & ~3);
         shB = (unsigned)(o & 3) * 8u;
-    } else {
-        wB = smem_base;
     }
 
     // ---- scalar staging: whatever the bulk copies do not cover ---------------------------------------
@@ -389,29 +392,39 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_co
 
     // ---- stream over the slots ------------------------------------------------------------------------
     const bool vec = S.vec != 0;
-    const long long cs = S.cs, xs = S.xs, ys = S.ys;
-    T *out_row = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * ys + (long long)x * xs;
-    const bool edge = !(inA && inB);  // uniform per thread; interior tiles have no edge threads
-    const int flip = P.flip, border = P.border;
+    const long long xs = S.xs;
+    const unsigned ys = (unsigned)S.ys;
+    T *pc[3];
+    {
+        T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys + (long long)x * xs;
+        pc[0] = p0;
+        pc[1] = p0 + S.cs;
+        pc[2] = p0 + 2 * S.cs;
+    }
+    unsigned off = 0;
+    const bool edge = !(inA && inB);  // interior tiles have no edge threads
+    const int flip = P.flip;
+    const unsigned tborder = (unsigned)P.border * 4u;
     int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
     int j = 0;
     int trig = (j < n_rows) ? sh.trig[0] : 0x7fffffff;
 
-    auto flush = [&](int k, const int *cur, const int *other) {
-        while (trig <= k) {
+    // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
+    auto flush = [&](int k, int *cur, int *other) {
+        while ((trig >> 1) <= k) {
             if (trig < 0) {
-                border_row<T>(out_row, cs, xs, border, two, vec);
+                border_row<T>(pc, off, xs, tborder, two, vec);
             } else {
-                const unsigned meta = sh.meta[j];
-                if (meta >> 24) {  // both taps in the same slot (clamped row or zero lower weight)
-                    if (edge) emit_row<T, true>(out_row, cs, xs, meta, cur, cur, flip, border, inA, inB, two, vec);
-                    else emit_row<T, false>(out_row, cs, xs, meta, cur, cur, flip, border, true, true, true, vec);
-                } else {
-                    if (edge) emit_row<T, true>(out_row, cs, xs, meta, other, cur, flip, border, inA, inB, two, vec);
-                    else emit_row<T, false>(out_row, cs, xs, meta, other, cur, flip, border, true, true, true, vec);
+                const unsigned b01 = sh.b01[j];
+                const unsigned b0s = b01 & 0xffffu, b1s = b01 >> 16;
+                if (trig & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
+#pragma unroll               // visited in source order, so slot k-1 is dead from here on
+                    for (int c = 0; c < 6; c++) other[c] = cur[c];
                 }
+                if (edge) emit_row<T, true>(pc, off, xs, b0s, b1s, other, cur, flip, tborder, inA, inB, two, vec);
+                else emit_row<T, false>(pc, off, xs, b0s, b1s, other, cur, flip, tborder, true, true, true, vec);
             }
-            out_row += ys;
+            off += ys;
             j++;
             trig = (j < n_rows) ? sh.trig[j] : 0x7fffffff;
         }
@@ -430,10 +443,10 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) pyramid_kernel(const __grid_co
         }
         slot_off += slot_bytes;
     }
-    // rows not tied to any slot (border rows at the end, or a tile without interior)
+    // rows not tied to any slot (a tile without interior)
     while (j < n_rows) {
-        border_row<T>(out_row, cs, xs, border, two, vec);
-        out_row += ys;
+        border_row<T>(pc, off, xs, tborder, two, vec);
+        off += ys;
         j++;
     }
 }
@@ -517,12 +530,14 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             S.scale_y = 1.0 / ((double)g.unpad_h / virt_h);
             S.dense_rows = S.scale_y <= 2.0;
             // tile: 320 columns (fewer when the staged rows would not fit), as many rows as the slots allow
-            int tw = 2 * PYR_THREADS, th = 16;
+            // odd integer scale: every vertical tap has weight 0 on the lower row -> one slot per output row
+            const bool y_point = S.scale_y == (double)(long long)S.scale_y && (((long long)S.scale_y) & 1);
+            int tw = 2 * PYR_THREADS, th = ctx->pyr_th;
             for (;;) {
-                int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : 2 * th;
+                int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : (y_point ? th : 2 * th);
                 int span_px = (int)(tw * S.scale_x) + 4;
                 S.slot_bytes = ((span_px * 3 + 15) & ~15) + 48;
-                if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= PYR_SMEM_BUDGET) {
+                if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= ctx->pyr_smem_budget) {
                     if (n_slots * S.slot_bytes > smem_max) smem_max = n_slots * S.slot_bytes;
                     break;
                 }

@@ -139,7 +139,7 @@ class MultiScaleFaceDetector:
                self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode)
         plan = self._plans.get(key)
         if plan is None:
-            out_cap = self.out_cap or min(self.cap * len(scales_levels), 4 * self.cap)
+            out_cap = self.out_cap or self.cap
             plan = ops.PostPlan(scales_levels, self.strides, self.anchors_px, in_h, orig_hw, self.conf_thres,
                                 self.iou_thres, self.cap, out_cap, iou_mode=self.iou_mode,
                                 with_kpts=self.with_landmarks)
@@ -163,7 +163,7 @@ class MultiScaleFaceDetector:
     def _collect(self, plan):
         """One device->host read of the results of `plan`; raises if a capacity was exceeded."""
         o, c = plan.out, plan.cands
-        both = torch.cat((o.n_out, torch.stack((c.count.max(), c.n_keep.min(), o.n_out.max())))).cpu().numpy()
+        both = torch.cat((o.n_out, torch.stack((c.count.max(), c.n_keep.min(), o.merged_in.max())))).cpu().numpy()
         n_out, head = both[:-3], both[-3:]  # one read, synchronises
         if head[0] > c.cap or head[2] > o.out_cap:
             return None, head
@@ -191,9 +191,10 @@ class MultiScaleFaceDetector:
             if res is not None:
                 break
             # capacity exceeded: grow to what this batch needs and redo (counts are exact even on overflow)
-            self.cap = max(self.cap * 2, int(head[0]))
-            if self.out_cap:
-                self.out_cap = max(self.out_cap * 2, int(head[2]))
+            if head[0] > self.cap:
+                self.cap = max(self.cap * 2, int(head[0]))
+            if head[2] > (self.out_cap or self.cap):
+                self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
             self._plans.clear()
         dets, n_out, kpts = res
         self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(plan.cands.count.sum()),

@@ -313,5 +313,5 @@ class PostPlan:
         self.ctx.check(rc, "fdms_postprocess")
         return self.out
 
-    # number of kernel launches of one run(): memset excluded; decode 1 + NMS 3 + prepare 1 + NMS 3 + emit 1
-    LAUNCHES = 9
+    # kernel launches of one run() for segments <= 4096 boxes: decode 2 + NMS 1 + prepare 1 + NMS 1 + emit 1 (memset excluded)
+    LAUNCHES = 6

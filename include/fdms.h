@@ -177,7 +177,8 @@ FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64
  * scale s; every image has original size (orig_h, orig_w).  The rescale is ALWAYS the api
  * transform, as in the reference (:144).
  * Output: dets (n_img, out_cap, 7) f32 [x1,y1,x2,y2,conf,cls,scale_idx] in weighted-score
- * order and n_out[img]; merged_in (n_img) optionally receives sum_s n_keep (may be NULL).
+ * order and n_out[img]; merged_in (n_img) optionally receives sum_s n_keep (may be NULL).  At most out_cap
+ * per-scale survivors of an image enter the merge: callers treat merged_in > out_cap as overflow.
  * If kpts_out != NULL it receives (n_img, out_cap, 15) landmarks of the kept detections
  * rescaled with the same transform (extension: the reference drops them, :151-153). */
 FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,

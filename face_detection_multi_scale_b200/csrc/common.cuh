@@ -24,7 +24,7 @@ struct fdms_ctx {
     int smem_optin = 0;
     char err[512] = {0};
     int pyr_attr = 0;
-    int pyr_smem_budget = 56 * 1024, pyr_th = 16;  // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
+    int pyr_smem_budget = 40 * 1024, pyr_th = 8;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 4096;  // FDMS_NMS_SMALL_LIMIT overrides (0 forces the generic sort/mask/sweep path)
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
@@ -38,6 +38,8 @@ struct fdms_ctx {
     fdms_buf merge_cnt;        // merge: counts
     fdms_buf merge_keep;       // merge: keep + n_keep
     fdms_buf flags;            // misc device flags
+    fdms_buf pyr_tab;          // pyramid tap tables of the last geometry
+    unsigned long long pyr_tab_key = 0;
 };
 
 static inline int fdms_fail(fdms_ctx *ctx, int code, const char *fmt, ...) {

@@ -36,12 +36,16 @@ struct DecLevel {
 struct DecParams {
     DecLevel lv[FDMS_MAX_LEVELS];
     int n_levels, n_scales, bs, cap;
+    int scale_first[FDMS_MAX_SCALES + 1];  // levels of scale s are lv[scale_first[s] .. scale_first[s+1])
     float conf_thres;
+    float thr_lo, thr_hi;  // band around conf_thres inside which the fast sigmoid is not trusted
     float logit_lo;  // conservative lower bound on logit(conf_thres): x < logit_lo => sigmoid(x) <= thres
     float *cand;
     int32_t *cand_row;
     int32_t *count;
 };
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return f_div(1.0f, f_add(1.0f, expf(-x))); }
 
 __device__ __forceinline__ float sigmoid_exact(float x) {
     float e = (float)exp(-(double)x);  // fp64 exp rounded once == correctly rounded expf
@@ -127,24 +131,21 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     const bool aligned = (cells % DEC_VEC == 0) && ((uintptr_t)L.data % 16 == 0);
 
     unsigned pass = 0;
-    float conf[DEC_VEC];
     if (n_valid > 0) {
         float xo[DEC_VEC], xc[DEC_VEC];
         load_vec8<T>(base + 4 * cells, cell0, n_valid, aligned, xo);
         load_vec8<T>(base + 5 * cells, cell0, n_valid, aligned, xc);
 #pragma unroll
         for (int k = 0; k < DEC_VEC; k++) {
-            conf[k] = 0.f;
             // cheap necessary condition: sigmoid(obj) > thres and sigmoid(cls) > thres
             if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) {
-                float so = sigmoid_exact(xo[k]);
-                if (so > P.conf_thres) {                    // general.py:515
-                    float c = f_mul(sigmoid_exact(xc[k]), so);  // :547
-                    if (c > P.conf_thres) {                 // :563
-                        pass |= 1u << k;
-                        conf[k] = c;
-                    }
-                }
+                // decision with the fast fp32 sigmoid (<= 2 ulp expf); only a +-4e-6 relative band around the
+                // threshold needs the exact arithmetic.  The exact confidence itself is recomputed by
+                // decode_candidates_kernel.  obj > thres (general.py:515) is implied by cls*obj > thres (:563).
+                const float cf = f_mul(sigmoid_fast(xc[k]), sigmoid_fast(xo[k]));
+                bool ok = cf > P.thr_hi;
+                if (!ok && cf >= P.thr_lo) ok = f_mul(sigmoid_exact(xc[k]), sigmoid_exact(xo[k])) > P.conf_thres;  // :547,563
+                if (ok) pass |= 1u << k;
             }
         }
     }
@@ -165,15 +166,14 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     if (lane == 31) basepos = atomicAdd(P.count + seg, total);
     basepos = __shfl_sync(0xffffffffu, basepos, 31);
     int pos = basepos + incl - n;
-    // Survivors are only RECORDED here (row index + confidence); decode_candidates_kernel decodes them with
-    // one lane per channel.  Decoding in place would run the long exact path at 1/32 lane efficiency.
+    // Survivors are only RECORDED here (row index); decode_candidates_kernel decodes them one per thread on
+    // dense warps.  Decoding in place would run the long exact path at ~1/32 lane efficiency.
 #pragma unroll
     for (int k = 0; k < DEC_VEC; k++) {
         if ((pass >> k) & 1u) {
             if (pos < P.cap) {
                 const long long slot = (long long)seg * P.cap + pos;
                 P.cand_row[slot] = L.row_offset + a * (int)cells + (int)(cell0 + k);
-                P.cand[slot * NO + 4] = conf[k];
             }
             pos++;
         }
@@ -190,61 +190,37 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid
     else decode_filter_body<float>(P, L, blockIdx.x - L.block_begin);
 }
 
-// Second half of the fused decode: one warp per recorded candidate, lane c < 21 owns channel c of the row
-// (one strided load, at most one exact sigmoid, one coalesced 84-byte store).  models/yolo.py:290-295 and
-// utils/general.py:299-306,547-563.
-constexpr int CAND_THREADS = 256;
-
-template <typename T>
-__device__ __forceinline__ float load_ch(const void *data, long long i) {
-    return (float)__ldg(reinterpret_cast<const T *>(data) + i);
-}
+// Second half of the fused decode: one thread per recorded candidate (dense warps after the compaction):
+// 21 strided loads, exact sigmoids, models/yolo.py:290-295, then utils/general.py:547 (conf = cls*obj) and
+// :299-306 (xywh2xyxy), one 84-byte row per thread.
+constexpr int CAND_THREADS = 128;
 
 __global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const __grid_constant__ DecParams P) {
     const int seg = blockIdx.y;
     const int n = min(P.count[seg], P.cap);
-    const int warp = threadIdx.x >> 5, c = threadIdx.x & 31;
     const int b = seg / P.n_scales, scale = seg - b * P.n_scales;
-    const bool sig = c < 4 || (c >= 8 && c < NO && (c - 8) % 3 == 0);  // obj/cls are already folded into conf
-    for (int i = blockIdx.x * (CAND_THREADS / 32) + warp; i < n; i += gridDim.x * (CAND_THREADS / 32)) {
+    for (int i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
         const long long slot = (long long)seg * P.cap + i;
         const int row = P.cand_row[slot];
-        // level of this row inside its scale (rows are level-major)
-        int li = -1;
+        int li = -1;  // level of this row inside its scale (rows are level-major)
 #pragma unroll 1
-        for (int l = 0; l < P.n_levels; l++) {
-            const DecLevel &Lc = P.lv[l];
-            if (Lc.scale == scale && row >= Lc.row_offset && row < Lc.row_offset + NA * Lc.ny * Lc.nx) li = l;
-        }
+        for (int l = P.scale_first[scale]; l < P.scale_first[scale + 1]; l++)
+            if (row >= P.lv[l].row_offset) li = l;
         if (li < 0) continue;
         const DecLevel &L = P.lv[li];
         const int cells = L.ny * L.nx;
         const int r = row - L.row_offset;
         const int a = r / cells, cell = r - a * cells;
         const int gy = cell / L.nx, gx = cell - gy * L.nx;
-        float val = 0.f;
-        if (c < NO) {
-            const long long idx = ((long long)b * NA * NO + (long long)a * NO + c) * cells + cell;
-            const float v = L.dtype == FDMS_F16 ? load_ch<__half>(L.data, idx) : load_ch<float>(L.data, idx);
-            const float s = sig ? sigmoid_exact(v) : 0.f;
-            const float g = (c == 0 || (c >= 6 && (c - 6) % 3 == 0)) ? (float)gx : (float)gy;
-            if (c < 2) val = f_mul(f_add(f_sub(f_mul(s, 2.f), 0.5f), g), L.stride);  // yolo.py:290
-            else if (c < 4) {
-                const float t2 = f_mul(s, 2.f);
-                val = f_mul(f_mul(t2, t2), L.anchors[2 * a + (c - 2)]);  // :291
-            } else if (c == 4) val = P.cand[slot * NO + 4];  // conf recorded by the filter (general.py:547)
-            else if (c == 5) val = 0.f;                     // class index
-            else if ((c - 6) % 3 == 2) val = s;             // yolo.py:295
-            else val = f_mul(f_add(f_sub(f_mul(v, 2.f), 0.5f), g), L.stride);  // :293-294 (raw logits)
-        }
-        // xywh2xyxy (general.py:299-306) on lanes 0..3
-        const float cx = __shfl_sync(0xffffffffu, val, 0), cy = __shfl_sync(0xffffffffu, val, 1);
-        const float bw = __shfl_sync(0xffffffffu, val, 2), bh = __shfl_sync(0xffffffffu, val, 3);
-        if (c == 0) val = f_sub(cx, f_div(bw, 2.f));
-        else if (c == 1) val = f_sub(cy, f_div(bh, 2.f));
-        else if (c == 2) val = f_add(cx, f_div(bw, 2.f));
-        else if (c == 3) val = f_add(cy, f_div(bh, 2.f));
-        if (c < NO) P.cand[slot * NO + c] = val;
+        const long long base = ((long long)b * NA * NO + (long long)a * NO) * cells + cell;
+        float v[NO], o[NO];
+#pragma unroll
+        for (int c = 0; c < NO; c++) v[c] = ld_f(L.data, L.dtype, base + (long long)c * cells);
+        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+        row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
+        float *dst = P.cand + slot * NO;
+#pragma unroll
+        for (int c = 0; c < NO; c++) dst[c] = o[c];
     }
 }
 
@@ -387,7 +363,18 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
     P.bs = bs;
     P.cap = cap;
     P.conf_thres = conf_thres;
+    // levels must be grouped by scale, ascending row_offset inside a scale (how every caller builds them)
+    for (int sidx = 0, l = 0; sidx <= n_scales; sidx++) {
+        while (l < n_levels && levels[l].scale < sidx) l++;
+        P.scale_first[sidx] = l;
+    }
+    for (int l = 1; l < n_levels; l++)
+        if (levels[l].scale < levels[l - 1].scale ||
+            (levels[l].scale == levels[l - 1].scale && levels[l].row_offset <= levels[l - 1].row_offset))
+            return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: levels must be sorted by (scale, row_offset)");
     P.logit_lo = logit_lower_bound(conf_thres);
+    P.thr_lo = conf_thres - 4e-6f * fabsf(conf_thres) - 1e-37f;
+    P.thr_hi = conf_thres + 4e-6f * fabsf(conf_thres) + 1e-37f;
     P.cand = cand;
     P.cand_row = cand_row;
     P.count = count;
@@ -397,8 +384,8 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
     FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
     const int n_seg = bs * n_scales;
     if (n_seg > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_filter: more than 65535 segments");
-    int gx = ceil_div(cap, CAND_THREADS / 32);
-    if (gx > 16) gx = 16;
+    int gx = ceil_div(cap, CAND_THREADS);
+    if (gx > 8) gx = 8;
     decode_candidates_kernel<<<dim3(gx, n_seg), CAND_THREADS, 0, st>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "decode_candidates_kernel");
     return FDMS_OK;

@@ -38,6 +38,8 @@ struct PyrScale {
     int vec;           // paired stores allowed
     int pad_;
     double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
+    const int2 *xtab;         // per output column: {source column sx, a0 | a1 << 16}; sx = -1 on the border
+    const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, 0}; r0 = -1 on the border
 };
 
 struct PyrParams {
@@ -179,8 +181,9 @@ template <> struct Out<uint8_t> {
 };
 
 struct TileShared {
-    unsigned b01[PYR_MAX_TH];  // b0 | b1 << 16
-    int trig[PYR_MAX_TH];      // 2 * (slot after which the row is emitted) + same-slot flag; -2: border row
+    // per row: x = 2 * (slot after which the row is emitted) + same-slot flag (-2: border row), y = b0 | b1 << 16;
+    // one sentinel entry past the last row
+    int2 rowmeta[PYR_MAX_TH + 1];
     int slot_row[PYR_MAX_SLOTS];
     int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
     alignas(8) unsigned long long bar;
@@ -222,6 +225,28 @@ __device__ __forceinline__ void border_row(T *const *pc, unsigned off, long long
     }
 }
 
+// Tap tables of a pyramid geometry (OpenCV's coefficient set-up).  Runs once per geometry:
+// the tables are cached in the ctx, so the main kernel carries no fp64 and no conversions.
+__global__ void pyramid_tables_kernel(const __grid_constant__ PyrParams P) {
+    const PyrScale &S = P.sc[blockIdx.x];
+    int2 *xt = const_cast<int2 *>(S.xtab);
+    int4 *yt = const_cast<int4 *>(S.ytab);
+    for (int x = threadIdx.x; x < S.dst_w; x += blockDim.x) {
+        const int dx = x - S.left;
+        int sx = -1;
+        unsigned a01 = 0;
+        if (dx >= 0 && dx < S.unpad_w) coeff_x(dx, S.scale_x, P.virt_w, sx, a01);
+        xt[x] = make_int2(sx, (int)a01);
+    }
+    for (int y = threadIdx.x; y < S.dst_h; y += blockDim.x) {
+        const int dy = y - S.top;
+        int r0 = -1, r1 = -1;
+        unsigned b01 = 0;
+        if (dy >= 0 && dy < S.unpad_h) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01);
+        yt[y] = make_int4(r0, r1, (int)b01, 0);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_constant__ PyrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -253,13 +278,18 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
     const int x = ox0 + 2 * tid;
     const bool active = x < x_end && tid * 2 < tw;
     const bool two = x + 1 < x_end;
-    const int dxA = x - left, dxB = x + 1 - left;
-    const bool inA = active && dxA >= 0 && dxA < unpad_w;
-    const bool inB = active && two && dxB >= 0 && dxB < unpad_w;
-    int sxA = 0, sxB = 0;
+    int sxA = -1, sxB = -1;
     unsigned aA = 0, aB = 0;
-    if (inA) coeff_x(dxA, S.scale_x, P.virt_w, sxA, aA);
-    if (inB) coeff_x(dxB, S.scale_x, P.virt_w, sxB, aB);
+    if (active) {
+        if (two) {  // x is even and the table is 16-byte aligned: both entries in one load
+            const int4 e = __ldg(reinterpret_cast<const int4 *>(S.xtab + x));
+            sxA = e.x; aA = (unsigned)e.y; sxB = e.z; aB = (unsigned)e.w;
+        } else {
+            const int2 e = __ldg(S.xtab + x);
+            sxA = e.x; aA = (unsigned)e.y;
+        }
+    }
+    const bool inA = sxA >= 0, inB = sxB >= 0;
 
     // ---- warp 0: vertical taps, slot assignment, bulk copies ------------------------------------
     if (tid < 32) {
@@ -268,11 +298,13 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             mbar_init(reinterpret_cast<uint64_t *>(&sh.bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        const int oy = oy0 + lane, dy = oy - top;
-        const bool valid = has_cols && lane < n_rows && dy >= 0 && dy < unpad_h;
-        int r0 = 0, r1 = 0;
+        int r0 = -1, r1 = 0;
         unsigned b01 = 0;
-        if (valid) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01);
+        if (has_cols && lane < n_rows) {
+            const int4 e = __ldg(S.ytab + oy0 + lane);
+            r0 = e.x; r1 = e.y; b01 = (unsigned)e.z;
+        }
+        const bool valid = r0 >= 0;
         const int b1 = (int)(b01 >> 16);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         int slot0 = 0, slot1 = 0, n_used = 0, rmin = 0;
@@ -298,8 +330,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
         }
         // source byte range of the tile's columns
         int sx = 0;
-        unsigned dummy;
-        if (has_cols && lane < 2) coeff_x(lane == 0 ? dxa : dxb - 1, S.scale_x, P.virt_w, sx, dummy);
+        if (has_cols && lane < 2) sx = __ldg(S.xtab + left + (lane == 0 ? dxa : dxb - 1)).x;
         const int sxa = __shfl_sync(0xffffffffu, sx, 0);
         const int sxb = min(__shfl_sync(0xffffffffu, sx, 1) + 1, P.virt_w - 1);
         const int g0 = (3 * sxa) & ~15;
@@ -345,10 +376,9 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             sh.need_scalar = (bulk_bytes < row_bytes) || any_virt;
             sh.n_rows = n_rows;
         }
-        if (lane < n_rows) {
-            sh.trig[lane] = valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2;
-            sh.b01[lane] = b01;
-        }
+        if (lane <= n_rows)
+            sh.rowmeta[lane] = lane == n_rows ? make_int2(0x7ffffffe, 0)
+                                              : make_int2(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2, (int)b01);
     }
     __syncthreads();
     const int n_used = sh.n_used, g0 = sh.g0;
@@ -397,27 +427,27 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
     T *pc[3];
     {
         T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys + (long long)x * xs;
-        pc[0] = p0;
+        // channel flip (img[:, :, ::-1]) = source channel c goes to output plane 2 - c: swap the plane pointers
+        pc[0] = P.flip ? p0 + 2 * S.cs : p0;
         pc[1] = p0 + S.cs;
-        pc[2] = p0 + 2 * S.cs;
+        pc[2] = P.flip ? p0 : p0 + 2 * S.cs;
     }
     unsigned off = 0;
     const bool edge = !(inA && inB);  // interior tiles have no edge threads
-    const int flip = P.flip;
+    const int flip = 0;  // folded into pc[]
     const unsigned tborder = (unsigned)P.border * 4u;
     int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
     int j = 0;
-    int trig = (j < n_rows) ? sh.trig[0] : 0x7fffffff;
+    int2 rm = sh.rowmeta[0];
 
     // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
     auto flush = [&](int k, int *cur, int *other) {
-        while ((trig >> 1) <= k) {
-            if (trig < 0) {
+        while ((rm.x >> 1) <= k) {
+            if (rm.x < 0) {
                 border_row<T>(pc, off, xs, tborder, two, vec);
             } else {
-                const unsigned b01 = sh.b01[j];
-                const unsigned b0s = b01 & 0xffffu, b1s = b01 >> 16;
-                if (trig & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
+                const unsigned b0s = (unsigned)rm.y & 0xffffu, b1s = (unsigned)rm.y >> 16;
+                if (rm.x & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
 #pragma unroll               // visited in source order, so slot k-1 is dead from here on
                     for (int c = 0; c < 6; c++) other[c] = cur[c];
                 }
@@ -426,7 +456,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             }
             off += ys;
             j++;
-            trig = (j < n_rows) ? sh.trig[j] : 0x7fffffff;
+            rm = sh.rowmeta[j];
         }
     };
 
@@ -553,6 +583,35 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
         }
         if (n == 0) continue;
         P.n_scales = n;
+        // tap tables: cached per geometry (FNV-1a over everything they depend on)
+        {
+            size_t bytes = 0;
+            unsigned long long key = 1469598103934665603ull;
+            auto mix = [&](long long v) {
+                for (int q = 0; q < 8; q++) { key ^= (unsigned long long)(v >> (8 * q)) & 0xff; key *= 1099511628211ull; }
+            };
+            mix(dt); mix(src_h); mix(src_w); mix(virt_h); mix(virt_w); mix(n);
+            for (int q = 0; q < n; q++) {
+                const PyrScale &S = P.sc[q];
+                mix(S.dst_h); mix(S.dst_w); mix(S.unpad_h); mix(S.unpad_w); mix(S.top); mix(S.left);
+                bytes += (((size_t)S.dst_w * 8 + 15) & ~(size_t)15) + (size_t)S.dst_h * 16;
+            }
+            if (int rc = fdms_reserve(ctx, ctx->pyr_tab, bytes)) return rc;
+            uint8_t *base = reinterpret_cast<uint8_t *>(ctx->pyr_tab.p);
+            for (int q = 0; q < n; q++) {
+                PyrScale &S = P.sc[q];
+                S.xtab = reinterpret_cast<const int2 *>(base);
+                base += ((size_t)S.dst_w * 8 + 15) & ~(size_t)15;
+                S.ytab = reinterpret_cast<const int4 *>(base);
+                base += (size_t)S.dst_h * 16;
+            }
+            mix((long long)(uintptr_t)ctx->pyr_tab.p);
+            if (key != ctx->pyr_tab_key) {
+                pyramid_tables_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(P);
+                FDMS_LAUNCH_CHECK(ctx, "pyramid_tables_kernel");
+                ctx->pyr_tab_key = key;
+            }
+        }
         int rc;
         if (dt == FDMS_F16) rc = launch_group<__half>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
         else if (dt == FDMS_F32) rc = launch_group<float>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);

@@ -29,7 +29,8 @@ def _ptr(t):
 
 
 # ---------------------------------------------------------------------------------------------- pyramid
-def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, border=114, virt_hw=None, outs=None):
+def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, border=114, virt_hw=None, outs=None,
+            ctx=None):
     """Fused letterbox pyramid.  src: (B, H, W, 3) uint8 CUDA (any row pitch: stride(1) bytes).
     geoms: list of _lib.Geom (one per scale, from letterbox_geometry on the virtual size).
     Returns one tensor per scale: (B, 3, h, w) for layout 'chw' or (B, h, w, 3) for 'hwc'."""
@@ -57,7 +58,7 @@ def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, bor
         arr[s].out_img_stride = 3 * g.dst_h * g.dst_w
         arr[s].out_dtype = _DT[out_dtype]
         arr[s].out_layout = FDMS_CHW if layout == "chw" else FDMS_HWC
-    c = _lib.ctx(dev)
+    c = ctx if ctx is not None else _lib.ctx(dev)
     rc = _lib.lib().fdms_pyramid(c.handle, _ptr(src), B, src.stride(0) if B > 1 else H * src.stride(1), src.stride(1),
                                  H, W, vh, vw, arr, n, int(bool(flip_rb)), int(border), _stream(dev))
     c.check(rc, "fdms_pyramid")

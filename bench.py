@@ -32,7 +32,7 @@ WORKLOADS = {
                  h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=60, conf=0.5, iou=0.5, radius=1, cap=4096),
     # configs[2]: dense crowd, ~20k pre-NMS candidates per image
     "cfg3": dict(desc="cfg3: dense-crowd stress, ~20k pre-NMS candidates/image, 3-scale pyramid, batch 32 1920x1080",
-                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=420, conf=0.5, iou=0.5, radius=2, cap=16384),
+                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=1300, conf=0.5, iou=0.5, radius=1, cap=16384),
     # configs[4]: single-scale high throughput (per-GPU shard of the batch-512 job)
     "cfg5": dict(desc="cfg5: lite-t head, single scale 640, batch 64/GPU synthetic 1920x1080 images",
                  h=1080, w=1920, sizes=[640], batch=64, faces=40, conf=0.5, iou=0.5, radius=1, cap=4096),

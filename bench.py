@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on
     "cfg2": dict(desc="cfg2: yolov7s-face head, 3-scale pyramid (640/960/1280), batch 32 synthetic 1920x1080 images",
-                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=60, conf=0.5, iou=0.5, radius=1, cap=4096),
+                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=60, conf=0.5, iou=0.5, radius=1, cap=1024),
     # configs[2]: dense crowd, ~20k pre-NMS candidates per image
     "cfg3": dict(desc="cfg3: dense-crowd stress, ~20k pre-NMS candidates/image, 3-scale pyramid, batch 32 1920x1080",
                  h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=1300, conf=0.5, iou=0.5, radius=1, cap=16384),

@@ -26,7 +26,8 @@ struct fdms_ctx {
     int pyr_attr = 0;
     int pyr_smem_budget = 40 * 1024, pyr_th = 8;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
     bool nms_attr = false, nms_small_attr = false;
-    int nms_small_limit = 4096;  // FDMS_NMS_SMALL_LIMIT overrides (0 forces the generic sort/mask/sweep path)
+    int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
+    int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
     fdms_buf sort_a, sort_b;   // NMS: 64-bit keys ping-pong

@@ -448,6 +448,129 @@ __global__ void __launch_bounds__(SMALL_THREADS)
     if (tid == 0) n_keep[g] = s_nkeep;
 }
 
+// Blocked greedy NMS for larger segments, one CTA per segment, after nms_sort_kernel.  Boxes arrive in score
+// order in global scratch; the boxes kept so far are compacted IN PLACE at the front of the same array (the
+// write position never passes the read position) and streamed through shared memory in tiles.  Per step 256
+// candidates are (1) tested against the kept list with early exit, (2) masked against each other (256 x 256
+// bits), (3) resolved by warp 0 with one step per KEPT box, (4) appended.  Work ~ K * n_kept / 2 pair tests
+// instead of K^2 / 2, and no K^2 bit-matrix.
+constexpr int GREEDY_THREADS = 1024;
+constexpr int GREEDY_BS = 256;
+constexpr int GREEDY_TILE = 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(GREEDY_THREADS)
+    nms_greedy_kernel(const SegInfo *__restrict__ seginfo, int cap_e, float4 *sorted_boxes,
+                      const uint32_t *__restrict__ sorted_idx, float thr, int inclusive, int32_t *__restrict__ keep,
+                      int32_t *__restrict__ n_keep, int cap, const int32_t *__restrict__ count, int skip_le) {
+    __shared__ float4 s_blk[GREEDY_BS];
+    __shared__ float4 s_tile[GREEDY_TILE];
+    __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
+    __shared__ unsigned long long s_sup[4], s_keptbits[4];
+    __shared__ int s_nkeep;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (max(0, min(count[g], cap)) <= skip_le) return;  // handled by nms_small_kernel
+    const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
+    const int K = seginfo[g].n;
+    float4 *boxes = sorted_boxes + (long long)g * cap_e;
+    const uint32_t *sidx = sorted_idx + (long long)g * cap_e;
+    int32_t *kout = keep + (long long)g * cap;
+    if (tid == 0) s_nkeep = 0;
+    __syncthreads();
+    const int i = tid & (GREEDY_BS - 1), grp = tid >> 8;  // 4 groups of 256 threads
+    for (int base = 0; base < K; base += GREEDY_BS) {
+        const int nb = min(GREEDY_BS, K - base), nk = s_nkeep;
+        if (tid < GREEDY_BS) s_blk[tid] = tid < nb ? boxes[base + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 4) s_sup[tid] = 0ull;
+        __syncthreads();
+        const float4 bi = s_blk[i];
+        // (1) against the kept list, tile by tile
+        bool sup = false;
+        for (int t0 = 0; t0 < nk; t0 += GREEDY_TILE) {
+            const int tn = min(GREEDY_TILE, nk - t0);
+            if (t0) __syncthreads();  // readers of the previous tile are done
+            if (tid < tn) s_tile[tid] = boxes[t0 + tid];
+            __syncthreads();
+            if (i < nb && !sup) {
+                for (int q = grp; q < tn; q += 4) {
+                    const float4 a = s_tile[q];
+                    if (iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick)) {
+                        sup = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (sup) atomicOr(&s_sup[i >> 6], 1ull << (i & 63));
+        // (2) in-block mask: row i suppresses later columns j; thread (i, grp) owns word grp of row i
+        {
+            unsigned long long bits = 0ull;
+            if (i < nb) {
+                const float area_i = f_mul(f_sub(bi.z, bi.x), f_sub(bi.w, bi.y));
+                const int j0 = max(grp * 64, i + 1), j1 = min(grp * 64 + 64, nb);
+                for (int j = j0; j < j1; j++)
+                    if (iou_gt<MODE>(bi, area_i, s_blk[j], thr, inclusive != 0, quick)) bits |= 1ull << (j & 63);
+            }
+            s_rowmask[i][grp] = bits;
+        }
+        __syncthreads();
+        // (3) greedy resolution, one step per kept box (warp 0, all lanes redundant)
+        if (tid < 32) {
+            unsigned long long alive[4], kb[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int left = nb - w * 64;
+                const unsigned long long valid = left >= 64 ? ~0ull : (left > 0 ? ((1ull << left) - 1ull) : 0ull);
+                alive[w] = ~s_sup[w] & valid;
+                kb[w] = 0ull;
+            }
+            for (;;) {
+                int w = -1;
+#pragma unroll
+                for (int v = 3; v >= 0; v--)
+                    if (alive[v]) w = v;
+                if (w < 0) break;
+                unsigned long long aw = 0ull;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    if (v == w) aw = alive[v];
+                const int b = __ffsll((long long)aw) - 1, q = w * 64 + b;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    alive[v] &= ~s_rowmask[q][v];
+                    if (v == w) {
+                        alive[v] &= ~(1ull << b);
+                        kb[v] |= 1ull << b;
+                    }
+                }
+            }
+            if (tid < 4) {
+                unsigned long long mine = 0ull;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    if (v == tid) mine = kb[v];
+                s_keptbits[tid] = mine;
+            }
+        }
+        __syncthreads();
+        // (4) append the kept boxes (in place) and their item indices
+        if (tid < nb) {
+            const int w = tid >> 6, b = tid & 63;
+            if ((s_keptbits[w] >> b) & 1ull) {
+                int pos = nk + __popcll(s_keptbits[w] & ((1ull << b) - 1ull));
+                for (int v = 0; v < w; v++) pos += __popcll(s_keptbits[v]);
+                boxes[pos] = s_blk[tid];
+                kout[pos] = (int32_t)sidx[base + tid];
+            }
+        }
+        if (tid == 0)
+            s_nkeep = nk + __popcll(s_keptbits[0]) + __popcll(s_keptbits[1]) + __popcll(s_keptbits[2]) +
+                      __popcll(s_keptbits[3]);
+        __syncthreads();
+    }
+    if (tid == 0) n_keep[g] = s_nkeep;
+}
+
 __global__ void gather_rows_kernel(const float *__restrict__ rows, int row_stride, int n_cols,
                                    const int32_t *__restrict__ keep, const int32_t *__restrict__ n_keep, int cap,
                                    float *__restrict__ out, int out_cap) {
@@ -527,11 +650,17 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     const bool fresh_plan = ctx->seginfo.bytes < sizeof(PlanHeader) + (size_t)(n_seg + 1) * sizeof(SegInfo);
     if (int rc = fdms_reserve(ctx, ctx->seginfo, sizeof(PlanHeader) + (size_t)(n_seg + 1) * sizeof(SegInfo))) return rc;
     if (fresh_plan) FDMS_CUDA(ctx, cudaMemsetAsync(ctx->seginfo.p, 0, ctx->seginfo.bytes, st));
-    const long long nblk_e = (cap_e + 63) / 64;
-    size_t mask_upper = (size_t)n_seg * (size_t)cap_e * (size_t)nblk_e * 8;
-    size_t mask_bytes = mask_upper < ctx->mask_budget ? mask_upper : ctx->mask_budget;
-    if (int rc = fdms_reserve(ctx, ctx->mask, mask_bytes)) return rc;
-    const long long budget_words = (long long)(ctx->mask.bytes / 8);
+    // many segments: one CTA per segment doing the work-efficient blocked greedy sweep; few segments: the
+    // bit-matrix path spreads the K^2/2 pair tests over all SMs
+    const bool greedy = n_seg >= ctx->nms_greedy_min_seg;
+    long long budget_words = 0;
+    if (!greedy) {
+        const long long nblk_e = (cap_e + 63) / 64;
+        size_t mask_upper = (size_t)n_seg * (size_t)cap_e * (size_t)nblk_e * 8;
+        size_t mask_bytes = mask_upper < ctx->mask_budget ? mask_upper : ctx->mask_budget;
+        if (int rc = fdms_reserve(ctx, ctx->mask, mask_bytes)) return rc;
+        budget_words = (long long)(ctx->mask.bytes / 8);
+    }
 
     PlanHeader *hdr = reinterpret_cast<PlanHeader *>(ctx->seginfo.p);
     SegInfo *seginfo = reinterpret_cast<SegInfo *>(hdr + 1);
@@ -546,6 +675,18 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         reinterpret_cast<uint32_t *>(ctx->idx_b.p), reinterpret_cast<float4 *>(ctx->boxes.p), seginfo, hdr,
         budget_words, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
+    if (greedy) {
+        if (iou_mode == FDMS_IOU_TV_CUDA)
+            nms_greedy_kernel<FDMS_IOU_TV_CUDA><<<n_seg, GREEDY_THREADS, 0, st>>>(
+                seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p), reinterpret_cast<const uint32_t *>(ctx->idx_b.p),
+                thr_f, inclusive, keep, n_keep, cap, count, skip_le);
+        else
+            nms_greedy_kernel<FDMS_IOU_TV_CPU><<<n_seg, GREEDY_THREADS, 0, st>>>(
+                seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p), reinterpret_cast<const uint32_t *>(ctx->idx_b.p),
+                thr_f, inclusive, keep, n_keep, cap, count, skip_le);
+        FDMS_LAUNCH_CHECK(ctx, "nms_greedy_kernel");
+        return FDMS_OK;
+    }
     const int mask_grid = ctx->sm_count * 8;
     if (iou_mode == FDMS_IOU_TV_CUDA)
         nms_mask_kernel<FDMS_IOU_TV_CUDA><<<mask_grid, MASK_THREADS, 0, st>>>(

@@ -225,6 +225,62 @@ __device__ __forceinline__ void border_row(T *const *pc, unsigned off, long long
     }
 }
 
+// The per-thread streaming loop of pyramid_kernel: horizontal pass of each slot in source-row order, then every
+// output row whose lower tap is that slot.  FAST = interior tile with paired stores (no per-pixel predicates).
+template <typename T, bool FAST>
+__device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, unsigned ys, long long xs_, uint32_t wA,
+                                            unsigned shA, unsigned aA, uint32_t wB, unsigned shB, unsigned aB,
+                                            int n_used, int n_rows, int slot_bytes, unsigned tborder, bool inA_,
+                                            bool inB_, bool two_, bool vec_) {
+    const long long xs = FAST ? 1 : xs_;
+    const bool inA = FAST ? true : inA_, inB = FAST ? true : inB_, two = FAST ? true : two_, vec = FAST ? true : vec_;
+    const bool edge = !(inA && inB);
+    unsigned off = 0;
+    int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
+    int j = 0;
+    int2 rm = sh.rowmeta[0];
+
+    // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
+    auto flush = [&](int k, int *cur, int *other) {
+        while ((rm.x >> 1) <= k) {
+            if (rm.x < 0) {
+                border_row<T>(pc, off, xs, tborder, two, vec);
+            } else {
+                const unsigned b0s = (unsigned)rm.y & 0xffffu, b1s = (unsigned)rm.y >> 16;
+                if (rm.x & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
+#pragma unroll               // visited in source order, so slot k-1 is dead from here on
+                    for (int c = 0; c < 6; c++) other[c] = cur[c];
+                }
+                if (!FAST && edge) emit_row<T, true>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, inA, inB, two, vec);
+                else emit_row<T, false>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, true, true, true, vec);
+            }
+            off += ys;
+            j++;
+            rm = sh.rowmeta[j];
+        }
+    };
+
+    uint32_t slot_off = 0;
+    for (int k = 0; k < n_used; k += 2) {
+        hpass(wA + slot_off, shA, aA, E);
+        hpass(wB + slot_off, shB, aB, E + 3);
+        flush(k, E, O);
+        slot_off += slot_bytes;
+        if (k + 1 < n_used) {
+            hpass(wA + slot_off, shA, aA, O);
+            hpass(wB + slot_off, shB, aB, O + 3);
+            flush(k + 1, O, E);
+        }
+        slot_off += slot_bytes;
+    }
+    // rows not tied to any slot (a tile without interior)
+    while (j < n_rows) {
+        border_row<T>(pc, off, xs, tborder, two, vec);
+        off += ys;
+        j++;
+    }
+}
+
 // Tap tables of a pyramid geometry (OpenCV's coefficient set-up).  Runs once per geometry:
 // the tables are cached in the ctx, so the main kernel carries no fp64 and no conversions.
 __global__ void pyramid_tables_kernel(const __grid_constant__ PyrParams P) {
@@ -421,64 +477,25 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
     if (!active) return;
 
     // ---- stream over the slots ------------------------------------------------------------------------
-    const bool vec = S.vec != 0;
-    const long long xs = S.xs;
-    const unsigned ys = (unsigned)S.ys;
     T *pc[3];
     {
-        T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys + (long long)x * xs;
+        T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys +
+                (long long)x * S.xs;
         // channel flip (img[:, :, ::-1]) = source channel c goes to output plane 2 - c: swap the plane pointers
         pc[0] = P.flip ? p0 + 2 * S.cs : p0;
         pc[1] = p0 + S.cs;
         pc[2] = P.flip ? p0 : p0 + 2 * S.cs;
     }
-    unsigned off = 0;
-    const bool edge = !(inA && inB);  // interior tiles have no edge threads
-    const int flip = 0;  // folded into pc[]
     const unsigned tborder = (unsigned)P.border * 4u;
-    int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
-    int j = 0;
-    int2 rm = sh.rowmeta[0];
-
-    // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
-    auto flush = [&](int k, int *cur, int *other) {
-        while ((rm.x >> 1) <= k) {
-            if (rm.x < 0) {
-                border_row<T>(pc, off, xs, tborder, two, vec);
-            } else {
-                const unsigned b0s = (unsigned)rm.y & 0xffffu, b1s = (unsigned)rm.y >> 16;
-                if (rm.x & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
-#pragma unroll               // visited in source order, so slot k-1 is dead from here on
-                    for (int c = 0; c < 6; c++) other[c] = cur[c];
-                }
-                if (edge) emit_row<T, true>(pc, off, xs, b0s, b1s, other, cur, flip, tborder, inA, inB, two, vec);
-                else emit_row<T, false>(pc, off, xs, b0s, b1s, other, cur, flip, tborder, true, true, true, vec);
-            }
-            off += ys;
-            j++;
-            rm = sh.rowmeta[j];
-        }
-    };
-
-    uint32_t slot_off = 0;
-    for (int k = 0; k < n_used; k += 2) {
-        hpass(wA + slot_off, shA, aA, E);
-        hpass(wB + slot_off, shB, aB, E + 3);
-        flush(k, E, O);
-        slot_off += slot_bytes;
-        if (k + 1 < n_used) {
-            hpass(wA + slot_off, shA, aA, O);
-            hpass(wB + slot_off, shB, aB, O + 3);
-            flush(k + 1, O, E);
-        }
-        slot_off += slot_bytes;
-    }
-    // rows not tied to any slot (a tile without interior)
-    while (j < n_rows) {
-        border_row<T>(pc, off, xs, tborder, two, vec);
-        off += ys;
-        j++;
-    }
+    // fast tiles: every column interior, every thread owns a full pixel pair, paired stores allowed -- the
+    // common case (letterbox pads rows only; 320 | 640, 960, 1280); CTA-uniform, so no divergence
+    const bool fast = S.vec != 0 && ox0 >= left && x_end <= left + unpad_w && ((x_end - ox0) & 1) == 0;
+    if (fast)
+        stream_tile<T, true>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes, tborder,
+                             true, true, true, true);
+    else
+        stream_tile<T, false>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
+                              tborder, inA, inB, two, S.vec != 0);
 }
 
 template <typename T>

@@ -24,6 +24,7 @@ struct fdms_ctx {
     int smem_optin = 0;
     char err[512] = {0};
     int pyr_attr = 0;
+    int pyr_special = 1;  // FDMS_PYR_SPECIAL=0 disables the integer-scale fast paths (testing)
     int pyr_smem_budget = 40 * 1024, pyr_th = 8;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)

@@ -34,6 +34,7 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (c->sm_count <= 0) c->sm_count = FDMS_SM_COUNT_FALLBACK;
+    if (const char *e = getenv("FDMS_PYR_SPECIAL")) c->pyr_special = atoi(e);
     if (const char *e = getenv("FDMS_PYR_SMEM_KB")) c->pyr_smem_budget = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_TH")) c->pyr_th = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
     if (const char *e = getenv("FDMS_NMS_SMALL_LIMIT")) c->nms_small_limit = atoi(e);

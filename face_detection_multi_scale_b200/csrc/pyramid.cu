@@ -26,6 +26,11 @@ constexpr int PYR_THREADS = 160;  // 2 columns per thread: 320-column tiles divi
 constexpr int PYR_MAX_TH = 32;    // rows per tile are handled by the lanes of warp 0
 constexpr int PYR_MAX_SLOTS = 64;
 constexpr int PYR_SMEM_BUDGET = 56 * 1024;  // per CTA: >= 4 CTAs per SM
+// Exact integer scale factors make OpenCV's fixed-point weights constant: an odd factor k gives
+// f == 0 on both axes (weights 2048/0: the output IS source pixel (k*d + (k-1)/2)), an even factor gives f == 0.5
+// (weights 1024/1024: (((1024*(64*(a+b)))>>16) + ... + 2) >> 2 == (a + b + c + d + 2) >> 2).  Same results as the
+// general path, fewer instructions.
+enum { PM_GENERAL = 0, PM_POINT = 1, PM_HALF = 2 };
 
 struct PyrScale {
     void *out;
@@ -36,7 +41,7 @@ struct PyrScale {
     int dense_rows;    // row slots cover a contiguous source-row range (scale_y <= 2)
     int slot_bytes;    // multiple of 16
     int vec;           // paired stores allowed
-    int pad_;
+    int mode;          // PM_GENERAL / PM_POINT / PM_HALF: strength-reduced arithmetic for exact integer scales
     double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
     const int2 *xtab;         // per output column: {source column sx, a0 | a1 << 16}; sx = -1 on the border
     const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, 0}; r0 = -1 on the border
@@ -129,6 +134,30 @@ __device__ __forceinline__ void hpass(uint32_t w, unsigned sh, unsigned a01, int
     h[2] = (int)(__dp2a_lo(a01, p2, 0u) >> 4);
 }
 
+// PM_POINT: the output pixel is source pixel sx; PRMT drops byte c straight into the 2^23 magic number, so the
+// three values leave as float bits (2^23 + v).
+__device__ __forceinline__ void hpass_point(uint32_t w, unsigned sh, unsigned *h) {
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(w));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(w));
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);  // c0 c1 c2 ..
+    h[0] = __byte_perm(lo, 0x4B000000u, 0x7650);
+    h[1] = __byte_perm(lo, 0x4B000000u, 0x7651);
+    h[2] = __byte_perm(lo, 0x4B000000u, 0x7652);
+}
+// PM_HALF: h[c] = S[sx][c] + S[sx+1][c]
+__device__ __forceinline__ void hpass_half(uint32_t w, unsigned sh, int *h) {
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(w));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(w));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(w));
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    const uint32_t p01 = __byte_perm(lo, hi, 0x4130), p2 = __byte_perm(lo, hi, 0x0052);
+    h[0] = (int)__dp2a_lo(0x00010001u, p01, 0u);
+    h[1] = (int)__dp2a_hi(0x00010001u, p01, 0u);
+    h[2] = (int)__dp2a_lo(0x00010001u, p2, 0u);
+}
+
 // Vertical pass.  OpenCV: (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  Returns the sum t before the
 // final shift: two full-rate IMADs, one PRMT gathering the two high halves, one IDP.2A adding them (+2).
 // t >> 2 cannot exceed 255: b0+b1 <= 2049 and R>>4 <= 32654, so the two floors sum to at most 1020.
@@ -159,8 +188,17 @@ template <> struct Out<__half> {
         }
     }
     static __device__ __forceinline__ void store1(__half *p, unsigned a) { p[0] = __float2half_rn(f(a)); }
+    // value already in magic-number form (float bits of 2^23 + v)
+    static __device__ __forceinline__ void store2_bits(__half *p, unsigned a, unsigned b) {
+        const float c = 0.003921568859368563f;
+        *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(__fmaf_rn(__uint_as_float(a), c, -8388608.0f * c),
+                                                            __fmaf_rn(__uint_as_float(b), c, -8388608.0f * c));
+    }
 };
 template <> struct Out<float> {
+    static __device__ __forceinline__ void store2_bits(float *p, unsigned a, unsigned b) {
+        *reinterpret_cast<float2 *>(p) = make_float2(f((a & 0xffu) << 2), f((b & 0xffu) << 2));
+    }
     static __device__ __forceinline__ float f(unsigned t) { return __fdiv_rn((float)(t >> 2), 255.0f); }  // true division
     static __device__ __forceinline__ void store2(float *p, long long xs, unsigned a, unsigned b, bool vec) {
         if (vec) {
@@ -173,6 +211,10 @@ template <> struct Out<float> {
     static __device__ __forceinline__ void store1(float *p, unsigned a) { p[0] = f(a); }
 };
 template <> struct Out<uint8_t> {
+    static __device__ __forceinline__ void store2_bits(uint8_t *p, unsigned a, unsigned b) {
+        p[0] = (uint8_t)a;
+        p[1] = (uint8_t)b;
+    }
     static __device__ __forceinline__ void store2(uint8_t *p, long long xs, unsigned a, unsigned b, bool) {
         p[0] = (uint8_t)(a >> 2);
         p[xs] = (uint8_t)(b >> 2);
@@ -227,7 +269,7 @@ __device__ __forceinline__ void border_row(T *const *pc, unsigned off, long long
 
 // The per-thread streaming loop of pyramid_kernel: horizontal pass of each slot in source-row order, then every
 // output row whose lower tap is that slot.  FAST = interior tile with paired stores (no per-pixel predicates).
-template <typename T, bool FAST>
+template <typename T, bool FAST, int MODE>
 __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, unsigned ys, long long xs_, uint32_t wA,
                                             unsigned shA, unsigned aA, uint32_t wB, unsigned shB, unsigned aB,
                                             int n_used, int n_rows, int slot_bytes, unsigned tborder, bool inA_,
@@ -236,9 +278,28 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     const bool inA = FAST ? true : inA_, inB = FAST ? true : inB_, two = FAST ? true : two_, vec = FAST ? true : vec_;
     const bool edge = !(inA && inB);
     unsigned off = 0;
-    int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
     int j = 0;
     int2 rm = sh.rowmeta[0];
+
+    if (MODE == PM_POINT) {  // one slot per interior row; border rows interleave
+        for (int k = 0;; k++) {
+            while (rm.x < 0) {  // border rows due before slot k
+                border_row<T>(pc, off, xs, tborder, true, true);
+                off += ys;
+                rm = sh.rowmeta[++j];
+            }
+            if (k >= n_used) break;
+            unsigned hA[3], hB[3];
+            hpass_point(wA + (uint32_t)k * slot_bytes, shA, hA);
+            hpass_point(wB + (uint32_t)k * slot_bytes, shB, hB);
+#pragma unroll
+            for (int c = 0; c < 3; c++) Out<T>::store2_bits(pc[c] + off, hA[c], hB[c]);
+            off += ys;
+            rm = sh.rowmeta[++j];
+        }
+        return;
+    }
+    int E[6] = {0, 0, 0, 0, 0, 0}, O[6] = {0, 0, 0, 0, 0, 0};
 
     // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
     auto flush = [&](int k, int *cur, int *other) {
@@ -251,8 +312,16 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
 #pragma unroll               // visited in source order, so slot k-1 is dead from here on
                     for (int c = 0; c < 6; c++) other[c] = cur[c];
                 }
-                if (!FAST && edge) emit_row<T, true>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, inA, inB, two, vec);
-                else emit_row<T, false>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, true, true, true, vec);
+                if (MODE == PM_HALF) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        Out<T>::store2(pc[c] + off, 1, (unsigned)(other[c] + cur[c] + 2), (unsigned)(other[3 + c] + cur[3 + c] + 2),
+                                       true);
+                } else if (!FAST && edge) {
+                    emit_row<T, true>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, inA, inB, two, vec);
+                } else {
+                    emit_row<T, false>(pc, off, xs, b0s, b1s, other, cur, 0, tborder, true, true, true, vec);
+                }
             }
             off += ys;
             j++;
@@ -262,13 +331,23 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
 
     uint32_t slot_off = 0;
     for (int k = 0; k < n_used; k += 2) {
-        hpass(wA + slot_off, shA, aA, E);
-        hpass(wB + slot_off, shB, aB, E + 3);
+        if (MODE == PM_HALF) {
+            hpass_half(wA + slot_off, shA, E);
+            hpass_half(wB + slot_off, shB, E + 3);
+        } else {
+            hpass(wA + slot_off, shA, aA, E);
+            hpass(wB + slot_off, shB, aB, E + 3);
+        }
         flush(k, E, O);
         slot_off += slot_bytes;
         if (k + 1 < n_used) {
-            hpass(wA + slot_off, shA, aA, O);
-            hpass(wB + slot_off, shB, aB, O + 3);
+            if (MODE == PM_HALF) {
+                hpass_half(wA + slot_off, shA, O);
+                hpass_half(wB + slot_off, shB, O + 3);
+            } else {
+                hpass(wA + slot_off, shA, aA, O);
+                hpass(wB + slot_off, shB, aB, O + 3);
+            }
             flush(k + 1, O, E);
         }
         slot_off += slot_bytes;
@@ -490,12 +569,18 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
     // fast tiles: every column interior, every thread owns a full pixel pair, paired stores allowed -- the
     // common case (letterbox pads rows only; 320 | 640, 960, 1280); CTA-uniform, so no divergence
     const bool fast = S.vec != 0 && ox0 >= left && x_end <= left + unpad_w && ((x_end - ox0) & 1) == 0;
-    if (fast)
-        stream_tile<T, true>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes, tborder,
-                             true, true, true, true);
+    if (fast && S.mode == PM_POINT)
+        stream_tile<T, true, PM_POINT>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
+                                       tborder, true, true, true, true);
+    else if (fast && S.mode == PM_HALF)
+        stream_tile<T, true, PM_HALF>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
+                                      tborder, true, true, true, true);
+    else if (fast)
+        stream_tile<T, true, PM_GENERAL>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows,
+                                         slot_bytes, tborder, true, true, true, true);
     else
-        stream_tile<T, false>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
-                              tborder, inA, inB, two, S.vec != 0);
+        stream_tile<T, false, PM_GENERAL>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows,
+                                          slot_bytes, tborder, inA, inB, two, S.vec != 0);
 }
 
 template <typename T>
@@ -579,6 +664,18 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             // tile: 320 columns (fewer when the staged rows would not fit), as many rows as the slots allow
             // odd integer scale: every vertical tap has weight 0 on the lower row -> one slot per output row
             const bool y_point = S.scale_y == (double)(long long)S.scale_y && (((long long)S.scale_y) & 1);
+            {
+                // exact integer factors on both axes, no clamped taps (virt == k * unpad), no virtual zeros
+                const long long kx = (long long)S.scale_x, ky = (long long)S.scale_y;
+                const bool int_x = S.scale_x == (double)kx && kx >= 2 && kx * g.unpad_w == virt_w;
+                const bool int_y = S.scale_y == (double)ky && ky >= 2 && ky * g.unpad_h == virt_h;
+                const bool real = virt_h == src_h && virt_w == src_w;
+                S.mode = PM_GENERAL;
+                if (int_x && int_y && real && ctx->pyr_special) {
+                    if ((kx & 1) && (ky & 1)) S.mode = PM_POINT;
+                    else if (!(kx & 1) && !(ky & 1)) S.mode = PM_HALF;
+                }
+            }
             int tw = 2 * PYR_THREADS, th = ctx->pyr_th;
             for (;;) {
                 int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : (y_point ? th : 2 * th);

@@ -43,7 +43,7 @@ METRIC = "images/sec (3-scale pyramid, device-timed)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="fdms", choices=["fdms", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -92,7 +92,7 @@ def host_threads():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -328,7 +328,30 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # same call with the head maps already resident in HBM (where an on-device backbone leaves them): only
+        # the images cross PCIe.  Reported next to the conservative number, not instead of it.
+        model_dev = standin.SyntheticHeadModel()
+        for s_, hw in enumerate(shapes):
+            model_dev.set_heads(hw, heads[s_], device=dev)
+        det2 = MultiScaleFaceDetector(model_dev, device=dev, img_sizes=sizes, conf_thres=wl["conf"], iou_thres=wl["iou"],
+                                      cap=wl["cap"], out_cap=wl["cap"])
+        for _ in range(3):
+            det2.detect_multi_scale_batch(pinned)
+        y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        y0.record()
+        for _ in range(Ke):
+            det2.detect_multi_scale_batch(pinned)
+        y1.record()
+        barrier()
+        dt2 = y0.elapsed_time(y1) / 1e3
+        if world > 1:
+            t = torch.tensor([dt2], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt2 = float(t.item())
         e2e = {"value": round(world * B * Ke / dt, 1), "unit": "images/s", "steps": Ke,
+               "images_only_h2d": {"value": round(world * B * Ke / dt2, 1), "h2d_bytes_per_step": int(pinned.numel()),
+                                   "note": "head maps resident in HBM as an on-device backbone leaves them"},
                "h2d_bytes_per_step": int(pinned.numel() + model.h2d_bytes // Ke), "d2h_bytes_per_step": int(d2h),
                "api": "MultiScaleFaceDetector.detect_multi_scale_batch(pinned host uint8 batch) -> list of ndarray",
                "final_detections_per_step": int(sum(len(r) for r in res))}

@@ -29,8 +29,11 @@ constexpr int SORT_SMEM_ITEMS = 8192;  // 8 B key + 4 B index each = 96 KB
 constexpr int MASK_THREADS = 256;      // 64 rows x 4 column blocks
 constexpr int SWEEP_THREADS = 512;
 constexpr int SWEEP_MAX_NBLK = 4096;   // 262144 boxes per segment
-constexpr int SMALL_THREADS = 256;
-constexpr int SMALL_LIMIT = 4096;      // largest segment the fused single-CTA kernel takes (112 KB of shared memory)
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_LIMIT = 1024;      // largest segment the fused single-CTA kernel takes (one box per thread)
+constexpr int GREEDY_THREADS = 1024;
+constexpr int GREEDY_BS = 256;         // candidates per greedy step
+constexpr int GREEDY_TILE = 1024;      // kept boxes staged per tile (large-segment kernel)
 
 struct SegInfo {
     int n;               // boxes entering suppression (after the max_nms cut)
@@ -326,123 +329,173 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
     if (tid == 0) n_keep[g] = s_nkeep;
 }
 
-// Fused single-CTA NMS for segments of at most SMALL_LIMIT boxes: bitonic sort, boxes in score
-// order and the kept list all live in shared memory; suppression is a blocked greedy sweep
-// (64 boxes per step: test against the boxes kept so far, build the 64x64 in-block mask, resolve it
-// in warp 0 with shuffles).  No global scratch, no K^2 mask, one launch.
+// Steps (2)+(3) of a blocked greedy step, shared by nms_small_kernel and nms_greedy_kernel.
+// blk[0..nb) = the step's candidates in score order (shared memory); s_sup = candidates already suppressed by
+// boxes kept in earlier steps.  (2) column masks: colmask[i] = earlier candidates j < i of this block that
+// would suppress i (pairs with a pre-suppressed member are skipped -- they cannot matter).  (3) parallel
+// resolution to the greedy fixpoint: an undecided candidate is removed as soon as a KEPT earlier candidate
+// suppresses it, and kept as soon as no undecided or kept earlier candidate does; the first undecided one
+// always qualifies, and typical suppression graphs settle in a handful of rounds (vs one serial step per kept
+// box).  Result: s_K = bitset of kept candidates.  All CTA threads must call this (it contains barriers).
+template <int MODE>
+__device__ __forceinline__ void greedy_block(const float4 *blk, int nb, float thr, bool inclusive, bool quick,
+                                             unsigned long long (*s_colmask)[4], unsigned long long *s_sup,
+                                             unsigned long long *s_U, unsigned long long *s_K) {
+    const int tid = threadIdx.x;
+    const int i = tid & (GREEDY_BS - 1), grp = tid >> 8;
+    const int iw = i >> 6;
+    const unsigned long long ibit = 1ull << (i & 63);
+    __syncthreads();  // s_sup complete
+    {
+        unsigned long long bits = 0ull;
+        if (i < nb && !(s_sup[iw] & ibit)) {
+            const float4 bi = blk[i];
+            const unsigned long long skip = s_sup[grp];
+            const int j0 = grp * 64, j1 = min(grp * 64 + 64, i);
+            for (int j = j0; j < j1; j++) {
+                if ((skip >> (j & 63)) & 1ull) continue;
+                const float4 a = blk[j];
+                if (iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive, quick))
+                    bits |= 1ull << (j & 63);
+            }
+        }
+        s_colmask[i][grp] = bits;
+    }
+    if (tid < 4) {
+        const int left = nb - tid * 64;
+        const unsigned long long valid = left >= 64 ? ~0ull : (left > 0 ? ((1ull << left) - 1ull) : 0ull);
+        s_U[tid] = ~s_sup[tid] & valid;
+        s_K[tid] = 0ull;
+    }
+    __syncthreads();
+    for (;;) {
+        const unsigned long long u0 = s_U[0], u1 = s_U[1], u2 = s_U[2], u3 = s_U[3];
+        if ((u0 | u1 | u2 | u3) == 0ull) break;  // uniform
+        bool undecided = false, by_kept = false, by_undecided = false;
+        if (tid < GREEDY_BS) {
+            const unsigned long long uw = iw == 0 ? u0 : (iw == 1 ? u1 : (iw == 2 ? u2 : u3));
+            undecided = (uw & ibit) != 0ull;
+            if (undecided) {
+                const unsigned long long c0 = s_colmask[i][0], c1 = s_colmask[i][1], c2 = s_colmask[i][2],
+                                         c3 = s_colmask[i][3];
+                by_kept = ((c0 & s_K[0]) | (c1 & s_K[1]) | (c2 & s_K[2]) | (c3 & s_K[3])) != 0ull;
+                by_undecided = ((c0 & u0) | (c1 & u1) | (c2 & u2) | (c3 & u3)) != 0ull;
+            }
+        }
+        __syncthreads();  // every thread has read U and K of this round
+        if (undecided) {
+            if (by_kept) {
+                atomicAnd(&s_U[iw], ~ibit);
+            } else if (!by_undecided) {
+                atomicOr(&s_K[iw], ibit);
+                atomicAnd(&s_U[iw], ~ibit);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Fused single-CTA NMS for segments of at most SMALL_LIMIT (1024) boxes, everything in shared memory:
+//   rank sort  : thread i counts the keys smaller than its own (keys are unique: score desc, tie asc) -- no
+//                barriers, broadcast shared-memory reads -- and scatters its box to that rank;
+//   suppression: the same blocked greedy sweep as nms_greedy_kernel (256 candidates per step, kept boxes
+//                compacted in place at the front of the box array).
+// No global scratch, one launch, ~3 barriers per 256 boxes.
 template <int MODE>
 __global__ void __launch_bounds__(SMALL_THREADS)
     nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
                      const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int cap, int max_nms,
-                     int small_cap, int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
+                     int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
                      int32_t *__restrict__ n_keep) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    __shared__ unsigned long long s_rowmask[64];
-    __shared__ unsigned long long s_sup;
+    __shared__ unsigned long long s_keys[SMALL_LIMIT];
+    __shared__ float4 s_box[SMALL_LIMIT];
+    __shared__ uint32_t s_idx[SMALL_LIMIT];
+    __shared__ int s_rank[SMALL_LIMIT];
+    __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
+    __shared__ unsigned long long s_sup[4], s_keptbits[4], s_U[4];
     __shared__ int s_nkeep;
-    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int g = blockIdx.x, tid = threadIdx.x;
     const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
-    int n = max(0, min(count[g], cap));
-    if (n > small_limit) return;  // the generic three-kernel path takes it
+    const int n = max(0, min(count[g], cap));
+    if (n > small_limit) return;  // the sort + greedy / bit-matrix path takes it
     if (n == 0) {
         if (tid == 0) n_keep[g] = 0;
         return;
     }
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm);
-    float4 *boxes = reinterpret_cast<float4 *>(sm + (size_t)small_cap * 8);
-    uint32_t *idx = reinterpret_cast<uint32_t *>(sm + (size_t)small_cap * 24);
-    uint32_t *kept = reinterpret_cast<uint32_t *>(sm);  // aliases keys once the sort is done
-    int pad = 64;
-    while (pad < n) pad <<= 1;
     const float *seg_rows = rows + (long long)g * cap * row_stride;
-    for (int i = tid; i < pad; i += SMALL_THREADS) {
-        if (i < n) {
-            float s = seg_rows[(long long)i * row_stride + score_off];
-            uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + i] : (uint32_t)i;
-            keys[i] = ((unsigned long long)score_key_desc(s) << 32) | t;
-            idx[i] = (uint32_t)i;
-        } else {
-            keys[i] = ~0ull;
-            idx[i] = 0xffffffffu;
-        }
+    // ---- rank sort ----------------------------------------------------------------------------------------
+    // keys are unique (tie = row index or item index; callers must not pass duplicate ties inside a segment), so
+    // the rank of an item is the number of smaller keys.  All 1024 threads take part: item i = tid % pad, and the
+    // 1024 / pad threads of an item split the key range and add their partial counts.
+    int pad = 32;
+    while (pad < n) pad <<= 1;
+    const int parts = SMALL_THREADS / pad;
+    const int item = tid & (pad - 1), part = tid / pad;
+    if (tid < n) {
+        const float *r = seg_rows + (long long)tid * row_stride;
+        const uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + tid] : (uint32_t)tid;
+        s_keys[tid] = ((unsigned long long)score_key_desc(r[score_off]) << 32) | t;
+    }
+    if (tid < pad) s_rank[tid] = 0;
+    if (tid == 0) s_nkeep = 0;
+    __syncthreads();
+    if (item < n) {
+        const unsigned long long mykey = s_keys[item];
+        const int per = (n + parts - 1) / parts, j0 = part * per, j1 = min(n, j0 + per);
+        int cnt = 0;
+#pragma unroll 4
+        for (int j = j0; j < j1; j++) cnt += s_keys[j] < mykey;
+        if (parts == 1) s_rank[item] = cnt;
+        else if (cnt) atomicAdd(&s_rank[item], cnt);
     }
     __syncthreads();
-    if (n > 1) {
-        for (int k = 2; k <= pad; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (pad >> 1); t += SMALL_THREADS) {
-                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    int p = i + j;
-                    bool up = (i & k) == 0;
-                    unsigned long long a = keys[i], b = keys[p];
-                    if ((a > b) == up) {
-                        keys[i] = b;
-                        keys[p] = a;
-                        uint32_t ia = idx[i], ib = idx[p];
-                        idx[i] = ib;
-                        idx[p] = ia;
-                    }
-                }
-                __syncthreads();
-            }
-        }
+    if (tid < n) {
+        const float *r = seg_rows + (long long)tid * row_stride + box_off;
+        const int rank = s_rank[tid];
+        s_box[rank] = make_float4(r[0], r[1], r[2], r[3]);
+        s_idx[rank] = (uint32_t)tid;
     }
-    const int K = (max_nms > 0) ? min(n, max_nms) : n;
-    for (int k = tid; k < K; k += SMALL_THREADS) {
-        const float *r = seg_rows + (long long)idx[k] * row_stride + box_off;
-        boxes[k] = make_float4(r[0], r[1], r[2], r[3]);
-    }
-    if (tid == 0) s_nkeep = 0;
-    __syncthreads();  // keys are dead from here on: `kept` may overwrite them
+    __syncthreads();
+    const int K = (max_nms > 0) ? min(n, max_nms) : n;  // utils/general.py:578-579
+    // ---- blocked greedy suppression ---------------------------------------------------------------------------
     int32_t *kout = keep + (long long)g * cap;
-    const int nblk = (K + 63) >> 6;
-    const int i = tid & 63, quarter = tid >> 6;
-    for (int c = 0; c < nblk; c++) {
-        const int base = c * 64, nb = min(64, K - base);
-        const int nk = s_nkeep;
-        if (tid < 64) s_rowmask[tid] = 0ull;
-        if (tid == 0) s_sup = 0ull;
+    const int i = tid & (GREEDY_BS - 1), grp = tid >> 8;
+    for (int base = 0; base < K; base += GREEDY_BS) {
+        const int nb = min(GREEDY_BS, K - base), nk = s_nkeep;
+        if (tid < 4) s_sup[tid] = 0ull;
         __syncthreads();
+        const float4 bi = i < nb ? s_box[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // (1) against the boxes kept in earlier steps (compacted at the front of s_box)
         if (i < nb) {
-            const float4 bi = boxes[base + i];
-            // (1) suppressed by a box kept in an earlier block?
             bool sup = false;
-            for (int q = quarter; q < nk && !sup; q += 4) {
-                const float4 a = boxes[kept[q]];
-                sup = iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick);
+            for (int q = grp; q < nk; q += 4) {
+                const float4 a = s_box[q];
+                sup |= iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick);
             }
-            if (sup) atomicOr(&s_sup, 1ull << i);
-            // (2) in-block mask: row i suppresses later columns j
-            const float area_i = f_mul(f_sub(bi.z, bi.x), f_sub(bi.w, bi.y));
-            unsigned long long bits = 0ull;
-            const int j0 = max(quarter * 16, i + 1), j1 = min(quarter * 16 + 16, nb);
-            for (int j = j0; j < j1; j++)
-                if (iou_gt<MODE>(bi, area_i, boxes[base + j], thr, inclusive != 0, quick)) bits |= 1ull << j;
-            if (bits) atomicOr(&s_rowmask[i], bits);
+            if (sup) atomicOr(&s_sup[i >> 6], 1ull << (i & 63));
         }
-        __syncthreads();
-        if (tid < 32) {
-            // greedy resolution of the block: visit only boxes that are still alive (one step per KEPT box)
-            const unsigned long long valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
-            unsigned long long alive = ~s_sup & valid, kb = 0ull;
-            while (alive) {
-                const int q = __ffsll((long long)alive) - 1;
-                kb |= 1ull << q;
-                alive &= ~(s_rowmask[q] | (1ull << q));  // row masks only hold later columns
+        // (2) + (3): column masks and parallel greedy resolution
+        greedy_block<MODE>(s_box + base, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_U, s_keptbits);
+        // (4) append: kept boxes move to the front of s_box (never past the read position), indices go out
+        float4 kbox = bi;
+        uint32_t kidx = 0;
+        int pos = -1;
+        if (tid < nb) {
+            const int w = tid >> 6, b = tid & 63;
+            if ((s_keptbits[w] >> b) & 1ull) {
+                pos = nk + __popcll(s_keptbits[w] & ((1ull << b) - 1ull));
+                for (int v = 0; v < w; v++) pos += __popcll(s_keptbits[v]);
+                kidx = s_idx[base + tid];
             }
-            kb &= valid;
-            if ((kb >> lane) & 1ull) {
-                const int pos = nk + __popcll(kb & ((1ull << lane) - 1ull));
-                kept[pos] = (uint32_t)(base + lane);
-                kout[pos] = (int32_t)idx[base + lane];
-            }
-            if ((kb >> (lane + 32)) & 1ull) {
-                const int pos = nk + __popcll(kb & ((1ull << (lane + 32)) - 1ull));
-                kept[pos] = (uint32_t)(base + lane + 32);
-                kout[pos] = (int32_t)idx[base + lane + 32];
-            }
-            if (lane == 0) s_nkeep = nk + __popcll(kb);
         }
+        __syncthreads();  // every reader of s_box[base ..] is done before the in-place compaction
+        if (pos >= 0) {
+            s_box[pos] = kbox;
+            kout[pos] = (int32_t)kidx;
+        }
+        if (tid == 0)
+            s_nkeep = nk + __popcll(s_keptbits[0]) + __popcll(s_keptbits[1]) + __popcll(s_keptbits[2]) +
+                      __popcll(s_keptbits[3]);
         __syncthreads();
     }
     if (tid == 0) n_keep[g] = s_nkeep;
@@ -454,10 +507,6 @@ __global__ void __launch_bounds__(SMALL_THREADS)
 // candidates are (1) tested against the kept list with early exit, (2) masked against each other (256 x 256
 // bits), (3) resolved by warp 0 with one step per KEPT box, (4) appended.  Work ~ K * n_kept / 2 pair tests
 // instead of K^2 / 2, and no K^2 bit-matrix.
-constexpr int GREEDY_THREADS = 1024;
-constexpr int GREEDY_BS = 256;
-constexpr int GREEDY_TILE = 1024;
-
 template <int MODE>
 __global__ void __launch_bounds__(GREEDY_THREADS)
     nms_greedy_kernel(const SegInfo *__restrict__ seginfo, int cap_e, float4 *sorted_boxes,
@@ -466,7 +515,7 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
     __shared__ float4 s_blk[GREEDY_BS];
     __shared__ float4 s_tile[GREEDY_TILE];
     __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
-    __shared__ unsigned long long s_sup[4], s_keptbits[4];
+    __shared__ unsigned long long s_sup[4], s_keptbits[4], s_U[4];
     __shared__ int s_nkeep;
     const int g = blockIdx.x, tid = threadIdx.x;
     if (max(0, min(count[g], cap)) <= skip_le) return;  // handled by nms_small_kernel
@@ -502,57 +551,8 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
             }
         }
         if (sup) atomicOr(&s_sup[i >> 6], 1ull << (i & 63));
-        // (2) in-block mask: row i suppresses later columns j; thread (i, grp) owns word grp of row i
-        {
-            unsigned long long bits = 0ull;
-            if (i < nb) {
-                const float area_i = f_mul(f_sub(bi.z, bi.x), f_sub(bi.w, bi.y));
-                const int j0 = max(grp * 64, i + 1), j1 = min(grp * 64 + 64, nb);
-                for (int j = j0; j < j1; j++)
-                    if (iou_gt<MODE>(bi, area_i, s_blk[j], thr, inclusive != 0, quick)) bits |= 1ull << (j & 63);
-            }
-            s_rowmask[i][grp] = bits;
-        }
-        __syncthreads();
-        // (3) greedy resolution, one step per kept box (warp 0, all lanes redundant)
-        if (tid < 32) {
-            unsigned long long alive[4], kb[4];
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const int left = nb - w * 64;
-                const unsigned long long valid = left >= 64 ? ~0ull : (left > 0 ? ((1ull << left) - 1ull) : 0ull);
-                alive[w] = ~s_sup[w] & valid;
-                kb[w] = 0ull;
-            }
-            for (;;) {
-                int w = -1;
-#pragma unroll
-                for (int v = 3; v >= 0; v--)
-                    if (alive[v]) w = v;
-                if (w < 0) break;
-                unsigned long long aw = 0ull;
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (v == w) aw = alive[v];
-                const int b = __ffsll((long long)aw) - 1, q = w * 64 + b;
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    alive[v] &= ~s_rowmask[q][v];
-                    if (v == w) {
-                        alive[v] &= ~(1ull << b);
-                        kb[v] |= 1ull << b;
-                    }
-                }
-            }
-            if (tid < 4) {
-                unsigned long long mine = 0ull;
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (v == tid) mine = kb[v];
-                s_keptbits[tid] = mine;
-            }
-        }
-        __syncthreads();
+        // (2) + (3): column masks and parallel greedy resolution
+        greedy_block<MODE>(s_blk, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_U, s_keptbits);
         // (4) append the kept boxes (in place) and their item indices
         if (tid < nb) {
             const int w = tid >> 6, b = tid & 63;
@@ -613,24 +613,12 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     // ---- segments of at most small_limit boxes: one fused launch -------------------------------------------
     const int small_limit = ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
     if (small_limit > 0) {
-        int small_cap = 64;
-        while (small_cap < cap && small_cap < small_limit) small_cap <<= 1;
-        const int smem = small_cap * 28;
-        if (!ctx->nms_small_attr) {
-            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_small_kernel<FDMS_IOU_TV_CUDA>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_LIMIT * 28));
-            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_small_kernel<FDMS_IOU_TV_CPU>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_LIMIT * 28));
-            ctx->nms_small_attr = true;
-        }
         if (iou_mode == FDMS_IOU_TV_CUDA)
-            nms_small_kernel<FDMS_IOU_TV_CUDA><<<n_seg, SMALL_THREADS, smem, st>>>(
-                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_cap, small_limit, thr_f, inclusive,
-                keep, n_keep);
+            nms_small_kernel<FDMS_IOU_TV_CUDA><<<n_seg, SMALL_THREADS, 0, st>>>(
+                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_limit, thr_f, inclusive, keep, n_keep);
         else
-            nms_small_kernel<FDMS_IOU_TV_CPU><<<n_seg, SMALL_THREADS, smem, st>>>(
-                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_cap, small_limit, thr_f, inclusive,
-                keep, n_keep);
+            nms_small_kernel<FDMS_IOU_TV_CPU><<<n_seg, SMALL_THREADS, 0, st>>>(
+                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_limit, thr_f, inclusive, keep, n_keep);
         FDMS_LAUNCH_CHECK(ctx, "nms_small_kernel");
         if (cap <= small_limit) return FDMS_OK;  // no segment can be larger
     }

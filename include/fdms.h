@@ -145,7 +145,7 @@ FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs
  * IoU > thr, no +1, NaN never suppresses.  n_seg independent segments in one call.
  * Segment g reads n = min(count[g], cap) items: box (x1,y1,x2,y2) at
  * rows + (g*cap + i)*row_stride + box_off, score at ... + score_off, tie[g*cap + i]
- * (tie == NULL means tie = i).  If n > max_nms only the max_nms best-ranked are considered
+ * (tie == NULL means tie = i; tie values must be unique inside a segment).  If n > max_nms only the max_nms best-ranked are considered
  * (utils/general.py:578-579).  keep[g*cap + k] = item index i of the k-th kept box in score
  * order; n_keep[g] = number kept. */
 FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off,

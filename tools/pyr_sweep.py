@@ -17,8 +17,8 @@ geoms = [_lib.letterbox_geometry(H, W, s, auto=True, stride=32) for s in sizes]
 outs = [torch.empty((B, 3, g.dst_h, g.dst_w), dtype=torch.float16, device=dev) for g in geoms]
 bytes_ = B * (H * W * 3 + sum(3 * g.dst_h * g.dst_w * 2 for g in geoms))
 ref = None
-for kb in (56, 40, 32, 24, 16, 12):
-    for th in (32, 16, 8, 4):
+for kb in (56, 40, 32, 24):
+    for th in (16, 8, 4):
         os.environ["FDMS_PYR_SMEM_KB"], os.environ["FDMS_PYR_TH"] = str(kb), str(th)
         _lib._tls.ctx = {}
         for i in range(5):

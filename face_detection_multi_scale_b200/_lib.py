@@ -51,8 +51,8 @@ _SIGS = {
     "fdms_decode_dense": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "fdms_decode_filter": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "fdms_filter_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_int, C.c_void_p]),
+    "fdms_filter_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fdms_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                            C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -65,6 +65,9 @@ _SIGS = {
                                     C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_weighted_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdms_bbox_overlaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fdms_pack_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_postprocess": (C.c_int, [C.c_void_p, C.POINTER(PostDesc), C.c_void_p]),
 }
 

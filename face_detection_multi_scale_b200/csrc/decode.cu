@@ -269,18 +269,18 @@ __global__ void __launch_bounds__(DENSE_THREADS) decode_dense_kernel(const __gri
 constexpr int FLT_THREADS = 256;
 
 __global__ void __launch_bounds__(FLT_THREADS)
-    filter_pred_kernel(const void *__restrict__ pred, int dtype, int bs, long long rows, float thres,
+    filter_pred_kernel(const void *__restrict__ pred, int dtype, int bs, long long rows, int no, float thres,
                        float *__restrict__ cand, int32_t *__restrict__ cand_row, int32_t *__restrict__ count, int cap) {
     const int b = blockIdx.y;
     const long long r = (long long)blockIdx.x * FLT_THREADS + threadIdx.x;
     bool pass = false;
     float conf = 0.f;
-    const long long base = ((long long)b * rows + r) * NO;
+    const long long base = ((long long)b * rows + r) * no;
     if (r < rows) {
         float obj = ld_f(pred, dtype, base + 4);
-        if (obj > thres) {
-            conf = f_mul(ld_f(pred, dtype, base + 5), obj);
-            pass = conf > thres;
+        if (obj > thres) {                                       // general.py:515
+            conf = f_mul(ld_f(pred, dtype, base + 5), obj);      // :547
+            pass = conf > thres;                                 // :563
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -292,13 +292,16 @@ __global__ void __launch_bounds__(FLT_THREADS)
     if (pass) {
         int pos = basepos + __popc(m & ((1u << lane) - 1u));
         if (pos < cap) {
-            float o[NO];
-#pragma unroll
-            for (int c = 0; c < NO; c++) o[c] = ld_f(pred, dtype, base + c);
-            row_to_candidate(o, conf);
-            float *dst = cand + ((long long)b * cap + pos) * NO;
-#pragma unroll
-            for (int c = 0; c < NO; c++) dst[c] = o[c];
+            const float cx = ld_f(pred, dtype, base), cy = ld_f(pred, dtype, base + 1);
+            const float hw = f_div(ld_f(pred, dtype, base + 2), 2.f), hh = f_div(ld_f(pred, dtype, base + 3), 2.f);
+            float *dst = cand + ((long long)b * cap + pos) * no;
+            dst[0] = f_sub(cx, hw);  // xywh2xyxy, general.py:299-306
+            dst[1] = f_sub(cy, hh);
+            dst[2] = f_add(cx, hw);
+            dst[3] = f_add(cy, hh);
+            dst[4] = conf;
+            dst[5] = 0.f;  // class index (nc == 1)
+            for (int c = 6; c < no; c++) dst[c] = ld_f(pred, dtype, base + c);  // keypoints pass through (:561)
             cand_row[(long long)b * cap + pos] = (int)r;
         }
     }
@@ -412,16 +415,17 @@ FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_le
     return FDMS_OK;
 }
 
-FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, float conf_thres,
-                              float *cand, int32_t *cand_row, int32_t *count, int cap, fdms_stream stream) {
+FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, int no,
+                              float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
+                              fdms_stream stream) {
     if (int rc = fdms_bind(ctx)) return rc;
-    if (!pred || !cand || !cand_row || !count || bs <= 0 || bs > 65535 || rows <= 0 || cap <= 0 ||
-        (dtype != FDMS_F16 && dtype != FDMS_F32) || rows > 0x7fffffffLL)
+    if (!pred || !cand || !cand_row || !count || bs <= 0 || bs > 65535 || rows <= 0 || cap <= 0 || no < 6 ||
+        (no - 6) % 3 != 0 || (dtype != FDMS_F16 && dtype != FDMS_F32) || rows > 0x7fffffffLL)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_filter_pred: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs, st));
     dim3 grid((unsigned)ceil_div64(rows, FLT_THREADS), bs);
-    filter_pred_kernel<<<grid, FLT_THREADS, 0, st>>>(pred, dtype, bs, rows, conf_thres, cand, cand_row, count, cap);
+    filter_pred_kernel<<<grid, FLT_THREADS, 0, st>>>(pred, dtype, bs, rows, no, conf_thres, cand, cand_row, count, cap);
     FDMS_LAUNCH_CHECK(ctx, "filter_pred_kernel");
     return FDMS_OK;
 }

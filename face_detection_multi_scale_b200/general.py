@@ -40,17 +40,20 @@ def _cuda(t):
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
                         labels=(), kpt_label=5, nc=None, iou_mode=None):
-    """utils/general.py:506.  prediction (bs, rows, 21) -> list of (n, 21) tensors
-    [x1, y1, x2, y2, conf, cls, 15 kpt] per image, (0, 6) zeros for images without detections (:527).
+    """utils/general.py:506.  prediction (bs, rows, no) with nc == 1 (no = 21 for the face head, 6 without
+    keypoints) -> list of (n, no) tensors [x1, y1, x2, y2, conf, cls, kpts...] per image, (0, 6) zeros for images
+    without detections (:527).
     One filter launch + one batched NMS (3 launches) + one gather for the whole batch; a single
     device->host read of the per-image counts."""
     if prediction.dim() != 3:
         raise ValueError("non_max_suppression: prediction must be (bs, rows, no)")
     if nc is None:
         nc = prediction.shape[2] - 5 if not kpt_label else prediction.shape[2] - 5 - kpt_label * 3
-    if prediction.shape[2] != ops.NO or kpt_label != 5 or nc != 1:
-        raise NotImplementedError("non_max_suppression on libfdms covers the face head (no=21: nc=1, kpt_label=5); got "
-                                  "no=%d kpt_label=%r nc=%r" % (prediction.shape[2], kpt_label, nc))
+    no = prediction.shape[2]
+    if nc != 1 or no < 6 or (no - 6) % 3:
+        raise NotImplementedError("non_max_suppression on libfdms covers single-class heads (nc=1, no = 6 + 3*kpt: the "
+                                  "face head no=21, or the [..., :6] fallback of msfd:134); got no=%d kpt_label=%r nc=%r"
+                                  % (no, kpt_label, nc))
     if labels:
         raise NotImplementedError("non_max_suppression: autolabelling `labels` is not on the hot path")
     # multi_label &= nc > 1 (:522) -> always False here; agnostic only changes the class offset, 0 for nc == 1
@@ -81,7 +84,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     kmax = int(n_keep.max())
     if kmax == 0:
         return [empty] * bs
-    out = ops.gather_rows(c.cand, c.keep, c.n_keep, ops.NO, kmax)
+    out = ops.gather_rows(c.cand, c.keep, c.n_keep, no, kmax)
     if out.dtype != src_dtype:
         out = out.to(src_dtype)
     if out.device != src_device:

@@ -112,9 +112,9 @@ def decode_dense(levels, strides, anchors_px):
 class Candidates:
     """Device-side candidate lists of n_seg segments (see include/fdms.h fdms_decode_filter)."""
 
-    def __init__(self, n_seg, cap, device):
+    def __init__(self, n_seg, cap, device, no=NO):
         self.n_seg, self.cap = n_seg, cap
-        self.cand = torch.empty((n_seg, cap, NO), dtype=torch.float32, device=device)
+        self.cand = torch.empty((n_seg, cap, no), dtype=torch.float32, device=device)
         self.row = torch.empty((n_seg, cap), dtype=torch.int32, device=device)
         self.count = torch.zeros((n_seg,), dtype=torch.int32, device=device)
         self.keep = torch.empty((n_seg, cap), dtype=torch.int32, device=device)
@@ -136,16 +136,16 @@ def decode_filter(scales_levels, strides, anchors_px, conf_thres, cap, out=None)
 
 
 def filter_pred(pred, conf_thres, cap, out=None):
-    """Confidence filter + xywh2xyxy on a decoded pred (bs, rows, 21) fp16/fp32."""
+    """Confidence filter + xywh2xyxy on a decoded pred (bs, rows, 6 + 3*kpt) fp16/fp32 (nc == 1)."""
     dev = _dev(pred)
-    if pred.dim() != 3 or pred.shape[2] != NO or pred.dtype not in (torch.float16, torch.float32):
-        raise ValueError("filter_pred: pred must be (bs, rows, 21) fp16/fp32")
+    if pred.dim() != 3 or pred.shape[2] < 6 or (pred.shape[2] - 6) % 3 or pred.dtype not in (torch.float16, torch.float32):
+        raise ValueError("filter_pred: pred must be (bs, rows, 6 + 3*kpt) fp16/fp32")
     pred = pred.contiguous()
-    bs, rows, _ = pred.shape
+    bs, rows, no = pred.shape
     if out is None:
-        out = Candidates(bs, cap, pred.device)
+        out = Candidates(bs, cap, pred.device, no)
     c = _lib.ctx(dev)
-    rc = _lib.lib().fdms_filter_pred(c.handle, _ptr(pred), _DT[pred.dtype], bs, rows, float(np.float32(conf_thres)),
+    rc = _lib.lib().fdms_filter_pred(c.handle, _ptr(pred), _DT[pred.dtype], bs, rows, no, float(np.float32(conf_thres)),
                                      _ptr(out.cand), _ptr(out.row), _ptr(out.count), out.cap, _stream(dev))
     c.check(rc, "fdms_filter_pred")
     return out

@@ -134,10 +134,14 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
                                 float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
                                 fdms_stream stream);
 
-/* Same filter + box conversion, reading an already decoded pred (bs, rows, 21) f16/f32:
- * the front half of utils/general.py:506-600 non_max_suppression.  Segment g = b. */
-FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, float conf_thres,
-                              float *cand, int32_t *cand_row, int32_t *count, int cap, fdms_stream stream);
+/* Same filter + box conversion, reading an already decoded pred (bs, rows, no) f16/f32 with
+ * no = 6 + 3*kpt_label columns (nc == 1): the front half of utils/general.py:506-600
+ * non_max_suppression for kpt_label = 5 (no = 21, every cfg of the reference), kpt_label = 0
+ * (no = 6, the `pred[..., :6]` fallback at multi_scale_face_detector.py:134) or any other keypoint
+ * count.  Candidate rows have `no` floats.  Segment g = b. */
+FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, int no,
+                              float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
+                              fdms_stream stream);
 
 /* ---- batched NMS -------------------------------------------------------------------------
  * torchvision.ops.nms as called at utils/general.py:584 and multi_scale_face_detector.py:234:
@@ -213,6 +217,21 @@ typedef struct fdms_post_desc {
 } fdms_post_desc;
 
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_stream stream);
+
+/* ---- "next" rows around the hot path ---------------------------------------------
+ * widerface_evaluate/box_overlaps.pyx:15-55 bbox_overlaps: (n,4) x (k,4) float64 boxes -> (n,k) float64
+ * IoU with the +1 pixel convention (0 where the boxes do not overlap). */
+FDMS_API int fdms_bbox_overlaps(fdms_ctx *ctx, const double *boxes, int64_t n, const double *query, int64_t k,
+                                double *overlaps, fdms_stream stream);
+
+/* Padded per-frame output tensors of the production driver: normalised boxes x/img_w, y/img_h in float64
+ * (utils/preprocess_yolo_predict.py:26-49, yolov7_face_multi_scale_dataframe_predict.py:699-716) padded with
+ * -1 to max_faces per frame (utils/preprocess_yolo_predict.py:478-520).  dets/n_out as produced by
+ * fdms_merge_scales.  bboxes (n_img, max_faces, 4) f64, confidence (n_img, max_faces) f64,
+ * class_indexes / scale_used (n_img, max_faces) i32. */
+FDMS_API int fdms_pack_frames(fdms_ctx *ctx, const float *dets, const int32_t *n_out, int n_img, int out_cap,
+                              int max_faces, int img_w, int img_h, double *bboxes, double *confidence,
+                              int32_t *class_indexes, int32_t *scale_used, fdms_stream stream);
 
 #ifdef __cplusplus
 }

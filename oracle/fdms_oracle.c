@@ -413,3 +413,27 @@ FO_EXPORT int64_t fo_weighted_nms(const double *dets, int64_t n, int n_scales, d
     free(w); free(boxes); free(scores);
     return nk;
 }
+
+/* ------------------------------------------------------------------------- */
+/* "next" row: WIDER-FACE evaluation IoU matrix             */
+/*     widerface_evaluate/box_overlaps.pyx:15-55 (float64, +1 pixel convention; */
+/*     entries stay 0 where iw <= 0 or ih <= 0).  overlaps is (N, K) row major.  */
+/* ------------------------------------------------------------------------- */
+FO_EXPORT void fo_bbox_overlaps(const double *boxes, int64_t N, const double *query, int64_t K, double *overlaps) {
+    for (int64_t i = 0; i < N * K; i++) overlaps[i] = 0.0;
+    for (int64_t k = 0; k < K; k++) {
+        const double *q = query + k * 4;
+        double box_area = (q[2] - q[0] + 1) * (q[3] - q[1] + 1); /* :33-36 */
+        for (int64_t n = 0; n < N; n++) {
+            const double *b = boxes + n * 4;
+            double iw = fmin(b[2], q[2]) - fmax(b[0], q[0]) + 1; /* :38-41 */
+            if (iw > 0) {
+                double ih = fmin(b[3], q[3]) - fmax(b[1], q[1]) + 1; /* :43-46 */
+                if (ih > 0) {
+                    double ua = (b[2] - b[0] + 1) * (b[3] - b[1] + 1) + box_area - iw * ih; /* :48-52 */
+                    overlaps[n * K + k] = iw * ih / ua;                                    /* :53 */
+                }
+            }
+        }
+    }
+}

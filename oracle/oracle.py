@@ -225,3 +225,12 @@ def detect_from_heads(heads_per_scale, in_hw_per_scale, img0_shape, strides, anc
         return np.array([]), per_scale  # msfd:285
     merged = np.vstack(nonempty)
     return weighted_nms(merged, len(heads_per_scale), iou_thres), per_scale
+
+
+# ---- next row: widerface_evaluate/box_overlaps.pyx:15-55 ----------------------------------------
+def bbox_overlaps(boxes, query_boxes):
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+    query_boxes = np.ascontiguousarray(query_boxes, np.float64).reshape(-1, 4)
+    out = np.zeros((boxes.shape[0], query_boxes.shape[0]), np.float64)
+    lib().fo_bbox_overlaps(_p(boxes), C.c_int64(boxes.shape[0]), _p(query_boxes), C.c_int64(query_boxes.shape[0]), _p(out))
+    return out

@@ -335,10 +335,89 @@ def gen_e2e():
     save("e2e", **out)
 
 
+def gen_nms6():
+    """non_max_suppression on a 6-column prediction (kpt_label=0: the no-keypoint single-class head) and on a
+    12-column one (kpt_label=2), both cut from the tiny model's decoded output."""
+    out = {}
+    g = np.load(os.path.join(HERE, "head.npz"))
+    pred = torch.from_numpy(g["tiny_pred"])
+    thr = float(g["tiny_conf_thres"])
+    for cols, kl in ((6, 0), (12, 2)):
+        p = pred[..., :cols].contiguous()
+        res = quiet(non_max_suppression, p, thr, 0.45, kpt_label=kl)
+        for b, r in enumerate(res):
+            out["c%d_b%d" % (cols, b)] = r.numpy()
+    out["thr"] = np.array(thr)
+    save("nms6", **out)
+
+
+def gen_bbox():
+    """widerface_evaluate/box_overlaps.pyx::bbox_overlaps, the reference's own Cython code built by
+    `make -C oracle _ref/box_overlaps.so` (np.float was removed from NumPy; the module only needs the alias)."""
+    import importlib.machinery
+    import importlib.util
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/box_overlaps.so"])
+    np.float = float
+    loader = importlib.machinery.ExtensionFileLoader("box_overlaps", os.path.join(ROOT, "oracle", "_ref", "box_overlaps.so"))
+    mod = importlib.util.module_from_spec(importlib.util.spec_from_loader("box_overlaps", loader))
+    loader.exec_module(mod)
+    rng = np.random.default_rng(3)
+    out = {}
+    for i, (n, k, integer) in enumerate([(300, 40, True), (1000, 7, False), (1, 1, True), (50, 0, True), (0, 5, True)]):
+        def boxes(m):
+            xy = rng.uniform(0, 400, (m, 2)); wh = rng.uniform(0, 120, (m, 2))
+            b = np.concatenate([xy, xy + wh], 1)
+            return np.round(b) if integer else b
+        a, q = boxes(n), boxes(k)
+        out["b%d" % i], out["q%d" % i] = a, q
+        out["o%d" % i] = mod.bbox_overlaps(np.ascontiguousarray(a, np.float64), np.ascontiguousarray(q, np.float64))
+    save("bbox", **out)
+
+
+def gen_pack():
+    """normalize_bbox + create_yolo_json_format (utils/preprocess_yolo_predict.py:26-49,478-571) on synthetic merged
+    detections, assembled per frame exactly like yolov7_face_multi_scale_dataframe_predict.py:699-716."""
+    from utils.preprocess_yolo_predict import create_yolo_json_format, normalize_bbox
+    rng = np.random.default_rng(21)
+    W, H = 1920, 1080
+    counts = [5, 0, 12, 1]
+    frames, dets_all = [], []
+    for fi, n in enumerate(counts):
+        xy = np.round(rng.uniform(0, 1000, (n, 2))); wh = np.round(rng.uniform(5, 300, (n, 2)))
+        d = np.zeros((n, 7), np.float32)
+        d[:, :2], d[:, 2:4] = xy, xy + wh
+        d[:, 4] = rng.uniform(0.5, 1, n).astype(np.float32)
+        d[:, 6] = rng.integers(0, 3, n)
+        dets_all.append(d)
+        fd = {"num_faces": n, "bboxes": [], "confidence": [], "class_names": [], "class_indexes": [], "class_groups": [],
+              "infer_time": 0.01 * (fi + 1)}
+        for r in d:  # :708-716
+            fd["bboxes"].append(normalize_bbox([float(v) for v in r[:4]], W, H))
+            fd["confidence"].append(float(r[4]))
+            fd["class_names"].append("face"); fd["class_indexes"].append(0); fd["class_groups"].append("face")
+        frames.append(fd)
+    js = create_yolo_json_format(frames)["yolo_face_prediction"]
+    out = {"counts": np.array(counts), "wh": np.array([W, H])}
+    for fi, d in enumerate(dets_all):
+        out["dets%d" % fi] = d
+    out["bboxes"] = np.array(js[0]["data"], np.float64)
+    out["confidence"] = np.array(js[1]["data"], np.float64)
+    out["class_indexes"] = np.array(js[3]["data"], np.int32)
+    out["shape"] = np.array(js[0]["shape"])
+    save("pack", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        globals()["gen_" + sys.argv[1]]()
+        sys.exit(0)
     gen_letterbox()
     gen_head()
     gen_nms()
     gen_rescale()
     gen_merge()
     gen_e2e()
+    gen_nms6()
+    gen_bbox()
+    gen_pack()

@@ -227,3 +227,16 @@ def test_detector_batch_equals_single_and_capacity_growth():
         assert det.last_landmarks[b].shape == (len(ref), 15)
     with pytest.raises(RuntimeError):
         MultiScaleFaceDetector(model, device="cpu")
+
+
+def test_nms_other_keypoint_counts(golden):
+    """kpt_label = 0 (no = 6: the head without landmarks / the [..., :6] call of msfd:134) and kpt_label = 2."""
+    g, h = golden("nms6"), golden("head")
+    thr = float(g["thr"])
+    for cols, kl in ((6, 0), (12, 2)):
+        pred = torch.from_numpy(np.ascontiguousarray(h["tiny_pred"][..., :cols])).to(DEV)
+        res = general.non_max_suppression(pred, thr, 0.45, kpt_label=kl, iou_mode=ops.IOU_TV_CPU)
+        for b in range(2):
+            assert np.array_equal(res[b].cpu().numpy(), g["c%d_b%d" % (cols, b)])
+    with pytest.raises(NotImplementedError):  # kpt_label=5 on 6 columns gives nc = -14 in the reference
+        general.non_max_suppression(torch.zeros((1, 10, 6), device=DEV), kpt_label=5)

@@ -203,3 +203,13 @@ def test_e2e_golden(golden, case):
     assert np.array_equal(final, ref)
     if n_faces:
         assert ref.shape[0] >= 3
+
+
+def test_nms_other_keypoint_counts(golden):
+    """non_max_suppression on 6- and 12-column predictions (kpt_label 0 / 2, nc = 1): reference golden."""
+    g, h = golden("nms6"), golden("head")
+    thr = float(g["thr"])
+    for cols in (6, 12):
+        res = O.non_max_suppression(np.ascontiguousarray(h["tiny_pred"][..., :cols]), thr, 0.45, O.TV_CPU)
+        for b in range(2):
+            assert np.array_equal(res[b], g["c%d_b%d" % (cols, b)])

@@ -223,9 +223,9 @@ template <> struct Out<uint8_t> {
 };
 
 struct TileShared {
-    // per row: x = 2 * (slot after which the row is emitted) + same-slot flag (-2: border row), y = b0 | b1 << 16;
+    // per row: x = 2 * (slot after which the row is emitted) + same-slot flag (-2: border row), y = b0, z = b1;
     // one sentinel entry past the last row
-    int2 rowmeta[PYR_MAX_TH + 1];
+    int4 rowmeta[PYR_MAX_TH + 1];
     int slot_row[PYR_MAX_SLOTS];
     int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
     alignas(8) unsigned long long bar;
@@ -279,14 +279,16 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     const bool edge = !(inA && inB);
     unsigned off = 0;
     int j = 0;
-    int2 rm = sh.rowmeta[0];
+    const int4 *rmp = sh.rowmeta;
+    int4 rm = rmp[0];
 
     if (MODE == PM_POINT) {  // one slot per interior row; border rows interleave
         for (int k = 0;; k++) {
             while (rm.x < 0) {  // border rows due before slot k
                 border_row<T>(pc, off, xs, tborder, true, true);
                 off += ys;
-                rm = sh.rowmeta[++j];
+                ++j;
+                rm = *++rmp;
             }
             if (k >= n_used) break;
             unsigned hA[3], hB[3];
@@ -295,7 +297,8 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
 #pragma unroll
             for (int c = 0; c < 3; c++) Out<T>::store2_bits(pc[c] + off, hA[c], hB[c]);
             off += ys;
-            rm = sh.rowmeta[++j];
+            ++j;
+            rm = *++rmp;
         }
         return;
     }
@@ -307,10 +310,11 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
             if (rm.x < 0) {
                 border_row<T>(pc, off, xs, tborder, two, vec);
             } else {
-                const unsigned b0s = (unsigned)rm.y & 0xffffu, b1s = (unsigned)rm.y >> 16;
-                if (rm.x & 1) {  // both taps in the same slot (clamped row / zero lower weight): rows are
-#pragma unroll               // visited in source order, so slot k-1 is dead from here on
+                const unsigned b0s = (unsigned)rm.y, b1s = (unsigned)rm.z;
+                if (__builtin_expect(rm.x & 1, 0)) {  // both taps in the same slot (clamped row / zero lower weight):
+#pragma unroll                                        // rows are visited in source order, so slot k-1 is dead from here on
                     for (int c = 0; c < 6; c++) other[c] = cur[c];
+                    asm volatile("" ::: "memory");  // keep this a (CTA-uniform) branch, not six predicated moves
                 }
                 if (MODE == PM_HALF) {
 #pragma unroll
@@ -325,7 +329,7 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
             }
             off += ys;
             j++;
-            rm = sh.rowmeta[j];
+            rm = *++rmp;
         }
     };
 
@@ -512,8 +516,9 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             sh.n_rows = n_rows;
         }
         if (lane <= n_rows)
-            sh.rowmeta[lane] = lane == n_rows ? make_int2(0x7ffffffe, 0)
-                                              : make_int2(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2, (int)b01);
+            sh.rowmeta[lane] = lane == n_rows ? make_int4(0x7ffffffe, 0, 0, 0)
+                                              : make_int4(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2,
+                                                          (int)(b01 & 0xffffu), (int)(b01 >> 16), 0);
     }
     __syncthreads();
     const int n_used = sh.n_used, g0 = sh.g0;

@@ -43,7 +43,12 @@ def build_lib(force=False, verbose=False):
     """Compile csrc/*.cu into libfdms.so if missing or older than its sources. Returns the path."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
+    try:
+        nvcc = _nvcc()
+    except RuntimeError:
+        if os.path.exists(LIB) and not force:  # e.g. a deployment box without the toolkit: use the shipped build
+            return LIB
+        raise
     os.makedirs(OBJ_DIR, exist_ok=True)
 
     def compile_one(src):

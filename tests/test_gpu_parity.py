@@ -347,3 +347,67 @@ def test_e2e_postprocess_golden(golden, case):
     nk = plan.cands.n_keep.cpu().numpy()
     for si in range(len(sizes)):
         assert nk[si] == g["%s_scale%d" % (name, si)].shape[0]
+
+
+# =============================================================================== edge cases
+def test_edge_thresholds_and_degenerate_boxes():
+    """conf/iou thresholds at the ends of their range, NaN / zero-area / identical boxes, negative coordinates."""
+    rng = np.random.default_rng(3)
+    n = 700
+    xy = rng.uniform(-50, 300, (n, 2)); wh = rng.uniform(0, 60, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    boxes[::50, 2:] = boxes[::50, :2]            # zero-area boxes (IoU 0/0 = NaN never suppresses)
+    boxes[5] = boxes[6] = boxes[7]               # exact duplicates
+    boxes[11, 0] = np.nan                        # NaN coordinate: never suppressed, never suppresses
+    scores = rng.uniform(0, 1, n).astype(np.float32)
+    scores[5] = scores[6] = scores[7] = 0.5
+    for t in (0.0, 1e-9, 0.3, 0.999999, 1.0):
+        for mode in (ops.IOU_TV_CPU, ops.IOU_TV_CUDA):
+            ref = O.nms(boxes, scores, t, mode)
+            got = ops.nms(gpu(boxes), gpu(scores), t, mode).cpu().numpy()
+            assert np.array_equal(got, ref), (t, mode)
+
+
+@pytest.mark.parametrize("conf", [0.0, 1.0, 0.999999])
+def test_decode_filter_extreme_conf_thresholds(conf):
+    levels = _crowd("crowdB")
+    ref_pred = O.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    c = ops.decode_filter([[gpu(l) for l in levels]], synth.P5_STRIDES, synth.P5_ANCHORS, conf, cap=ref_pred.shape[1])
+    for b in range(ref_pred.shape[0]):
+        rc, rr = O.filter_xyxy(ref_pred[b], conf)
+        cand, rows = _sorted_cands(c, b)
+        assert np.array_equal(rows, rr)
+        if len(rr):
+            assert np.max(np.abs(cand - rc)) <= TOL_PX
+
+
+def test_postprocess_all_empty_and_single_scale():
+    """No candidate anywhere (background only) and a 1-scale detector (weights: S=1 => s >= S-2 and s == S//2)."""
+    rng = np.random.default_rng(0)
+    lv = [rng.standard_normal((2, 63, 12, 20)).astype(np.float32) - 8.0, rng.standard_normal((2, 63, 6, 10)).astype(np.float32) - 8.0,
+          rng.standard_normal((2, 63, 3, 5)).astype(np.float32) - 8.0]
+    plan = ops.PostPlan([[gpu(l) for l in lv]], synth.P5_STRIDES, synth.P5_ANCHORS, [96], (270, 480), 0.5, 0.5, cap=64,
+                        out_cap=64)
+    out = plan.run()
+    assert out.n_out.cpu().tolist() == [0, 0] and plan.cands.count.cpu().tolist() == [0, 0]
+    heads, shapes = H.e2e_heads(200, 200, [128], 10, False, 34)
+    sl = [[gpu(l[None]) for l in heads[shapes[0]]]]
+    plan = ops.PostPlan(sl, synth.P5_STRIDES, synth.P5_ANCHORS, [shapes[0][0]], (200, 200), 0.5, 0.5, cap=512, out_cap=512,
+                        iou_mode=ops.IOU_TV_CPU)
+    out = plan.run()
+    ref, _ = O.detect_from_heads([[l[None] for l in heads[shapes[0]]]], shapes, (200, 200, 3), synth.P5_STRIDES,
+                                 synth.P5_ANCHORS, 0.5, 0.5, O.TV_CPU)
+    n = int(out.n_out[0])
+    assert n == len(ref) and np.array_equal(out.dets[0, :n].cpu().numpy().astype(np.float64), ref)
+
+
+def test_w6_maximum_rows_single_segment():
+    """The largest pred of the reference's configs: yolov7-w6 at 1536 (85 680 rows), every row a candidate, so the
+    candidate count exceeds max_nms = 30000 and the best 30000 enter NMS (utils/general.py:578-579)."""
+    rows = 85680
+    p = synth.synth_pred(rows, 2000, 40, 5, extent=(896.0, 1536.0))
+    p[:, 4] = np.maximum(p[:, 4], 0.8); p[:, 5] = np.maximum(p[:, 5], 0.8)
+    from face_detection_multi_scale_b200 import general
+    res = general.non_max_suppression(torch.from_numpy(p[None]).to(DEV), 0.5, 0.45, iou_mode=ops.IOU_TV_CPU)[0]
+    ref = O.non_max_suppression(p[None], 0.5, 0.45, O.TV_CPU)[0]
+    assert res.shape == ref.shape and np.array_equal(res.cpu().numpy(), ref)

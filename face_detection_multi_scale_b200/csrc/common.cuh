@@ -31,15 +31,14 @@ struct fdms_ctx {
     int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
-    fdms_buf sort_a, sort_b;   // NMS: 64-bit keys ping-pong
-    fdms_buf idx_a, idx_b;     // NMS: item indices ping-pong
+    fdms_buf sort_a;           // NMS: 64-bit keys of segments too large for shared memory
+    fdms_buf idx_a, idx_b;     // NMS: item indices (sort scratch / score order)
     fdms_buf boxes;            // NMS: boxes in score order (float4)
     fdms_buf mask;             // NMS: suppression bit matrix
     fdms_buf seginfo;          // NMS: per segment {n, nblk, mask_off}
     fdms_buf merge_rows;       // merge: (n_img, mcap, 8) rows
     fdms_buf merge_cnt;        // merge: counts
     fdms_buf merge_keep;       // merge: keep + n_keep
-    fdms_buf flags;            // misc device flags
     fdms_buf pyr_tab;          // pyramid tap tables of the last geometry
     unsigned long long pyr_tab_key = 0;
 };

@@ -94,13 +94,13 @@ class MultiScaleFaceDetector:
             return img0
         return img
 
-    def _pyramid(self, batch_dev, sizes=None):
+    def _pyramid(self, batch_dev, sizes=None, ctx=None):
         """(B, H, W, 3) uint8 BGR on the device -> one (B, 3, Hs, Ws) model input per scale, one launch."""
         _, h, w, _ = batch_dev.shape
         geoms, virt = self._geoms(h, w, sizes)
         dtype = torch.float16 if self.half else torch.float32
         # cv2 decodes BGR; both branches of the reference feed RGB to the model (msfd:96 / ppyp:363)
-        outs = ops.pyramid(batch_dev, geoms, out_dtype=dtype, layout="chw", flip_rb=True, virt_hw=virt)
+        outs = ops.pyramid(batch_dev, geoms, out_dtype=dtype, layout="chw", flip_rb=True, virt_hw=virt, ctx=ctx)
         return outs, geoms
 
     def preprocess_image(self, img_path, img_size):
@@ -133,38 +133,102 @@ class MultiScaleFaceDetector:
         return a
 
     # ------------------------------------------------------------------ fused batch path
-    def _plan(self, scales_levels, in_h, orig_hw):
+    def _plan(self, scales_levels, in_h, orig_hw, lane=None):
+        plans = self._plans if lane is None else lane.plans
         bs = scales_levels[0][0].shape[0]
         key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), tuple(orig_hw),
                self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode)
-        plan = self._plans.get(key)
+        plan = plans.get(key)
         if plan is None:
             out_cap = self.out_cap or self.cap
             plan = ops.PostPlan(scales_levels, self.strides, self.anchors_px, in_h, orig_hw, self.conf_thres,
                                 self.iou_thres, self.cap, out_cap, iou_mode=self.iou_mode,
-                                with_kpts=self.with_landmarks)
-            if len(self._plans) > 8:
-                self._plans.clear()
-            self._plans[key] = plan
+                                with_kpts=self.with_landmarks, ctx=None if lane is None else lane.ctx)
+            if len(plans) > 8:
+                plans.clear()
+            plans[key] = plan
         else:
             plan.rebind(scales_levels)
         return plan
 
-    def detect_batch_device(self, batch_dev):
-        """Enqueue the whole multi-scale path for a (B, H, W, 3) uint8 BGR device batch.  Returns the plan whose
-        `.out` (dets, n_out) and `.cands` (count, n_keep) stay on the device -- no synchronisation here."""
+    def detect_batch_device(self, batch_dev, lane=None):
+        """Enqueue the whole multi-scale path for a (B, H, W, 3) uint8 BGR device batch on the current stream.
+        Returns the plan whose `.out` (dets, n_out) and `.cands` (count, n_keep) stay on the device -- no
+        synchronisation here.  `lane` (see detect_stream) supplies its own native context and plan cache."""
         _, h, w, _ = batch_dev.shape
-        xs, geoms = self._pyramid(batch_dev)
+        xs, geoms = self._pyramid(batch_dev, ctx=None if lane is None else lane.ctx)
         scales_levels = [self._raw_heads(x) for x in xs]
-        plan = self._plan(scales_levels, [g.dst_h for g in geoms], (h, w))
+        plan = self._plan(scales_levels, [g.dst_h for g in geoms], (h, w), lane)
         plan.run()
         return plan
+
+    @staticmethod
+    def _meta(plan):
+        """Device vector [n_out..., max count, min n_keep, max merged_in, sum count, sum n_keep] (one D2H)."""
+        o, c = plan.out, plan.cands
+        return torch.cat((o.n_out, torch.stack((c.count.max(), c.n_keep.min(), o.merged_in.max(), c.count.sum(),
+                                                c.n_keep.sum())).to(torch.int32)))
+
+    class _Lane:
+        """Resources of one in-flight batch of detect_stream: stream, native context, plan cache, pinned results."""
+
+        def __init__(self, device):
+            self.stream = torch.cuda.Stream(device)
+            self.ctx = _lib.Ctx(device.index)
+            self.plans = {}
+            self.img_dev = self.h_dets = self.h_meta = self.h_kpts = None
+            self.done = torch.cuda.Event()
+            self.plan = None
+            self.src = None
+
+    def detect_stream(self, batches, depth=2):
+        """Pipelined detection over an iterable of (B, H, W, 3) uint8 BGR host batches (pinned memory overlaps best):
+        the H2D copy and kernels of batch i+1 are enqueued while batch i is in flight and batch i-1 is being read
+        back, on `depth` streams with one native context each.  Yields, in order, the same per-batch result as
+        detect_multi_scale_batch.  A batch that exceeds a capacity is transparently redone synchronously."""
+        lanes = [self._Lane(self.device) for _ in range(max(1, int(depth)))]
+        pending = []
+
+        def finish(lane):
+            lane.done.synchronize()
+            meta = lane.h_meta.numpy()
+            n_out, head = meta[:-5], meta[-5:]
+            if head[0] > lane.plan.cands.cap or head[2] > lane.plan.out.out_cap or head[1] < 0:
+                return self.detect_multi_scale_batch(lane.src)  # rare: grow capacities on the synchronous path
+            kmax = int(n_out.max()) if n_out.size else 0
+            dets = lane.h_dets[:, :kmax].numpy().astype(np.float64)
+            return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
+
+        for i, batch in enumerate(batches):
+            lane = lanes[i % len(lanes)]
+            if lane.plan is not None and any(l is lane for l in pending):
+                pending.remove(lane)
+                yield finish(lane)
+            t = batch if isinstance(batch, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(batch))
+            if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
+                raise ValueError("detect_stream: expected (B, H, W, 3) uint8 batches")
+            with torch.cuda.stream(lane.stream):
+                if lane.img_dev is None or lane.img_dev.shape != t.shape:
+                    lane.img_dev = torch.empty(t.shape, dtype=torch.uint8, device=self.device)
+                lane.img_dev.copy_(t, non_blocking=True)
+                plan = self.detect_batch_device(lane.img_dev, lane)
+                o = plan.out
+                if lane.h_dets is None or lane.h_dets.shape != o.dets.shape:
+                    lane.h_dets = torch.empty(o.dets.shape, dtype=torch.float32).pin_memory()
+                    lane.h_meta = torch.empty((o.n_out.numel() + 5,), dtype=torch.int32).pin_memory()
+                lane.h_dets.copy_(o.dets, non_blocking=True)
+                lane.h_meta.copy_(self._meta(plan), non_blocking=True)
+                lane.done.record(lane.stream)
+            lane.plan, lane.src = plan, t
+            pending.append(lane)
+        for lane in pending:
+            yield finish(lane)
 
     def _collect(self, plan):
         """One device->host read of the results of `plan`; raises if a capacity was exceeded."""
         o, c = plan.out, plan.cands
-        both = torch.cat((o.n_out, torch.stack((c.count.max(), c.n_keep.min(), o.merged_in.max())))).cpu().numpy()
-        n_out, head = both[:-3], both[-3:]  # one read, synchronises
+        both = self._meta(plan).cpu().numpy()
+        n_out, head = both[:-5], both[-5:]  # one read, synchronises
         if head[0] > c.cap or head[2] > o.out_cap:
             return None, head
         if head[1] < 0:
@@ -197,8 +261,8 @@ class MultiScaleFaceDetector:
                 self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
             self._plans.clear()
         dets, n_out, kpts = res
-        self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(plan.cands.count.sum()),
-                           "kept_per_scale": int(plan.cands.n_keep.sum()), "final": int(n_out.sum())}
+        self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]),
+                           "kept_per_scale": int(head[4]), "final": int(n_out.sum())}
         self.last_landmarks = [kpts[b, :n_out[b]] for b in range(len(n_out))] if kpts is not None else None
         return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
 

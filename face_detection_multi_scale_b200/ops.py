@@ -275,7 +275,7 @@ class PostPlan:
     run, so the launches go out back to back (and can be captured in a CUDA graph)."""
 
     def __init__(self, scales_levels, strides, anchors_px, in_h, orig_hw, conf_thres, iou_thres, cap, out_cap,
-                 iou_mode=IOU_TV_CUDA, with_kpts=False):
+                 iou_mode=IOU_TV_CUDA, with_kpts=False, ctx=None):
         self.dev = _dev(scales_levels[0][0])
         device = scales_levels[0][0].device
         self._strides, self._anchors = list(strides), np.asarray(anchors_px, np.float32)
@@ -299,7 +299,7 @@ class PostPlan:
         d.merged_in = self.out.merged_in.data_ptr()
         d.kpts_out = self.out.kpts.data_ptr() if with_kpts else None
         self.desc = d
-        self.ctx = _lib.ctx(self.dev)
+        self.ctx = ctx if ctx is not None else _lib.ctx(self.dev)
 
     def rebind(self, scales_levels):
         """Point the plan at a new set of raw head tensors of the same shapes (buffers are reused)."""

@@ -45,7 +45,6 @@ typedef enum fdms_dtype { FDMS_U8 = 0, FDMS_F16 = 1, FDMS_F32 = 2 } fdms_dtype;
 typedef enum fdms_layout { FDMS_CHW = 0, FDMS_HWC = 1 } fdms_layout;
 /* torchvision.ops.nms arithmetic flavours */
 typedef enum fdms_iou_mode { FDMS_IOU_TV_CPU = 0, FDMS_IOU_TV_CUDA = 1 } fdms_iou_mode;
-typedef enum fdms_pre_mode { FDMS_PRE_LETTERBOX = 0, FDMS_PRE_API = 1 } fdms_pre_mode;
 
 #define FDMS_MAX_SCALES 8
 #define FDMS_MAX_LEVELS 32
@@ -149,7 +148,8 @@ FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs
  * IoU > thr, no +1, NaN never suppresses.  n_seg independent segments in one call.
  * Segment g reads n = min(count[g], cap) items: box (x1,y1,x2,y2) at
  * rows + (g*cap + i)*row_stride + box_off, score at ... + score_off, tie[g*cap + i]
- * (tie == NULL means tie = i; tie values must be unique inside a segment).  If n > max_nms only the max_nms best-ranked are considered
+ * (tie == NULL means tie = i; tie values must be unique inside a segment).
+ * If n > max_nms only the max_nms best-ranked are considered
  * (utils/general.py:578-579).  keep[g*cap + k] = item index i of the k-th kept box in score
  * order; n_keep[g] = number kept. */
 FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off,

@@ -240,3 +240,26 @@ def test_nms_other_keypoint_counts(golden):
             assert np.array_equal(res[b].cpu().numpy(), g["c%d_b%d" % (cols, b)])
     with pytest.raises(NotImplementedError):  # kpt_label=5 on 6 columns gives nc = -14 in the reference
         general.non_max_suppression(torch.zeros((1, 10, 6), device=DEV), kpt_label=5)
+
+
+def test_detect_stream_matches_batch_calls():
+    """Pipelined multi-batch API == one synchronous call per batch (different content per batch, 2 and 3 lanes)."""
+    h, w, sizes, B = 270, 480, [160, 256, 320], 2
+    images, heads, shapes = standin.make_batch(h, w, sizes, B, n_faces=20, seed=9, dtype=np.float16)
+    model = standin.SyntheticHeadModel()
+    for s, hw in enumerate(shapes):
+        model.set_heads(hw, heads[s], pin=True)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU)
+    batches = [np.roll(images, k, axis=2) if k else images for k in range(5)]
+    ref = [det.detect_multi_scale_batch(b) for b in batches]
+    for depth in (1, 2, 3):
+        got = list(det.detect_stream([torch.from_numpy(b).pin_memory() for b in batches], depth=depth))
+        assert len(got) == len(ref)
+        for g_, r_ in zip(got, ref):
+            for a, b in zip(g_, r_):
+                assert a.shape == b.shape and np.array_equal(a, b)
+    det2 = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, cap=16)  # overflow path
+    got = list(det2.detect_stream(batches[:2]))
+    for g_, r_ in zip(got, ref[:2]):
+        for a, b in zip(g_, r_):
+            assert np.array_equal(a, b)

@@ -285,7 +285,7 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     if (MODE == PM_POINT) {  // one slot per interior row; border rows interleave
         for (int k = 0;; k++) {
             while (rm.x < 0) {  // border rows due before slot k
-                border_row<T>(pc, off, xs, tborder, true, true);
+                border_row<T>(pc, off, xs, rm.x == -4 ? 0u : tborder, true, true);
                 off += ys;
                 ++j;
                 rm = *++rmp;
@@ -307,8 +307,8 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
     auto flush = [&](int k, int *cur, int *other) {
         while ((rm.x >> 1) <= k) {
-            if (rm.x < 0) {
-                border_row<T>(pc, off, xs, tborder, two, vec);
+            if (rm.x < 0) {  // -2: letterbox border, -4: virtual zero rows of the api mode
+                border_row<T>(pc, off, xs, rm.x == -4 ? 0u : tborder, two, vec);
             } else {
                 const unsigned b0s = (unsigned)rm.y, b1s = (unsigned)rm.z;
                 if (__builtin_expect(rm.x & 1, 0)) {  // both taps in the same slot (clamped row / zero lower weight):
@@ -358,9 +358,10 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     }
     // rows not tied to any slot (a tile without interior)
     while (j < n_rows) {
-        border_row<T>(pc, off, xs, tborder, two, vec);
+        border_row<T>(pc, off, xs, rm.x == -4 ? 0u : tborder, two, vec);
         off += ys;
         j++;
+        rm = *++rmp;
     }
 }
 
@@ -443,7 +444,10 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             const int4 e = __ldg(S.ytab + oy0 + lane);
             r0 = e.x; r1 = e.y; b01 = (unsigned)e.z;
         }
-        const bool valid = r0 >= 0;
+        // api mode: rows whose BOTH taps lie in the virtual zero padding need no source at all -- the result is
+        // (0 + 0 + 2) >> 2 = 0, written like a border row with value 0
+        const bool zero_row = r0 >= P.src_h;
+        const bool valid = r0 >= 0 && !zero_row;
         const int b1 = (int)(b01 >> 16);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         int slot0 = 0, slot1 = 0, n_used = 0, rmin = 0;
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
         }
         if (lane <= n_rows)
             sh.rowmeta[lane] = lane == n_rows ? make_int4(0x7ffffffe, 0, 0, 0)
-                                              : make_int4(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : -2,
+                                              : make_int4(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : (zero_row ? -4 : -2),
                                                           (int)(b01 & 0xffffu), (int)(b01 >> 16), 0);
     }
     __syncthreads();

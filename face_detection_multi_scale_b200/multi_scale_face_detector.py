@@ -7,6 +7,7 @@ one backbone forward per scale (unchanged PyTorch), and ONE post-processing call
 batched NMS, rescale, cross-scale weighted NMS) with a single device->host read at the end.
 No prints on the hot path, no per-image host synchronisation, no CPU fallback.
 """
+import threading
 import time
 
 import numpy as np
@@ -73,7 +74,7 @@ class MultiScaleFaceDetector:
         self.with_landmarks = bool(with_landmarks)
         self.head = yolo_head.patch_head(yolo_head.find_head(self.model))
         self.strides, self.anchors_px = yolo_head.head_geometry(self.head)
-        self._plans = {}
+        self._tls = threading.local()  # plan caches hold device buffers + a native ctx: one set per calling thread
         self.last_stats = {}
 
     # ------------------------------------------------------------------ geometry / preprocessing
@@ -113,12 +114,12 @@ class MultiScaleFaceDetector:
     # ------------------------------------------------------------------ model
     def _raw_heads(self, x):
         """Backbone forward (unchanged PyTorch) returning the head's raw NCHW conv maps."""
-        self.head.fdms_fused = True
+        yolo_head.set_fused(self.head, True)
         try:
             with torch.no_grad():
                 raw = self.model(x, augment=False) if self._accepts_augment() else self.model(x)
         finally:
-            self.head.fdms_fused = False
+            yolo_head.set_fused(self.head, False)
         return list(raw)
 
     def _accepts_augment(self):
@@ -134,7 +135,7 @@ class MultiScaleFaceDetector:
 
     # ------------------------------------------------------------------ fused batch path
     def _plan(self, scales_levels, in_h, orig_hw, lane=None):
-        plans = self._plans if lane is None else lane.plans
+        plans = self._thread_plans() if lane is None else lane.plans
         bs = scales_levels[0][0].shape[0]
         key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), tuple(orig_hw),
                self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode)
@@ -150,6 +151,12 @@ class MultiScaleFaceDetector:
         else:
             plan.rebind(scales_levels)
         return plan
+
+    def _thread_plans(self):
+        plans = getattr(self._tls, "plans", None)
+        if plans is None:
+            plans = self._tls.plans = {}
+        return plans
 
     def detect_batch_device(self, batch_dev, lane=None):
         """Enqueue the whole multi-scale path for a (B, H, W, 3) uint8 BGR device batch on the current stream.
@@ -259,7 +266,7 @@ class MultiScaleFaceDetector:
                 self.cap = max(self.cap * 2, int(head[0]))
             if head[2] > (self.out_cap or self.cap):
                 self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
-            self._plans.clear()
+            self._thread_plans().clear()
         dets, n_out, kpts = res
         self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]),
                            "kept_per_scale": int(head[4]), "final": int(n_out.sum())}

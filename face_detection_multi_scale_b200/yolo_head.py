@@ -9,6 +9,7 @@ landmark decode, cat -- is one kernel reading the conv outputs in place.
                                keeps the raw NCHW maps in head.fdms_raw for the fused path
     head_geometry(head)        (strides, anchors in pixels) of a reference head module
 """
+import threading
 import types
 
 import numpy as np
@@ -52,7 +53,7 @@ def _forward(self, x):
         raise RuntimeError("the libfdms head replaces the inference branch only (call model.eval())")
     raw = head_convs(self, x)
     self.fdms_raw = raw
-    if getattr(self, "fdms_fused", False):  # fused level: the detector consumes fdms_raw directly
+    if getattr(self._fdms_tls, "fused", False):  # fused level (per calling thread): the detector consumes the raw maps
         return raw
     strides, anchors = self._fdms_geom
     pred = decode_head(raw, strides, anchors)
@@ -71,9 +72,14 @@ def patch_head(head):
         raise NotImplementedError("libfdms decodes the face head only (na=3, no=21); got na=%d no=%d" % (head.na, head.no))
     head._fdms_geom = head_geometry(head)
     head.fdms_raw = None
-    head.fdms_fused = False
+    head._fdms_tls = threading.local()  # the fused/compat switch is per thread: one detector may serve a thread pool
     head.forward = types.MethodType(_forward, head)
     return head
+
+
+def set_fused(head, on):
+    """Route this THREAD's next forward of `head` to the raw (fused-level) output."""
+    head._fdms_tls.fused = bool(on)
 
 
 def find_head(model):

@@ -263,3 +263,27 @@ def test_detect_stream_matches_batch_calls():
     for g_, r_ in zip(got, ref[:2]):
         for a, b in zip(g_, r_):
             assert np.array_equal(a, b)
+
+
+def test_detector_shared_by_thread_pool():
+    """One detector served from a ThreadPoolExecutor (the reference's directory mode,
+    yolov7_face_multi_scale_dataframe_predict.py:279-282): per-thread native contexts, plan caches and head mode."""
+    import concurrent.futures
+    h, w, sizes = 270, 480, [160, 256, 320]
+    images, heads, shapes = standin.make_batch(h, w, sizes, 1, n_faces=20, seed=12, dtype=np.float16)
+    model = standin.SyntheticHeadModel()
+    for s, hw in enumerate(shapes):
+        model.set_heads(hw, heads[s], pin=False, device=DEV)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU)
+    ref, _ = det.detect_multi_scale(images[0])
+
+    def work(i):
+        out, shape0 = det.detect_multi_scale(images[0])
+        pred, xs = det.head([l.clone() for l in model._heads[tuple(shapes[i % 3])]])  # compat-level call in between
+        return out, pred.shape
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=4) as ex:
+        results = list(ex.map(work, range(24)))
+    for out, pshape in results:
+        assert out.shape == ref.shape and np.array_equal(out, ref)
+        assert pshape[2] == 21

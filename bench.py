@@ -10,8 +10,8 @@ two halves is out of scope (BASELINE.json north_star: it stays unchanged) and is
 outputs are synthetic raw head maps with planted faces (random-init weights yield no candidates).
 
 Prints ONE JSON line (rank 0).  `value` = images/s with all inputs resident in HBM; `e2e` = the same metric
-through the public API (MultiScaleFaceDetector.detect_multi_scale_batch) with pinned HOST inputs, H2D of the
-images and of the head maps and D2H of the detections inside the timed region.
+through the public API (MultiScaleFaceDetector.detect_stream, the pipelined form of detect_multi_scale_batch) with
+pinned HOST inputs: H2D of the images and of the head maps and D2H of the detections inside the timed region.
 """
 import argparse
 import concurrent.futures
@@ -404,7 +404,7 @@ def main():
                        "letterboxed_hw": [list(s) for s in shapes], "conf_thres": wl["conf"], "iou_thres": wl["iou"],
                        "planted_faces_per_image": wl["faces"], "candidates_per_step": cand_per_step,
                        "backbone": "excluded (unchanged PyTorch, out of scope); raw head maps are synthetic fp16",
-                       "l2": "inputs larger than L2 (340 MB/step) and two input sets rotated",
+                       "l2": "inputs larger than L2 (%d MB/step) and two input sets rotated" % ((B * src_bytes + head_bytes) // 1000000),
                        "parallelism": "image-sharded, no collective" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + ops.PostPlan.LAUNCHES),
             "roofline": roofline, "cpu_baseline": cpu,

@@ -408,6 +408,37 @@ def gen_pack():
     save("pack", **out)
 
 
+def gen_ikeypoint():
+    """A REAL reference IKeypoint head (models/yolo.py:215-313: ImplicitA -> 1x1 conv -> ImplicitM, plus the
+    keypoint conv, cat, view/permute, decode) with seeded random weights on small feature maps.  The weights, the
+    inputs and the reference's outputs are stored so that the patched head (yolo_head.patch_head on a structurally
+    identical module) can be checked against the reference's own forward on the GPU box."""
+    torch.manual_seed(7)
+    ch = (8, 16, 32)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = IKeypoint(nc=1, anchors=synth.P5_ANCHORS.reshape(3, -1).tolist(), nkpt=5, ch=ch)
+    m.stride = torch.tensor([8., 16., 32.])
+    m.eval()
+    for p_ in m.parameters():  # spread the logits so that the confidence filter sees both sides
+        p_.data.mul_(3.0)
+    out = {}
+    for k, v in m.state_dict().items():
+        out["w_" + k.replace(".", "__")] = v.numpy()
+    xs = [torch.randn(2, c, 96 // s, 160 // s) for c, s in zip(ch, (8, 16, 32))]
+    for i, x in enumerate(xs):
+        out["x%d" % i] = x.numpy()
+    pred, raw = m([x.clone() for x in xs])
+    out["pred"] = pred.numpy()
+    for i, r in enumerate(raw):
+        out["raw%d" % i] = r.numpy()
+    conf = (pred[..., 4] * pred[..., 5]).flatten()
+    thr = float(torch.quantile(conf, 0.97))
+    out["thr"] = np.array(thr)
+    for b, r in enumerate(quiet(non_max_suppression, pred, thr, 0.45)):
+        out["nms_b%d" % b] = r.numpy()
+    save("ikeypoint", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()["gen_" + sys.argv[1]]()
@@ -421,3 +452,4 @@ if __name__ == "__main__":
     gen_nms6()
     gen_bbox()
     gen_pack()
+    gen_ikeypoint()

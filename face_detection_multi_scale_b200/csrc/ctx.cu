@@ -36,6 +36,8 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (c->sm_count <= 0) c->sm_count = FDMS_SM_COUNT_FALLBACK;
     if (const char *e = getenv("FDMS_PYR_SPECIAL")) c->pyr_special = atoi(e);
     if (const char *e = getenv("FDMS_PYR_SMEM_KB")) c->pyr_smem_budget = atoi(e) * 1024;
+    if (const char *e = getenv("FDMS_PYR_DIRECT")) c->pyr_direct = atoi(e);
+    if (const char *e = getenv("FDMS_PYR_TH_DIRECT")) c->pyr_th_direct = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("FDMS_PYR_TH")) c->pyr_th = atoi(e) < 1 ? 1 : (atoi(e) > 31 ? 31 : atoi(e));  // rows + sentinel are written by one warp
     if (const char *e = getenv("FDMS_NMS_SMALL_LIMIT")) c->nms_small_limit = atoi(e);
     if (const char *e = getenv("FDMS_NMS_GREEDY_MIN_SEG")) c->nms_greedy_min_seg = atoi(e);

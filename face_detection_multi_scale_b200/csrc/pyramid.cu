@@ -23,9 +23,11 @@
 namespace {
 
 constexpr int PYR_THREADS = 160;  // 2 columns per thread: 320-column tiles divide 640/960/1280 evenly
+#ifndef PYR_MIN_CTAS
+#define PYR_MIN_CTAS 8  // resident CTAs per SM the register allocation of the fp16 instantiation is held to (48 registers)
+#endif
 constexpr int PYR_MAX_TH = 32;    // rows per tile are handled by the lanes of warp 0
 constexpr int PYR_MAX_SLOTS = 64;
-constexpr int PYR_SMEM_BUDGET = 56 * 1024;  // per CTA: >= 4 CTAs per SM
 // Exact integer scale factors make OpenCV's fixed-point weights constant: an odd factor k gives
 // f == 0 on both axes (weights 2048/0: the output IS source pixel (k*d + (k-1)/2)), an even factor gives f == 0.5
 // (weights 1024/1024: (((1024*(64*(a+b)))>>16) + ... + 2) >> 2 == (a + b + c + d + 2) >> 2).  Same results as the
@@ -42,9 +44,11 @@ struct PyrScale {
     int slot_bytes;    // multiple of 16
     int vec;           // paired stores allowed
     int mode;          // PM_GENERAL / PM_POINT / PM_HALF: strength-reduced arithmetic for exact integer scales
+    int direct;        // exact integer scale, no column padding: taps are read straight from global memory (no staging)
+    int kx, ky;        // the integer factors when mode != PM_GENERAL
     double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
     const int2 *xtab;         // per output column: {source column sx, a0 | a1 << 16}; sx = -1 on the border
-    const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, 0}; r0 = -1 on the border
+    const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, s}: clamped tap rows, weights, unclamped upper tap row; r0 = -1 on the border
 };
 
 struct PyrParams {
@@ -107,8 +111,7 @@ __device__ __forceinline__ void coeff_x(int d, double scale, int n_src, int &s, 
     a01 = pack_w(f);
 }
 // y axis: weights are kept, the two source ROWS are clamped (resizeGeneric_Invoker)
-__device__ __forceinline__ void coeff_y(int d, double scale, int n_src, int &r0, int &r1, unsigned &b01) {
-    int s;
+__device__ __forceinline__ void coeff_y(int d, double scale, int n_src, int &r0, int &r1, unsigned &b01, int &s) {
     float f;
     lin_coeff(d, scale, s, f);
     r0 = min(max(s, 0), n_src - 1);
@@ -223,8 +226,11 @@ template <> struct Out<uint8_t> {
 };
 
 struct TileShared {
-    // per row: x = 2 * (slot after which the row is emitted) + same-slot flag (-2: border row), y = b0, z = b1;
-    // one sentinel entry past the last row
+    // per row: x = slot of the row's lower tap -- the row is emitted once that slot's horizontal pass is done
+    // (-2: border row, -4: virtual zero row), y / z = weights of the slot before / of that slot; one sentinel entry
+    // past the last row.  A clamped row (both taps on the first / last source row) gets that row staged twice and a
+    // row with a zero lower weight is emitted from its upper tap alone with weights (0, b0), so the two taps of a
+    // row are ALWAYS the previous and the current slot.
     int4 rowmeta[PYR_MAX_TH + 1];
     int slot_row[PYR_MAX_SLOTS];
     int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
@@ -306,16 +312,11 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
 
     // emit every row whose lower tap is slot k; `cur` = horizontal results of slot k, `other` = slot k-1
     auto flush = [&](int k, int *cur, int *other) {
-        while ((rm.x >> 1) <= k) {
+        while (rm.x <= k) {
             if (rm.x < 0) {  // -2: letterbox border, -4: virtual zero rows of the api mode
                 border_row<T>(pc, off, xs, rm.x == -4 ? 0u : tborder, two, vec);
             } else {
-                const unsigned b0s = (unsigned)rm.y, b1s = (unsigned)rm.z;
-                if (__builtin_expect(rm.x & 1, 0)) {  // both taps in the same slot (clamped row / zero lower weight):
-#pragma unroll                                        // rows are visited in source order, so slot k-1 is dead from here on
-                    for (int c = 0; c < 6; c++) other[c] = cur[c];
-                    asm volatile("" ::: "memory");  // keep this a (CTA-uniform) branch, not six predicated moves
-                }
+                const unsigned b0s = (unsigned)rm.y, b1s = (unsigned)rm.z;  // weights of slot k-1 / slot k
                 if (MODE == PM_HALF) {
 #pragma unroll
                     for (int c = 0; c < 3; c++)
@@ -365,6 +366,160 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct tiles.  With an exact integer factor every tap position is an affine function of the output coordinate,
+// a thread's two pixels read a fixed, word-aligned byte window per source row and neighbouring threads read
+// neighbouring windows: the loads coalesce by themselves, so these tiles skip the staging (no shared memory, no
+// barrier, no tap prologue) and run at much higher occupancy.
+//   PM_HALF, kx == 2: pixels A and B are the 12 contiguous bytes [a b | c d] (4 source pixels) at 6 * dx; the sum of
+//                     the 2 x 2 block of each channel is a chain of byte dot products (IDP.4A) seeded with the
+//                     rounding constant, the second source row accumulating onto the first.
+//   PM_POINT:         the pixel is source pixel (kx * dx + kx / 2, ky * dy + ky / 2).
+// Only rows are padded here (host guarantees left == 0 and dst_w == unpad_w), so a row is either all border or all
+// interior.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &S, int img, int oy0, int ox0, int tid) {
+    const int x = ox0 + 2 * tid;
+    if (x >= S.dst_w || 2 * tid >= S.tw) return;
+    const int4 e = __ldg(reinterpret_cast<const int4 *>(S.xtab + x));
+    const int sxA = e.x, sxB = e.z;
+    const uint8_t *src = P.src + (long long)img * P.img_stride;
+    T *pc[3];
+    {
+        T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys + x;
+        pc[0] = P.flip ? p0 + 2 * S.cs : p0;
+        pc[1] = p0 + S.cs;
+        pc[2] = P.flip ? p0 : p0 + 2 * S.cs;
+    }
+    const unsigned ys = (unsigned)S.ys;
+    const unsigned tborder = (unsigned)P.border * 4u;
+    const int y_end = min(oy0 + S.th, S.dst_h);
+    const int ya = min(max(oy0, S.top), y_end), yb = max(min(y_end, S.top + S.unpad_h), ya);  // interior rows [ya, yb)
+    unsigned off = 0;
+    for (int y = oy0; y < ya; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+    const long long pitch = P.pitch;
+    if (MODE == PM_HALF) {
+        const int ky = S.ky;
+        const uint8_t *row = src + 3 * sxA + (long long)(ky * (ya - S.top) + (ky >> 1) - 1) * pitch;
+        const long long step = (long long)ky * pitch;
+#pragma unroll 4
+        for (int y = ya; y < yb; y++, off += ys, row += step) {
+            const uint32_t *p0 = reinterpret_cast<const uint32_t *>(row);
+            const uint32_t *p1 = reinterpret_cast<const uint32_t *>(row + pitch);
+            const uint32_t w0 = __ldg(p0), w1 = __ldg(p0 + 1), w2 = __ldg(p0 + 2);
+            const uint32_t v0 = __ldg(p1), v1 = __ldg(p1 + 1), v2 = __ldg(p1 + 2);
+            // bytes: w0 = a0 a1 a2 b0, w1 = b1 b2 c0 c1, w2 = c2 d0 d1 d2
+            unsigned tA[3], tB[3];
+            tA[0] = __dp4a(v0, 0x01000001u, __dp4a(w0, 0x01000001u, 2u));
+            tA[1] = __dp4a(v1, 0x00000001u, __dp4a(v0, 0x00000100u, __dp4a(w1, 0x00000001u, __dp4a(w0, 0x00000100u, 2u))));
+            tA[2] = __dp4a(v1, 0x00000100u, __dp4a(v0, 0x00010000u, __dp4a(w1, 0x00000100u, __dp4a(w0, 0x00010000u, 2u))));
+            tB[0] = __dp4a(v2, 0x00000100u, __dp4a(v1, 0x00010000u, __dp4a(w2, 0x00000100u, __dp4a(w1, 0x00010000u, 2u))));
+            tB[1] = __dp4a(v2, 0x00010000u, __dp4a(v1, 0x01000000u, __dp4a(w2, 0x00010000u, __dp4a(w1, 0x01000000u, 2u))));
+            tB[2] = __dp4a(v2, 0x01000001u, __dp4a(w2, 0x01000001u, 2u));
+#pragma unroll
+            for (int c = 0; c < 3; c++) Out<T>::store2(pc[c] + off, 1, tA[c], tB[c], true);
+        }
+    } else {
+        const int ky = S.ky;
+        const int oA = 3 * sxA, oB = 3 * sxB;
+        const unsigned shA = (unsigned)(oA & 3) * 8u, shB = (unsigned)(oB & 3) * 8u;
+        const bool a2 = (oA & 3) >= 2, b2 = (oB & 3) >= 2;  // the 3 bytes spill into the next word
+        const uint8_t *row = src + (long long)(ky * (ya - S.top) + (ky >> 1)) * pitch;
+        const long long step = (long long)ky * pitch;
+        const int wa = oA & ~3, wb = oB & ~3;
+#pragma unroll 4
+        for (int y = ya; y < yb; y++, off += ys, row += step) {
+            const uint32_t *pa = reinterpret_cast<const uint32_t *>(row + wa);
+            const uint32_t *pb = reinterpret_cast<const uint32_t *>(row + wb);
+            const uint32_t a0 = __ldg(pa), a1 = a2 ? __ldg(pa + 1) : 0u;
+            const uint32_t b0 = __ldg(pb), b1 = b2 ? __ldg(pb + 1) : 0u;
+            const uint32_t lA = __funnelshift_r(a0, a1, shA), lB = __funnelshift_r(b0, b1, shB);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                Out<T>::store2_bits(pc[c] + off, __byte_perm(lA, 0x4B000000u, 0x7650 + c), __byte_perm(lB, 0x4B000000u, 0x7650 + c));
+        }
+    }
+    for (int y = yb; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+}
+
+// Warp 0, all 32 lanes: vertical taps of one tile (lane = row; `e` = its ytab entry, r0 = -1 when the row is border
+// or the lane has no row), slot assignment, bulk copies into `buf`, row meta into `sh`, then the full-barrier arrive.
+__device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale &S, TileShared &sh, uint8_t *buf,
+                                              const uint8_t *src, int lane, int n_rows, int4 e, int g0, int row_bytes,
+                                              int bulk_bytes) {
+    const int r0 = e.x, r1 = e.y;
+    const unsigned b01 = (unsigned)e.z;
+    const bool zero_row = r0 >= P.src_h;  // api mode: both taps in the virtual zero padding
+    const bool valid = r0 >= 0 && !zero_row;
+    const int b1 = (int)(b01 >> 16);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int slot_bytes = S.slot_bytes;
+    int slot0 = 0, slot1 = 0, n_used = 0, rmin = 0;
+    if (vmask) {
+        if (S.dense_rows) {  // slot k = source row clamp(rmin + k): slots follow the UNCLAMPED tap rows
+            const int u0 = e.w, u1 = (b1 != 0) ? u0 + 1 : u0;
+            rmin = __shfl_sync(0xffffffffu, u0, __ffs(vmask) - 1);
+            const int rmax = __shfl_sync(0xffffffffu, u1, 31 - __clz(vmask));
+            n_used = min(rmax - rmin + 1, PYR_MAX_SLOTS);
+            slot0 = u0 - rmin;
+            slot1 = u1 - rmin;
+        } else {
+            const int cnt = valid ? (b1 != 0 ? 2 : 1) : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            n_used = __shfl_sync(0xffffffffu, incl, 31);
+            slot0 = incl - cnt;
+            slot1 = (b1 != 0) ? slot0 + 1 : slot0;
+        }
+    }
+    int n_bulk = 0;
+    bool virt_row = false;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(&sh.bar);
+    if (S.dense_rows) {
+        for (int k = lane; k < n_used; k += 32) {
+            const int row = min(max(rmin + k, 0), P.virt_h - 1);
+            sh.slot_row[k] = row;
+            if (row >= P.src_h) virt_row = true;
+            else if (bulk_bytes > 0) {
+                bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
+                n_bulk++;
+            }
+        }
+    } else if (valid) {
+        const int nk = (b1 != 0) ? 2 : 1;
+        for (int q = 0; q < nk; q++) {
+            const int k = slot0 + q, row = q ? r1 : r0;
+            sh.slot_row[k] = row;
+            if (row >= P.src_h) virt_row = true;
+            else if (bulk_bytes > 0) {
+                bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
+                n_bulk++;
+            }
+        }
+    }
+    n_bulk = __reduce_add_sync(0xffffffffu, n_bulk);
+    const bool any_virt = __any_sync(0xffffffffu, virt_row);
+    if (lane <= n_rows) {
+        const int b0 = (int)(b01 & 0xffffu);
+        sh.rowmeta[lane] = lane == n_rows ? make_int4(0x7ffffffe, 0, 0, 0)
+                                          : make_int4(valid ? slot1 : (zero_row ? -4 : -2), b1 != 0 ? b0 : 0,
+                                                      b1 != 0 ? b1 : b0, 0);
+    }
+    if (lane == 0) {
+        sh.n_used = n_used;
+        sh.need_scalar = (bulk_bytes < row_bytes && n_used > 0) || any_virt;
+        sh.n_rows = n_rows;
+    }
+    __syncwarp();  // every lane's meta is ordered before lane 0's releasing arrive
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_bulk * bulk_bytes));
+}
+
 // Tap tables of a pyramid geometry (OpenCV's coefficient set-up).  Runs once per geometry:
 // the tables are cached in the ctx, so the main kernel carries no fp64 and no conversions.
 __global__ void pyramid_tables_kernel(const __grid_constant__ PyrParams P) {
@@ -380,15 +535,15 @@ __global__ void pyramid_tables_kernel(const __grid_constant__ PyrParams P) {
     }
     for (int y = threadIdx.x; y < S.dst_h; y += blockDim.x) {
         const int dy = y - S.top;
-        int r0 = -1, r1 = -1;
+        int r0 = -1, r1 = -1, sy = 0;
         unsigned b01 = 0;
-        if (dy >= 0 && dy < S.unpad_h) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01);
-        yt[y] = make_int4(r0, r1, (int)b01, 0);
+        if (dy >= 0 && dy < S.unpad_h) coeff_y(dy, S.scale_y, P.virt_h, r0, r1, b01, sy);
+        yt[y] = make_int4(r0, r1, (int)b01, sy);
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_constant__ PyrParams P) {
+__global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6) pyramid_kernel(const __grid_constant__ PyrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ TileShared sh;
 
@@ -405,6 +560,11 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
     const int tw = S.tw, th = S.th;
     const int ty = tile / S.tiles_x, tx = tile - ty * S.tiles_x;
     const int oy0 = ty * th, ox0 = tx * tw;
+    if (S.direct) {  // CTA-uniform
+        if (S.mode == PM_HALF) direct_tile<T, PM_HALF>(P, S, img, oy0, ox0, tid);
+        else direct_tile<T, PM_POINT>(P, S, img, oy0, ox0, tid);
+        return;
+    }
     const int dst_h = S.dst_h, dst_w = S.dst_w, top = S.top, left = S.left, unpad_h = S.unpad_h, unpad_w = S.unpad_w;
     const int y_end = min(oy0 + th, dst_h), x_end = min(ox0 + tw, dst_w);
     const int n_rows = y_end - oy0;
@@ -438,39 +598,8 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
             mbar_init(reinterpret_cast<uint64_t *>(&sh.bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        int r0 = -1, r1 = 0;
-        unsigned b01 = 0;
-        if (has_cols && lane < n_rows) {
-            const int4 e = __ldg(S.ytab + oy0 + lane);
-            r0 = e.x; r1 = e.y; b01 = (unsigned)e.z;
-        }
-        // api mode: rows whose BOTH taps lie in the virtual zero padding need no source at all -- the result is
-        // (0 + 0 + 2) >> 2 = 0, written like a border row with value 0
-        const bool zero_row = r0 >= P.src_h;
-        const bool valid = r0 >= 0 && !zero_row;
-        const int b1 = (int)(b01 >> 16);
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        int slot0 = 0, slot1 = 0, n_used = 0, rmin = 0;
-        if (vmask) {
-            if (S.dense_rows) {
-                rmin = __shfl_sync(0xffffffffu, r0, __ffs(vmask) - 1);
-                const int rmax = __shfl_sync(0xffffffffu, r1, 31 - __clz(vmask));
-                n_used = min(rmax - rmin + 1, PYR_MAX_SLOTS);
-                slot0 = r0 - rmin;
-                slot1 = (b1 != 0) ? r1 - rmin : slot0;
-            } else {
-                const int cnt = valid ? (b1 != 0 ? 2 : 1) : 0;
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                n_used = __shfl_sync(0xffffffffu, incl, 31);
-                slot0 = incl - cnt;
-                slot1 = (b1 != 0) ? slot0 + 1 : slot0;
-            }
-        }
+        int4 e = make_int4(-1, 0, 0, 0);
+        if (has_cols && lane < n_rows) e = __ldg(S.ytab + oy0 + lane);
         // source byte range of the tile's columns
         int sx = 0;
         if (has_cols && lane < 2) sx = __ldg(S.xtab + left + (lane == 0 ? dxa : dxb - 1)).x;
@@ -480,49 +609,13 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
         const int row_bytes = ((3 * sxb + 3 + 15) & ~15) - g0;
         const int real_end = 3 * P.src_w;
         const int bulk_bytes = P.vec_ok ? max(0, min(g0 + row_bytes, real_end & ~15) - g0) : 0;
-        // slot -> source row, bulk copies
-        int n_bulk = 0;
-        bool virt_row = false;
-        __syncwarp();
-        if (S.dense_rows) {
-            for (int k = lane; k < n_used; k += 32) {
-                const int row = rmin + k;
-                sh.slot_row[k] = row;
-                if (row >= P.src_h) virt_row = true;
-                else if (bulk_bytes > 0) {
-                    bulk_g2s(smem + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes,
-                             reinterpret_cast<uint64_t *>(&sh.bar));
-                    n_bulk++;
-                }
-            }
-        } else if (valid) {
-            const int nk = (b1 != 0) ? 2 : 1;
-            for (int q = 0; q < nk; q++) {
-                const int k = slot0 + q, row = q ? r1 : r0;
-                sh.slot_row[k] = row;
-                if (row >= P.src_h) virt_row = true;
-                else if (bulk_bytes > 0) {
-                    bulk_g2s(smem + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes,
-                             reinterpret_cast<uint64_t *>(&sh.bar));
-                    n_bulk++;
-                }
-            }
-        }
-        n_bulk = __reduce_add_sync(0xffffffffu, n_bulk);
-        const bool any_virt = __any_sync(0xffffffffu, virt_row);
         if (lane == 0) {
-            mbar_expect_tx(reinterpret_cast<uint64_t *>(&sh.bar), (uint32_t)(n_bulk * bulk_bytes));
-            sh.n_used = n_used;
             sh.g0 = g0;
             sh.row_bytes = row_bytes;
             sh.bulk_bytes = bulk_bytes;
-            sh.need_scalar = (bulk_bytes < row_bytes) || any_virt;
-            sh.n_rows = n_rows;
         }
-        if (lane <= n_rows)
-            sh.rowmeta[lane] = lane == n_rows ? make_int4(0x7ffffffe, 0, 0, 0)
-                                              : make_int4(valid ? 2 * slot1 + (slot0 == slot1 ? 1 : 0) : (zero_row ? -4 : -2),
-                                                          (int)(b01 & 0xffffu), (int)(b01 >> 16), 0);
+        __syncwarp();
+        tile_prologue(P, S, sh, smem, src, lane, n_rows, e, g0, row_bytes, bulk_bytes);
     }
     __syncthreads();
     const int n_used = sh.n_used, g0 = sh.g0;
@@ -591,6 +684,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 6) pyramid_kernel(const __grid_co
         stream_tile<T, false, PM_GENERAL>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                           slot_bytes, tborder, inA, inB, two, S.vec != 0);
 }
+
 
 template <typename T>
 int launch_group(fdms_ctx *ctx, const PyrParams &P, int tiles, int n_img, int smem, cudaStream_t st) {
@@ -684,8 +778,17 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                     if ((kx & 1) && (ky & 1)) S.mode = PM_POINT;
                     else if (!(kx & 1) && !(ky & 1)) S.mode = PM_HALF;
                 }
+                S.kx = (int)kx;
+                S.ky = (int)ky;
+                // direct tiles: rows-only padding, paired stores, word-aligned source rows that end on a word
+                S.direct = S.mode != PM_GENERAL && ctx->pyr_direct && S.vec && P.vec_ok && g.left == 0 &&
+                           g.unpad_w == g.dst_w && src_w % 4 == 0 && (S.mode == PM_POINT || kx == 2);
             }
             int tw = 2 * PYR_THREADS, th = ctx->pyr_th;
+            if (S.direct) {  // no staging: no shared-memory constraint on the tile
+                th = ctx->pyr_th_direct;
+                S.slot_bytes = 0;
+            } else
             for (;;) {
                 int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : (y_point ? th : 2 * th);
                 int span_px = (int)(tw * S.scale_x) + 4;

@@ -200,19 +200,26 @@ __global__ void __launch_bounds__(SORT_THREADS)
 // arithmetic: inter == 0 gives iou == 0 (or NaN when the union is empty too), which never exceeds a
 // threshold >= 0 -- exact, not an approximation.  `quick` is false for thresholds where that does not hold.
 template <int MODE>
-__device__ __forceinline__ bool iou_gt(const float4 a, float area_a, const float4 b, float thr, bool inclusive,
-                                       bool quick) {
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr, bool inclusive, bool quick) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     if (quick && (!(xx2 > xx1) || !(yy2 > yy1))) return false;
     float w = fmaxf(f_sub(xx2, xx1), 0.f), h = fmaxf(f_sub(yy2, yy1), 0.f);
     float inter = f_mul(w, h);
+    float area_a = f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y));
     float bw = f_sub(b.z, b.x), bh = f_sub(b.w, b.y);
     float den;
     if (MODE == FDMS_IOU_TV_CUDA) den = f_sub(__fmaf_rn(bw, bh, area_a), inter);
     else den = f_sub(f_add(area_a, f_mul(bw, bh)), inter);
     float iou = f_div(inter, den);
     return inclusive ? (iou >= thr) : (iou > thr);  // NaN: false either way
+}
+
+// Pass 1 of every pair loop: do two boxes overlap at all?  This is iou_gt's own quick-reject test, evaluated
+// branch-free for a batch of boxes; only the survivors take the full IoU (pass 2).  The lanes of a warp hold
+// different boxes, so a fused loop would run the long path whenever ANY lane overlaps the broadcast box.
+__device__ __forceinline__ bool boxes_overlap(const float4 a, const float4 b) {
+    return (fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y));
 }
 
 template <int MODE>
@@ -250,14 +257,20 @@ __global__ void __launch_bounds__(MASK_THREADS)
         const int q = tid >> 6, cblk = cb0 + q;
         if (row < si.n && cblk < si.nblk && cblk >= rb) {
             const float4 a = boxes[row];
-            const float area_a = f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y));
             unsigned long long bits = 0;
             const int col0 = cblk * 64;
             const int jn = min(64, si.n - col0);
-            int j0 = (cblk == rb) ? (tid & 63) + 1 : 0;  // only later boxes can be suppressed
-#pragma unroll 4
-            for (int j = j0; j < jn; j++)
-                if (iou_gt<MODE>(a, area_a, s_col[q * 64 + j], thr, inclusive != 0, quick)) bits |= 1ull << j;
+            const int j0 = (cblk == rb) ? (tid & 63) + 1 : 0;  // only later boxes can be suppressed
+            unsigned long long ov = 0ull;
+#pragma unroll 8
+            for (int j = 0; j < 64; j++) ov |= boxes_overlap(a, s_col[q * 64 + j]) ? (1ull << j) : 0ull;
+            if (!quick) ov = ~0ull;
+            ov &= (jn >= 64 ? ~0ull : ((1ull << jn) - 1ull)) & (j0 >= 64 ? 0ull : (~0ull << j0));
+            while (ov) {
+                const int j = __ffsll((long long)ov) - 1;
+                ov &= ov - 1ull;
+                if (iou_gt<MODE>(a, s_col[q * 64 + j], thr, inclusive != 0, false)) bits |= 1ull << j;
+            }
             mask[si.mask_off + (long long)row * si.nblk + cblk] = bits;
         }
     }
@@ -332,75 +345,106 @@ __global__ void __launch_bounds__(SWEEP_THREADS)
 // Steps (2)+(3) of a blocked greedy step, shared by nms_small_kernel and nms_greedy_kernel.
 // blk[0..nb) = the step's candidates in score order (shared memory); s_sup = candidates already suppressed by
 // boxes kept in earlier steps.  (2) column masks: colmask[i] = earlier candidates j < i of this block that
-// would suppress i (pairs with a pre-suppressed member are skipped -- they cannot matter).  (3) parallel
-// resolution to the greedy fixpoint: an undecided candidate is removed as soon as a KEPT earlier candidate
-// suppresses it, and kept as soon as no undecided or kept earlier candidate does; the first undecided one
-// always qualifies, and typical suppression graphs settle in a handful of rounds (vs one serial step per kept
-// box).  Result: s_K = bitset of kept candidates.  All CTA threads must call this (it contains barriers).
+// would suppress i (pairs with a pre-suppressed member are skipped -- they cannot matter).  (3) resolution to the
+// greedy result by warp 0, chunk by chunk (see below).  Result: s_K = bitset of kept candidates.  All CTA threads
+// must call this (it contains barriers).
 template <int MODE>
 __device__ __forceinline__ void greedy_block(const float4 *blk, int nb, float thr, bool inclusive, bool quick,
                                              unsigned long long (*s_colmask)[4], unsigned long long *s_sup,
-                                             unsigned long long *s_U, unsigned long long *s_K) {
+                                             unsigned long long *s_K) {
     const int tid = threadIdx.x;
-    const int i = tid & (GREEDY_BS - 1), grp = tid >> 8;
-    const int iw = i >> 6;
-    const unsigned long long ibit = 1ull << (i & 63);
     __syncthreads();  // s_sup complete
     {
-        unsigned long long bits = 0ull;
-        if (i < nb && !(s_sup[iw] & ibit)) {
-            const float4 bi = blk[i];
-            const unsigned long long skip = s_sup[grp];
-            const int j0 = grp * 64, j1 = min(grp * 64 + 64, i);
-            for (int j = j0; j < j1; j++) {
-                if ((skip >> (j & 63)) & 1ull) continue;
-                const float4 a = blk[j];
-                if (iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive, quick))
-                    bits |= 1ull << (j & 63);
+        // Work units = (chunk of 32 candidates) x (16 earlier candidates), lower triangle only, dealt round-robin to
+        // the 32 warps: every warp gets the same number of units (+-1) instead of the triangular imbalance of one
+        // thread per (candidate, 64-column group).  lane = candidate; the earlier box is a broadcast read.
+        uint16_t (*cm16)[16] = reinterpret_cast<uint16_t (*)[16]>(s_colmask);  // [i][16]: same bits, little endian
+        const int warp = tid >> 5, lane = tid & 31;
+        const int nt = (nb + 31) >> 5, n_units = nt * (nt + 1);  // chunk ti has 2 * ti + 2 units
+        for (int u = warp; u < n_units; u += GREEDY_THREADS / 32) {
+            int ti = 0, tj = u;
+            while (tj >= 2 * ti + 2) {
+                tj -= 2 * ti + 2;
+                ti++;
             }
+            const int ci = ti * 32 + lane, j0 = tj * 16;
+            unsigned bits = 0u;
+            if (ci < nb && !((s_sup[ci >> 6] >> (ci & 63)) & 1ull)) {
+                const float4 bi = blk[ci];
+                const int jn = min(min(16, ci - j0), nb - j0);  // only earlier candidates
+                // pass 1, branch-free: which of the 16 boxes overlap this one at all (the exact quick-reject test);
+                // pass 2: the full IoU only for those.  Lanes of a warp are different candidates, so a fused loop
+                // would run the long path whenever ANY lane overlaps the broadcast box.
+                unsigned ov = 0u;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const float4 a = blk[j0 + j];  // in bounds of the block array for every j0; masked below
+                    const float xx1 = fmaxf(a.x, bi.x), yy1 = fmaxf(a.y, bi.y);
+                    const float xx2 = fminf(a.z, bi.z), yy2 = fminf(a.w, bi.w);
+                    ov |= ((xx2 > xx1) && (yy2 > yy1)) ? (1u << j) : 0u;
+                }
+                if (!quick) ov = 0xffffu;  // thresholds below zero: every pair takes the exact path
+                ov &= jn > 0 ? ((1u << jn) - 1u) : 0u;
+                ov &= ~(unsigned)(s_sup[j0 >> 6] >> (j0 & 63));  // pre-suppressed boxes suppress nothing
+                while (ov) {
+                    const int j = __ffs(ov) - 1;
+                    ov &= ov - 1u;
+                    if (iou_gt<MODE>(blk[j0 + j], bi, thr, inclusive, false)) bits |= 1u << j;
+                }
+            }
+            cm16[ci][tj] = (uint16_t)bits;
+            if (tj == 2 * ti + 1)  // last unit of the chunk: clear the words right of the diagonal
+                for (int z = tj + 1; z < 16; z++) cm16[ci][z] = 0;
         }
-        s_colmask[i][grp] = bits;
     }
-    if (tid < 4) {
-        const int left = nb - tid * 64;
-        const unsigned long long valid = left >= 64 ? ~0ull : (left > 0 ? ((1ull << left) - 1ull) : 0ull);
-        s_U[tid] = ~s_sup[tid] & valid;
-        s_K[tid] = 0ull;
+    __syncthreads();  // column masks complete
+    // (3) warp 0 resolves the block 32 candidates at a time.  A chunk's candidates are first tested against
+    // everything kept before the chunk (one AND per mask word); the dependencies INSIDE the chunk are settled with
+    // ballots: an undecided lane is removed once a kept earlier lane suppresses it and kept once no undecided or
+    // kept earlier lane does.  The lowest undecided lane always decides, typical chains settle in 2-4 rounds, and a
+    // round is two ballots -- no barrier, no shared-memory traffic.
+    if (tid < 32) {
+        const int lane = tid;
+        unsigned long long K0 = 0ull, K1 = 0ull, K2 = 0ull, K3 = 0ull;
+        for (int ch = 0; ch * 32 < nb; ch++) {
+            const int ci = ch * 32 + lane, w = ch >> 1, sh = (ch & 1) * 32;
+            const unsigned long long c0 = s_colmask[ci][0], c1 = s_colmask[ci][1], c2 = s_colmask[ci][2],
+                                     c3 = s_colmask[ci][3];
+            const bool alive = ci < nb && !((s_sup[w] >> (ci & 63)) & 1ull);
+            const bool prior = ((c0 & K0) | (c1 & K1) | (c2 & K2) | (c3 & K3)) != 0ull;
+            const unsigned long long cw = w == 0 ? c0 : (w == 1 ? c1 : (w == 2 ? c2 : c3));
+            const unsigned m = (unsigned)(cw >> sh);  // earlier lanes of this chunk that would suppress this lane
+            unsigned U = __ballot_sync(0xffffffffu, alive && !prior), Kc = 0u;
+            while (U) {
+                const bool mine = (U >> lane) & 1u;
+                const bool rem = mine && (m & Kc) != 0u;
+                const bool kp = mine && !rem && (m & U) == 0u;
+                const unsigned kb = __ballot_sync(0xffffffffu, kp), rb = __ballot_sync(0xffffffffu, rem);
+                Kc |= kb;
+                U &= ~(kb | rb);
+            }
+            const unsigned long long add = (unsigned long long)Kc << sh;
+            if (w == 0) K0 |= add;
+            else if (w == 1) K1 |= add;
+            else if (w == 2) K2 |= add;
+            else K3 |= add;
+        }
+        if (lane == 0) {
+            s_K[0] = K0;
+            s_K[1] = K1;
+            s_K[2] = K2;
+            s_K[3] = K3;
+        }
     }
     __syncthreads();
-    for (;;) {
-        const unsigned long long u0 = s_U[0], u1 = s_U[1], u2 = s_U[2], u3 = s_U[3];
-        if ((u0 | u1 | u2 | u3) == 0ull) break;  // uniform
-        bool undecided = false, by_kept = false, by_undecided = false;
-        if (tid < GREEDY_BS) {
-            const unsigned long long uw = iw == 0 ? u0 : (iw == 1 ? u1 : (iw == 2 ? u2 : u3));
-            undecided = (uw & ibit) != 0ull;
-            if (undecided) {
-                const unsigned long long c0 = s_colmask[i][0], c1 = s_colmask[i][1], c2 = s_colmask[i][2],
-                                         c3 = s_colmask[i][3];
-                by_kept = ((c0 & s_K[0]) | (c1 & s_K[1]) | (c2 & s_K[2]) | (c3 & s_K[3])) != 0ull;
-                by_undecided = ((c0 & u0) | (c1 & u1) | (c2 & u2) | (c3 & u3)) != 0ull;
-            }
-        }
-        __syncthreads();  // every thread has read U and K of this round
-        if (undecided) {
-            if (by_kept) {
-                atomicAnd(&s_U[iw], ~ibit);
-            } else if (!by_undecided) {
-                atomicOr(&s_K[iw], ibit);
-                atomicAnd(&s_U[iw], ~ibit);
-            }
-        }
-        __syncthreads();
-    }
 }
 
 // Fused single-CTA NMS for segments of at most SMALL_LIMIT (1024) boxes, everything in shared memory:
-//   rank sort  : thread i counts the keys smaller than its own (keys are unique: score desc, tie asc) -- no
-//                barriers, broadcast shared-memory reads -- and scatters its box to that rank;
+//   sort       : each warp sorts 32 keys in registers (keys are unique: score desc, tie asc); the rank of a key is
+//                found by binary search in the other runs; the box is scattered to that rank;
 //   suppression: the same blocked greedy sweep as nms_greedy_kernel (256 candidates per step, kept boxes
 //                compacted in place at the front of the box array).
-// No global scratch, one launch, ~3 barriers per 256 boxes.
+// No global scratch, one launch, a handful of barriers per 256 boxes.
 template <int MODE>
 __global__ void __launch_bounds__(SMALL_THREADS)
     nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
@@ -411,8 +455,9 @@ __global__ void __launch_bounds__(SMALL_THREADS)
     __shared__ float4 s_box[SMALL_LIMIT];
     __shared__ uint32_t s_idx[SMALL_LIMIT];
     __shared__ int s_rank[SMALL_LIMIT];
+    __shared__ uint16_t s_item[SMALL_LIMIT];
     __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
-    __shared__ unsigned long long s_sup[4], s_keptbits[4], s_U[4];
+    __shared__ unsigned long long s_sup[4], s_keptbits[4];
     __shared__ int s_nkeep;
     const int g = blockIdx.x, tid = threadIdx.x;
     const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
@@ -423,37 +468,72 @@ __global__ void __launch_bounds__(SMALL_THREADS)
         return;
     }
     const float *seg_rows = rows + (long long)g * cap * row_stride;
-    // ---- rank sort ----------------------------------------------------------------------------------------
-    // keys are unique (tie = row index or item index; callers must not pass duplicate ties inside a segment), so
-    // the rank of an item is the number of smaller keys.  All 1024 threads take part: item i = tid % pad, and the
-    // 1024 / pad threads of an item split the key range and add their partial counts.
+    // ---- sort: 32-key runs in registers, then rank by binary search ---------------------------------------------
+    // keys are unique (tie = row index or item index; callers must not pass duplicate ties inside a segment).  Every
+    // warp sorts the keys of its 32 items with a shuffle bitonic network (no shared memory, no barrier); the rank of
+    // a key is its position in its own run plus, for every other run, the number of smaller keys there (a 6-probe
+    // binary search).  n^2/32 warp-level compares become n * (n/32) * 6 probes; all 1024 threads take part: the
+    // 1024 / pad threads of an element split the runs and add their partial counts.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nr = (n + 31) >> 5;  // runs
     int pad = 32;
     while (pad < n) pad <<= 1;
     const int parts = SMALL_THREADS / pad;
-    const int item = tid & (pad - 1), part = tid / pad;
-    if (tid < n) {
-        const float *r = seg_rows + (long long)tid * row_stride;
-        const uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + tid] : (uint32_t)tid;
-        s_keys[tid] = ((unsigned long long)score_key_desc(r[score_off]) << 32) | t;
+    if (warp < nr) {
+        unsigned long long k = ~0ull;  // padding sorts last and is smaller than nothing
+        uint32_t id = (uint32_t)tid;
+        if (tid < n) {
+            const float *r = seg_rows + (long long)tid * row_stride;
+            const uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + tid] : (uint32_t)tid;
+            k = ((unsigned long long)score_key_desc(r[score_off]) << 32) | t;
+        }
+#pragma unroll
+        for (int sz = 2; sz <= 32; sz <<= 1) {
+#pragma unroll
+            for (int st = sz >> 1; st > 0; st >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, st);
+                const uint32_t oid = __shfl_xor_sync(0xffffffffu, id, st);
+                const bool take_min = ((lane & sz) == 0) == ((lane & st) == 0);
+                if (take_min ? (ok < k) : (ok > k)) {
+                    k = ok;
+                    id = oid;
+                }
+            }
+        }
+        s_keys[tid] = k;
+        s_item[tid] = (uint16_t)id;
     }
     if (tid < pad) s_rank[tid] = 0;
     if (tid == 0) s_nkeep = 0;
     __syncthreads();
-    if (item < n) {
-        const unsigned long long mykey = s_keys[item];
-        const int per = (n + parts - 1) / parts, j0 = part * per, j1 = min(n, j0 + per);
-        int cnt = 0;
-#pragma unroll 4
-        for (int j = j0; j < j1; j++) cnt += s_keys[j] < mykey;
-        if (parts == 1) s_rank[item] = cnt;
-        else if (cnt) atomicAdd(&s_rank[item], cnt);
+    {
+        const int e = tid & (pad - 1), part = tid / pad;
+        if (e < nr * 32) {
+            const unsigned long long mykey = s_keys[e];
+            if (mykey != ~0ull) {
+                const int run = e >> 5;
+                int cnt = part == 0 ? (e & 31) : 0;
+#pragma unroll 2
+                for (int q = part; q < nr; q += parts) {
+                    if (q == run) continue;
+                    const unsigned long long *A = s_keys + q * 32;
+                    int c = 0;
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1) c += (A[c + st - 1] < mykey) ? st : 0;
+                    c += (A[c] < mykey) ? 1 : 0;
+                    cnt += c;
+                }
+                if (parts == 1) s_rank[e] = cnt;
+                else if (cnt) atomicAdd(&s_rank[e], cnt);
+            }
+        }
     }
     __syncthreads();
-    if (tid < n) {
-        const float *r = seg_rows + (long long)tid * row_stride + box_off;
-        const int rank = s_rank[tid];
+    if (tid < nr * 32 && s_keys[tid] != ~0ull) {
+        const int item = s_item[tid], rank = s_rank[tid];
+        const float *r = seg_rows + (long long)item * row_stride + box_off;
         s_box[rank] = make_float4(r[0], r[1], r[2], r[3]);
-        s_idx[rank] = (uint32_t)tid;
+        s_idx[rank] = (uint32_t)item;
     }
     __syncthreads();
     const int K = (max_nms > 0) ? min(n, max_nms) : n;  // utils/general.py:578-579
@@ -466,16 +546,28 @@ __global__ void __launch_bounds__(SMALL_THREADS)
         __syncthreads();
         const float4 bi = i < nb ? s_box[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         // (1) against the boxes kept in earlier steps (compacted at the front of s_box)
+        bool sup = false;
         if (i < nb) {
-            bool sup = false;
-            for (int q = grp; q < nk; q += 4) {
-                const float4 a = s_box[q];
-                sup |= iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick);
+            for (int qb = grp * 32; qb < nk && !sup; qb += 128) {  // the 4 thread groups take 32 kept boxes each
+                unsigned ov = 0u;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) ov |= boxes_overlap(s_box[qb + j], bi) ? (1u << j) : 0u;  // < SMALL_LIMIT
+                if (!quick) ov = ~0u;
+                ov &= (nk - qb >= 32) ? ~0u : ((1u << (nk - qb)) - 1u);
+                while (ov && !sup) {
+                    const int j = __ffs(ov) - 1;
+                    ov &= ov - 1u;
+                    sup = iou_gt<MODE>(s_box[qb + j], bi, thr, inclusive != 0, false);
+                }
             }
-            if (sup) atomicOr(&s_sup[i >> 6], 1ull << (i & 63));
+        }
+        {   // one native 32-bit atomic per warp (a warp = 32 consecutive candidates); 64-bit shared-memory OR is a
+            // CAS loop and serialises badly when most of a block is suppressed
+            const unsigned sb = __ballot_sync(0xffffffffu, sup);
+            if ((tid & 31) == 0 && sb) atomicOr(reinterpret_cast<unsigned *>(s_sup) + (i >> 5), sb);
         }
         // (2) + (3): column masks and parallel greedy resolution
-        greedy_block<MODE>(s_box + base, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_U, s_keptbits);
+        greedy_block<MODE>(s_box + base, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_keptbits);
         // (4) append: kept boxes move to the front of s_box (never past the read position), indices go out
         float4 kbox = bi;
         uint32_t kidx = 0;
@@ -505,7 +597,7 @@ __global__ void __launch_bounds__(SMALL_THREADS)
 // order in global scratch; the boxes kept so far are compacted IN PLACE at the front of the same array (the
 // write position never passes the read position) and streamed through shared memory in tiles.  Per step 256
 // candidates are (1) tested against the kept list with early exit, (2) masked against each other (256 x 256
-// bits), (3) resolved by warp 0 with one step per KEPT box, (4) appended.  Work ~ K * n_kept / 2 pair tests
+// bits), (3) resolved by warp 0 in 32-candidate chunks with ballots, (4) appended.  Work ~ K * n_kept / 2 pair tests
 // instead of K^2 / 2, and no K^2 bit-matrix.
 template <int MODE>
 __global__ void __launch_bounds__(GREEDY_THREADS)
@@ -515,7 +607,7 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
     __shared__ float4 s_blk[GREEDY_BS];
     __shared__ float4 s_tile[GREEDY_TILE];
     __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
-    __shared__ unsigned long long s_sup[4], s_keptbits[4], s_U[4];
+    __shared__ unsigned long long s_sup[4], s_keptbits[4];
     __shared__ int s_nkeep;
     const int g = blockIdx.x, tid = threadIdx.x;
     if (max(0, min(count[g], cap)) <= skip_le) return;  // handled by nms_small_kernel
@@ -541,18 +633,26 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
             if (tid < tn) s_tile[tid] = boxes[t0 + tid];
             __syncthreads();
             if (i < nb && !sup) {
-                for (int q = grp; q < tn; q += 4) {
-                    const float4 a = s_tile[q];
-                    if (iou_gt<MODE>(a, f_mul(f_sub(a.z, a.x), f_sub(a.w, a.y)), bi, thr, inclusive != 0, quick)) {
-                        sup = true;
-                        break;
+                for (int qb = grp * 32; qb < tn && !sup; qb += 128) {
+                    unsigned ov = 0u;
+#pragma unroll 8
+                    for (int j = 0; j < 32; j++) ov |= boxes_overlap(s_tile[(qb + j) & (GREEDY_TILE - 1)], bi) ? (1u << j) : 0u;
+                    if (!quick) ov = ~0u;
+                    ov &= (tn - qb >= 32) ? ~0u : ((1u << (tn - qb)) - 1u);
+                    while (ov && !sup) {
+                        const int j = __ffs(ov) - 1;
+                        ov &= ov - 1u;
+                        sup = iou_gt<MODE>(s_tile[qb + j], bi, thr, inclusive != 0, false);
                     }
                 }
             }
         }
-        if (sup) atomicOr(&s_sup[i >> 6], 1ull << (i & 63));
+        {
+            const unsigned sb = __ballot_sync(0xffffffffu, sup);
+            if ((tid & 31) == 0 && sb) atomicOr(reinterpret_cast<unsigned *>(s_sup) + (i >> 5), sb);
+        }
         // (2) + (3): column masks and parallel greedy resolution
-        greedy_block<MODE>(s_blk, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_U, s_keptbits);
+        greedy_block<MODE>(s_blk, nb, thr, inclusive != 0, quick, s_rowmask, s_sup, s_keptbits);
         // (4) append the kept boxes (in place) and their item indices
         if (tid < nb) {
             const int w = tid >> 6, b = tid & 63;

@@ -266,7 +266,7 @@ def main():
         evs[i][0].record()
         ops.pyramid(img_d, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, outs=outs, ctx=pyr_ctx)
         evs[i][1].record()
-        ops.decode_filter(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, wl["conf"], wl["cap"], out=c)
+        ops.decode_filter(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, wl["conf"], wl["cap"], out=c, landmarks=False)
         evs[i][2].record()
         ops.nms_segments(c.cand, c.count, c.cap, wl["iou"], ops.IOU_TV_CUDA, tie=c.row, keep=c.keep, n_keep=c.n_keep)
         evs[i][3].record()

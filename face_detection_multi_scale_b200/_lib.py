@@ -51,6 +51,8 @@ _SIGS = {
     "fdms_decode_dense": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "fdms_decode_filter": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fdms_decode_filter_ex": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fdms_filter_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fdms_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

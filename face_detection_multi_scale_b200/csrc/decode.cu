@@ -38,14 +38,12 @@ struct DecParams {
     int n_levels, n_scales, bs, cap;
     int scale_first[FDMS_MAX_SCALES + 1];  // levels of scale s are lv[scale_first[s] .. scale_first[s+1])
     float conf_thres;
-    float thr_lo, thr_hi;  // band around conf_thres inside which the fast sigmoid is not trusted
+    float prod_pass, prod_fail;  // (1+e^-cls)(1+e^-obj) below / above which the fast decision is trusted
     float logit_lo;  // conservative lower bound on logit(conf_thres): x < logit_lo => sigmoid(x) <= thres
     float *cand;
     int32_t *cand_row;
     int32_t *count;
 };
-
-__device__ __forceinline__ float sigmoid_fast(float x) { return f_div(1.0f, f_add(1.0f, expf(-x))); }
 
 __device__ __forceinline__ float sigmoid_exact(float x) {
     float e = (float)exp(-(double)x);  // fp64 exp rounded once == correctly rounded expf
@@ -72,6 +70,19 @@ __device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, floa
     }
 }
 
+// The box / objectness / class part of decode_cell alone (candidates whose landmarks nobody reads).
+__device__ __forceinline__ void decode_box(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
+                                           float (&o)[NO]) {
+    float s0 = sigmoid_exact(v[0]), s1 = sigmoid_exact(v[1]), s2 = sigmoid_exact(v[2]), s3 = sigmoid_exact(v[3]);
+    o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
+    o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
+    float t2 = f_mul(s2, 2.f), t3 = f_mul(s3, 2.f);
+    o[2] = f_mul(f_mul(t2, t2), aw);
+    o[3] = f_mul(f_mul(t3, t3), ah);
+    o[4] = sigmoid_exact(v[4]);
+    o[5] = sigmoid_exact(v[5]);
+}
+
 // utils/general.py:547-563 + 299-306 on one decoded row: o -> candidate row (in place)
 __device__ __forceinline__ void row_to_candidate(float (&o)[NO], float conf) {
     float hw = f_div(o[2], 2.f), hh = f_div(o[3], 2.f);
@@ -83,6 +94,9 @@ __device__ __forceinline__ void row_to_candidate(float (&o)[NO], float conf) {
     o[4] = conf;
     o[5] = 0.f;  // class index j (nc == 1)
 }
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 
 template <typename T>
 __device__ __forceinline__ void load_vec8(const T *p, long long i, int n_valid, bool aligned, float (&v)[DEC_VEC]);
@@ -130,52 +144,48 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     const T *base = reinterpret_cast<const T *>(L.data) + ((long long)b * NA * NO + (long long)a * NO) * cells;
     const bool aligned = (cells % DEC_VEC == 0) && ((uintptr_t)L.data % 16 == 0);
 
-    unsigned pass = 0;
+    // cheap necessary condition on the raw logits: sigmoid(obj) > thres and sigmoid(cls) > thres
+    unsigned pre = 0;
     if (n_valid > 0) {
         float xo[DEC_VEC], xc[DEC_VEC];
         load_vec8<T>(base + 4 * cells, cell0, n_valid, aligned, xo);
         load_vec8<T>(base + 5 * cells, cell0, n_valid, aligned, xc);
 #pragma unroll
-        for (int k = 0; k < DEC_VEC; k++) {
-            // cheap necessary condition: sigmoid(obj) > thres and sigmoid(cls) > thres
-            if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) {
-                // decision with the fast fp32 sigmoid (<= 2 ulp expf); only a +-4e-6 relative band around the
-                // threshold needs the exact arithmetic.  The exact confidence itself is recomputed by
-                // decode_candidates_kernel.  obj > thres (general.py:515) is implied by cls*obj > thres (:563).
-                const float cf = f_mul(sigmoid_fast(xc[k]), sigmoid_fast(xo[k]));
-                bool ok = cf > P.thr_hi;
-                if (!ok && cf >= P.thr_lo) ok = f_mul(sigmoid_exact(xc[k]), sigmoid_exact(xo[k])) > P.conf_thres;  // :547,563
-                if (ok) pass |= 1u << k;
-            }
-        }
+        for (int k = 0; k < DEC_VEC; k++)
+            if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) pre |= 1u << k;
     }
-    if (!__any_sync(0xffffffffu, pass != 0)) return;
+    if (!__any_sync(0xffffffffu, pre != 0)) return;
 
-    // warp-aggregated slot reservation in the segment's candidate list
+    // The few cells that get here (~1 % of a head) are decided DENSELY: every lane with a pending cell takes its
+    // lowest one, so the warp runs the exponentials once per round (1-2 rounds) instead of once per cell index
+    // whenever any lane passes.  conf = sigmoid(cls) * sigmoid(obj) > thres  <=>  (1 + e^-cls)(1 + e^-obj) < 1/thres:
+    // two expf and no division; only a +-4e-6 relative band around the threshold needs the exact arithmetic
+    // (general.py:547,563; the exact confidence itself is recomputed by decode_candidates_kernel, and
+    // obj > thres (general.py:515) is implied by cls*obj > thres).
     const int seg = b * P.n_scales + L.scale;
     const int lane = threadIdx.x & 31;
-    int n = __popc(pass);
-    int incl = n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int basepos = 0;
-    if (lane == 31) basepos = atomicAdd(P.count + seg, total);
-    basepos = __shfl_sync(0xffffffffu, basepos, 31);
-    int pos = basepos + incl - n;
-    // Survivors are only RECORDED here (row index); decode_candidates_kernel decodes them one per thread on
-    // dense warps.  Decoding in place would run the long exact path at ~1/32 lane efficiency.
-#pragma unroll
-    for (int k = 0; k < DEC_VEC; k++) {
-        if ((pass >> k) & 1u) {
-            if (pos < P.cap) {
-                const long long slot = (long long)seg * P.cap + pos;
-                P.cand_row[slot] = L.row_offset + a * (int)cells + (int)(cell0 + k);
-            }
-            pos++;
+    const T *po = base + 4 * cells + cell0, *pc = base + 5 * cells + cell0;
+    while (__any_sync(0xffffffffu, pre != 0)) {
+        const bool have = pre != 0;
+        const int k = have ? __ffs(pre) - 1 : 0;
+        pre &= pre - 1u;
+        bool ok = false;
+        if (have) {
+            const float lo = to_f32(__ldg(po + k)), lc = to_f32(__ldg(pc + k));  // L1 hits: just read as vectors
+            const float prod = f_mul(f_add(1.0f, expf(-lc)), f_add(1.0f, expf(-lo)));
+            ok = prod < P.prod_pass;
+            if (!ok && !(prod > P.prod_fail)) ok = f_mul(sigmoid_exact(lc), sigmoid_exact(lo)) > P.conf_thres;
+        }
+        // warp-aggregated slot reservation in the segment's candidate list.  Survivors are only RECORDED here (row
+        // index; the order inside a segment is irrelevant, the NMS sort key restores the reference order);
+        // decode_candidates_kernel decodes them one per thread on dense warps.
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+            int basepos = 0;
+            if (lane == 0) basepos = atomicAdd(P.count + seg, __popc(m));
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            const int pos = basepos + __popc(m & ((1u << lane) - 1u));
+            if (ok && pos < P.cap) P.cand_row[(long long)seg * P.cap + pos] = L.row_offset + a * (int)cells + (int)(cell0 + k);
         }
     }
 }
@@ -195,7 +205,9 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid
 // :299-306 (xywh2xyxy), one 84-byte row per thread.
 constexpr int CAND_THREADS = 128;
 
+template <bool KPT>
 __global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const __grid_constant__ DecParams P) {
+    constexpr int NV = KPT ? NO : 6;  // planes read / columns written
     const int seg = blockIdx.y;
     const int n = min(P.count[seg], P.cap);
     const int b = seg / P.n_scales, scale = seg - b * P.n_scales;
@@ -214,13 +226,29 @@ __global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const _
         const int gy = cell / L.nx, gx = cell - gy * L.nx;
         const long long base = ((long long)b * NA * NO + (long long)a * NO) * cells + cell;
         float v[NO], o[NO];
+        // Every plane of a candidate is a different 32-byte DRAM sector (the head is plane-major), so this kernel
+        // is bound by sector traffic: ~21 sectors per candidate with landmarks, 6 without.  All loads are issued
+        // before the first conversion.
 #pragma unroll
-        for (int c = 0; c < NO; c++) v[c] = ld_f(L.data, L.dtype, base + (long long)c * cells);
-        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+        for (int c = NV; c < NO; c++) v[c] = 0.f;
+        if (L.dtype == FDMS_F16) {
+            const __half *p = reinterpret_cast<const __half *>(L.data) + base;
+            unsigned short raw[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) raw[c] = __ldg(reinterpret_cast<const unsigned short *>(p + (long long)c * cells));
+#pragma unroll
+            for (int c = 0; c < NV; c++) v[c] = __half2float(__ushort_as_half(raw[c]));
+        } else {
+            const float *p = reinterpret_cast<const float *>(L.data) + base;
+#pragma unroll
+            for (int c = 0; c < NV; c++) v[c] = __ldg(p + (long long)c * cells);
+        }
+        if (KPT) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+        else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
         row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
         float *dst = P.cand + slot * NO;
 #pragma unroll
-        for (int c = 0; c < NO; c++) dst[c] = o[c];
+        for (int c = 0; c < NV; c++) dst[c] = o[c];
     }
 }
 
@@ -350,9 +378,9 @@ int fill_levels(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_sca
 
 extern "C" {
 
-FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
-                                float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
-                                fdms_stream stream) {
+FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
+                                   float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap, int flags,
+                                   fdms_stream stream) {
     if (int rc = fdms_bind(ctx)) return rc;
     if (!cand || !cand_row || !count || cap <= 0 || n_scales <= 0 || n_scales > FDMS_MAX_SCALES)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: bad arguments");
@@ -376,8 +404,13 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
             (levels[l].scale == levels[l - 1].scale && levels[l].row_offset <= levels[l - 1].row_offset))
             return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: levels must be sorted by (scale, row_offset)");
     P.logit_lo = logit_lower_bound(conf_thres);
-    P.thr_lo = conf_thres - 4e-6f * fabsf(conf_thres) - 1e-37f;
-    P.thr_hi = conf_thres + 4e-6f * fabsf(conf_thres) + 1e-37f;
+    {   // conf > thres * (1 + 4e-6) certainly passes, conf < thres * (1 - 4e-6) certainly fails (the fast product is
+        // good to ~3e-7 relative); non-positive thresholds have no fast "fail" side
+        const double hi = (double)conf_thres + 4e-6 * fabs((double)conf_thres) + 1e-37;
+        const double lo = (double)conf_thres - 4e-6 * fabs((double)conf_thres) - 1e-37;
+        P.prod_pass = hi > 0.0 ? (float)(1.0 / hi) : INFINITY;
+        P.prod_fail = lo > 0.0 ? (float)(1.0 / lo) : INFINITY;
+    }
     P.cand = cand;
     P.cand_row = cand_row;
     P.count = count;
@@ -389,9 +422,16 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
     if (n_seg > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_filter: more than 65535 segments");
     int gx = ceil_div(cap, CAND_THREADS);
     if (gx > 8) gx = 8;
-    decode_candidates_kernel<<<dim3(gx, n_seg), CAND_THREADS, 0, st>>>(P);
+    if (flags & FDMS_DECODE_BOXES_ONLY) decode_candidates_kernel<false><<<dim3(gx, n_seg), CAND_THREADS, 0, st>>>(P);
+    else decode_candidates_kernel<true><<<dim3(gx, n_seg), CAND_THREADS, 0, st>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "decode_candidates_kernel");
     return FDMS_OK;
+}
+
+FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
+                                float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
+                                fdms_stream stream) {
+    return fdms_decode_filter_ex(ctx, levels, n_levels, n_scales, bs, conf_thres, cand, cand_row, count, cap, 0, stream);
 }
 
 FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, float *pred,

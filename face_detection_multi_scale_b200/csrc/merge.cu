@@ -291,8 +291,9 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_stream stream) {
     if (int rc = fdms_bind(ctx)) return rc;
     if (!d) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_postprocess: null descriptor");
-    if (int rc = fdms_decode_filter(ctx, d->levels, d->n_levels, d->n_scales, d->bs, d->conf_thres, d->cand, d->cand_row,
-                                    d->count, d->cap, stream))
+    // landmarks are decoded only when the caller asked for them in the merged output
+    if (int rc = fdms_decode_filter_ex(ctx, d->levels, d->n_levels, d->n_scales, d->bs, d->conf_thres, d->cand, d->cand_row,
+                                       d->count, d->cap, d->kpts_out ? 0 : FDMS_DECODE_BOXES_ONLY, stream))
         return rc;
     if (int rc = fdms_nms_impl(ctx, d->cand, NO, 0, 4, d->cand_row, d->count, d->bs * d->n_scales, d->cap, d->iou_thres,
                                d->iou_mode, FDMS_MAX_NMS, d->keep, d->n_keep, (cudaStream_t)stream))

@@ -109,6 +109,9 @@ def decode_dense(levels, strides, anchors_px):
     return pred
 
 
+DECODE_BOXES_ONLY = 1  # include/fdms.h FDMS_DECODE_BOXES_ONLY
+
+
 class Candidates:
     """Device-side candidate lists of n_seg segments (see include/fdms.h fdms_decode_filter)."""
 
@@ -121,17 +124,20 @@ class Candidates:
         self.n_keep = torch.zeros((n_seg,), dtype=torch.int32, device=device)
 
 
-def decode_filter(scales_levels, strides, anchors_px, conf_thres, cap, out=None):
-    """Fused decode + filter + compaction over all scales of a batch.  Segment = b * n_scales + s."""
+def decode_filter(scales_levels, strides, anchors_px, conf_thres, cap, out=None, landmarks=True):
+    """Fused decode + filter + compaction over all scales of a batch.  Segment = b * n_scales + s.
+    landmarks=False leaves the 15 landmark columns of the candidate rows unread and unwritten (what the multi-scale
+    path needs: multi_scale_face_detector.py:151-153 drops them before the merge)."""
     dev = _dev(scales_levels[0][0])
     arr, n, bs, _, hold = _level_table(scales_levels, strides, anchors_px)
     ns = len(scales_levels)
     if out is None:
         out = Candidates(bs * ns, cap, scales_levels[0][0].device)
     c = _lib.ctx(dev)
-    rc = _lib.lib().fdms_decode_filter(c.handle, arr, n, ns, bs, float(np.float32(conf_thres)), _ptr(out.cand),
-                                       _ptr(out.row), _ptr(out.count), out.cap, _stream(dev))
-    c.check(rc, "fdms_decode_filter")
+    rc = _lib.lib().fdms_decode_filter_ex(c.handle, arr, n, ns, bs, float(np.float32(conf_thres)), _ptr(out.cand),
+                                          _ptr(out.row), _ptr(out.count), out.cap, 0 if landmarks else DECODE_BOXES_ONLY,
+                                          _stream(dev))
+    c.check(rc, "fdms_decode_filter_ex")
     return out
 
 

@@ -133,6 +133,15 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
                                 float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
                                 fdms_stream stream);
 
+/* fdms_decode_filter with options.  FDMS_DECODE_BOXES_ONLY: the 15 landmark columns of a candidate row are neither
+ * read from the head nor written (columns 0..5 are identical to the full decode).  This is what the multi-scale
+ * path needs -- multi_scale_face_detector.py:151-153 drops the landmarks before the merge -- and it cuts the DRAM
+ * sectors touched per candidate from 21 to 6 (the head is plane-major). */
+#define FDMS_DECODE_BOXES_ONLY 1
+FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
+                                   float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap, int flags,
+                                   fdms_stream stream);
+
 /* Same filter + box conversion, reading an already decoded pred (bs, rows, no) f16/f32 with
  * no = 6 + 3*kpt_label columns (nc == 1): the front half of utils/general.py:506-600
  * non_max_suppression for kpt_label = 5 (no = 21, every cfg of the reference), kpt_label = 0

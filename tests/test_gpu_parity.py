@@ -187,6 +187,27 @@ def test_decode_filter_multi_scale_segments():
             assert np.max(np.abs(cand - rc)) <= TOL_PX
 
 
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_decode_filter_boxes_only_equals_full_decode(dtype):
+    """FDMS_DECODE_BOXES_ONLY: same candidate sets, columns 0..5 bit-identical to the full decode, landmark columns
+    untouched (the multi-scale path drops them: multi_scale_face_detector.py:151-153)."""
+    sl = [[l.astype(dtype) for l in H.crowd_levels(ih, iw, 12, 50 + si)]
+          for si, (ih, iw) in enumerate([(96, 160), (192, 320)])]
+    dev_levels = [[gpu(l) for l in lv] for lv in sl]
+    full = ops.decode_filter(dev_levels, synth.P5_STRIDES, synth.P5_ANCHORS, 0.3, cap=2048)
+    lite = ops.Candidates(full.n_seg, full.cap, full.cand.device)
+    lite.cand.fill_(-7.0)
+    ops.decode_filter(dev_levels, synth.P5_STRIDES, synth.P5_ANCHORS, 0.3, cap=2048, out=lite, landmarks=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(full.count.cpu().numpy(), lite.count.cpu().numpy())
+    for seg in range(full.n_seg):
+        cf, rf = _sorted_cands(full, seg)
+        cl, rl = _sorted_cands(lite, seg)
+        assert len(rf) > 0 and np.array_equal(rf, rl)
+        assert np.array_equal(cf[:, :6], cl[:, :6])
+        assert np.all(cl[:, 6:] == -7.0)
+
+
 def test_decode_filter_overflow_is_reported():
     levels = _crowd("crowdA")
     c = ops.decode_filter([[gpu(l) for l in levels]], synth.P5_STRIDES, synth.P5_ANCHORS, 0.01, cap=16)

@@ -154,15 +154,19 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
         for (int k = 0; k < DEC_VEC; k++)
             if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) pre |= 1u << k;
     }
-    if (!__any_sync(0xffffffffu, pre != 0)) return;
-
     // The few cells that get here (~1 % of a head) are decided DENSELY: every lane with a pending cell takes its
     // lowest one, so the warp runs the exponentials once per round (1-2 rounds) instead of once per cell index
     // whenever any lane passes.  conf = sigmoid(cls) * sigmoid(obj) > thres  <=>  (1 + e^-cls)(1 + e^-obj) < 1/thres:
     // two expf and no division; only a +-4e-6 relative band around the threshold needs the exact arithmetic
     // (general.py:547,563; the exact confidence itself is recomputed by decode_candidates_kernel, and
     // obj > thres (general.py:515) is implied by cls*obj > thres).
-    const int seg = b * P.n_scales + L.scale;
+    // Survivors are only RECORDED (row index; the order inside a segment is irrelevant, the NMS sort key restores
+    // the reference order): first in shared memory, then with ONE global atomic per CTA -- all CTAs of an image and
+    // scale reserve slots in the same counter, and same-address atomics serialise in L2.
+    __shared__ int s_rows[DEC_CELLS];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const T *po = base + 4 * cells + cell0, *pc = base + 5 * cells + cell0;
     while (__any_sync(0xffffffffu, pre != 0)) {
@@ -176,17 +180,23 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
             ok = prod < P.prod_pass;
             if (!ok && !(prod > P.prod_fail)) ok = f_mul(sigmoid_exact(lc), sigmoid_exact(lo)) > P.conf_thres;
         }
-        // warp-aggregated slot reservation in the segment's candidate list.  Survivors are only RECORDED here (row
-        // index; the order inside a segment is irrelevant, the NMS sort key restores the reference order);
-        // decode_candidates_kernel decodes them one per thread on dense warps.
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (m) {
             int basepos = 0;
-            if (lane == 0) basepos = atomicAdd(P.count + seg, __popc(m));
+            if (lane == 0) basepos = atomicAdd(&s_n, __popc(m));
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            const int pos = basepos + __popc(m & ((1u << lane) - 1u));
-            if (ok && pos < P.cap) P.cand_row[(long long)seg * P.cap + pos] = L.row_offset + a * (int)cells + (int)(cell0 + k);
+            if (ok) s_rows[basepos + __popc(m & ((1u << lane) - 1u))] = L.row_offset + a * (int)cells + (int)(cell0 + k);
         }
+    }
+    __syncthreads();
+    const int n_cta = s_n;
+    if (n_cta == 0) return;  // CTA-uniform
+    const int seg = b * P.n_scales + L.scale;
+    if (threadIdx.x == 0) s_base = atomicAdd(P.count + seg, n_cta);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_cta; i += DEC_THREADS) {
+        const int pos = s_base + i;
+        if (pos < P.cap) P.cand_row[(long long)seg * P.cap + pos] = s_rows[i];
     }
 }
 

@@ -8,7 +8,7 @@ from . import build as _build
 
 FDMS_U8, FDMS_F16, FDMS_F32 = 0, 1, 2
 FDMS_CHW, FDMS_HWC = 0, 1
-IOU_TV_CPU, IOU_TV_CUDA = 0, 1
+IOU_TV_CPU, IOU_TV_CUDA, IOU_NCNN = 0, 1, 2  # include/fdms.h fdms_iou_mode
 MAX_SCALES, MAX_LEVELS, MAX_NMS = 8, 32, 30000
 
 
@@ -71,6 +71,10 @@ _SIGS = {
     "fdms_pack_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_postprocess": (C.c_int, [C.c_void_p, C.POINTER(PostDesc), C.c_void_p]),
+    "fdms_scale_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "fdms_descale_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

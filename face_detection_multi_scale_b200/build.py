@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdms.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["ctx.cu", "pyramid.cu", "decode.cu", "nms.cu", "merge.cu", "eval.cu"]
+SOURCES = ["ctx.cu", "pyramid.cu", "decode.cu", "nms.cu", "merge.cu", "eval.cu", "tta.cu"]
 HEADERS = ["common.cuh", "nms.cuh", os.path.join("..", "..", "include", "fdms.h")]
 
 # -fmad=false: every fp32 rounding the reference performs is kept (fused ops are explicit).

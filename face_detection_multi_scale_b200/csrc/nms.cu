@@ -203,6 +203,16 @@ template <int MODE>
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr, bool inclusive, bool quick) {
     float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    if (MODE == FDMS_IOU_NCNN) {
+        // cpp/yolov7-face-ncnn/src/yolov7face.cpp:43-74: +1 pixel convention on every extent, `ovr >= thresh`
+        float w = fmaxf(0.f, f_add(f_sub(xx2, xx1), 1.f)), h = fmaxf(0.f, f_add(f_sub(yy2, yy1), 1.f));
+        if (quick && (!(w > 0.f) || !(h > 0.f))) return false;
+        float inter = f_mul(w, h);
+        float area_a = f_mul(f_add(f_sub(a.z, a.x), 1.f), f_add(f_sub(a.w, a.y), 1.f));
+        float area_b = f_mul(f_add(f_sub(b.z, b.x), 1.f), f_add(f_sub(b.w, b.y), 1.f));
+        float iou = f_div(inter, f_sub(f_add(area_a, area_b), inter));
+        return iou >= thr;
+    }
     if (quick && (!(xx2 > xx1) || !(yy2 > yy1))) return false;
     float w = fmaxf(f_sub(xx2, xx1), 0.f), h = fmaxf(f_sub(yy2, yy1), 0.f);
     float inter = f_mul(w, h);
@@ -218,7 +228,11 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
 // Pass 1 of every pair loop: do two boxes overlap at all?  This is iou_gt's own quick-reject test, evaluated
 // branch-free for a batch of boxes; only the survivors take the full IoU (pass 2).  The lanes of a warp hold
 // different boxes, so a fused loop would run the long path whenever ANY lane overlaps the broadcast box.
+template <int MODE>
 __device__ __forceinline__ bool boxes_overlap(const float4 a, const float4 b) {
+    if (MODE == FDMS_IOU_NCNN)  // extents carry +1: boxes up to one pixel apart still intersect
+        return (f_add(f_sub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f) > 0.f) &&
+               (f_add(f_sub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f) > 0.f);
     return (fminf(a.z, b.z) > fmaxf(a.x, b.x)) && (fminf(a.w, b.w) > fmaxf(a.y, b.y));
 }
 
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(MASK_THREADS)
             const int j0 = (cblk == rb) ? (tid & 63) + 1 : 0;  // only later boxes can be suppressed
             unsigned long long ov = 0ull;
 #pragma unroll 8
-            for (int j = 0; j < 64; j++) ov |= boxes_overlap(a, s_col[q * 64 + j]) ? (1ull << j) : 0ull;
+            for (int j = 0; j < 64; j++) ov |= boxes_overlap<MODE>(a, s_col[q * 64 + j]) ? (1ull << j) : 0ull;
             if (!quick) ov = ~0ull;
             ov &= (jn >= 64 ? ~0ull : ((1ull << jn) - 1ull)) & (j0 >= 64 ? 0ull : (~0ull << j0));
             while (ov) {
@@ -378,10 +392,8 @@ __device__ __forceinline__ void greedy_block(const float4 *blk, int nb, float th
                 unsigned ov = 0u;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    const float4 a = blk[j0 + j];  // in bounds of the block array for every j0; masked below
-                    const float xx1 = fmaxf(a.x, bi.x), yy1 = fmaxf(a.y, bi.y);
-                    const float xx2 = fminf(a.z, bi.z), yy2 = fminf(a.w, bi.w);
-                    ov |= ((xx2 > xx1) && (yy2 > yy1)) ? (1u << j) : 0u;
+                    // blk[j0 + j] is in bounds of the block array for every j0; masked below
+                    ov |= boxes_overlap<MODE>(blk[j0 + j], bi) ? (1u << j) : 0u;
                 }
                 if (!quick) ov = 0xffffu;  // thresholds below zero: every pair takes the exact path
                 ov &= jn > 0 ? ((1u << jn) - 1u) : 0u;
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(SMALL_THREADS)
             for (int qb = grp * 32; qb < nk && !sup; qb += 128) {  // the 4 thread groups take 32 kept boxes each
                 unsigned ov = 0u;
 #pragma unroll 8
-                for (int j = 0; j < 32; j++) ov |= boxes_overlap(s_box[qb + j], bi) ? (1u << j) : 0u;  // < SMALL_LIMIT
+                for (int j = 0; j < 32; j++) ov |= boxes_overlap<MODE>(s_box[qb + j], bi) ? (1u << j) : 0u;  // < SMALL_LIMIT
                 if (!quick) ov = ~0u;
                 ov &= (nk - qb >= 32) ? ~0u : ((1u << (nk - qb)) - 1u);
                 while (ov && !sup) {
@@ -636,7 +648,7 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
                 for (int qb = grp * 32; qb < tn && !sup; qb += 128) {
                     unsigned ov = 0u;
 #pragma unroll 8
-                    for (int j = 0; j < 32; j++) ov |= boxes_overlap(s_tile[(qb + j) & (GREEDY_TILE - 1)], bi) ? (1u << j) : 0u;
+                    for (int j = 0; j < 32; j++) ov |= boxes_overlap<MODE>(s_tile[(qb + j) & (GREEDY_TILE - 1)], bi) ? (1u << j) : 0u;
                     if (!quick) ov = ~0u;
                     ov &= (tn - qb >= 32) ? ~0u : ((1u << (tn - qb)) - 1u);
                     while (ov && !sup) {
@@ -693,6 +705,9 @@ void fdms_fold_threshold(double thr, int iou_mode, float *thr_f, int *inclusive)
     if (iou_mode == FDMS_IOU_TV_CUDA) {
         *thr_f = t;
         *inclusive = 0;
+    } else if (iou_mode == FDMS_IOU_NCNN) {  // float ovr >= float thresh
+        *thr_f = t;
+        *inclusive = 1;
     } else {
         // smallest float f with (double)f > thr: t itself if t > thr, else the next float up
         *thr_f = t;
@@ -704,7 +719,7 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
                   const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode, int max_nms, int32_t *keep,
                   int32_t *n_keep, cudaStream_t st) {
     if (!rows || !count || !keep || !n_keep || n_seg <= 0 || cap <= 0 || row_stride <= 0 || box_off < 0 ||
-        score_off < 0 || (iou_mode != FDMS_IOU_TV_CPU && iou_mode != FDMS_IOU_TV_CUDA))
+        score_off < 0 || (iou_mode != FDMS_IOU_TV_CPU && iou_mode != FDMS_IOU_TV_CUDA && iou_mode != FDMS_IOU_NCNN))
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_nms: bad arguments");
     const int cap_e = (max_nms > 0 && max_nms < cap) ? max_nms : cap;
     float thr_f;
@@ -713,12 +728,13 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     // ---- segments of at most small_limit boxes: one fused launch -------------------------------------------
     const int small_limit = ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
     if (small_limit > 0) {
-        if (iou_mode == FDMS_IOU_TV_CUDA)
-            nms_small_kernel<FDMS_IOU_TV_CUDA><<<n_seg, SMALL_THREADS, 0, st>>>(
-                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_limit, thr_f, inclusive, keep, n_keep);
-        else
-            nms_small_kernel<FDMS_IOU_TV_CPU><<<n_seg, SMALL_THREADS, 0, st>>>(
-                rows, row_stride, box_off, score_off, tie, count, cap, max_nms, small_limit, thr_f, inclusive, keep, n_keep);
+#define FDMS_NMS_SMALL(M)                                                                                             \
+    nms_small_kernel<M><<<n_seg, SMALL_THREADS, 0, st>>>(rows, row_stride, box_off, score_off, tie, count, cap, max_nms, \
+                                                         small_limit, thr_f, inclusive, keep, n_keep)
+        if (iou_mode == FDMS_IOU_TV_CUDA) FDMS_NMS_SMALL(FDMS_IOU_TV_CUDA);
+        else if (iou_mode == FDMS_IOU_NCNN) FDMS_NMS_SMALL(FDMS_IOU_NCNN);
+        else FDMS_NMS_SMALL(FDMS_IOU_TV_CPU);
+#undef FDMS_NMS_SMALL
         FDMS_LAUNCH_CHECK(ctx, "nms_small_kernel");
         if (cap <= small_limit) return FDMS_OK;  // no segment can be larger
     }
@@ -764,26 +780,26 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         budget_words, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
     if (greedy) {
-        if (iou_mode == FDMS_IOU_TV_CUDA)
-            nms_greedy_kernel<FDMS_IOU_TV_CUDA><<<n_seg, GREEDY_THREADS, 0, st>>>(
-                seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p), reinterpret_cast<const uint32_t *>(ctx->idx_b.p),
-                thr_f, inclusive, keep, n_keep, cap, count, skip_le);
-        else
-            nms_greedy_kernel<FDMS_IOU_TV_CPU><<<n_seg, GREEDY_THREADS, 0, st>>>(
-                seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p), reinterpret_cast<const uint32_t *>(ctx->idx_b.p),
-                thr_f, inclusive, keep, n_keep, cap, count, skip_le);
+#define FDMS_NMS_GREEDY(M)                                                                                         \
+    nms_greedy_kernel<M><<<n_seg, GREEDY_THREADS, 0, st>>>(seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p),  \
+                                                           reinterpret_cast<const uint32_t *>(ctx->idx_b.p), thr_f,   \
+                                                           inclusive, keep, n_keep, cap, count, skip_le)
+        if (iou_mode == FDMS_IOU_TV_CUDA) FDMS_NMS_GREEDY(FDMS_IOU_TV_CUDA);
+        else if (iou_mode == FDMS_IOU_NCNN) FDMS_NMS_GREEDY(FDMS_IOU_NCNN);
+        else FDMS_NMS_GREEDY(FDMS_IOU_TV_CPU);
+#undef FDMS_NMS_GREEDY
         FDMS_LAUNCH_CHECK(ctx, "nms_greedy_kernel");
         return FDMS_OK;
     }
     const int mask_grid = ctx->sm_count * 8;
-    if (iou_mode == FDMS_IOU_TV_CUDA)
-        nms_mask_kernel<FDMS_IOU_TV_CUDA><<<mask_grid, MASK_THREADS, 0, st>>>(
-            seginfo, hdr, n_seg, cap_e, reinterpret_cast<const float4 *>(ctx->boxes.p),
-            reinterpret_cast<unsigned long long *>(ctx->mask.p), thr_f, inclusive);
-    else
-        nms_mask_kernel<FDMS_IOU_TV_CPU><<<mask_grid, MASK_THREADS, 0, st>>>(
-            seginfo, hdr, n_seg, cap_e, reinterpret_cast<const float4 *>(ctx->boxes.p),
-            reinterpret_cast<unsigned long long *>(ctx->mask.p), thr_f, inclusive);
+#define FDMS_NMS_MASK(M)                                                                                                \
+    nms_mask_kernel<M><<<mask_grid, MASK_THREADS, 0, st>>>(seginfo, hdr, n_seg, cap_e,                                      \
+                                                           reinterpret_cast<const float4 *>(ctx->boxes.p),                 \
+                                                           reinterpret_cast<unsigned long long *>(ctx->mask.p), thr_f, inclusive)
+    if (iou_mode == FDMS_IOU_TV_CUDA) FDMS_NMS_MASK(FDMS_IOU_TV_CUDA);
+    else if (iou_mode == FDMS_IOU_NCNN) FDMS_NMS_MASK(FDMS_IOU_NCNN);
+    else FDMS_NMS_MASK(FDMS_IOU_TV_CPU);
+#undef FDMS_NMS_MASK
     FDMS_LAUNCH_CHECK(ctx, "nms_mask_kernel");
     nms_sweep_kernel<<<n_seg, SWEEP_THREADS, 0, st>>>(seginfo, reinterpret_cast<const unsigned long long *>(ctx->mask.p),
                                                       cap_e, reinterpret_cast<const uint32_t *>(ctx->idx_b.p), keep,

@@ -54,8 +54,9 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         raise NotImplementedError("non_max_suppression on libfdms covers single-class heads (nc=1, no = 6 + 3*kpt: the "
                                   "face head no=21, or the [..., :6] fallback of msfd:134); got no=%d kpt_label=%r nc=%r"
                                   % (no, kpt_label, nc))
-    if labels:
-        raise NotImplementedError("non_max_suppression: autolabelling `labels` is not on the hot path")
+    if labels and no != 6:
+        # :535-541 builds the label rows with nc + 5 columns; with keypoint columns torch.cat raises in the reference too
+        raise ValueError("non_max_suppression: apriori `labels` need a prediction without keypoint columns (no = 6)")
     # multi_label &= nc > 1 (:522) -> always False here; agnostic only changes the class offset, 0 for nc == 1
     src_device, src_dtype = prediction.device, prediction.dtype
     pred = _cuda(prediction)
@@ -69,8 +70,16 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         return [empty] * bs  # every detection has class 0 (:566-567)
     mode = IOU_MODE if iou_mode is None else iou_mode
     cap = min(rows, _DEFAULT_CAP)
+    if labels:  # autolabelling (:533-541): room for the apriori boxes after the filtered predictions
+        n_lab = [len(labels[b]) if b < len(labels) else 0 for b in range(bs)]
+        cap = min(rows, _DEFAULT_CAP) + max(n_lab)
     while True:
         c = ops.filter_pred(pred, conf_thres, cap)
+        if labels and max(n_lab):
+            cap_needed = _append_labels(c, labels, n_lab, rows, conf_thres)
+            if cap_needed > cap:
+                cap = cap_needed
+                continue
         ops.nms_segments(c.cand, c.count, cap, iou_thres, mode, max_nms=MAX_NMS, tie=c.row, keep=c.keep, n_keep=c.n_keep)
         counts = torch.stack((c.count, c.n_keep)).cpu()  # the one synchronisation of this call
         n_cand, n_keep = counts[0], counts[1]
@@ -90,6 +99,35 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     if out.device != src_device:
         out = out.to(src_device)
     return [out[b, :int(n_keep[b])] if int(n_keep[b]) else empty for b in range(bs)]
+
+
+def _append_labels(c, labels, n_lab, rows, conf_thres):
+    """utils/general.py:533-541 + 547-563 for the apriori label rows [cls, x, y, w, h]: box = xywh2xyxy, obj = cls = 1
+    so conf = 1.0, appended AFTER the image's filtered predictions (torchvision's stable sort keeps that order among
+    equal scores: the tie key continues after the prediction rows).  Returns the capacity the longest list needs."""
+    counts = c.count.cpu()  # host round trip: autolabelling is an offline tool of the reference, not the hot path
+    need = 0
+    for b, n in enumerate(n_lab):
+        if not n:
+            need = max(need, int(counts[b]))
+            continue
+        lab = torch.as_tensor(labels[b], dtype=torch.float32, device=c.cand.device).reshape(n, -1)
+        if bool((lab[:, 0].long() != 0).any()):
+            raise NotImplementedError("non_max_suppression: labels of class != 0 on a single-class head")
+        if not (1.0 > conf_thres):  # conf = 1.0 > conf_thres (:563) fails: the label rows are dropped
+            need = max(need, int(counts[b]))
+            continue
+        k0 = int(counts[b])
+        need = max(need, k0 + n)
+        if k0 + n > c.cap:
+            continue
+        v = torch.zeros((n, 6), dtype=torch.float32, device=c.cand.device)
+        v[:, :4] = xywh2xyxy(lab[:, 1:5])
+        v[:, 4] = 1.0
+        c.cand[b, k0:k0 + n] = v
+        c.row[b, k0:k0 + n] = torch.arange(rows, rows + n, dtype=torch.int32, device=c.cand.device)
+        c.count[b] = k0 + n
+    return need
 
 
 def xywh2xyxy(x):  # utils/general.py:299 (plain tensor arithmetic; the fused kernels do this inside the filter)

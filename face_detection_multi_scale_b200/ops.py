@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FDMS_CHW, FDMS_F16, FDMS_F32, FDMS_HWC, FDMS_U8, IOU_TV_CPU, IOU_TV_CUDA, MAX_NMS  # noqa: F401
+from ._lib import FDMS_CHW, FDMS_F16, FDMS_F32, FDMS_HWC, FDMS_U8, IOU_NCNN, IOU_TV_CPU, IOU_TV_CUDA, MAX_NMS  # noqa: F401
 
 NO = 21
 

@@ -44,7 +44,11 @@ typedef enum fdms_status {
 typedef enum fdms_dtype { FDMS_U8 = 0, FDMS_F16 = 1, FDMS_F32 = 2 } fdms_dtype;
 typedef enum fdms_layout { FDMS_CHW = 0, FDMS_HWC = 1 } fdms_layout;
 /* torchvision.ops.nms arithmetic flavours */
-typedef enum fdms_iou_mode { FDMS_IOU_TV_CPU = 0, FDMS_IOU_TV_CUDA = 1 } fdms_iou_mode;
+typedef enum fdms_iou_mode {
+    FDMS_IOU_TV_CPU = 0,  /* torchvision CPU kernel: (area_i + area_j) - inter, (double)iou > thr */
+    FDMS_IOU_TV_CUDA = 1, /* torchvision CUDA kernel: fma(w_j, h_j, area_i) - inter, iou > (float)thr */
+    FDMS_IOU_NCNN = 2     /* cpp/yolov7-face-ncnn/src/yolov7face.cpp:43-74: +1 pixel extents, iou >= (float)thr */
+} fdms_iou_mode;
 
 #define FDMS_MAX_SCALES 8
 #define FDMS_MAX_LEVELS 32
@@ -241,6 +245,23 @@ FDMS_API int fdms_bbox_overlaps(fdms_ctx *ctx, const double *boxes, int64_t n, c
 FDMS_API int fdms_pack_frames(fdms_ctx *ctx, const float *dets, const int32_t *n_out, int n_img, int out_cap,
                               int max_faces, int img_w, int img_h, double *bboxes, double *confidence,
                               int32_t *class_indexes, int32_t *scale_used, fdms_stream stream);
+
+/* Test-time augmentation around the (unchanged) backbone, models/yolo.py:363-374 Model.forward_augment:
+ * fdms_scale_img = utils/torch_utils.py:247-257 scale_img: F.interpolate(bilinear, align_corners=False) of an NCHW
+ * f16/f32 batch (n, c, h, w) to (resized_h, resized_w) = (int(h*ratio), int(w*ratio)), read through an optional flip
+ * of the source (0 none, 2 up-down, 3 left-right: `x.flip(fi)` at :368), and padded with pad_value (0.447) on the
+ * right / bottom to (out_h, out_w), the next multiple of the grid size.  dst is (n, c, out_h, out_w), same dtype. */
+FDMS_API int fdms_scale_img(fdms_ctx *ctx, const void *src, int dtype, int n, int c, int h, int w, int resized_h,
+                            int resized_w, int out_h, int out_w, int flip, float pad_value, void *dst,
+                            fdms_stream stream);
+
+/* models/yolo.py:402-417 _descale_pred on pred (bs, rows, no) f32: columns 0..3 /= scale, then y = img_h - y
+ * (flip 2) or x = img_w - x (flip 3); the other columns are copied (the reference leaves the landmarks as they
+ * are).  The rows are written at row_offset of dst (bs, rows_total, no): the torch.cat(y, 1) of :374.  dst may be
+ * pred itself when rows_total == rows and row_offset == 0. */
+FDMS_API int fdms_descale_pred(fdms_ctx *ctx, const float *pred, int bs, int64_t rows, int no, float scale, int flip,
+                               int img_h, int img_w, float *dst, int64_t rows_total, int64_t row_offset,
+                               fdms_stream stream);
 
 #ifdef __cplusplus
 }

@@ -317,6 +317,16 @@ FO_EXPORT int64_t fo_nms(const float *boxes /* n*4 xyxy */, const float *scores,
             const float *b = boxes + j * 4;
             float xx1 = a[0] > b[0] ? a[0] : b[0], yy1 = a[1] > b[1] ? a[1] : b[1];
             float xx2 = a[2] < b[2] ? a[2] : b[2], yy2 = a[3] < b[3] ? a[3] : b[3];
+            if (mode == 2) { /* cpp/yolov7-face-ncnn/src/yolov7face.cpp:43-74: +1 extents, ovr >= thresh */
+                float wn = xx2 - xx1 + 1, hn = yy2 - yy1 + 1;
+                if (!(wn > 0.f)) wn = 0.f;
+                if (!(hn > 0.f)) hn = 0.f;
+                float in_ = wn * hn;
+                float ai = (a[2] - a[0] + 1) * (a[3] - a[1] + 1), aj = (b[2] - b[0] + 1) * (b[3] - b[1] + 1);
+                float ovr = in_ / (ai + aj - in_);
+                if (ovr >= thr_f) sup[j] = 1;
+                continue;
+            }
             float w = xx2 - xx1, h = yy2 - yy1;
             if (!(w > 0.f)) w = 0.f;
             if (!(h > 0.f)) h = 0.f;

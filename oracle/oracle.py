@@ -134,7 +134,7 @@ def filter_xyxy(pred_img, conf_thres):
 
 
 # ---- B7 NMS: torchvision.ops.nms ---------------------------------------------------------------
-TV_CPU, TV_CUDA = 0, 1
+TV_CPU, TV_CUDA, NCNN = 0, 1, 2  # NCNN: cpp/yolov7-face-ncnn/src/yolov7face.cpp:43-74 (+1 extents, >=)
 
 
 def nms(boxes, scores, iou_thres, mode=TV_CPU):
@@ -149,12 +149,21 @@ def nms(boxes, scores, iou_thres, mode=TV_CPU):
 MAX_NMS = 30000  # utils/general.py:520
 
 
-def non_max_suppression(pred, conf_thres=0.25, iou_thres=0.45, mode=TV_CPU):
+def non_max_suppression(pred, conf_thres=0.25, iou_thres=0.45, mode=TV_CPU, labels=()):
     """utils/general.py:506-600 with kpt_label=5, nc=1, classes=None.  pred (bs, rows, 21) fp32.
-    Returns list of (n,21) arrays; empty images give (0,6) zeros like the reference (:527)."""
+    Returns list of (n,21) arrays; empty images give (0,6) zeros like the reference (:527).
+    labels (autolabelling, :533-541; 6-column predictions only): per image (n, 5) [cls, x, y, w, h], appended after
+    the obj > thres filter with obj = cls = 1."""
     out = []
     for xi in range(pred.shape[0]):
         cand, _ = filter_xyxy(pred[xi], conf_thres)
+        if labels and len(labels[xi]) and 1.0 > np.float32(conf_thres):
+            lab = np.asarray(labels[xi], np.float32).reshape(-1, 5)
+            v = np.zeros((len(lab), cand.shape[1]), np.float32)
+            half_w, half_h = lab[:, 3] / np.float32(2), lab[:, 4] / np.float32(2)
+            v[:, 0], v[:, 1], v[:, 2], v[:, 3] = lab[:, 1] - half_w, lab[:, 2] - half_h, lab[:, 1] + half_w, lab[:, 2] + half_h
+            v[:, 4] = 1.0
+            cand = np.concatenate([cand, v], 0)
         if cand.shape[0] == 0:
             out.append(np.zeros((0, 6), np.float32))
             continue
@@ -234,3 +243,47 @@ def bbox_overlaps(boxes, query_boxes):
     out = np.zeros((boxes.shape[0], query_boxes.shape[0]), np.float64)
     lib().fo_bbox_overlaps(_p(boxes), C.c_int64(boxes.shape[0]), _p(query_boxes), C.c_int64(query_boxes.shape[0]), _p(out))
     return out
+
+
+# ---- "next" row: test-time augmentation around the backbone --------------------------------
+def scale_img(img, ratio=1.0, same_shape=False, gs=32, flip=None):
+    """utils/torch_utils.py:247-257 (+ the x.flip(fi) of models/yolo.py:368) on an NCHW float32 array: ATen's
+    upsample_bilinear2d with align_corners=False and an explicit size (scale = in / out in fp32, source index
+    clamped at 0), then F.pad(value=0.447) to the next multiple of gs."""
+    import math
+    img = np.asarray(img, np.float32)
+    if flip:
+        img = np.flip(img, axis=flip)
+    if ratio == 1.0:
+        return np.ascontiguousarray(img)
+    n, c, h, w = img.shape
+    rh, rw = int(h * ratio), int(w * ratio)
+    oh, ow = (h, w) if same_shape else [math.ceil(v * ratio / gs) * gs for v in (h, w)]
+
+    def taps(n_in, n_out):
+        s = np.float32(n_in) / np.float32(n_out)
+        d = (np.arange(n_out, dtype=np.float32) + np.float32(0.5)).astype(np.float64)
+        f = np.maximum((np.float64(s) * d - 0.5).astype(np.float32), np.float32(0))  # fmaf(s, d + 0.5, -0.5): ATen's build contracts it
+        i0 = f.astype(np.int32)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (f - i0.astype(np.float32)).astype(np.float32)
+        return i0, i1, (np.float32(1) - l1).astype(np.float32), l1
+    y0, y1, hy, ly = taps(h, rh)
+    x0, x1, hx, lx = taps(w, rw)
+    top = hx * img[:, :, y0][:, :, :, x0] + lx * img[:, :, y0][:, :, :, x1]
+    bot = hx * img[:, :, y1][:, :, :, x0] + lx * img[:, :, y1][:, :, :, x1]
+    res = hy[:, None] * top + ly[:, None] * bot
+    out = np.full((n, c, oh, ow), np.float32(0.447), np.float32)
+    out[:, :, :rh, :rw] = res
+    return out
+
+
+def descale_pred(p, flips, scale, img_size):
+    """models/yolo.py:402-417 on a (bs, rows, no) float32 array (returns a new array)."""
+    p = np.array(p, np.float32, copy=True)
+    p[..., :4] = p[..., :4] / np.float32(scale)
+    if flips == 2:
+        p[..., 1] = np.float32(img_size[0]) - p[..., 1]
+    elif flips == 3:
+        p[..., 0] = np.float32(img_size[1]) - p[..., 0]
+    return p

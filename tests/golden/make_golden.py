@@ -351,6 +351,34 @@ def gen_nms6():
     save("nms6", **out)
 
 
+def gen_labels():
+    """non_max_suppression with apriori `labels` (autolabelling, utils/general.py:533-541) on the 6-column
+    prediction of the tiny model: label boxes [cls, x, y, w, h] partly overlap detections, one image has none."""
+    out = {}
+    g = np.load(os.path.join(HERE, "head.npz"))
+    pred = torch.from_numpy(g["tiny_pred"])[..., :6].contiguous()
+    thr = float(g["tiny_conf_thres"])
+    base = quiet(non_max_suppression, pred, thr, 0.45, kpt_label=0)
+    rng = np.random.default_rng(8)
+    labs = []
+    for b in range(pred.shape[0]):
+        d = base[b].numpy()
+        rows = []
+        for k in range(min(3, len(d))):  # a label right on top of a detection (suppresses it: conf 1.0 wins)
+            x1, y1, x2, y2 = d[k, :4]
+            rows.append([0, (x1 + x2) / 2 + rng.uniform(-1, 1), (y1 + y2) / 2, x2 - x1, y2 - y1])
+        for k in range(4):  # and labels elsewhere
+            rows.append([0, rng.uniform(20, 140), rng.uniform(20, 80), rng.uniform(8, 30), rng.uniform(8, 30)])
+        labs.append(torch.tensor(rows, dtype=torch.float32))
+    labs[1] = torch.zeros((0, 5))  # second image: no labels
+    res = quiet(non_max_suppression, pred, thr, 0.45, kpt_label=0, labels=labs)
+    for b, r in enumerate(res):
+        out["l%d" % b] = labs[b].numpy()
+        out["r%d" % b] = r.numpy()
+    out["thr"] = np.array(thr)
+    save("labels", **out)
+
+
 def gen_bbox():
     """widerface_evaluate/box_overlaps.pyx::bbox_overlaps, the reference's own Cython code built by
     `make -C oracle _ref/box_overlaps.so` (np.float was removed from NumPy; the module only needs the alias)."""
@@ -373,6 +401,64 @@ def gen_bbox():
         out["b%d" % i], out["q%d" % i] = a, q
         out["o%d" % i] = mod.bbox_overlaps(np.ascontiguousarray(a, np.float64), np.ascontiguousarray(q, np.float64))
     save("bbox", **out)
+
+
+def gen_ncnn():
+    """The reference's ncnn-demo NMS (cpp/yolov7-face-ncnn/src/yolov7face.cpp:35-74: std::sort by score, +1 pixel
+    extents, `ovr >= thresh`), the reference's own C++ cut out of its source file and built by
+    `make -C oracle _ref/ncnn_nms.so`.  Scores are made distinct (std::sort is not stable)."""
+    import ctypes as C
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/ncnn_nms.so"])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "ncnn_nms.so"))
+    lib.ref_ncnn_nms.restype = C.c_int64
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [(400, 40, 0.45, False), (1500, 60, 0.3, False), (3000, 25, 0.5, True), (1, 1, 0.5, False), (64, 4, 0.0, True)]
+    for i, (n, clusters, thr, integer) in enumerate(cases):
+        c = rng.uniform(40, 1200, (clusters, 2))
+        sz = rng.uniform(12, 160, (clusters, 2))
+        k = rng.integers(0, clusters, n)
+        ctr = c[k] + rng.normal(0, 0.08, (n, 2)) * sz[k]
+        wh = sz[k] * rng.uniform(0.8, 1.25, (n, 2))
+        b = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1).astype(np.float32)
+        if integer:
+            b = np.round(b)  # integer corners: touching boxes exercise the +1 convention and exact ties with thresh
+        s = rng.permutation(n).astype(np.float32) / np.float32(n) * np.float32(0.9) + np.float32(0.05)  # distinct
+        keep = np.empty((n,), np.int64)
+        m = lib.ref_ncnn_nms(b.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_float(thr),
+                             keep.ctypes.data_as(C.c_void_p))
+        out["b%d" % i], out["s%d" % i], out["t%d" % i], out["k%d" % i] = b, s, np.float32(thr), keep[:m].copy()
+    save("ncnn", **out)
+
+
+def gen_tta():
+    """utils/torch_utils.py::scale_img and models/yolo.py::Model._descale_pred / the concatenation of
+    forward_augment (:363-374), the reference's own functions on CPU fp32."""
+    import types
+    from models.yolo import Model
+    from utils.torch_utils import scale_img
+    torch.manual_seed(3)
+    out = {}
+    x = torch.rand(2, 3, 48, 80)
+    out["x"] = x.numpy()
+    for i, (ratio, flip, gs) in enumerate([(0.83, 3, 32), (0.67, None, 32), (0.5, 2, 16), (1.0, 3, 32), (0.83, None, 8)]):
+        xi = scale_img(x.flip(flip) if flip else x, ratio, gs=gs)
+        out["s%d" % i] = xi.numpy().copy()
+        out["s%d_args" % i] = np.array([ratio, flip or 0, gs], np.float64)
+    xs = scale_img(x, 0.67, same_shape=True)
+    out["same_shape"] = xs.numpy().copy()
+    dummy = types.SimpleNamespace(inplace=True)
+    p = torch.rand(2, 40, 21) * 300
+    out["p"] = p.numpy().copy()
+    ys = []
+    for i, (si, fi) in enumerate(zip([1, 0.83, 0.67], [None, 3, None])):
+        yi = Model._descale_pred(dummy, p.clone(), fi, si, (48, 80))
+        out["d%d" % i] = yi.numpy().copy()
+        ys.append(yi)
+    out["d_ud"] = Model._descale_pred(dummy, p.clone(), 2, 0.83, (48, 80)).numpy().copy()
+    out["cat"] = torch.cat(ys, 1).numpy().copy()
+    save("tta", **out)
 
 
 def gen_pack():
@@ -450,6 +536,9 @@ if __name__ == "__main__":
     gen_merge()
     gen_e2e()
     gen_nms6()
+    gen_labels()
     gen_bbox()
+    gen_ncnn()
+    gen_tta()
     gen_pack()
     gen_ikeypoint()

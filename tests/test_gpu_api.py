@@ -287,3 +287,16 @@ def test_detector_shared_by_thread_pool():
     for out, pshape in results:
         assert out.shape == ref.shape and np.array_equal(out, ref)
         assert pshape[2] == 21
+
+
+def test_non_max_suppression_with_apriori_labels(golden):
+    """general.non_max_suppression(labels=...) (utils/general.py:533-541, autolabelling) against the reference's own
+    output; with keypoint columns the reference's torch.cat raises, here a ValueError."""
+    g, h = golden("labels"), golden("head")
+    pred = torch.from_numpy(np.ascontiguousarray(h["tiny_pred"][..., :6])).to(DEV)
+    labs = [torch.from_numpy(g["l0"]).to(DEV), torch.from_numpy(g["l1"]).to(DEV)]
+    res = general.non_max_suppression(pred, float(g["thr"]), 0.45, kpt_label=0, labels=labs, iou_mode=ops.IOU_TV_CPU)
+    for b in range(2):
+        assert np.array_equal(res[b].cpu().numpy(), g["r%d" % b])
+    with pytest.raises(ValueError):
+        general.non_max_suppression(torch.from_numpy(h["tiny_pred"]).to(DEV), 0.3, 0.45, labels=labs)

@@ -253,6 +253,36 @@ def test_nms_vs_oracle_sizes(mode, n):
         assert np.array_equal(got, ref), (n, t)
 
 
+@pytest.mark.parametrize("case", range(5))
+def test_nms_ncnn_mode_golden(golden, case):
+    """FDMS_IOU_NCNN against the reference's own C++ (cpp/yolov7-face-ncnn/src/yolov7face.cpp:35-74, fixture made by
+    tests/golden/make_golden.py ncnn): +1 pixel extents, `>=`; 400 / 1500 / 3000 boxes take the fused, the sorted and
+    the blocked-greedy / bit-matrix kernels."""
+    g = golden("ncnn")
+    b, s, t, ref = g["b%d" % case], g["s%d" % case], float(g["t%d" % case]), g["k%d" % case]
+    got = ops.nms(gpu(b), gpu(s), t, ops.IOU_NCNN).cpu().numpy()
+    assert np.array_equal(got, ref)
+    # many segments at once (>= 8 segments: blocked greedy kernel for the large ones)
+    n = len(s)
+    rows = np.zeros((9, n, 6), np.float32)
+    rows[:, :, :4], rows[:, :, 4] = b, s
+    keep, n_keep = ops.nms_segments(gpu(rows), gpu(np.full((9,), n, np.int32)), n, t, ops.IOU_NCNN, max_nms=0)
+    torch.cuda.synchronize()
+    for seg in (0, 8):
+        assert np.array_equal(keep[seg, :int(n_keep[seg])].cpu().numpy(), ref)
+
+
+def test_nms_ncnn_mode_vs_oracle_with_ties():
+    rng = np.random.default_rng(5)
+    for n in (65, 700, 2500):
+        xy = rng.integers(0, 150, (n, 2)).astype(np.float32)
+        wh = rng.integers(0, 40, (n, 2)).astype(np.float32)  # zero-size boxes have area 1 here
+        boxes = np.concatenate([xy, xy + wh], 1)
+        scores = np.round(rng.uniform(0, 1, n), 2).astype(np.float32)
+        for t in (0.25, 0.5, 0.0):
+            assert np.array_equal(ops.nms(gpu(boxes), gpu(scores), t, ops.IOU_NCNN).cpu().numpy(), O.nms(boxes, scores, t, O.NCNN))
+
+
 def test_nms_matches_torchvision_cuda_kernel():
     """The TV_CUDA flavour against the real torchvision sm_100 kernel on the same box."""
     tv = pytest.importorskip("torchvision")

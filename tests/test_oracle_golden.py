@@ -127,6 +127,14 @@ def test_nms_golden(golden, name):
         assert np.array_equal(got, ref), (name, t)
 
 
+@pytest.mark.parametrize("case", range(5))
+def test_nms_ncnn_mode_golden(golden, case):
+    """Oracle mode 2 against the reference's own ncnn-demo C++ NMS (fixture: make_golden.py ncnn)."""
+    g = golden("ncnn")
+    got = O.nms(g["b%d" % case], g["s%d" % case], float(g["t%d" % case]), O.NCNN)
+    assert np.array_equal(got, g["k%d" % case])
+
+
 def test_nms_matches_torchvision_live():
     torch = pytest.importorskip("torch")
     tv = pytest.importorskip("torchvision")
@@ -213,3 +221,37 @@ def test_nms_other_keypoint_counts(golden):
         res = O.non_max_suppression(np.ascontiguousarray(h["tiny_pred"][..., :cols]), thr, 0.45, O.TV_CPU)
         for b in range(2):
             assert np.array_equal(res[b], g["c%d_b%d" % (cols, b)])
+
+
+# ---- "next" row: test-time augmentation around the backbone (models/yolo.py:363-417, utils/torch_utils.py:247-257)
+TTA_TOL = 2.4e-7  # 2 ulp at 1.0: ATen's build contracts the 4-tap sum differently; inputs are in [0, 1]
+
+
+def test_tta_scale_img_golden(golden):
+    g = golden("tta")
+    for i in range(5):
+        ratio, flip, gs = g["s%d_args" % i]
+        got = O.scale_img(g["x"], float(ratio), gs=int(gs), flip=int(flip) or None)
+        assert got.shape == g["s%d" % i].shape
+        assert np.max(np.abs(got - g["s%d" % i])) <= TTA_TOL
+    got = O.scale_img(g["x"], 0.67, same_shape=True)
+    assert got.shape == g["same_shape"].shape and np.max(np.abs(got - g["same_shape"])) <= TTA_TOL
+
+
+def test_tta_descale_pred_golden(golden):
+    g = golden("tta")
+    ys = []
+    for i, (si, fi) in enumerate(zip([1, 0.83, 0.67], [None, 3, None])):
+        ys.append(O.descale_pred(g["p"], fi, si, (48, 80)))
+        assert np.array_equal(ys[-1], g["d%d" % i])
+    assert np.array_equal(O.descale_pred(g["p"], 2, 0.83, (48, 80)), g["d_ud"])
+    assert np.array_equal(np.concatenate(ys, 1), g["cat"])
+
+
+def test_nms_with_apriori_labels_golden(golden):
+    """utils/general.py:533-541 (autolabelling) on the 6-column prediction; fixture: make_golden.py labels."""
+    g, h = golden("labels"), golden("head")
+    pred = np.ascontiguousarray(h["tiny_pred"][..., :6])
+    res = O.non_max_suppression(pred, float(g["thr"]), 0.45, O.TV_CPU, labels=[g["l0"], g["l1"]])
+    for b in range(2):
+        assert np.array_equal(res[b], g["r%d" % b])

@@ -170,7 +170,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (libfdms has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = 0
     if world > 1:
+        from face_detection_multi_scale_b200 import dist as fdist
+        numa_cores = fdist.bind_host_to_gpu(local)  # pinned buffers next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload (per-rank seed: every GPU processes its own shard of the image batch) ----
@@ -383,7 +386,7 @@ def main():
 
     # ---- CPU baseline: the oracle port of the reference's CPU path on this box's host cores (rank 0) ----
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline and not args.profile:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:  # N=1 only (measurement contract)
         thr = host_threads()
         n = args.cpu_sample or B
         cpu_run(images, heads, shapes, wl, min(2, n), min(2, thr))  # warm the library / page in
@@ -405,7 +408,8 @@ def main():
                        "planted_faces_per_image": wl["faces"], "candidates_per_step": cand_per_step,
                        "backbone": "excluded (unchanged PyTorch, out of scope); raw head maps are synthetic fp16",
                        "l2": "inputs larger than L2 (%d MB/step) and two input sets rotated" % ((B * src_bytes + head_bytes) // 1000000),
-                       "parallelism": "image-sharded, no collective" if world > 1 else "single GPU"},
+                       "parallelism": "image-sharded, no collective" if world > 1 else "single GPU",
+                       "host_cores_bound_to_gpu_numa": numa_cores},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + ops.PostPlan.LAUNCHES),
             "roofline": roofline, "cpu_baseline": cpu,
             "streams": "pyramid and post-processing on two CUDA streams (independent data, overlapped)",

@@ -85,3 +85,29 @@ def detect_sharded(detector, images, gather=True):
     local = shard(images)
     res = detector.detect_multi_scale_batch(local) if len(local) else []
     return gather_detections(res, n) if gather else res
+
+
+def bind_host_to_gpu(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to the GPU (its NUMA node), so that the pinned
+    host buffers allocated afterwards are first-touched next to the GPU's PCIe root.  On an 8-GPU node every rank
+    otherwise feeds its GPU across the inter-socket link.  The reference's production driver pins one worker per GPU
+    the same way (yolov7_face_multi_scale_dataframe_predict.py:569-596 sets CUDA_VISIBLE_DEVICES per worker).
+    Returns the number of cores bound to, or 0 when NVML / affinity are unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis else int(device_index)
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        cores &= allowed
+        if not cores or cores == allowed:
+            return 0
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0

@@ -46,6 +46,7 @@ struct PyrScale {
     int mode;          // PM_GENERAL / PM_POINT / PM_HALF: strength-reduced arithmetic for exact integer scales
     int direct;        // exact integer scale, no column padding: taps are read straight from global memory (no staging)
     int kx, ky;        // the integer factors when mode != PM_GENERAL
+    int real_rows;     // direct tiles: interior rows whose taps are real image rows; the rest read the virtual zeros
     double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
     const int2 *xtab;         // per output column: {source column sx, a0 | a1 << 16}; sx = -1 on the border
     const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, s}: clamped tap rows, weights, unclamped upper tap row; r0 = -1 on the border
@@ -396,7 +397,8 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
     const unsigned ys = (unsigned)S.ys;
     const unsigned tborder = (unsigned)P.border * 4u;
     const int y_end = min(oy0 + S.th, S.dst_h);
-    const int ya = min(max(oy0, S.top), y_end), yb = max(min(y_end, S.top + S.unpad_h), ya);  // interior rows [ya, yb)
+    const int ya = min(max(oy0, S.top), y_end), yz = max(min(y_end, S.top + S.unpad_h), ya);  // interior rows [ya, yz)
+    const int yb = max(min(yz, S.top + S.real_rows), ya);  // [ya, yb) have real taps, [yb, yz) are virtual zeros (api mode)
     unsigned off = 0;
     for (int y = oy0; y < ya; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
     const long long pitch = P.pitch;
@@ -441,7 +443,8 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
                 Out<T>::store2_bits(pc[c] + off, __byte_perm(lA, 0x4B000000u, 0x7650 + c), __byte_perm(lB, 0x4B000000u, 0x7650 + c));
         }
     }
-    for (int y = yb; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+    for (int y = yb; y < yz; y++, off += ys) border_row<T>(pc, off, 1, 0u, true, true);  // all taps zero -> pixel 0
+    for (int y = yz; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
 }
 
 // Warp 0, all 32 lanes: vertical taps of one tile (lane = row; `e` = its ytab entry, r0 = -1 when the row is border
@@ -773,8 +776,11 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 const bool int_x = S.scale_x == (double)kx && kx >= 2 && kx * g.unpad_w == virt_w;
                 const bool int_y = S.scale_y == (double)ky && ky >= 2 && ky * g.unpad_h == virt_h;
                 const bool real = virt_h == src_h && virt_w == src_w;
+                // api mode on a landscape image: the virtual square only adds zero ROWS below the image; when the
+                // image height is a multiple of the factor no output row mixes real and virtual taps
+                const bool api_rows = int_y && virt_w == src_w && virt_h > src_h && src_h % ky == 0;
                 S.mode = PM_GENERAL;
-                if (int_x && int_y && real && ctx->pyr_special) {
+                if (int_x && int_y && (real || api_rows) && ctx->pyr_special) {
                     if ((kx & 1) && (ky & 1)) S.mode = PM_POINT;
                     else if (!(kx & 1) && !(ky & 1)) S.mode = PM_HALF;
                 }
@@ -783,6 +789,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 // direct tiles: rows-only padding, paired stores, word-aligned source rows that end on a word
                 S.direct = S.mode != PM_GENERAL && ctx->pyr_direct && S.vec && P.vec_ok && g.left == 0 &&
                            g.unpad_w == g.dst_w && src_w % 4 == 0 && (S.mode == PM_POINT || kx == 2);
+                if (!real && !S.direct) S.mode = PM_GENERAL;  // the staged specialisations assume no virtual rows
+                S.real_rows = (S.direct && !real) ? src_h / (int)ky : g.unpad_h;
             }
             int tw = 2 * PYR_THREADS, th = ctx->pyr_th;
             if (S.direct) {  // no staging: no shared-memory constraint on the tile

@@ -91,6 +91,22 @@ def test_api_preprocess(golden, i):
     assert sha(chw) == str(g["api%d_sha" % i])
 
 
+@pytest.mark.parametrize("hw,sizes", [((120, 160), (80, 32, 96)), ((1080, 1920), (640, 960, 1280)), ((90, 160), (32, 80))])
+def test_api_mode_integer_scales_direct_tiles(hw, sizes):
+    """api mode (virtual zero-padded square) on landscape images whose square is an integer multiple of the model
+    size: the 2:1 and odd:1 scales run as direct tiles with the virtual rows written as zeros, the others staged --
+    all in one launch, fp16 CHW like the hot path, bit-exact against the oracle's preprocess_api + pack."""
+    h, w = hw
+    img = synth.synth_image(h, w, 7 + h)
+    s = max(h, w)
+    geoms = [_lib.letterbox_geometry(s, s, size, auto=False, stride=32) for size in sizes]
+    outs = _pyr(img, geoms, torch.float16, layout="chw", flip=False, virt=(s, s))
+    for size, got in zip(sizes, outs):
+        ref = O.preprocess_api(img, size).astype(np.float32) / np.float32(255)
+        assert got.shape == ref.shape
+        assert np.array_equal(got.view(np.uint16), ref.astype(np.float16).view(np.uint16)), size
+
+
 @pytest.mark.parametrize("shape", [((211, 173), (64, 53)), ((53, 37), (143, 100)), ((480, 640), (960, 1280)),
                                    ((1, 9), (4, 31)), ((300, 300), (300, 300)), ((719, 1279), (360, 640)),
                                    ((2160, 3840), (360, 640)), ((33, 2000), (17, 40))])

@@ -32,7 +32,8 @@ WORKLOADS = {
                  h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=60, conf=0.5, iou=0.5, radius=1, cap=1024),
     # configs[2]: dense crowd, ~20k pre-NMS candidates per image
     "cfg3": dict(desc="cfg3: dense-crowd stress, ~20k pre-NMS candidates/image, 3-scale pyramid, batch 32 1920x1080",
-                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=1300, conf=0.5, iou=0.5, radius=1, cap=16384),
+                 h=1080, w=1920, sizes=[640, 960, 1280], batch=32, faces=1300, conf=0.5, iou=0.5, radius=1, cap=16384,
+                 kpts=True),  # "landmarks on": the 15 landmark columns are decoded and carried through the merge
     # configs[4]: single-scale high throughput (per-GPU shard of the batch-512 job)
     "cfg5": dict(desc="cfg5: lite-t head, single scale 640, batch 64/GPU synthetic 1920x1080 images",
                  h=1080, w=1920, sizes=[640], batch=64, faces=40, conf=0.5, iou=0.5, radius=1, cap=4096),
@@ -188,7 +189,8 @@ def main():
         heads_d = [[torch.from_numpy(l if k == 0 else np.roll(l, k, axis=0)).to(dev) for l in hs] for hs in heads]
         outs = [torch.empty((B, 3, g.dst_h, g.dst_w), dtype=torch.float16, device=dev) for g in geoms]
         plan = ops.PostPlan(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, [g.dst_h for g in geoms], (wl["h"], wl["w"]),
-                            wl["conf"], wl["iou"], cap=wl["cap"], out_cap=wl["cap"], iou_mode=ops.IOU_TV_CUDA)
+                            wl["conf"], wl["iou"], cap=wl["cap"], out_cap=wl["cap"], iou_mode=ops.IOU_TV_CUDA,
+                            with_kpts=bool(wl.get("kpts")))
         sets.append((img_d, heads_d, outs, plan))
 
     # The two halves of a step work on independent data (the backbone that links them is out of scope), exactly
@@ -269,11 +271,12 @@ def main():
         evs[i][0].record()
         ops.pyramid(img_d, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, outs=outs, ctx=pyr_ctx)
         evs[i][1].record()
-        ops.decode_filter(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, wl["conf"], wl["cap"], out=c, landmarks=False)
+        ops.decode_filter(heads_d, synth.P5_STRIDES, synth.P5_ANCHORS, wl["conf"], wl["cap"], out=c, landmarks=bool(wl.get("kpts")))
         evs[i][2].record()
         ops.nms_segments(c.cand, c.count, c.cap, wl["iou"], ops.IOU_TV_CUDA, tie=c.row, keep=c.keep, n_keep=c.n_keep)
         evs[i][3].record()
-        ops.merge_scales(c, B, len(sizes), [g.dst_h for g in geoms], (wl["h"], wl["w"]), wl["iou"], wl["cap"], out=plan.out)
+        ops.merge_scales(c, B, len(sizes), [g.dst_h for g in geoms], (wl["h"], wl["w"]), wl["iou"], wl["cap"],
+                         with_kpts=bool(wl.get("kpts")), out=plan.out)
         evs[i][4].record()
     torch.cuda.synchronize()
     stage_ms = {n: float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K2)]))

@@ -26,7 +26,7 @@ struct fdms_ctx {
     int pyr_attr = 0;
     int pyr_special = 1;  // FDMS_PYR_SPECIAL=0 disables the integer-scale fast paths (testing)
     int pyr_smem_budget = 32 * 1024, pyr_th = 12;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
-    int pyr_direct = 1, pyr_th_direct = 24;  // FDMS_PYR_DIRECT / FDMS_PYR_TH_DIRECT: unstaged tiles for integer scales
+    int pyr_direct = 3, pyr_th_direct = 16;  // FDMS_PYR_DIRECT (bit 0: integer factors, bit 1: the 3:2 factor) / FDMS_PYR_TH_DIRECT: unstaged tiles
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
     int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path

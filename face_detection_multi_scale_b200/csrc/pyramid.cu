@@ -23,16 +23,23 @@
 namespace {
 
 constexpr int PYR_THREADS = 160;  // 2 columns per thread: 320-column tiles divide 640/960/1280 evenly
+#ifndef PYR_UNROLL32
+#define PYR_UNROLL32 2  // row pairs of the 3:2 direct tile whose loads are in flight together
+#endif
+#ifndef PYR_UNROLL_INT
+#define PYR_UNROLL_INT 4  // rows of the integer-factor direct tiles in flight together
+#endif
 #ifndef PYR_MIN_CTAS
 #define PYR_MIN_CTAS 8  // resident CTAs per SM the register allocation of the fp16 instantiation is held to (48 registers)
 #endif
+constexpr int K_UNROLL32 = PYR_UNROLL32, K_UNROLL_INT = PYR_UNROLL_INT;
 constexpr int PYR_MAX_TH = 32;    // rows per tile are handled by the lanes of warp 0
 constexpr int PYR_MAX_SLOTS = 64;
 // Exact integer scale factors make OpenCV's fixed-point weights constant: an odd factor k gives
 // f == 0 on both axes (weights 2048/0: the output IS source pixel (k*d + (k-1)/2)), an even factor gives f == 0.5
 // (weights 1024/1024: (((1024*(64*(a+b)))>>16) + ... + 2) >> 2 == (a + b + c + d + 2) >> 2).  Same results as the
 // general path, fewer instructions.
-enum { PM_GENERAL = 0, PM_POINT = 1, PM_HALF = 2 };
+enum { PM_GENERAL = 0, PM_POINT = 1, PM_HALF = 2, PM_RATIO32 = 3 };
 
 struct PyrScale {
     void *out;
@@ -406,7 +413,7 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
         const int ky = S.ky;
         const uint8_t *row = src + 3 * sxA + (long long)(ky * (ya - S.top) + (ky >> 1) - 1) * pitch;
         const long long step = (long long)ky * pitch;
-#pragma unroll 4
+#pragma unroll(K_UNROLL_INT)
         for (int y = ya; y < yb; y++, off += ys, row += step) {
             const uint32_t *p0 = reinterpret_cast<const uint32_t *>(row);
             const uint32_t *p1 = reinterpret_cast<const uint32_t *>(row + pitch);
@@ -431,7 +438,7 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
         const uint8_t *row = src + (long long)(ky * (ya - S.top) + (ky >> 1)) * pitch;
         const long long step = (long long)ky * pitch;
         const int wa = oA & ~3, wb = oB & ~3;
-#pragma unroll 4
+#pragma unroll(K_UNROLL_INT)
         for (int y = ya; y < yb; y++, off += ys, row += step) {
             const uint32_t *pa = reinterpret_cast<const uint32_t *>(row + wa);
             const uint32_t *pb = reinterpret_cast<const uint32_t *>(row + wb);
@@ -444,6 +451,75 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
         }
     }
     for (int y = yb; y < yz; y++, off += ys) border_row<T>(pc, off, 1, 0u, true, true);  // all taps zero -> pixel 0
+    for (int y = yz; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+}
+
+
+// PM_RATIO32: the exact 3:2 scale (1920x1080 -> 1280x720 and every other 1.5:1 letterbox).  The taps are periodic:
+// output columns 2m, 2m+1 read source pixels 3m..3m+2 (nine contiguous bytes at 9m) and output rows 2n, 2n+1 read
+// source rows 3n..3n+2, so like the integer factors a thread's window is a fixed affine function of its position --
+// three aligned words per source row, no staging, no per-row tap look-up, and all loads of two row pairs are issued
+// before the first is reduced.  Per source row the nine bytes are turned into the six horizontal sums with 3 SHF +
+// 3 PRMT + 6 IDP.2A (the staged path needs two independent 6-byte windows: 26 instructions).  The WEIGHTS are not
+// assumed: the two column phases and the two row phases are read from the same tap tables the general path uses.
+template <typename T>
+__device__ __forceinline__ void direct_tile_32(const PyrParams &P, const PyrScale &S, int img, int oy0, int ox0, int tid) {
+    const int x = ox0 + 2 * tid;
+    if (x >= S.dst_w || 2 * tid >= S.tw) return;
+    const int4 e = __ldg(reinterpret_cast<const int4 *>(S.xtab + x));  // {3m, a(even), 3m+1, a(odd)}
+    const unsigned aA = (unsigned)e.y, aB = (unsigned)e.w;
+    const int o = 3 * e.x;  // byte offset of source pixel 3m
+    const unsigned sh = (unsigned)(o & 3) * 8u;
+    const uint8_t *src = P.src + (long long)img * P.img_stride + (o & ~3);
+    T *pc[3];
+    {
+        T *p0 = reinterpret_cast<T *>(S.out) + (long long)img * S.img_stride + (long long)oy0 * S.ys + x;
+        pc[0] = P.flip ? p0 + 2 * S.cs : p0;
+        pc[1] = p0 + S.cs;
+        pc[2] = P.flip ? p0 : p0 + 2 * S.cs;
+    }
+    const unsigned ys = (unsigned)S.ys;
+    const unsigned tborder = (unsigned)P.border * 4u;
+    const int y_end = min(oy0 + S.th, S.dst_h);
+    // interior rows [ya, yz): [ya, yb) have real taps, [yb, yz) read the virtual zeros of the api mode.  top, th and
+    // the interior heights are even (host), so every range starts on an even row and holds whole row pairs.
+    const int ya = min(max(oy0, S.top), y_end), yz = max(min(y_end, S.top + S.unpad_h), ya);
+    const int yb = max(min(yz, S.top + S.real_rows), ya);
+    unsigned off = 0;
+    for (int y = oy0; y < ya; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+    if (ya < yb) {
+        const int4 r0 = __ldg(S.ytab + ya), r1 = __ldg(S.ytab + ya + 1);  // the two row phases: {3n, ., b01, .}, {3n+1, ...}
+        const unsigned b0e = (unsigned)r0.z & 0xffffu, b1e = (unsigned)r0.z >> 16;
+        const unsigned b0o = (unsigned)r1.z & 0xffffu, b1o = (unsigned)r1.z >> 16;
+        const long long pitch = P.pitch;
+        const uint8_t *row = src + (long long)r0.x * pitch;
+        auto hsum = [&](const uint8_t *p, int *h) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+            const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+            const uint32_t lo = __funnelshift_r(w0, w1, sh);   // p0c0 p0c1 p0c2 p1c0
+            const uint32_t mid = __funnelshift_r(w1, w2, sh);  // p1c1 p1c2 p2c0 p2c1
+            const uint32_t hi = w2 >> sh;                      // p2c2 (byte 0)
+            const uint32_t a01 = __byte_perm(lo, mid, 0x4130);   // (p0c0 p1c0) (p0c1 p1c1)
+            const uint32_t a2b0 = __byte_perm(lo, mid, 0x6352);  // (p0c2 p1c2) (p1c0 p2c0)
+            const uint32_t b12 = __byte_perm(mid, hi, 0x4130);   // (p1c1 p2c1) (p1c2 p2c2)
+            h[0] = (int)(__dp2a_lo(aA, a01, 0u) >> 4);
+            h[1] = (int)(__dp2a_hi(aA, a01, 0u) >> 4);
+            h[2] = (int)(__dp2a_lo(aA, a2b0, 0u) >> 4);
+            h[3] = (int)(__dp2a_hi(aB, a2b0, 0u) >> 4);
+            h[4] = (int)(__dp2a_lo(aB, b12, 0u) >> 4);
+            h[5] = (int)(__dp2a_hi(aB, b12, 0u) >> 4);
+        };
+#pragma unroll(K_UNROLL32)
+        for (int y = ya; y < yb; y += 2, off += 2 * ys, row += 3 * pitch) {
+            int h0[6], h1[6], h2[6];
+            hsum(row, h0);
+            hsum(row + pitch, h1);
+            hsum(row + 2 * pitch, h2);
+            emit_row<T, false>(pc, off, 1, b0e, b1e, h0, h1, 0, tborder, true, true, true, true);
+            emit_row<T, false>(pc, off + ys, 1, b0o, b1o, h1, h2, 0, tborder, true, true, true, true);
+        }
+    }
+    for (int y = yb; y < yz; y++, off += ys) border_row<T>(pc, off, 1, 0u, true, true);
     for (int y = yz; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
 }
 
@@ -565,6 +641,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     const int oy0 = ty * th, ox0 = tx * tw;
     if (S.direct) {  // CTA-uniform
         if (S.mode == PM_HALF) direct_tile<T, PM_HALF>(P, S, img, oy0, ox0, tid);
+        else if (S.mode == PM_RATIO32) direct_tile_32<T>(P, S, img, oy0, ox0, tid);
         else direct_tile<T, PM_POINT>(P, S, img, oy0, ox0, tid);
         return;
     }
@@ -791,6 +868,16 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                            g.unpad_w == g.dst_w && src_w % 4 == 0 && (S.mode == PM_POINT || kx == 2);
                 if (!real && !S.direct) S.mode = PM_GENERAL;  // the staged specialisations assume no virtual rows
                 S.real_rows = (S.direct && !real) ? src_h / (int)ky : g.unpad_h;
+                // the exact 3:2 scale as a direct tile too (direct only: there is no staged flavour of it)
+                const bool r32 = 2LL * virt_w == 3LL * g.unpad_w && 2LL * virt_h == 3LL * g.unpad_h && S.scale_x == 1.5 &&
+                                 S.scale_y == 1.5;
+                const bool rows32 = real || (virt_w == src_w && virt_h > src_h && src_h % 3 == 0);
+                if (S.mode == PM_GENERAL && r32 && rows32 && (ctx->pyr_direct & 2) && ctx->pyr_special && S.vec && P.vec_ok &&
+                    g.left == 0 && g.unpad_w == g.dst_w && src_w % 4 == 0 && g.top % 2 == 0 && ctx->pyr_th_direct % 2 == 0) {
+                    S.mode = PM_RATIO32;
+                    S.direct = 1;
+                    S.real_rows = real ? g.unpad_h : 2 * (src_h / 3);
+                }
             }
             int tw = 2 * PYR_THREADS, th = ctx->pyr_th;
             if (S.direct) {  // no staging: no shared-memory constraint on the tile

@@ -152,6 +152,17 @@ class MultiScaleFaceDetector:
             plan.rebind(scales_levels)
         return plan
 
+    def _stream_lanes(self, depth):
+        """The lanes of detect_stream are kept per calling thread: streams, native contexts (device scratch), plans and
+        pinned result buffers are created once, not per call -- cudaMalloc / cudaHostAlloc / cudaFree synchronise the
+        device and would stall the pipeline at the start and the end of every call."""
+        lanes = getattr(self._tls, "lanes", None)
+        if lanes is None:
+            lanes = self._tls.lanes = []
+        while len(lanes) < depth:
+            lanes.append(self._Lane(self.device))
+        return lanes[:depth]
+
     def _thread_plans(self):
         plans = getattr(self._tls, "plans", None)
         if plans is None:
@@ -193,7 +204,9 @@ class MultiScaleFaceDetector:
         the H2D copy and kernels of batch i+1 are enqueued while batch i is in flight and batch i-1 is being read
         back, on `depth` streams with one native context each.  Yields, in order, the same per-batch result as
         detect_multi_scale_batch.  A batch that exceeds a capacity is transparently redone synchronously."""
-        lanes = [self._Lane(self.device) for _ in range(max(1, int(depth)))]
+        lanes = self._stream_lanes(max(1, int(depth)))
+        for lane in lanes:
+            lane.plan = lane.src = None
         pending = []
 
         def finish(lane):

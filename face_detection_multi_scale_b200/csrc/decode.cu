@@ -5,7 +5,9 @@
 //                          (utils/general.py:515,531,547-563,299-306).  Reads the raw conv
 //                          outputs (bs, 63, ny, nx) in place: no view/permute/contiguous/clone/cat
 //                          and no (rows x 21) tensor.  Only the obj/cls planes are streamed; the
-//                          other 19 channel planes are touched only at surviving cells.
+//                          other 19 channel planes are touched only at surviving cells (by
+//                          decode_candidates_kernel, one candidate per thread; 4 planes instead of 19
+//                          when the caller does not need landmarks).
 //   decode_dense_kernel  : the same decode writing every row (compat level, IKeypoint.forward's
 //                          first return value).
 //   filter_pred_kernel   : the same filter reading an already decoded pred (compat level).

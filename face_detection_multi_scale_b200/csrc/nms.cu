@@ -2,6 +2,10 @@
 // multi_scale_face_detector.py:234), all segments (image x scale) of a batch per launch and
 // no host synchronisation between the stages:
 //
+//   nms_small_kernel : segments of <= 1024 boxes (the common case), one CTA per segment, everything in shared
+//                      memory: register-sorted 32-key runs + binary-search ranks, then a blocked greedy
+//                      sweep (kept-list test, balanced two-pass 256x256 pair masks, ballot resolver).
+//   Larger segments:
 //   nms_sort_kernel  : one CTA per segment.  64-bit key = (score descending, tie ascending),
 //                      bitonic network in shared memory (<= 8192 items, else in L2-resident
 //                      global scratch); emits item indices and boxes in score order and, in
@@ -13,9 +17,13 @@
 //                      shuffles, then the CTA ORs the mask rows of the boxes it kept into the
 //                      `removed` bitmap in shared memory (coalesced row reads).
 //
+//   nms_greedy_kernel: >= 8 large segments: one CTA per segment, the blocked greedy sweep of the small kernel
+//                      with the kept list streamed through shared-memory tiles (no K^2 memory).
+//
 // IoU arithmetic, selected by iou_mode:
 //   TV_CPU : inter / ((area_i + area_j) - inter), suppressed iff (double)iou > thr (double)
 //   TV_CUDA: inter / (fma(w_j, h_j, area_i) - inter), suppressed iff iou > (float)thr
+//   NCNN   : +1 pixel on every extent, suppressed iff iou >= (float)thr (cpp/yolov7-face-ncnn/src/yolov7face.cpp:43)
 // The double comparison is folded on the host into a float threshold plus an inclusive flag.
 #include <math.h>
 

@@ -7,17 +7,22 @@
 // Work decomposition (HBM-bound byte kernel; no tensor cores):
 //   grid = (tiles of all scales of one image, image).  All scales of an image are adjacent
 //   in launch order, so the u8 source (6.2 MB at 1080p) is fetched from HBM once and the
-//   other scales re-read it from the 126 MB L2.
-//   A CTA owns a tw x th tile of one scale's output.  Warp 0 derives the vertical taps of the
-//   tile's rows, assigns the source rows to shared-memory slots and stages every slot with ONE
-//   bulk async copy (TMA, cp.async.bulk -> UBLKCP) completing on an mbarrier; ragged /
-//   misaligned / virtual-zero sources take a scalar staging path.
-//   Each thread owns 2 adjacent output columns.  It streams over the slots in source-row
-//   order: horizontal pass of the slot for its two pixels (16x8-bit dot products, IDP.2A)
-//   into registers, then emits every output row whose lower tap is that slot (vertical pass,
-//   /255, pack, one 32-bit store per channel: a warp writes 128 contiguous bytes of a plane).
-//   Horizontal results are therefore computed once per (source row, column) even when output
-//   rows share source rows (scale < 2).
+//   other scales re-read it from the 126 MB L2.  A CTA (160 threads, each owning 2 adjacent
+//   output columns) owns a tw x th tile of one scale's output; the host picks one of two
+//   tile kinds per scale:
+//   * staged tiles (any scale factor).  Warp 0 derives the vertical taps of the tile's rows,
+//     assigns the source rows to shared-memory slots and stages every slot with ONE bulk async
+//     copy (TMA, cp.async.bulk -> UBLKCP) completing on an mbarrier; ragged / misaligned /
+//     virtual-zero sources take a scalar staging path.  Threads stream over the slots in
+//     source-row order: horizontal pass of the slot for their two pixels (16x8-bit dot
+//     products, IDP.2A) into registers, then every output row whose lower tap is that slot is
+//     emitted (vertical pass, /255, pack, one 32-bit store per channel: a warp writes 128
+//     contiguous bytes of a plane).  Horizontal results are computed once per (source row,
+//     column) even when output rows share source rows (scale < 2).
+//   * direct tiles (exact factors k:1 and 3:2 with rows-only padding).  The taps are an affine /
+//     periodic function of the output position, a thread's window of every source row is a few
+//     aligned words next to its neighbours' windows, so plain loads coalesce: no shared memory,
+//     no barrier, no tap prologue, several rows of loads in flight per thread.
 #include "common.cuh"
 
 namespace {

@@ -409,6 +409,11 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
     const unsigned ys = (unsigned)S.ys;
     const unsigned tborder = (unsigned)P.border * 4u;
     const int y_end = min(oy0 + S.th, S.dst_h);
+    if (sxA < 0) {  // a column pair of the left / right letterbox border (left and unpad_w are even: never half a pair)
+        unsigned off = 0;
+        for (int y = oy0; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+        return;
+    }
     const int ya = min(max(oy0, S.top), y_end), yz = max(min(y_end, S.top + S.unpad_h), ya);  // interior rows [ya, yz)
     const int yb = max(min(yz, S.top + S.real_rows), ya);  // [ya, yb) have real taps, [yb, yz) are virtual zeros (api mode)
     unsigned off = 0;
@@ -486,6 +491,11 @@ __device__ __forceinline__ void direct_tile_32(const PyrParams &P, const PyrScal
     const unsigned ys = (unsigned)S.ys;
     const unsigned tborder = (unsigned)P.border * 4u;
     const int y_end = min(oy0 + S.th, S.dst_h);
+    if (e.x < 0) {  // a column pair of the left / right letterbox border
+        unsigned off = 0;
+        for (int y = oy0; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+        return;
+    }
     // interior rows [ya, yz): [ya, yb) have real taps, [yb, yz) read the virtual zeros of the api mode.  top, th and
     // the interior heights are even (host), so every range starts on an even row and holds whole row pairs.
     const int ya = min(max(oy0, S.top), y_end), yz = max(min(y_end, S.top + S.unpad_h), ya);
@@ -730,9 +740,18 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
                 for (int i = tid * 4; i < row_bytes; i += PYR_THREADS * 4) *reinterpret_cast<uint32_t *>(dst + i) = 0u;
             } else {
                 const uint8_t *srow = src + (long long)row * P.pitch;
-                for (int i = tid; i < rest; i += PYR_THREADS) {
-                    const int pos = g0 + bulk_bytes + i;
-                    dst[bulk_bytes + i] = pos < real_end ? __ldg(srow + pos) : (uint8_t)0;
+                const uint8_t *from = srow + g0 + bulk_bytes;  // g0 and bulk_bytes are multiples of 16
+                const int valid = real_end - (g0 + bulk_bytes);  // bytes of the row that exist from here on
+                if (((uintptr_t)from & 7) == 0 && (real_end & 7) == 0) {  // rows that start on 8 bytes (e.g. 1080 px wide)
+                    for (int i = tid * 8; i < rest; i += PYR_THREADS * 8)
+                        *reinterpret_cast<uint2 *>(dst + bulk_bytes + i) =
+                            i < valid ? __ldg(reinterpret_cast<const uint2 *>(from + i)) : make_uint2(0u, 0u);
+                } else if (((uintptr_t)from & 3) == 0 && (real_end & 3) == 0) {
+                    for (int i = tid * 4; i < rest; i += PYR_THREADS * 4)
+                        *reinterpret_cast<uint32_t *>(dst + bulk_bytes + i) =
+                            i < valid ? __ldg(reinterpret_cast<const uint32_t *>(from + i)) : 0u;
+                } else {
+                    for (int i = tid; i < rest; i += PYR_THREADS) dst[bulk_bytes + i] = i < valid ? __ldg(from + i) : (uint8_t)0;
                 }
             }
         }
@@ -819,6 +838,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
         P.flip = flip_rb ? 1 : 0;
         P.border = border;
         P.vec_ok = ((uintptr_t)src % 16 == 0) && (img_stride % 16 == 0) && (row_pitch % 16 == 0);
+        // direct tiles read aligned 32-bit words: every source row must start on a word
+        const bool words_ok = ((uintptr_t)src % 4 == 0) && (img_stride % 4 == 0) && (row_pitch % 4 == 0);
         int tiles = 0, smem_max = 0, n = 0;
         for (int s = 0; s < n_scales; s++) {
             const fdms_scale_out &in = scales[s];
@@ -868,17 +889,19 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 }
                 S.kx = (int)kx;
                 S.ky = (int)ky;
-                // direct tiles: rows-only padding, paired stores, word-aligned source rows that end on a word
-                S.direct = S.mode != PM_GENERAL && ctx->pyr_direct && S.vec && P.vec_ok && g.left == 0 &&
-                           g.unpad_w == g.dst_w && src_w % 4 == 0 && (S.mode == PM_POINT || kx == 2);
+                // direct tiles: paired stores, word-aligned source rows that end on a word
+                // (column padding is fine as long as no column PAIR straddles the border)
+                const bool cols_ok = g.left % 2 == 0 && g.unpad_w % 2 == 0 && g.dst_w % 2 == 0;
+                S.direct = S.mode != PM_GENERAL && ctx->pyr_direct && S.vec && words_ok && cols_ok && src_w % 4 == 0 &&
+                           (S.mode == PM_POINT || kx == 2);
                 if (!real && !S.direct) S.mode = PM_GENERAL;  // the staged specialisations assume no virtual rows
                 S.real_rows = (S.direct && !real) ? src_h / (int)ky : g.unpad_h;
                 // the exact 3:2 scale as a direct tile too (direct only: there is no staged flavour of it)
                 const bool r32 = 2LL * virt_w == 3LL * g.unpad_w && 2LL * virt_h == 3LL * g.unpad_h && S.scale_x == 1.5 &&
                                  S.scale_y == 1.5;
                 const bool rows32 = real || (virt_w == src_w && virt_h > src_h && src_h % 3 == 0);
-                if (S.mode == PM_GENERAL && r32 && rows32 && (ctx->pyr_direct & 2) && ctx->pyr_special && S.vec && P.vec_ok &&
-                    g.left == 0 && g.unpad_w == g.dst_w && src_w % 4 == 0 && g.top % 2 == 0 && ctx->pyr_th_direct % 2 == 0) {
+                if (S.mode == PM_GENERAL && r32 && rows32 && (ctx->pyr_direct & 2) && ctx->pyr_special && S.vec && words_ok &&
+                    cols_ok && src_w % 4 == 0 && g.top % 2 == 0 && ctx->pyr_th_direct % 2 == 0) {
                     S.mode = PM_RATIO32;
                     S.direct = 1;
                     S.real_rows = real ? g.unpad_h : 2 * (src_h / 3);

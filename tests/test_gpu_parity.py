@@ -91,6 +91,20 @@ def test_api_preprocess(golden, i):
     assert sha(chw) == str(g["api%d_sha" % i])
 
 
+@pytest.mark.parametrize("hw,sizes", [((384, 216), (128, 192, 256)), ((1920, 1080), (640, 960, 1280)), ((216, 384), (128, 192, 256)),
+                                      ((360, 640), (320, 160, 480))])
+def test_letterbox_exact_factors_with_column_padding(hw, sizes):
+    """Portrait (column-padded) and landscape letterboxes at exact 3:1 / 2:1 / 3:2 factors: the direct tiles incl.
+    their border column pairs, fp16 CHW with the channel flip like the hot path, bit-exact against the oracle."""
+    h, w = hw
+    img = synth.synth_image(h, w, 11 + w)
+    geoms = [_lib.letterbox_geometry(h, w, size, auto=True, stride=32) for size in sizes]
+    outs = _pyr(img, geoms, torch.float16)
+    for size, got in zip(sizes, outs):
+        lb, _, _ = O.letterbox(img, size, auto=True, stride=32)
+        assert np.array_equal(got.view(np.uint16), O.pack_chw(lb, True, np.float16).view(np.uint16)), size
+
+
 @pytest.mark.parametrize("hw,sizes", [((120, 160), (80, 32, 96)), ((1080, 1920), (640, 960, 1280)), ((90, 160), (32, 80))])
 def test_api_mode_integer_scales_direct_tiles(hw, sizes):
     """api mode (virtual zero-padded square) on landscape images whose square is an integer multiple of the model

@@ -69,6 +69,7 @@ struct PyrParams {
     long long img_stride, pitch;
     int src_h, src_w, virt_h, virt_w;
     int n_scales, flip, border, vec_ok;
+    int shifted;  // !vec_ok: rows are staged with a per-slot byte shift (see TileShared::slot_shift)
     PyrScale sc[FDMS_MAX_SCALES];
 };
 
@@ -246,7 +247,10 @@ struct TileShared {
     // row are ALWAYS the previous and the current slot.
     int4 rowmeta[PYR_MAX_TH + 1];
     int slot_row[PYR_MAX_SLOTS];
-    int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows;
+    // sources whose rows do not start on 16 bytes: a slot is staged from the 16-byte boundary below its first byte,
+    // so its data starts slot_shift bytes into the slot; the bulk copy covers the first slot_cov bytes of the slot
+    int slot_shift[PYR_MAX_SLOTS], slot_cov[PYR_MAX_SLOTS];
+    int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows, tail_max;
     alignas(8) unsigned long long bar;
 };
 
@@ -288,7 +292,7 @@ __device__ __forceinline__ void border_row(T *const *pc, unsigned off, long long
 
 // The per-thread streaming loop of pyramid_kernel: horizontal pass of each slot in source-row order, then every
 // output row whose lower tap is that slot.  FAST = interior tile with paired stores (no per-pixel predicates).
-template <typename T, bool FAST, int MODE>
+template <typename T, bool FAST, int MODE, bool SHIFT = false>
 __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, unsigned ys, long long xs_, uint32_t wA,
                                             unsigned shA, unsigned aA, uint32_t wB, unsigned shB, unsigned aB,
                                             int n_used, int n_rows, int slot_bytes, unsigned tborder, bool inA_,
@@ -347,25 +351,28 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
         }
     };
 
+    // horizontal pass of slot k for both pixels.  SHIFT: the slot's data starts slot_shift[k] bytes into the slot
+    // (rows that do not start on 16 bytes), shA / shB are byte offsets and the word / bit split is redone per slot.
+    auto hslot = [&](int k, uint32_t slot_off, int *h) {
+        if (SHIFT) {
+            const unsigned d = (unsigned)sh.slot_shift[k], oa = shA + d, ob = shB + d;
+            hpass(wA + slot_off + (oa & ~3u), (oa & 3u) * 8u, aA, h);
+            hpass(wB + slot_off + (ob & ~3u), (ob & 3u) * 8u, aB, h + 3);
+        } else if (MODE == PM_HALF) {
+            hpass_half(wA + slot_off, shA, h);
+            hpass_half(wB + slot_off, shB, h + 3);
+        } else {
+            hpass(wA + slot_off, shA, aA, h);
+            hpass(wB + slot_off, shB, aB, h + 3);
+        }
+    };
     uint32_t slot_off = 0;
     for (int k = 0; k < n_used; k += 2) {
-        if (MODE == PM_HALF) {
-            hpass_half(wA + slot_off, shA, E);
-            hpass_half(wB + slot_off, shB, E + 3);
-        } else {
-            hpass(wA + slot_off, shA, aA, E);
-            hpass(wB + slot_off, shB, aB, E + 3);
-        }
+        hslot(k, slot_off, E);
         flush(k, E, O);
         slot_off += slot_bytes;
         if (k + 1 < n_used) {
-            if (MODE == PM_HALF) {
-                hpass_half(wA + slot_off, shA, O);
-                hpass_half(wB + slot_off, shB, O + 3);
-            } else {
-                hpass(wA + slot_off, shA, aA, O);
-                hpass(wB + slot_off, shB, aB, O + 3);
-            }
+            hslot(k + 1, slot_off, O);
             flush(k + 1, O, E);
         }
         slot_off += slot_bytes;
@@ -572,32 +579,49 @@ __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale
             slot1 = (b1 != 0) ? slot0 + 1 : slot0;
         }
     }
-    int n_bulk = 0;
+    int tx_bytes = 0, tail = 0;
     bool virt_row = false;
     uint64_t *bar = reinterpret_cast<uint64_t *>(&sh.bar);
+    auto stage = [&](int k, int row) {
+        sh.slot_row[k] = row;
+        if (row >= P.src_h) {
+            virt_row = true;
+            return;
+        }
+        if (!P.shifted) {
+            if (bulk_bytes > 0) {
+                bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
+                tx_bytes += bulk_bytes;
+            }
+            return;
+        }
+        // g0 = first needed byte of the row (unaligned), row_bytes = needed bytes.  Copy the whole 16-byte chunks
+        // between the boundary below that byte and the end of the row's real bytes; the rest is the scalar tail.
+        const uint8_t *srow = src + (long long)row * P.pitch;
+        const uintptr_t g = (uintptr_t)(srow + g0), a = g & ~(uintptr_t)15;
+        const int d = (int)(g - a);
+        const uintptr_t row_end = (uintptr_t)srow + (uintptr_t)(3 * P.src_w);
+        long long cov = (long long)(row_end & ~(uintptr_t)15) - (long long)a;
+        cov = min(cov, (long long)((d + row_bytes + 15) & ~15));
+        if (cov < 0 || a < (uintptr_t)P.src) cov = 0;
+        sh.slot_shift[k] = d;
+        sh.slot_cov[k] = (int)cov;
+        // bytes after the bulk copy up to the end of the real data (rounded up to a word; what follows are the
+        // virtual zero columns of the api mode, written as words)
+        tail = max(tail, min(d + row_bytes, (d + 3 * P.src_w - g0 + 3) & ~3) - (int)cov);
+        if (cov > 0) {
+            bulk_g2s(buf + (size_t)k * slot_bytes, reinterpret_cast<const void *>(a), (uint32_t)cov, bar);
+            tx_bytes += (int)cov;
+        }
+    };
     if (S.dense_rows) {
-        for (int k = lane; k < n_used; k += 32) {
-            const int row = min(max(rmin + k, 0), P.virt_h - 1);
-            sh.slot_row[k] = row;
-            if (row >= P.src_h) virt_row = true;
-            else if (bulk_bytes > 0) {
-                bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
-                n_bulk++;
-            }
-        }
+        for (int k = lane; k < n_used; k += 32) stage(k, min(max(rmin + k, 0), P.virt_h - 1));
     } else if (valid) {
-        const int nk = (b1 != 0) ? 2 : 1;
-        for (int q = 0; q < nk; q++) {
-            const int k = slot0 + q, row = q ? r1 : r0;
-            sh.slot_row[k] = row;
-            if (row >= P.src_h) virt_row = true;
-            else if (bulk_bytes > 0) {
-                bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
-                n_bulk++;
-            }
-        }
+        stage(slot0, r0);
+        if (b1 != 0) stage(slot0 + 1, r1);
     }
-    n_bulk = __reduce_add_sync(0xffffffffu, n_bulk);
+    tx_bytes = __reduce_add_sync(0xffffffffu, tx_bytes);
+    tail = __reduce_max_sync(0xffffffffu, tail);
     const bool any_virt = __any_sync(0xffffffffu, virt_row);
     if (lane <= n_rows) {
         const int b0 = (int)(b01 & 0xffffu);
@@ -607,11 +631,12 @@ __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale
     }
     if (lane == 0) {
         sh.n_used = n_used;
-        sh.need_scalar = (bulk_bytes < row_bytes && n_used > 0) || any_virt;
+        sh.need_scalar = P.shifted ? (n_used > 0 && (tail > 0 || any_virt)) : ((bulk_bytes < row_bytes && n_used > 0) || any_virt);
+        sh.tail_max = tail;
         sh.n_rows = n_rows;
     }
     __syncwarp();  // every lane's meta is ordered before lane 0's releasing arrive
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_bulk * bulk_bytes));
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)tx_bytes);
 }
 
 // Tap tables of a pyramid geometry (OpenCV's coefficient set-up).  Runs once per geometry:
@@ -700,10 +725,11 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
         if (has_cols && lane < 2) sx = __ldg(S.xtab + left + (lane == 0 ? dxa : dxb - 1)).x;
         const int sxa = __shfl_sync(0xffffffffu, sx, 0);
         const int sxb = min(__shfl_sync(0xffffffffu, sx, 1) + 1, P.virt_w - 1);
-        const int g0 = (3 * sxa) & ~15;
-        const int row_bytes = ((3 * sxb + 3 + 15) & ~15) - g0;
+        const int g0 = P.shifted ? 3 * sxa : ((3 * sxa) & ~15);
+        const int row_bytes = P.shifted ? 3 * (sxb - sxa + 1) : ((3 * sxb + 3 + 15) & ~15) - g0;
         const int real_end = 3 * P.src_w;
         const int bulk_bytes = P.vec_ok ? max(0, min(g0 + row_bytes, real_end & ~15) - g0) : 0;
+        if (sxa >= P.src_w && e.x >= 0) e.x = P.src_h;  // the whole tile reads virtual zero columns (api mode, portrait)
         if (lane == 0) {
             sh.g0 = g0;
             sh.row_bytes = row_bytes;
@@ -716,21 +742,59 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     const int n_used = sh.n_used, g0 = sh.g0;
 
     // ---- per-thread byte offsets inside a slot --------------------------------------------------------
+    // (shifted sources: wA / wB stay the slot base and shA / shB carry the BYTE offset; the per-slot shift is added
+    // in stream_tile)
     uint32_t wA = smem_u32(smem), wB = wA;  // out-of-image pixels read in bounds; their value is replaced
     unsigned shA = 0, shB = 0;
     if (inA) {
         const int o = 3 * sxA - g0;
-        wA += (uint32_t)(o & ~3);
-        shA = (unsigned)(o & 3) * 8u;
+        if (P.shifted) shA = (unsigned)o;
+        else {
+            wA += (uint32_t)(o & ~3);
+            shA = (unsigned)(o & 3) * 8u;
+        }
     }
     if (inB) {
         const int o = 3 * sxB - g0;
-        wB += (uint32_t)(o & ~3);
-        shB = (unsigned)(o & 3) * 8u;
+        if (P.shifted) shB = (unsigned)o;
+        else {
+            wB += (uint32_t)(o & ~3);
+            shB = (unsigned)(o & 3) * 8u;
+        }
     }
 
     // ---- scalar staging: whatever the bulk copies do not cover ---------------------------------------
-    if (sh.need_scalar) {
+    if (sh.need_scalar && P.shifted) {
+        // tails of the shifted slots, flattened over (slot, byte) so that the usual <= 31 bytes per slot cost a few
+        // iterations in total; virtual rows are zero-filled whole
+        const int need = sh.row_bytes, tail_max = sh.tail_max;
+        const int real_len = 3 * P.src_w - g0;  // real bytes of a row from g0 on (may exceed `need`, may be <= 0)
+        for (int idx = tid; idx < n_used * tail_max; idx += PYR_THREADS) {
+            const int k = idx / tail_max, j = idx - k * tail_max;
+            const int row = sh.slot_row[k];
+            if (row >= P.src_h) continue;
+            const int d = sh.slot_shift[k], i = sh.slot_cov[k] + j;
+            if (i >= min(d + need, (d + real_len + 3) & ~3)) continue;
+            const uint8_t *srow = src + (long long)row * P.pitch;
+            const int pos = g0 - d + i;  // byte of the row this slot byte mirrors
+            smem[(size_t)k * slot_bytes + i] = (pos >= 0 && pos < 3 * P.src_w) ? __ldg(srow + pos) : (uint8_t)0;
+        }
+        if (real_len < need) {  // CTA-uniform: the tile reaches into the virtual zero columns -> word-wise zeros
+            const int zwords = (need - max(real_len, 0)) / 4 + 2;
+            for (int idx = tid; idx < n_used * zwords; idx += PYR_THREADS) {
+                const int k = idx / zwords, j = idx - k * zwords;
+                if (sh.slot_row[k] >= P.src_h) continue;
+                const int d = sh.slot_shift[k];
+                const int i = ((d + max(real_len, 0) + 3) & ~3) + 4 * j;
+                if (i < d + need) *reinterpret_cast<uint32_t *>(smem + (size_t)k * slot_bytes + i) = 0u;
+            }
+        }
+        for (int k = 0; k < n_used; k++)
+            if (sh.slot_row[k] >= P.src_h)
+                for (int i = tid * 4; i < need + 16; i += PYR_THREADS * 4)
+                    *reinterpret_cast<uint32_t *>(smem + (size_t)k * slot_bytes + i) = 0u;
+        __syncthreads();
+    } else if (sh.need_scalar) {
         const int row_bytes = sh.row_bytes, bulk_bytes = sh.bulk_bytes, rest = row_bytes - bulk_bytes;
         const int real_end = 3 * P.src_w;
         for (int k = 0; k < n_used; k++) {
@@ -781,9 +845,15 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     else if (fast && S.mode == PM_HALF)
         stream_tile<T, true, PM_HALF>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
                                       tborder, true, true, true, true);
+    else if (fast && P.shifted)
+        stream_tile<T, true, PM_GENERAL, true>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows,
+                                               slot_bytes, tborder, true, true, true, true);
     else if (fast)
         stream_tile<T, true, PM_GENERAL>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                          slot_bytes, tborder, true, true, true, true);
+    else if (P.shifted)
+        stream_tile<T, false, PM_GENERAL, true>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows,
+                                                slot_bytes, tborder, inA, inB, two, S.vec != 0);
     else
         stream_tile<T, false, PM_GENERAL>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                           slot_bytes, tborder, inA, inB, two, S.vec != 0);
@@ -838,6 +908,7 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
         P.flip = flip_rb ? 1 : 0;
         P.border = border;
         P.vec_ok = ((uintptr_t)src % 16 == 0) && (img_stride % 16 == 0) && (row_pitch % 16 == 0);
+        P.shifted = !P.vec_ok;
         // direct tiles read aligned 32-bit words: every source row must start on a word
         const bool words_ok = ((uintptr_t)src % 4 == 0) && (img_stride % 4 == 0) && (row_pitch % 4 == 0);
         int tiles = 0, smem_max = 0, n = 0;
@@ -894,7 +965,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 const bool cols_ok = g.left % 2 == 0 && g.unpad_w % 2 == 0 && g.dst_w % 2 == 0;
                 S.direct = S.mode != PM_GENERAL && ctx->pyr_direct && S.vec && words_ok && cols_ok && src_w % 4 == 0 &&
                            (S.mode == PM_POINT || kx == 2);
-                if (!real && !S.direct) S.mode = PM_GENERAL;  // the staged specialisations assume no virtual rows
+                // the staged specialisations assume no virtual rows and rows that start on 16 bytes
+                if ((!real || P.shifted) && !S.direct) S.mode = PM_GENERAL;
                 S.real_rows = (S.direct && !real) ? src_h / (int)ky : g.unpad_h;
                 // the exact 3:2 scale as a direct tile too (direct only: there is no staged flavour of it)
                 const bool r32 = 2LL * virt_w == 3LL * g.unpad_w && 2LL * virt_h == 3LL * g.unpad_h && S.scale_x == 1.5 &&
@@ -915,7 +987,7 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             for (;;) {
                 int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : (y_point ? th : 2 * th);
                 int span_px = (int)(tw * S.scale_x) + 4;
-                S.slot_bytes = ((span_px * 3 + 15) & ~15) + 48;
+                S.slot_bytes = ((span_px * 3 + 15) & ~15) + 64;  // slack: tap pairs past the span, word reads, slot shift
                 if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= ctx->pyr_smem_budget) {
                     if (n_slots * S.slot_bytes > smem_max) smem_max = n_slots * S.slot_bytes;
                     break;

@@ -105,11 +105,13 @@ def test_letterbox_exact_factors_with_column_padding(hw, sizes):
         assert np.array_equal(got.view(np.uint16), O.pack_chw(lb, True, np.float16).view(np.uint16)), size
 
 
-@pytest.mark.parametrize("hw,sizes", [((120, 160), (80, 32, 96)), ((1080, 1920), (640, 960, 1280)), ((90, 160), (32, 80))])
+@pytest.mark.parametrize("hw,sizes", [((120, 160), (80, 32, 96)), ((1080, 1920), (640, 960, 1280)), ((90, 160), (32, 80)),
+                                      ((640, 360), (320, 160, 96)), ((1920, 1080), (640, 1280)), ((768, 1366), (640,))])
 def test_api_mode_integer_scales_direct_tiles(hw, sizes):
-    """api mode (virtual zero-padded square) on landscape images whose square is an integer multiple of the model
-    size: the 2:1 and odd:1 scales run as direct tiles with the virtual rows written as zeros, the others staged --
-    all in one launch, fp16 CHW like the hot path, bit-exact against the oracle's preprocess_api + pack."""
+    """api mode (virtual zero-padded square).  Landscape images whose square is an integer multiple of the model size:
+    the 2:1 and odd:1 scales run as direct tiles with the virtual rows written as zeros, the others staged.  Portrait
+    and odd-width images: virtual zero COLUMNS and rows that do not start on 16 bytes (shifted bulk staging).  All
+    scales in one launch, fp16 CHW like the hot path, bit-exact against the oracle's preprocess_api + pack."""
     h, w = hw
     img = synth.synth_image(h, w, 7 + h)
     s = max(h, w)

@@ -947,8 +947,9 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             {
                 // exact integer factors on both axes, no clamped taps (virt == k * unpad), no virtual zeros
                 const long long kx = (long long)S.scale_x, ky = (long long)S.scale_y;
-                const bool int_x = S.scale_x == (double)kx && kx >= 2 && kx * g.unpad_w == virt_w;
-                const bool int_y = S.scale_y == (double)ky && ky >= 2 && ky * g.unpad_h == virt_h;
+                // (factor 1 -- the image already has the model size -- is the odd factor whose point sample is the pixel)
+                const bool int_x = S.scale_x == (double)kx && kx >= 1 && kx * g.unpad_w == virt_w;
+                const bool int_y = S.scale_y == (double)ky && ky >= 1 && ky * g.unpad_h == virt_h;
                 const bool real = virt_h == src_h && virt_w == src_w;
                 // api mode on a landscape image: the virtual square only adds zero ROWS below the image; when the
                 // image height is a multiple of the factor no output row mixes real and virtual taps

@@ -92,7 +92,7 @@ def test_api_preprocess(golden, i):
 
 
 @pytest.mark.parametrize("hw,sizes", [((384, 216), (128, 192, 256)), ((1920, 1080), (640, 960, 1280)), ((216, 384), (128, 192, 256)),
-                                      ((360, 640), (320, 160, 480))])
+                                      ((360, 640), (320, 160, 480)), ((720, 1280), (640, 960, 1280)), ((96, 160), (160,))])
 def test_letterbox_exact_factors_with_column_padding(hw, sizes):
     """Portrait (column-padded) and landscape letterboxes at exact 3:1 / 2:1 / 3:2 factors: the direct tiles incl.
     their border column pairs, fp16 CHW with the channel flip like the hot path, bit-exact against the oracle."""

@@ -124,3 +124,41 @@ def test_nms_idempotent_and_sorted_large():
     assert np.all(s[:-1] >= s[1:]) and len(s) > 500
     again = ops.nms(kept[:, :4].contiguous(), kept[:, 4].contiguous(), 0.45, ops.IOU_TV_CUDA)
     assert torch.equal(again, torch.arange(len(s), device=DEV))
+
+
+def test_repeated_runs_are_bit_identical():
+    """The whole path 40 times on the same inputs (cfg2 shapes, batch 8) with other work in flight on a second stream:
+    pyramid planes, per-scale keep counts and merged detections must not change from run to run.  Candidate ORDER in
+    the scratch lists is free (atomics); everything observable is not.  Guards the barrier-free parts of the kernels
+    (mbarrier staging, ballot resolver, warp-aggregated atomics) against races -- compute-sanitizer is not available
+    on this GPU pool."""
+    h, w, sizes, bs = 1080, 1920, [640, 960, 1280], 8
+    images, heads, shapes = standin.make_batch(h, w, sizes, bs, n_faces=60, seed=23, dtype=np.float16)
+    img = gpu(images)
+    geoms = [_lib.letterbox_geometry(h, w, s, auto=True, stride=32) for s in sizes]
+    sl = [[gpu(l) for l in heads[s]] for s in range(3)]
+    plan = ops.PostPlan(sl, synth.P5_STRIDES, synth.P5_ANCHORS, [s[0] for s in shapes], (h, w), 0.5, 0.5, cap=1024,
+                        out_cap=1024, iou_mode=ops.IOU_TV_CUDA)
+    side = torch.cuda.Stream()
+    noise = torch.empty((64 << 20,), dtype=torch.uint8, device=DEV)
+    first = None
+    for it in range(40):
+        with torch.cuda.stream(side):  # unrelated traffic perturbs the scheduling from run to run
+            noise.fill_(it & 0xff)
+        outs = ops.pyramid(img, geoms, out_dtype=torch.float16)
+        out = plan.run()
+        torch.cuda.synchronize()
+        n_out = out.n_out.cpu().numpy().copy()
+        dets = [out.dets[b, :n_out[b]].cpu().numpy().copy() for b in range(bs)]
+        sig = ([o.view(torch.int16).to(torch.int64).sum().item() for o in outs], plan.cands.count.cpu().numpy().copy(),
+               plan.cands.n_keep.cpu().numpy().copy(), n_out)
+        if first is None:
+            first = (sig, dets, [o.clone() for o in outs])
+            continue
+        for a, b_ in zip(sig, first[0]):
+            assert np.array_equal(np.asarray(a), np.asarray(b_)), it
+        for a, b_ in zip(dets, first[1]):
+            assert np.array_equal(a, b_), it
+        if it % 13 == 0:
+            for a, b_ in zip(outs, first[2]):
+                assert torch.equal(a, b_), it

@@ -44,3 +44,86 @@ def letterbox_shape(src_hw, new_shape=640, auto=True, scaleup=True, stride=32):
     """(H, W) of the letterboxed image without touching pixels."""
     g = _lib.letterbox_geometry(src_hw[0], src_hw[1], new_shape, auto=auto, scaleup=scaleup, stride=stride)
     return g.dst_h, g.dst_w
+
+
+IMG_FORMATS = ('bmp', 'jpg', 'jpeg', 'png', 'tif', 'tiff', 'dng', 'webp', 'mpo')  # utils/datasets.py:29
+VID_FORMATS = ('mov', 'avi', 'mp4', 'mpg', 'mpeg', 'm4v', 'wmv', 'mkv')           # utils/datasets.py:30
+
+
+class LoadImages:
+    """Drop-in for utils/datasets.py:124-201 (the inference loader of detect.py:61): iterates over the images and
+    videos of a path / glob / directory and yields `(path, img, img0, cap)` with `img` = letterbox(img0, img_size,
+    stride, auto=False) flipped to RGB and transposed to CHW -- produced by ONE libfdms launch (u8 CHW output with the
+    channel flip), bit-identical to the reference's cv2 + numpy sequence.  The file is decoded once on the host
+    (cv2, like the reference).  `device_out=True` yields the CHW image as a CUDA tensor instead of an ndarray; the
+    per-file progress prints of the reference are dropped (SURVEY: no prints on the path)."""
+
+    def __init__(self, path, img_size=640, stride=32, device=None, device_out=False):
+        import glob
+        import os
+        from pathlib import Path
+        p = str(Path(path).absolute())
+        if '*' in p:
+            files = sorted(glob.glob(p, recursive=True))
+        elif os.path.isdir(p):
+            files = sorted(glob.glob(os.path.join(p, '*.*')))
+        elif os.path.isfile(p):
+            files = [p]
+        else:
+            raise Exception(f'ERROR: {p} does not exist')
+        images = [x for x in files if x.split('.')[-1].lower() in IMG_FORMATS]
+        videos = [x for x in files if x.split('.')[-1].lower() in VID_FORMATS]
+        ni, nv = len(images), len(videos)
+        self.img_size, self.stride = img_size, stride
+        self.files = images + videos
+        self.nf = ni + nv
+        self.video_flag = [False] * ni + [True] * nv
+        self.mode = 'image'
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device_out = device_out
+        self.cap = None
+        if any(videos):
+            self.new_video(videos[0])
+        assert self.nf > 0, f'No images or videos found in {p}. Supported formats are:\nimages: {IMG_FORMATS}\n' \
+                            f'videos: {VID_FORMATS}'
+
+    def __iter__(self):
+        self.count = 0
+        return self
+
+    def __next__(self):
+        import cv2
+        if self.count == self.nf:
+            raise StopIteration
+        path = self.files[self.count]
+        if self.video_flag[self.count]:
+            self.mode = 'video'
+            ret_val, img0 = self.cap.read()
+            if not ret_val:
+                self.count += 1
+                self.cap.release()
+                if self.count == self.nf:
+                    raise StopIteration
+                path = self.files[self.count]
+                self.new_video(path)
+                ret_val, img0 = self.cap.read()
+            self.frame += 1
+        else:
+            self.count += 1
+            img0 = cv2.imread(path)  # BGR
+            assert img0 is not None, 'Image Not Found ' + path
+        # letterbox(auto=False) + [:, :, ::-1] + transpose(2, 0, 1) + ascontiguousarray (:187-191) in one launch
+        t = _to_device_u8(img0, self.device)
+        g = _lib.letterbox_geometry(t.shape[0], t.shape[1], self.img_size, auto=False, stride=self.stride)
+        (out,) = ops.pyramid(t[None], [g], out_dtype=torch.uint8, layout="chw", flip_rb=True)
+        img = out[0] if self.device_out else out[0].cpu().numpy()
+        return path, img, img0, self.cap
+
+    def new_video(self, path):
+        import cv2
+        self.frame = 0
+        self.cap = cv2.VideoCapture(path)
+        self.nframes = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
+
+    def __len__(self):
+        return self.nf

@@ -300,3 +300,26 @@ def test_non_max_suppression_with_apriori_labels(golden):
         assert np.array_equal(res[b].cpu().numpy(), g["r%d" % b])
     with pytest.raises(ValueError):
         general.non_max_suppression(torch.from_numpy(h["tiny_pred"]).to(DEV), 0.3, 0.45, labels=labs)
+
+
+def test_load_images_matches_reference_sequence(tmp_path):
+    """datasets.LoadImages (utils/datasets.py:124-201): letterbox(auto=False) + BGR->RGB + CHW of every file, against
+    the oracle's restatement of the same cv2 / numpy sequence on the decoded file (PNG: lossless)."""
+    import cv2
+    from face_detection_multi_scale_b200.datasets import LoadImages
+    from oracle import oracle as O
+    shapes = [(120, 160), (200, 90), (64, 64)]
+    for i, (h, w) in enumerate(shapes):
+        assert cv2.imwrite(str(tmp_path / ("im%d.png" % i)), synth.synth_image(h, w, 40 + i))
+    (tmp_path / "notes.txt").write_text("not an image")
+    ds = LoadImages(str(tmp_path), img_size=96, stride=32)
+    assert len(ds) == 3 and ds.mode == "image"
+    seen = 0
+    for path, img, img0, cap in ds:
+        assert cap is None and img0.shape[:2] == shapes[seen]
+        ref, _, _ = O.letterbox(img0, 96, auto=False, stride=32)
+        assert np.array_equal(img, np.ascontiguousarray(ref[:, :, ::-1].transpose(2, 0, 1)))
+        seen += 1
+    assert seen == 3
+    (p, dev_img, _, _) = next(iter(LoadImages(str(tmp_path / "im0.png"), img_size=96, device_out=True)))
+    assert dev_img.is_cuda and dev_img.shape == (3, 96, 96)

@@ -494,3 +494,38 @@ def test_w6_maximum_rows_single_segment():
     res = general.non_max_suppression(torch.from_numpy(p[None]).to(DEV), 0.5, 0.45, iou_mode=ops.IOU_TV_CPU)[0]
     ref = O.non_max_suppression(p[None], 0.5, 0.45, O.TV_CPU)[0]
     assert res.shape == ref.shape and np.array_equal(res.cpu().numpy(), ref)
+
+
+def test_non_finite_head_values_do_not_hang_and_match_oracle():
+    """NaN / +-Inf logits in the raw head (a diverged backbone): NaN confidences never pass the filter, infinite
+    logits saturate the sigmoid; the candidate sets still equal the oracle's and the NMS terminates (IoU with
+    non-finite boxes is NaN, which never suppresses)."""
+    levels = [l.copy() for l in _crowd("crowdB")]
+    rng = np.random.default_rng(0)
+    for l in levels:
+        flat = l.reshape(-1)
+        idx = rng.choice(flat.size, 40, replace=False)
+        flat[idx[:15]] = np.nan
+        flat[idx[15:28]] = np.inf
+        flat[idx[28:]] = -np.inf
+    c = ops.decode_filter([[gpu(l) for l in levels]], synth.P5_STRIDES, synth.P5_ANCHORS, 0.3, cap=4096)
+    torch.cuda.synchronize()
+    with np.errstate(all="ignore"):
+        pred = O.decode_head(levels, synth.P5_STRIDES, synth.P5_ANCHORS)
+    for b in range(2):
+        with np.errstate(all="ignore"):
+            rc, rr = O.filter_xyxy(pred[b], 0.3)
+        cand, rows = _sorted_cands(c, b)
+        assert np.array_equal(rows, rr)
+        assert np.array_equal(np.isnan(cand), np.isnan(rc))
+        fin = np.isfinite(rc)
+        assert np.max(np.abs(cand[fin] - rc[fin]), initial=0) <= TOL_PX
+    keep, n_keep = ops.nms_segments(c.cand, c.count, c.cap, 0.45, ops.IOU_TV_CPU, tie=c.row)
+    torch.cuda.synchronize()
+    for b in range(2):
+        with np.errstate(all="ignore"):
+            rc, rr = O.filter_xyxy(pred[b], 0.3)
+            ref = O.nms(rc[:, :4], rc[:, 4], 0.45, O.TV_CPU)
+        cand, rows = _sorted_cands(c, b)
+        got_rows = c.row[b][keep[b, :int(n_keep[b])].long()].cpu().numpy()
+        assert np.array_equal(got_rows, rr[ref])

@@ -42,6 +42,8 @@ struct fdms_ctx {
     fdms_buf merge_keep;       // merge: keep + n_keep
     fdms_buf pyr_tab;          // pyramid tap tables of the last geometry
     unsigned long long pyr_tab_key = 0;
+    fdms_buf dec_tab;          // decode filter: per-CTA table of the last head geometry
+    unsigned long long dec_tab_key = 0;
 };
 
 static inline int fdms_fail(fdms_ctx *ctx, int code, const char *fmt, ...) {

@@ -50,7 +50,7 @@ FDMS_API void fdms_destroy(fdms_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab};
+                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab};
     for (fdms_buf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete ctx;
@@ -61,7 +61,7 @@ FDMS_API const char *fdms_last_error(const fdms_ctx *ctx) { return ctx ? ctx->er
 FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx) {
     if (!ctx) return 0;
     const fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab};
+                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab};
     int64_t t = 0;
     for (const fdms_buf *b : bufs) t += (int64_t)b->bytes;
     return t;

@@ -45,6 +45,19 @@ struct DecParams {
     float *cand;
     int32_t *cand_row;
     int32_t *count;
+    const struct DecCta *cta_tab;  // per CTA of decode_filter_kernel (cached per geometry in the ctx)
+};
+
+// What a CTA of decode_filter_kernel needs to know about itself.  Deriving it in the kernel (level search, two
+// integer divisions, 64-bit plane offsets) cost about half of the instructions of a CTA that finds no candidate,
+// i.e. of nearly every CTA; the table is built once per head geometry by decode_tab_kernel.
+struct DecCta {
+    long long elem_off;  // element offset of channel 0 of this CTA's (image, anchor) plane group in the level's data
+    int level, cells;    // level index; cells per plane (ny * nx)
+    int cell0;           // first cell of this CTA inside the plane
+    int row_base;        // row index of cell 0 of this plane: row_offset + a * cells
+    int seg;             // candidate segment: b * n_scales + scale
+    int pad_;
 };
 
 __device__ __forceinline__ float sigmoid_exact(float x) {
@@ -135,23 +148,19 @@ __device__ __forceinline__ void load_vec8<float>(const float *p, long long i, in
 }
 
 template <typename T>
-__device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, int local_block) {
-    const int planes = P.bs * NA;
-    const int chunk = local_block / planes;  // chunk-major: neighbouring CTAs read different planes
-    const int plane = local_block - chunk * planes;
-    const int b = plane / NA, a = plane - b * NA;
-    const long long cells = (long long)L.ny * L.nx;
-    const long long cell0 = (long long)chunk * DEC_CELLS + (long long)threadIdx.x * DEC_VEC;
-    const int n_valid = (int)max(0LL, min((long long)DEC_VEC, cells - cell0));
-    const T *base = reinterpret_cast<const T *>(L.data) + ((long long)b * NA * NO + (long long)a * NO) * cells;
+__device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, const DecCta &C) {
+    const int cells = C.cells;
+    const int cell0 = C.cell0 + (int)threadIdx.x * DEC_VEC;
+    const int n_valid = max(0, min(DEC_VEC, cells - cell0));
+    const T *base = reinterpret_cast<const T *>(L.data) + C.elem_off;
     const bool aligned = (cells % DEC_VEC == 0) && ((uintptr_t)L.data % 16 == 0);
 
     // cheap necessary condition on the raw logits: sigmoid(obj) > thres and sigmoid(cls) > thres
     unsigned pre = 0;
     if (n_valid > 0) {
         float xo[DEC_VEC], xc[DEC_VEC];
-        load_vec8<T>(base + 4 * cells, cell0, n_valid, aligned, xo);
-        load_vec8<T>(base + 5 * cells, cell0, n_valid, aligned, xc);
+        load_vec8<T>(base + 4LL * cells, cell0, n_valid, aligned, xo);
+        load_vec8<T>(base + 5LL * cells, cell0, n_valid, aligned, xc);
 #pragma unroll
         for (int k = 0; k < DEC_VEC; k++)
             if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) pre |= 1u << k;
@@ -170,7 +179,7 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const T *po = base + 4 * cells + cell0, *pc = base + 5 * cells + cell0;
+    const T *po = base + 4LL * cells + cell0, *pc = base + 5LL * cells + cell0;
     while (__any_sync(0xffffffffu, pre != 0)) {
         const bool have = pre != 0;
         const int k = have ? __ffs(pre) - 1 : 0;
@@ -187,13 +196,13 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
             int basepos = 0;
             if (lane == 0) basepos = atomicAdd(&s_n, __popc(m));
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (ok) s_rows[basepos + __popc(m & ((1u << lane) - 1u))] = L.row_offset + a * (int)cells + (int)(cell0 + k);
+            if (ok) s_rows[basepos + __popc(m & ((1u << lane) - 1u))] = C.row_base + cell0 + k;
         }
     }
     __syncthreads();
     const int n_cta = s_n;
     if (n_cta == 0) return;  // CTA-uniform
-    const int seg = b * P.n_scales + L.scale;
+    const int seg = C.seg;
     if (threadIdx.x == 0) s_base = atomicAdd(P.count + seg, n_cta);
     __syncthreads();
     for (int i = threadIdx.x; i < n_cta; i += DEC_THREADS) {
@@ -202,14 +211,34 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     }
 }
 
-__global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
+__global__ void decode_tab_kernel(const __grid_constant__ DecParams P, DecCta *tab, int n_blocks) {
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= n_blocks) return;
     int li = 0;
-#pragma unroll 1
     for (int l = 1; l < P.n_levels; l++)
-        if ((int)blockIdx.x >= P.lv[l].block_begin) li = l;
+        if (blk >= P.lv[l].block_begin) li = l;
     const DecLevel &L = P.lv[li];
-    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, blockIdx.x - L.block_begin);
-    else decode_filter_body<float>(P, L, blockIdx.x - L.block_begin);
+    const int local = blk - L.block_begin, planes = P.bs * NA;
+    const int chunk = local / planes;  // chunk-major: neighbouring CTAs read different planes
+    const int plane = local - chunk * planes;
+    const int b = plane / NA, a = plane - b * NA;
+    const long long cells = (long long)L.ny * L.nx;
+    DecCta c;
+    c.elem_off = ((long long)b * NA * NO + (long long)a * NO) * cells;
+    c.level = li;
+    c.cells = (int)cells;
+    c.cell0 = chunk * DEC_CELLS;
+    c.row_base = L.row_offset + a * (int)cells;
+    c.seg = b * P.n_scales + L.scale;
+    c.pad_ = 0;
+    tab[blk] = c;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
+    const DecCta C = P.cta_tab[blockIdx.x];
+    const DecLevel &L = P.lv[C.level];
+    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, C);
+    else decode_filter_body<float>(P, L, C);
 }
 
 // Second half of the fused decode: one thread per recorded candidate (dense warps after the compaction):
@@ -427,6 +456,22 @@ FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int 
     P.cand_row = cand_row;
     P.count = count;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // per-CTA table, cached per head geometry (FNV-1a over everything it depends on)
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](long long v) {
+            for (int q = 0; q < 8; q++) { key ^= (unsigned long long)(v >> (8 * q)) & 0xff; key *= 1099511628211ull; }
+        };
+        mix(n_levels); mix(n_scales); mix(bs); mix(n_blocks);
+        for (int l = 0; l < n_levels; l++) { mix(levels[l].ny); mix(levels[l].nx); mix(levels[l].scale); mix(levels[l].row_offset); }
+        if (int rc = fdms_reserve(ctx, ctx->dec_tab, (size_t)n_blocks * sizeof(DecCta))) return rc;
+        mix((long long)(uintptr_t)ctx->dec_tab.p);
+        if (key != ctx->dec_tab_key) {
+            decode_tab_kernel<<<ceil_div(n_blocks, 256), 256, 0, st>>>(P, reinterpret_cast<DecCta *>(ctx->dec_tab.p), n_blocks);
+            FDMS_LAUNCH_CHECK(ctx, "decode_tab_kernel");
+            ctx->dec_tab_key = key;
+        }
+        P.cta_tab = reinterpret_cast<const DecCta *>(ctx->dec_tab.p);
+    }
     FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs * n_scales, st));
     decode_filter_kernel<<<n_blocks, DEC_THREADS, 0, st>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");

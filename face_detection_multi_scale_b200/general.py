@@ -43,7 +43,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     """utils/general.py:506.  prediction (bs, rows, no) with nc == 1 (no = 21 for the face head, 6 without
     keypoints) -> list of (n, no) tensors [x1, y1, x2, y2, conf, cls, kpts...] per image, (0, 6) zeros for images
     without detections (:527).
-    One filter launch + one batched NMS (3 launches) + one gather for the whole batch; a single
+    One filter launch + one batched NMS (one launch for segments of <= 1024 boxes) + one gather for the whole batch; a single
     device->host read of the per-image counts."""
     if prediction.dim() != 3:
         raise ValueError("non_max_suppression: prediction must be (bs, rows, no)")

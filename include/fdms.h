@@ -158,7 +158,8 @@ FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs
 /* ---- batched NMS -------------------------------------------------------------------------
  * torchvision.ops.nms as called at utils/general.py:584 and multi_scale_face_detector.py:234:
  * stable descending sort on score (ties -> ascending `tie`), greedy suppression with strict
- * IoU > thr, no +1, NaN never suppresses.  n_seg independent segments in one call.
+ * IoU > thr, no +1, NaN never suppresses (iou_mode FDMS_IOU_TV_CPU / FDMS_IOU_TV_CUDA; FDMS_IOU_NCNN
+ * is the ncnn demo's flavour: +1 pixel extents, IoU >= thr).  n_seg independent segments in one call.
  * Segment g reads n = min(count[g], cap) items: box (x1,y1,x2,y2) at
  * rows + (g*cap + i)*row_stride + box_off, score at ... + score_off, tie[g*cap + i]
  * (tie == NULL means tie = i; tie values must be unique inside a segment).

@@ -50,6 +50,26 @@ IMG_FORMATS = ('bmp', 'jpg', 'jpeg', 'png', 'tif', 'tiff', 'dng', 'webp', 'mpo')
 VID_FORMATS = ('mov', 'avi', 'mp4', 'mpg', 'mpeg', 'm4v', 'wmv', 'mkv')           # utils/datasets.py:30
 
 
+def _suffix(name):
+    return name.rsplit('.', 1)[-1].lower()
+
+
+def _expand_source(path):
+    """Files named by `path`: a glob pattern (recursive), every `*.*` of a directory, or one file -- sorted, absolute,
+    exactly the candidates utils/datasets.py:126-134 considers."""
+    import glob
+    import os
+    from pathlib import Path
+    spec = str(Path(path).absolute())
+    if '*' in spec:
+        return sorted(glob.glob(spec, recursive=True))
+    if os.path.isdir(spec):
+        return sorted(glob.glob(os.path.join(spec, '*.*')))
+    if os.path.isfile(spec):
+        return [spec]
+    raise Exception(f'ERROR: {spec} does not exist')
+
+
 class LoadImages:
     """Drop-in for utils/datasets.py:124-201 (the inference loader of detect.py:61): iterates over the images and
     videos of a path / glob / directory and yields `(path, img, img0, cap)` with `img` = letterbox(img0, img_size,
@@ -59,33 +79,21 @@ class LoadImages:
     per-file progress prints of the reference are dropped (SURVEY: no prints on the path)."""
 
     def __init__(self, path, img_size=640, stride=32, device=None, device_out=False):
-        import glob
-        import os
-        from pathlib import Path
-        p = str(Path(path).absolute())
-        if '*' in p:
-            files = sorted(glob.glob(p, recursive=True))
-        elif os.path.isdir(p):
-            files = sorted(glob.glob(os.path.join(p, '*.*')))
-        elif os.path.isfile(p):
-            files = [p]
-        else:
-            raise Exception(f'ERROR: {p} does not exist')
-        images = [x for x in files if x.split('.')[-1].lower() in IMG_FORMATS]
-        videos = [x for x in files if x.split('.')[-1].lower() in VID_FORMATS]
-        ni, nv = len(images), len(videos)
         self.img_size, self.stride = img_size, stride
-        self.files = images + videos
-        self.nf = ni + nv
-        self.video_flag = [False] * ni + [True] * nv
-        self.mode = 'image'
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device_out = device_out
+        found = _expand_source(path)
+        stills = [f for f in found if _suffix(f) in IMG_FORMATS]
+        clips = [f for f in found if _suffix(f) in VID_FORMATS]
+        self.files = stills + clips                       # images first, then videos (same order as the reference)
+        self.video_flag = [False] * len(stills) + [True] * len(clips)
+        self.nf = len(self.files)
+        self.mode = 'image'
         self.cap = None
-        if any(videos):
-            self.new_video(videos[0])
-        assert self.nf > 0, f'No images or videos found in {p}. Supported formats are:\nimages: {IMG_FORMATS}\n' \
-                            f'videos: {VID_FORMATS}'
+        if clips:
+            self.new_video(clips[0])
+        assert self.nf > 0, ('No images or videos found in %s. Supported formats are:\nimages: %s\nvideos: %s'
+                             % (path, list(IMG_FORMATS), list(VID_FORMATS)))
 
     def __iter__(self):
         self.count = 0

@@ -196,7 +196,8 @@ def main():
     # The two halves of a step work on independent data (the backbone that links them is out of scope), exactly
     # like consecutive batches of a pipelined deployment (pyramid of batch i+1 while batch i is post-processed):
     # they are enqueued on two streams so the latency-bound NMS kernels overlap the HBM-bound pyramid kernel.
-    s_pyr, s_post = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)  # small latency-bound kernels first
+    prio = [int(v) for v in os.environ.get("FDMS_BENCH_PRIO", "0,-1").split(",")]  # (pyramid, post): small latency-bound kernels first
+    s_pyr, s_post = torch.cuda.Stream(dev, priority=prio[0]), torch.cuda.Stream(dev, priority=prio[1])
     pyr_ctx = _lib.Ctx(local)  # own scratch for the stream that runs the pyramid (a ctx serves one stream)
 
     pyr_events = []  # (before, after) CUDA events around sampled pyramid launches of the timed region, on s_pyr

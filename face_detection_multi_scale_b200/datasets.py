@@ -135,3 +135,52 @@ class LoadImages:
 
     def __len__(self):
         return self.nf
+
+
+def read_batch(items, threads=None, out=None):
+    """Decode a list of same-sized image files (paths) / already decoded (H, W, 3) uint8 arrays into ONE pinned
+    (B, H, W, 3) uint8 BGR host tensor, files in parallel on `threads` host threads (cv2 releases the GIL).  The
+    decoder is cv2.imread, i.e. exactly the pixels the reference works on (multi_scale_face_detector.py:84), and each
+    file is decoded once for all scales instead of once per scale.  `out` recycles a previous batch buffer."""
+    import concurrent.futures
+    import os
+
+    import cv2
+
+    def load(it):
+        if isinstance(it, (str, bytes)) or hasattr(it, "__fspath__"):
+            img = cv2.imread(os.fsdecode(it))
+            if img is None:
+                raise ValueError(f"Could not read image: {it}")  # msfd:86
+            return img
+        return np.asarray(it)
+
+    items = list(items)
+    if not items:
+        raise ValueError("read_batch: empty batch")
+    first = load(items[0])
+    if first.ndim != 3 or first.shape[2] != 3 or first.dtype != np.uint8:
+        raise ValueError("read_batch: images must decode to (H, W, 3) uint8")
+    shape = (len(items),) + first.shape
+    if out is None or tuple(out.shape) != shape or out.dtype != torch.uint8:
+        out = torch.empty(shape, dtype=torch.uint8)
+        if torch.cuda.is_available():
+            out = out.pin_memory()
+    dst = out.numpy()
+    dst[0] = first
+
+    def work(i):
+        img = load(items[i])
+        if img.shape != first.shape:
+            raise ValueError("read_batch: image %d is %s, the batch is %s" % (i, img.shape, first.shape))
+        dst[i] = img
+
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+    if len(items) > 1:
+        with concurrent.futures.ThreadPoolExecutor(max(1, min(int(threads), len(items) - 1))) as ex:
+            list(ex.map(work, range(1, len(items))))
+    return out

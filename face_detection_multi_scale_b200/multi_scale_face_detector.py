@@ -263,7 +263,8 @@ class MultiScaleFaceDetector:
         images / paths.  Returns a list of (k, 7) float64 arrays [x1,y1,x2,y2,conf,cls,scale_idx] per image, rows
         in weighted-score order (msfd:242-288); images without detections give np.array([]) (msfd:285)."""
         if isinstance(images, (list, tuple)):
-            images = np.stack([self._read(i) for i in images])
+            from .datasets import read_batch
+            images = read_batch(images)  # parallel host decode, once per image, into a pinned batch
         t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
         if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
             raise ValueError("detect_multi_scale_batch: expected (B, H, W, 3) uint8 images")

@@ -323,3 +323,24 @@ def test_load_images_matches_reference_sequence(tmp_path):
     assert seen == 3
     (p, dev_img, _, _) = next(iter(LoadImages(str(tmp_path / "im0.png"), img_size=96, device_out=True)))
     assert dev_img.is_cuda and dev_img.shape == (3, 96, 96)
+
+
+def test_read_batch_and_detect_from_paths(tmp_path):
+    """datasets.read_batch: files decoded in parallel into one pinned batch, identical to np.stack(cv2.imread(..));
+    detect_multi_scale_batch(list of paths) goes through it."""
+    import cv2
+    from face_detection_multi_scale_b200.datasets import read_batch
+    paths = []
+    for i in range(5):
+        p = tmp_path / ("im%d.png" % i)
+        assert cv2.imwrite(str(p), synth.synth_image(96, 160, 70 + i))
+        paths.append(str(p))
+    batch = read_batch(paths, threads=3)
+    assert batch.is_pinned() and tuple(batch.shape) == (5, 96, 160, 3)
+    assert np.array_equal(batch.numpy(), np.stack([cv2.imread(p) for p in paths]))
+    again = read_batch(paths[::-1], out=batch)
+    assert again.data_ptr() == batch.data_ptr() and np.array_equal(again.numpy()[0], cv2.imread(paths[-1]))
+    with pytest.raises(ValueError):
+        read_batch([paths[0], synth.synth_image(64, 64, 1)])
+    with pytest.raises(ValueError):
+        read_batch([str(tmp_path / "missing.png")])

@@ -40,9 +40,24 @@ def _stale():
 
 
 def build_lib(force=False, verbose=False):
-    """Compile csrc/*.cu into libfdms.so if missing or older than its sources. Returns the path."""
+    """Compile csrc/*.cu into libfdms.so if missing or older than its sources. Returns the path.
+    Concurrent callers (the ranks of a torchrun job on a box whose snapshot lost the file times) serialise on a
+    lock file; the ones that waited find the library fresh and return."""
     if not force and not _stale():
         return LIB
+    import fcntl
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     try:
         nvcc = _nvcc()
     except RuntimeError:

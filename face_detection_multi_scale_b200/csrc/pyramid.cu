@@ -248,8 +248,10 @@ struct TileShared {
     int4 rowmeta[PYR_MAX_TH + 1];
     int slot_row[PYR_MAX_SLOTS];
     // sources whose rows do not start on 16 bytes: a slot is staged from the 16-byte boundary below its first byte,
-    // so its data starts slot_shift bytes into the slot; the bulk copy covers the first slot_cov bytes of the slot
-    int slot_shift[PYR_MAX_SLOTS], slot_cov[PYR_MAX_SLOTS];
+    // so its data starts slot_shift bytes into the slot; the bulk copy covers the first slot_cov bytes of the slot.
+    // The two arrays live outside this struct (only the SHIFTED kernel allocates them: static shared memory of the
+    // common kernel decides its L1 carve-out).
+    int *slot_shift, *slot_cov;
     int n_used, g0, row_bytes, bulk_bytes, need_scalar, n_rows, tail_max;
     alignas(8) unsigned long long bar;
 };
@@ -399,7 +401,15 @@ __device__ __forceinline__ void stream_tile(const TileShared &sh, T *const *pc, 
 // Only rows are padded here (host guarantees left == 0 and dst_w == unpad_w), so a row is either all border or all
 // interior.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+// Column pairs of a direct tile that lie in the left / right letterbox border: rare (portrait sources), kept out of line.
+template <typename T>
+__device__ __noinline__ void border_columns(T *const *pc, unsigned ys, unsigned tborder, int rows) {
+    unsigned off = 0;
+    for (int y = 0; y < rows; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+}
+
+// COLS (CTA-uniform): the tile contains letterbox border columns.
+template <typename T, int MODE, bool COLS>
 __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &S, int img, int oy0, int ox0, int tid) {
     const int x = ox0 + 2 * tid;
     if (x >= S.dst_w || 2 * tid >= S.tw) return;
@@ -416,9 +426,8 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
     const unsigned ys = (unsigned)S.ys;
     const unsigned tborder = (unsigned)P.border * 4u;
     const int y_end = min(oy0 + S.th, S.dst_h);
-    if (sxA < 0) {  // a column pair of the left / right letterbox border (left and unpad_w are even: never half a pair)
-        unsigned off = 0;
-        for (int y = oy0; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+    if (COLS && sxA < 0) {  // a column pair of the left / right letterbox border (left, unpad_w even: never half a pair)
+        border_columns<T>(pc, ys, tborder, y_end - oy0);
         return;
     }
     const int ya = min(max(oy0, S.top), y_end), yz = max(min(y_end, S.top + S.unpad_h), ya);  // interior rows [ya, yz)
@@ -479,7 +488,7 @@ __device__ __forceinline__ void direct_tile(const PyrParams &P, const PyrScale &
 // before the first is reduced.  Per source row the nine bytes are turned into the six horizontal sums with 3 SHF +
 // 3 PRMT + 6 IDP.2A (the staged path needs two independent 6-byte windows: 26 instructions).  The WEIGHTS are not
 // assumed: the two column phases and the two row phases are read from the same tap tables the general path uses.
-template <typename T>
+template <typename T, bool COLS>
 __device__ __forceinline__ void direct_tile_32(const PyrParams &P, const PyrScale &S, int img, int oy0, int ox0, int tid) {
     const int x = ox0 + 2 * tid;
     if (x >= S.dst_w || 2 * tid >= S.tw) return;
@@ -498,9 +507,8 @@ __device__ __forceinline__ void direct_tile_32(const PyrParams &P, const PyrScal
     const unsigned ys = (unsigned)S.ys;
     const unsigned tborder = (unsigned)P.border * 4u;
     const int y_end = min(oy0 + S.th, S.dst_h);
-    if (e.x < 0) {  // a column pair of the left / right letterbox border
-        unsigned off = 0;
-        for (int y = oy0; y < y_end; y++, off += ys) border_row<T>(pc, off, 1, tborder, true, true);
+    if (COLS && e.x < 0) {  // a column pair of the left / right letterbox border
+        border_columns<T>(pc, ys, tborder, y_end - oy0);
         return;
     }
     // interior rows [ya, yz): [ya, yb) have real taps, [yb, yz) read the virtual zeros of the api mode.  top, th and
@@ -547,6 +555,7 @@ __device__ __forceinline__ void direct_tile_32(const PyrParams &P, const PyrScal
 
 // Warp 0, all 32 lanes: vertical taps of one tile (lane = row; `e` = its ytab entry, r0 = -1 when the row is border
 // or the lane has no row), slot assignment, bulk copies into `buf`, row meta into `sh`, then the full-barrier arrive.
+template <bool SHIFTED>
 __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale &S, TileShared &sh, uint8_t *buf,
                                               const uint8_t *src, int lane, int n_rows, int4 e, int g0, int row_bytes,
                                               int bulk_bytes) {
@@ -588,7 +597,7 @@ __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale
             virt_row = true;
             return;
         }
-        if (!P.shifted) {
+        if (!SHIFTED) {
             if (bulk_bytes > 0) {
                 bulk_g2s(buf + (size_t)k * slot_bytes, src + (long long)row * P.pitch + g0, (uint32_t)bulk_bytes, bar);
                 tx_bytes += bulk_bytes;
@@ -631,7 +640,7 @@ __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale
     }
     if (lane == 0) {
         sh.n_used = n_used;
-        sh.need_scalar = P.shifted ? (n_used > 0 && (tail > 0 || any_virt)) : ((bulk_bytes < row_bytes && n_used > 0) || any_virt);
+        sh.need_scalar = SHIFTED ? (n_used > 0 && (tail > 0 || any_virt)) : ((bulk_bytes < row_bytes && n_used > 0) || any_virt);
         sh.tail_max = tail;
         sh.n_rows = n_rows;
     }
@@ -661,10 +670,13 @@ __global__ void pyramid_tables_kernel(const __grid_constant__ PyrParams P) {
     }
 }
 
-template <typename T>
+// SHIFTED (launch-uniform): the source rows do not start on 16 bytes, see TileShared::slot_shift.  A separate
+// instantiation keeps that machinery out of the kernel every aligned source runs.
+template <typename T, bool SHIFTED>
 __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6) pyramid_kernel(const __grid_constant__ PyrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ TileShared sh;
+    __shared__ int s_slotx[SHIFTED ? 2 * PYR_MAX_SLOTS : 2];
 
     const int tid = threadIdx.x;
     int tile = blockIdx.x;
@@ -680,9 +692,14 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     const int ty = tile / S.tiles_x, tx = tile - ty * S.tiles_x;
     const int oy0 = ty * th, ox0 = tx * tw;
     if (S.direct) {  // CTA-uniform
-        if (S.mode == PM_HALF) direct_tile<T, PM_HALF>(P, S, img, oy0, ox0, tid);
-        else if (S.mode == PM_RATIO32) direct_tile_32<T>(P, S, img, oy0, ox0, tid);
-        else direct_tile<T, PM_POINT>(P, S, img, oy0, ox0, tid);
+        const bool cols = ox0 < S.left || ox0 + tw > S.left + S.unpad_w;  // portrait sources: rare, own instantiation
+        if (cols) {
+            if (S.mode == PM_HALF) direct_tile<T, PM_HALF, true>(P, S, img, oy0, ox0, tid);
+            else if (S.mode == PM_RATIO32) direct_tile_32<T, true>(P, S, img, oy0, ox0, tid);
+            else direct_tile<T, PM_POINT, true>(P, S, img, oy0, ox0, tid);
+        } else if (S.mode == PM_HALF) direct_tile<T, PM_HALF, false>(P, S, img, oy0, ox0, tid);
+        else if (S.mode == PM_RATIO32) direct_tile_32<T, false>(P, S, img, oy0, ox0, tid);
+        else direct_tile<T, PM_POINT, false>(P, S, img, oy0, ox0, tid);
         return;
     }
     const int dst_h = S.dst_h, dst_w = S.dst_w, top = S.top, left = S.left, unpad_h = S.unpad_h, unpad_w = S.unpad_w;
@@ -717,7 +734,10 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
         if (lane == 0) {
             mbar_init(reinterpret_cast<uint64_t *>(&sh.bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            sh.slot_shift = s_slotx;
+            sh.slot_cov = s_slotx + (SHIFTED ? PYR_MAX_SLOTS : 1);
         }
+        __syncwarp();
         int4 e = make_int4(-1, 0, 0, 0);
         if (has_cols && lane < n_rows) e = __ldg(S.ytab + oy0 + lane);
         // source byte range of the tile's columns
@@ -725,8 +745,8 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
         if (has_cols && lane < 2) sx = __ldg(S.xtab + left + (lane == 0 ? dxa : dxb - 1)).x;
         const int sxa = __shfl_sync(0xffffffffu, sx, 0);
         const int sxb = min(__shfl_sync(0xffffffffu, sx, 1) + 1, P.virt_w - 1);
-        const int g0 = P.shifted ? 3 * sxa : ((3 * sxa) & ~15);
-        const int row_bytes = P.shifted ? 3 * (sxb - sxa + 1) : ((3 * sxb + 3 + 15) & ~15) - g0;
+        const int g0 = SHIFTED ? 3 * sxa : ((3 * sxa) & ~15);
+        const int row_bytes = SHIFTED ? 3 * (sxb - sxa + 1) : ((3 * sxb + 3 + 15) & ~15) - g0;
         const int real_end = 3 * P.src_w;
         const int bulk_bytes = P.vec_ok ? max(0, min(g0 + row_bytes, real_end & ~15) - g0) : 0;
         if (sxa >= P.src_w && e.x >= 0) e.x = P.src_h;  // the whole tile reads virtual zero columns (api mode, portrait)
@@ -736,7 +756,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
             sh.bulk_bytes = bulk_bytes;
         }
         __syncwarp();
-        tile_prologue(P, S, sh, smem, src, lane, n_rows, e, g0, row_bytes, bulk_bytes);
+        tile_prologue<SHIFTED>(P, S, sh, smem, src, lane, n_rows, e, g0, row_bytes, bulk_bytes);
     }
     __syncthreads();
     const int n_used = sh.n_used, g0 = sh.g0;
@@ -748,7 +768,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     unsigned shA = 0, shB = 0;
     if (inA) {
         const int o = 3 * sxA - g0;
-        if (P.shifted) shA = (unsigned)o;
+        if (SHIFTED) shA = (unsigned)o;
         else {
             wA += (uint32_t)(o & ~3);
             shA = (unsigned)(o & 3) * 8u;
@@ -756,7 +776,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     }
     if (inB) {
         const int o = 3 * sxB - g0;
-        if (P.shifted) shB = (unsigned)o;
+        if (SHIFTED) shB = (unsigned)o;
         else {
             wB += (uint32_t)(o & ~3);
             shB = (unsigned)(o & 3) * 8u;
@@ -764,7 +784,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     }
 
     // ---- scalar staging: whatever the bulk copies do not cover ---------------------------------------
-    if (sh.need_scalar && P.shifted) {
+    if (SHIFTED && sh.need_scalar) {
         // tails of the shifted slots, flattened over (slot, byte) so that the usual <= 31 bytes per slot cost a few
         // iterations in total; virtual rows are zero-filled whole
         const int need = sh.row_bytes, tail_max = sh.tail_max;
@@ -794,7 +814,7 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
                 for (int i = tid * 4; i < need + 16; i += PYR_THREADS * 4)
                     *reinterpret_cast<uint32_t *>(smem + (size_t)k * slot_bytes + i) = 0u;
         __syncthreads();
-    } else if (sh.need_scalar) {
+    } else if (!SHIFTED && sh.need_scalar) {
         const int row_bytes = sh.row_bytes, bulk_bytes = sh.bulk_bytes, rest = row_bytes - bulk_bytes;
         const int real_end = 3 * P.src_w;
         for (int k = 0; k < n_used; k++) {
@@ -845,13 +865,13 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
     else if (fast && S.mode == PM_HALF)
         stream_tile<T, true, PM_HALF>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows, slot_bytes,
                                       tborder, true, true, true, true);
-    else if (fast && P.shifted)
+    else if (fast && SHIFTED)
         stream_tile<T, true, PM_GENERAL, true>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                                slot_bytes, tborder, true, true, true, true);
     else if (fast)
         stream_tile<T, true, PM_GENERAL>(sh, pc, (unsigned)S.ys, 1, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                          slot_bytes, tborder, true, true, true, true);
-    else if (P.shifted)
+    else if (SHIFTED)
         stream_tile<T, false, PM_GENERAL, true>(sh, pc, (unsigned)S.ys, S.xs, wA, shA, aA, wB, shB, aB, n_used, n_rows,
                                                 slot_bytes, tborder, inA, inB, two, S.vec != 0);
     else
@@ -864,11 +884,13 @@ template <typename T>
 int launch_group(fdms_ctx *ctx, const PyrParams &P, int tiles, int n_img, int smem, cudaStream_t st) {
     const int bit = 1 << (int)sizeof(T);
     if (!(ctx->pyr_attr & bit)) {  // dynamic shared memory opt-in, once per ctx and instantiation
-        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ctx->pyr_attr |= bit;
     }
     dim3 grid(tiles, n_img);
-    pyramid_kernel<T><<<grid, PYR_THREADS, smem, st>>>(P);
+    if (P.shifted) pyramid_kernel<T, true><<<grid, PYR_THREADS, smem, st>>>(P);
+    else pyramid_kernel<T, false><<<grid, PYR_THREADS, smem, st>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "pyramid_kernel");
     return FDMS_OK;
 }
@@ -988,7 +1010,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
             for (;;) {
                 int n_slots = S.dense_rows ? (int)((th - 1) * S.scale_y) + 4 : (y_point ? th : 2 * th);
                 int span_px = (int)(tw * S.scale_x) + 4;
-                S.slot_bytes = ((span_px * 3 + 15) & ~15) + 64;  // slack: tap pairs past the span, word reads, slot shift
+                // slack: tap pairs past the span and whole-word reads; shifted sources start up to 15 bytes into the slot
+                S.slot_bytes = ((span_px * 3 + 15) & ~15) + (P.shifted ? 64 : 48);
                 if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= ctx->pyr_smem_budget) {
                     if (n_slots * S.slot_bytes > smem_max) smem_max = n_slots * S.slot_bytes;
                     break;

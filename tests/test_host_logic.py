@@ -160,3 +160,29 @@ def test_gather_world_size_2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+def test_hot_pyramid_kernel_does_not_spill():
+    """pyramid_kernel<__half, false> is held to 48 registers (8 CTAs/SM) and sits right at the spill boundary: a build
+    that spills loses 4-20 % (measured A/B on the B200).  Guard it at build time: ptxas must report no
+    spill stores / loads for that instantiation."""
+    import re
+    import shutil
+    import subprocess
+    import tempfile
+    from face_detection_multi_scale_b200 import build as B
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    with tempfile.TemporaryDirectory() as td:
+        r = subprocess.run([nvcc] + B.NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, "pyramid.cu"), "-o",
+                                                    os.path.join(td, "p.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    blocks = re.split(r"ptxas info\s+: Compiling entry function", r.stderr)
+    hot = [b for b in blocks if "pyramid_kernelI6__halfLb0E" in b]
+    assert len(hot) == 1
+    m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", hot[0])
+    regs = re.search(r"Used (\d+) registers", hot[0])
+    assert m and regs
+    assert (int(m.group(1)), int(m.group(2))) == (0, 0), hot[0]
+    assert int(regs.group(1)) <= 48

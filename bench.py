@@ -12,6 +12,10 @@ outputs are synthetic raw head maps with planted faces (random-init weights yiel
 Prints ONE JSON line (rank 0).  `value` = images/s with all inputs resident in HBM; `e2e` = the same metric
 through the public API (MultiScaleFaceDetector.detect_stream, the pipelined form of detect_multi_scale_batch) with
 pinned HOST inputs: H2D of the images and of the head maps and D2H of the detections inside the timed region.
+`roofline` = algorithmic bytes of a pyramid launch / its duration (CUDA events on the kernel's own stream around every
+4th launch of the timed region, where the post-processing stream shares the SMs; `roofline.isolated` = the same kernel
+alone) against MEASURED_PEAKS.json; `cpu_baseline` (N=1) and `--impl reference` = the oracle port of the reference's CPU
+path on the host cores of the box.
 """
 import argparse
 import concurrent.futures

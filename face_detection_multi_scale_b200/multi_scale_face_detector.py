@@ -350,6 +350,40 @@ class MultiScaleFaceDetector:
         out = self.detect_multi_scale_batch(img0[None])
         return out[0], img0.shape
 
+    def detect_files(self, paths, batch_size=32, decode_threads=None, depth=2):
+        """Generator over image files (all of one size): yields `(path, detections (k,7) float64 or np.array([]))` in
+        input order.  The production driver of the reference builds a detector per item and decodes every file once
+        per scale (yolov7_face_multi_scale_dataframe_predict.py:607-700); here batch i+1 is decoded on host threads
+        (datasets.read_batch, cv2.imread: the reference's pixels) into a recycled pinned buffer while batch i runs
+        through detect_stream (H2D, kernels and D2H pipelined over `depth` streams)."""
+        import concurrent.futures
+        from .datasets import read_batch
+        paths = list(paths)
+        chunks = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
+        if not chunks:
+            return
+        bufs = {}  # pinned batch buffers, recycled per (slot, batch length); depth + 2 slots are never in flight together
+
+        def load(ci):
+            key = (ci % (depth + 2), len(chunks[ci]))
+            bufs[key] = read_batch(chunks[ci], threads=decode_threads, out=bufs.get(key))
+            return bufs[key]
+
+        with concurrent.futures.ThreadPoolExecutor(1) as ex:
+            nxt = ex.submit(load, 0)
+
+            def batches():
+                nonlocal nxt
+                for ci in range(len(chunks)):
+                    cur = nxt.result()
+                    if ci + 1 < len(chunks):
+                        nxt = ex.submit(load, ci + 1)
+                    yield cur
+
+            for ci, dets in enumerate(self.detect_stream(batches(), depth=depth)):
+                for pth, d in zip(chunks[ci], dets):
+                    yield pth, d
+
     def get_detection_statistics(self, detections):
         """Subset of the reference's statistics helper used by detect_multi_scale's log line (msfd:281-282)."""
         detections = np.asarray(detections)

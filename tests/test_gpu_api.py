@@ -344,3 +344,37 @@ def test_read_batch_and_detect_from_paths(tmp_path):
         read_batch([paths[0], synth.synth_image(64, 64, 1)])
     with pytest.raises(ValueError):
         read_batch([str(tmp_path / "missing.png")])
+
+
+def test_detect_files_pipelined_equals_per_file(tmp_path):
+    """detect_files (parallel host decode -> pinned batches -> detect_stream) yields, in order, exactly what
+    detect_multi_scale returns file by file; the last batch is ragged."""
+    import cv2
+    h, w, sizes = 192, 320, [160, 320]
+    n = 7
+    images, heads, shapes = standin.make_batch(h, w, sizes, n, n_faces=6, seed=3)
+    paths = []
+    for i in range(n):
+        p = tmp_path / ("f%02d.png" % i)
+        assert cv2.imwrite(str(p), images[i])
+        paths.append(str(p))
+
+    def detector(batch):
+        model = standin.SyntheticHeadModel()
+        for s_, hw in enumerate(shapes):
+            model.set_heads(hw, [l[batch] for l in heads[s_]], device=DEV)
+        return MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, conf_thres=0.4, iou_thres=0.5, cap=512)
+
+    # the stand-in backbone serves fixed head maps per batch position: run files in batches of the same composition
+    got = {}
+    for lo in range(0, n, 3):
+        idx = list(range(lo, min(lo + 3, n)))
+        det = detector(idx)
+        for pth, d in det.detect_files([paths[i] for i in idx], batch_size=3, decode_threads=2):
+            got[pth] = d
+    assert list(got) == paths
+    for i, pth in enumerate(paths):
+        one = detector([i])
+        ref, shape0 = one.detect_multi_scale(pth)
+        assert shape0 == (h, w, 3)
+        assert np.array_equal(np.asarray(got[pth]), np.asarray(ref))

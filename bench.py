@@ -443,6 +443,13 @@ def main():
             "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "nms_candidates_per_sec": round(world * cand_per_step / (stage_ms["nms"] * 1e-3), 0),
             "decode_algorithmic_gbs": round(decode_gbs, 1),
+            "roofline_decode": {"kernels": "decode_filter_kernel + decode_candidates_kernel", "bound": "hbm",
+                                "achieved": round(decode_gbs, 1), "peak": peaks, "unit": "GB/s",
+                                "frac": round(decode_gbs / peaks, 4), "launch_ms": round(stage_ms["decode_filter"], 4),
+                                "algorithmic_bytes_per_step": head_bytes,
+                                "note": "SURVEY 8(d) algorithmic bytes = the whole raw head (rows x 21 x fp16); the kernels "
+                                        "stream only the obj / cls planes and gather 4 more values per candidate (ncu: 13.7 + "
+                                        "10.5 MB of DRAM reads for 141 MB of head maps), so this figure is not HBM-bound"},
         }
         print(json.dumps(line))
     if world > 1:

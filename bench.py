@@ -278,6 +278,10 @@ def main():
     stage_names = ["pyramid", "decode_filter", "nms", "merge"]
     K2 = min(args.steps, 50) if not args.profile else 2
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(K2)]
+    # the four host calls of an iteration take about as long as their kernels: park the GPU behind a spin kernel while
+    # the whole loop is enqueued, so that the event intervals are kernel time and not launch latency of a starved queue
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(int(40e6))
     for i in range(K2):
         img_d, heads_d, outs, plan = sets[i % n_sets]
         c = plan.cands

@@ -529,3 +529,39 @@ def test_non_finite_head_values_do_not_hang_and_match_oracle():
         cand, rows = _sorted_cands(c, b)
         got_rows = c.row[b][keep[b, :int(n_keep[b])].long()].cpu().numpy()
         assert np.array_equal(got_rows, rr[ref])
+
+
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA, ops.IOU_NCNN])
+def test_nms_fuzz_vs_oracle(mode):
+    """Randomised differential test of the batched NMS against the oracle: segment sizes straddling every kernel
+    boundary (32-key runs, 256-candidate steps, the 1024-box fused kernel, sorted path), tight and loose clusters,
+    quantised scores (exact ties), integer corners (IoU exactly on the threshold), several segments per call."""
+    rng = np.random.default_rng(1234 + mode)
+    sizes = [1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 1500, 2600]
+    for it in range(48):
+        n_seg = int(rng.integers(1, 5))
+        cap = int(max(rng.choice(sizes, n_seg)))
+        rows = np.zeros((n_seg, cap, 6), np.float32)
+        counts = np.zeros((n_seg,), np.int32)
+        thr = float(rng.choice([0.1, 0.3, 0.45, 0.5, 1 / 3, 0.7]))
+        for g in range(n_seg):
+            n = int(rng.integers(1, cap + 1)) if g else cap
+            k = int(rng.integers(1, max(2, n // int(rng.integers(2, 12)) + 1)))
+            ctr = rng.uniform(0, 600, (k, 2))
+            sz = rng.uniform(6, 120, (k, 2))
+            idx = rng.integers(0, k, n)
+            c = ctr[idx] + rng.normal(0, rng.choice([0.02, 0.1, 0.4]), (n, 2)) * sz[idx]
+            wh = sz[idx] * rng.uniform(0.7, 1.4, (n, 2))
+            b = np.concatenate([c - wh / 2, c + wh / 2], 1)
+            if it % 3 == 0:
+                b = np.round(b)
+            rows[g, :n, :4] = b
+            rows[g, :n, 4] = np.round(rng.uniform(0.05, 1, n), int(rng.choice([2, 3, 6])))
+            counts[g] = n
+        keep, n_keep = ops.nms_segments(gpu(rows), gpu(counts), cap, thr, mode, max_nms=0)
+        torch.cuda.synchronize()
+        for g in range(n_seg):
+            n = counts[g]
+            ref = O.nms(rows[g, :n, :4], rows[g, :n, 4], thr, mode)
+            got = keep[g, :int(n_keep[g])].cpu().numpy()
+            assert np.array_equal(got, ref), (it, g, n, thr, mode)

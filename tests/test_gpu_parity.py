@@ -565,3 +565,35 @@ def test_nms_fuzz_vs_oracle(mode):
             ref = O.nms(rows[g, :n, :4], rows[g, :n, 4], thr, mode)
             got = keep[g, :int(n_keep[g])].cpu().numpy()
             assert np.array_equal(got, ref), (it, g, n, thr, mode)
+
+
+def test_letterbox_fuzz_vs_oracle():
+    """Randomised letterbox pyramid against the oracle: random source sizes (odd widths -> rows off the 16-byte grid,
+    portrait and landscape), random target sizes incl. exact 1:1 / 2:1 / 3:1 / 3:2 factors, api mode and plain mode,
+    two or three scales per launch, fp16 CHW with the channel flip -- every tile kind and staging path, bit for bit."""
+    rng = np.random.default_rng(99)
+    for it in range(40):
+        if it % 4 == 0:  # shapes that hit the exact factors
+            base = int(rng.choice([32, 64, 96]))
+            k = rng.choice([1, 2, 3, 1.5])
+            h, w = int(base * k * rng.choice([1, 2])), int(base * k * rng.choice([2, 3]))
+            if rng.random() < 0.5:
+                h, w = w, h
+            sizes = [int(max(h, w) / k), int(rng.integers(24, 200))]
+        else:
+            h, w = int(rng.integers(9, 300)), int(rng.integers(9, 300))
+            sizes = [int(s) for s in rng.integers(16, 260, int(rng.integers(2, 4)))]
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        api = it % 3 == 0
+        if api:
+            s_ = max(h, w)
+            geoms = [_lib.letterbox_geometry(s_, s_, size, auto=False, stride=32) for size in sizes]
+            outs = _pyr(img, geoms, torch.float16, layout="chw", flip=False, virt=(s_, s_))
+            refs = [(O.preprocess_api(img, size).astype(np.float32) / np.float32(255)).astype(np.float16) for size in sizes]
+        else:
+            geoms = [_lib.letterbox_geometry(h, w, size, auto=True, stride=32) for size in sizes]
+            outs = _pyr(img, geoms, torch.float16)
+            refs = [O.pack_chw(O.letterbox(img, size, auto=True, stride=32)[0], True, np.float16) for size in sizes]
+        for size, got, ref in zip(sizes, outs, refs):
+            assert got.shape == ref.shape, (it, h, w, size)
+            assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), (it, h, w, size, api)

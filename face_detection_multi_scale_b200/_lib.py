@@ -61,6 +61,9 @@ _SIGS = {
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "fdms_scale_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p]),
+    "fdms_debug_poison_smem": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fdms_scale_coords_ratio_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_double,
+                                              C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fdms_scale_coords_api": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p]),
     "fdms_merge_scales": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -5,9 +5,31 @@
 
 #include "common.cuh"
 
+namespace {
+// Test hook: fills the whole shared memory of an SM with one byte value, so that a kernel reading shared memory it
+// never wrote sees that value instead of whatever the previous kernel left there.
+__global__ void poison_smem_kernel(unsigned word, int n_words) {
+    extern __shared__ unsigned poison_buf[];
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) poison_buf[i] = word;
+    __syncthreads();
+    if (poison_buf[(threadIdx.x * 97) % n_words] != word) __trap();  // keeps the stores alive
+}
+}  // namespace
+
 extern "C" {
 
 FDMS_API int fdms_version(void) { return FDMS_VERSION; }
+
+FDMS_API int fdms_debug_poison_smem(fdms_ctx *ctx, int byte_value, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    const int bytes = ctx->smem_optin > 0 ? ctx->smem_optin : 48 * 1024;
+    FDMS_CUDA(ctx, cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    const unsigned b = (unsigned)byte_value & 0xffu, word = b * 0x01010101u;
+    // one CTA owns the whole shared memory of an SM; a few waves so that every SM gets at least one
+    poison_smem_kernel<<<4 * ctx->sm_count, 256, bytes, (cudaStream_t)stream>>>(word, bytes / 4);
+    FDMS_LAUNCH_CHECK(ctx, "poison_smem_kernel");
+    return FDMS_OK;
+}
 
 FDMS_API const char *fdms_build_info(void) {
     return "libfdms " __DATE__ " " __TIME__ " sm_100a nvcc " FDMS_STR_(__CUDACC_VER_MAJOR__) "." FDMS_STR_(__CUDACC_VER_MINOR__)

@@ -21,7 +21,7 @@ constexpr int MROW = 8;  // merge row: x1 y1 x2 y2 wscore conf cls scale
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// utils/general.py:374-404, ratio_pad=None.  gain/pad are computed in double on the host like
+// utils/general.py:374-404 (ratio_pad None or given).  gain/pad are computed in double on the host like
 // the Python floats they are, then cast to the tensor dtype by the in-place ops.
 __global__ void scale_coords_kernel(float *coords, long long n, int cols, long long row_stride, float padx, float pady,
                                     float gain, float w0, float h0, int kpt_step) {
@@ -179,15 +179,27 @@ extern "C" {
 
 FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride, int in_h,
                                int in_w, int orig_h, int orig_w, int kpt_step, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
-    if (n == 0) return FDMS_OK;
-    if (!coords || n < 0 || cols <= 0 || row_stride < cols || in_h <= 0 || in_w <= 0 || orig_h <= 0 || orig_w <= 0 ||
-        (kpt_step != 0 && kpt_step < 2) || (kpt_step == 0 && cols < 4))
-        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
+    if (in_h <= 0 || in_w <= 0 || orig_h <= 0 || orig_w <= 0) {
+        if (int rc = fdms_bind(ctx)) return rc;
+        return n == 0 ? FDMS_OK : fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
+    }
     double gain = fmin((double)in_h / orig_h, (double)in_w / orig_w);  // general.py:377
     double padx = ((double)in_w - orig_w * gain) / 2, pady = ((double)in_h - orig_h * gain) / 2;  // :378
+    return fdms_scale_coords_ratio_pad(ctx, coords, n, cols, row_stride, gain, padx, pady, orig_h, orig_w, kpt_step,
+                                       stream);
+}
+
+FDMS_API int fdms_scale_coords_ratio_pad(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride,
+                                         double gain, double pad_x, double pad_y, int orig_h, int orig_w,
+                                         int kpt_step, fdms_stream stream) {
+    if (int rc = fdms_bind(ctx)) return rc;
+    if (n == 0) return FDMS_OK;
+    if (!coords || n < 0 || cols <= 0 || row_stride < cols || orig_h <= 0 || orig_w <= 0 ||
+        (kpt_step != 0 && kpt_step < 2) || (kpt_step == 0 && cols < 4))
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
+    // the Python floats of general.py:377-381 meet an fp32 tensor: each in-place op rounds its scalar to fp32 first
     scale_coords_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        coords, n, cols, row_stride, (float)padx, (float)pady, (float)gain, (float)orig_w, (float)orig_h, kpt_step);
+        coords, n, cols, row_stride, (float)pad_x, (float)pad_y, (float)gain, (float)orig_w, (float)orig_h, kpt_step);
     FDMS_LAUNCH_CHECK(ctx, "scale_coords_kernel");
     return FDMS_OK;
 }

@@ -593,8 +593,12 @@ __device__ __forceinline__ void tile_prologue(const PyrParams &P, const PyrScale
     uint64_t *bar = reinterpret_cast<uint64_t *>(&sh.bar);
     auto stage = [&](int k, int row) {
         sh.slot_row[k] = row;
-        if (row >= P.src_h) {
+        if (row >= P.src_h) {  // virtual zero row (api mode): zero-filled from the slot base by the scalar staging
             virt_row = true;
+            if (SHIFTED) {  // stream_tile adds slot_shift[k] to every read of the slot: it must not be left-over shared memory
+                sh.slot_shift[k] = 0;
+                sh.slot_cov[k] = 0;
+            }
             return;
         }
         if (!SHIFTED) {

@@ -25,8 +25,9 @@ def letterbox(img, new_shape=(640, 640), color=(114, 114, 114), auto=True, scale
               device=None):
     """utils/datasets.py:873.  Returns (ndarray HWC uint8, (rw, rh), (dw, dh)) like the reference.
     A torch CUDA uint8 image is accepted too and then a CUDA tensor is returned (no host round trip)."""
-    if len(set(int(c) for c in color)) != 1:
-        raise NotImplementedError("letterbox: only a grey border colour (r == g == b) is supported")
+    color = [int(c) for c in color]
+    if len(color) != 3 or min(color) < 0 or max(color) > 255:
+        raise ValueError("letterbox: color must be three values in 0..255")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     on_device = isinstance(img, torch.Tensor) and img.is_cuda
     t = _to_device_u8(img, img.device if on_device else dev)
@@ -34,6 +35,16 @@ def letterbox(img, new_shape=(640, 640), color=(114, 114, 114), auto=True, scale
     g = _lib.letterbox_geometry(h, w, new_shape, auto=auto, scaleFill=scaleFill, scaleup=scaleup, stride=stride)
     (out,) = ops.pyramid(t[None], [g], out_dtype=torch.uint8, layout="hwc", flip_rb=False, border=int(color[0]))
     out = out[0]
+    if color[1] != color[0] or color[2] != color[0]:
+        # cv2.copyMakeBorder takes one value per channel (:902).  The kernel fills the border with ONE value (all the
+        # detector ever uses is grey); the other two channels of the four border strips are set here, on the device.
+        y1, x1 = g.top + g.unpad_h, g.left + g.unpad_w
+        for ch in (1, 2):
+            plane = out[:, :, ch]
+            plane[:g.top].fill_(color[ch])
+            plane[y1:].fill_(color[ch])
+            plane[g.top:y1, :g.left].fill_(color[ch])
+            plane[g.top:y1, x1:].fill_(color[ch])
     ratio, pad = (g.ratio_w, g.ratio_h), (g.dw, g.dh)
     if on_device:
         return out, ratio, pad

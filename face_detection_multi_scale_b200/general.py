@@ -152,13 +152,16 @@ def _inplace_on_device(coords, fn):
 
 def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, kpt_label=False, step=2):
     """utils/general.py:374.  Mutates `coords` in place and returns it, including the reference's
-    clip quirk (boxes: only ROWS 0..3 are clipped, :389)."""
-    if ratio_pad is not None:
-        raise NotImplementedError("scale_coords: explicit ratio_pad is only used by test.py (out of the hot path)")
+    clip quirk (boxes: only ROWS 0..3 are clipped, :389).  `ratio_pad` = (gain or (gain, ...), (pad_x, pad_y))."""
+    if ratio_pad is not None:  # :379-383 (test.py:172 passes the dataset's ((h/h0, w/w0), (dw, dh)))
+        gain = ratio_pad[0]
+        if isinstance(gain, (list, tuple)):
+            gain = gain[0]
+        ratio_pad = (float(gain), (float(ratio_pad[1][0]), float(ratio_pad[1][1])))
     if coords.shape[0] == 0:
         return coords
     kstep = int(step) if kpt_label else 0
-    return _inplace_on_device(coords, lambda t: ops.scale_coords_(img1_shape, t, img0_shape, kstep))
+    return _inplace_on_device(coords, lambda t: ops.scale_coords_(img1_shape, t, img0_shape, kstep, ratio_pad))
 
 
 def clip_coords(boxes, img_shape, step=2):  # utils/general.py:401

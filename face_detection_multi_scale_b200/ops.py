@@ -65,6 +65,13 @@ def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, bor
     return result
 
 
+def debug_poison_smem(byte_value=0xFF, device=None):
+    """Test hook: fill the shared memory of every SM with one byte value (see include/fdms.h)."""
+    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    c = _lib.ctx(dev)
+    c.check(_lib.lib().fdms_debug_poison_smem(c.handle, int(byte_value), _stream(dev)), "fdms_debug_poison_smem")
+
+
 # ---------------------------------------------------------------------------------------------- decode
 def _level_table(scales_levels, strides, anchors_px):
     """scales_levels: list over scales of list over levels of (bs, 63, ny, nx) tensors."""
@@ -210,15 +217,22 @@ def _rows_view(coords, min_cols):
     return coords.shape[0], coords.shape[1], coords.stride(0) if coords.shape[0] > 1 else coords.shape[1]
 
 
-def scale_coords_(img1_shape, coords, img0_shape, kpt_step=0):
-    """In place utils/general.py:374-404 (ratio_pad=None) on a CUDA fp32 (n, cols) tensor/view."""
+def scale_coords_(img1_shape, coords, img0_shape, kpt_step=0, ratio_pad=None):
+    """In place utils/general.py:374-404 on a CUDA fp32 (n, cols) tensor/view.  ratio_pad = (gain, (pad_x, pad_y))
+    replaces the gain / padding derived from the two shapes (:379-383)."""
     n, cols, rs = _rows_view(coords, 4 if kpt_step == 0 else 2)
     if n == 0:
         return coords
     dev = _dev(coords)
     c = _lib.ctx(dev)
-    rc = _lib.lib().fdms_scale_coords(c.handle, _ptr(coords), n, cols, rs, int(img1_shape[0]), int(img1_shape[1]),
-                                      int(img0_shape[0]), int(img0_shape[1]), int(kpt_step), _stream(dev))
+    if ratio_pad is None:
+        rc = _lib.lib().fdms_scale_coords(c.handle, _ptr(coords), n, cols, rs, int(img1_shape[0]), int(img1_shape[1]),
+                                          int(img0_shape[0]), int(img0_shape[1]), int(kpt_step), _stream(dev))
+    else:
+        gain, pad = ratio_pad
+        rc = _lib.lib().fdms_scale_coords_ratio_pad(c.handle, _ptr(coords), n, cols, rs, float(gain), float(pad[0]),
+                                                    float(pad[1]), int(img0_shape[0]), int(img0_shape[1]),
+                                                    int(kpt_step), _stream(dev))
     c.check(rc, "fdms_scale_coords")
     return coords
 

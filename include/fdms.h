@@ -61,6 +61,9 @@ FDMS_API int fdms_create(fdms_ctx **out, int device);
 FDMS_API void fdms_destroy(fdms_ctx *ctx);
 /* message of the last failing call made with this ctx (empty string if none) */
 FDMS_API const char *fdms_last_error(const fdms_ctx *ctx);
+/* Test hook (no reference counterpart): overwrite the shared memory of every SM with `byte_value`, so that a later
+ * kernel that reads shared memory it never wrote fails reproducibly instead of depending on its predecessor. */
+FDMS_API int fdms_debug_poison_smem(fdms_ctx *ctx, int byte_value, fdms_stream stream);
 /* bytes of device scratch currently owned by the ctx */
 FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx);
 
@@ -182,6 +185,11 @@ FDMS_API int fdms_gather_rows(fdms_ctx *ctx, const float *rows, int row_stride, 
  * `cols` columns, every row clipped. */
 FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride, int in_h,
                                int in_w, int orig_h, int orig_w, int kpt_step, fdms_stream stream);
+/* The same with an explicit ratio_pad = ((gain, gain), (pad_x, pad_y)) (general.py:379-383; test.py:172 passes what
+ * the dataset's letterbox returned): gain and pad are the caller's Python floats, the original size only clips. */
+FDMS_API int fdms_scale_coords_ratio_pad(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride,
+                                         double gain, double pad_x, double pad_y, int orig_h, int orig_w,
+                                         int kpt_step, fdms_stream stream);
 /* utils/preprocess_yolo_predict.py:122-157 scale_coords_api_approach on (n,4) boxes;
  * do_round applies torch.round (half to even) as multi_scale_face_detector.py:144 does. */
 FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64_t row_stride, int in_h,

@@ -368,11 +368,11 @@ FO_EXPORT void fo_scale_coords_api(float *boxes, int64_t n, int in_h, int orig_h
 /* utils/general.py:374-404.  kpt_step == 0: box path (cols 0..3; clip touches ROWS 0..3 only -- the
  * reference slices coords[0:4], general.py:389).  kpt_step == 3: keypoint path over `cols` columns,
  * cols 0::3 and 1::3 shifted/scaled and clipped on every row, conf columns untouched. */
-FO_EXPORT void fo_scale_coords_std(float *coords, int64_t n, int cols, int in_h, int in_w, int orig_h, int orig_w,
-                                   int kpt_step) {
-    double gain_d = fmin((double)in_h / orig_h, (double)in_w / orig_w);
-    float padx = (float)(((double)in_w - orig_w * gain_d) / 2), pady = (float)(((double)in_h - orig_h * gain_d) / 2);
-    float gain = (float)gain_d;
+/* general.py:379-383: gain / pad handed in by the caller (ratio_pad); the Python floats are rounded to fp32 by each
+ * in-place tensor op. */
+FO_EXPORT void fo_scale_coords_rp(float *coords, int64_t n, int cols, double gain_d, double padx_d, double pady_d,
+                                  int orig_h, int orig_w, int kpt_step) {
+    float padx = (float)padx_d, pady = (float)pady_d, gain = (float)gain_d;
     for (int64_t i = 0; i < n; i++) {
         float *r = coords + i * cols;
         if (!kpt_step) {
@@ -389,6 +389,13 @@ FO_EXPORT void fo_scale_coords_std(float *coords, int64_t n, int cols, int in_h,
             }
         }
     }
+}
+
+FO_EXPORT void fo_scale_coords_std(float *coords, int64_t n, int cols, int in_h, int in_w, int orig_h, int orig_w,
+                                   int kpt_step) {
+    double gain = fmin((double)in_h / orig_h, (double)in_w / orig_w);  /* general.py:377-378 */
+    fo_scale_coords_rp(coords, n, cols, gain, ((double)in_w - orig_w * gain) / 2, ((double)in_h - orig_h * gain) / 2,
+                       orig_h, orig_w, kpt_step);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -73,10 +73,14 @@ def letterbox(img, new_shape=(640, 640), color=(114, 114, 114), auto=True, scale
     h, w, _ = img.shape
     vh, vw = virt_hw if virt_hw else (h, w)
     g = letterbox_geometry(vh, vw, new_shape, auto, scaleFill, scaleup, stride)
-    assert color[0] == color[1] == color[2]
     out = np.empty((g.dst_h, g.dst_w, 3), np.uint8)
     rc = lib().fo_letterbox_u8(_p(img), h, w, C.c_int64(w * 3), vh, vw, C.byref(g), int(color[0]), _p(out))
     assert rc == 0
+    if not (color[0] == color[1] == color[2]):  # cv2.copyMakeBorder(value=color): one value per channel (:902)
+        inner = np.zeros((g.dst_h, g.dst_w), bool)
+        inner[g.top:g.top + g.unpad_h, g.left:g.left + g.unpad_w] = True
+        for c in (1, 2):
+            out[..., c][~inner] = int(color[c])
     return out, (g.ratio_w, g.ratio_h), (g.dw, g.dh)
 
 
@@ -183,10 +187,16 @@ def scale_coords_api(in_hw, boxes, img0_shape, do_round=False):
     return boxes
 
 
-def scale_coords(img1_shape, coords, img0_shape, kpt_label=False, step=2):
-    """utils/general.py:374-404 (ratio_pad=None); in place on a contiguous (n,cols) fp32 array."""
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, kpt_label=False, step=2):
+    """utils/general.py:374-404; in place on a contiguous (n,cols) fp32 array."""
     assert coords.dtype == np.float32 and coords.flags.c_contiguous
     n, cols = coords.shape
+    if ratio_pad is not None:  # :379-383
+        gain = ratio_pad[0][0] if isinstance(ratio_pad[0], (list, tuple)) else ratio_pad[0]
+        lib().fo_scale_coords_rp(_p(coords), C.c_int64(n), cols, C.c_double(float(gain)),
+                                 C.c_double(float(ratio_pad[1][0])), C.c_double(float(ratio_pad[1][1])),
+                                 int(img0_shape[0]), int(img0_shape[1]), int(step) if kpt_label else 0)
+        return coords
     lib().fo_scale_coords_std(_p(coords), C.c_int64(n), cols, int(img1_shape[0]), int(img1_shape[1]),
                               int(img0_shape[0]), int(img0_shape[1]), int(step) if kpt_label else 0)
     return coords

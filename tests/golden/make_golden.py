@@ -257,6 +257,50 @@ def gen_rescale():
     save("rescale", **out)
 
 
+def gen_letterbox_color():
+    """letterbox with a per-channel border colour (cv2.copyMakeBorder value=color, utils/datasets.py:902)."""
+    out = {}
+    cases = [(97, 131, 64, True, (10, 200, 30), 41), (131, 97, 96, False, (0, 255, 114), 42),
+             (64, 64, 64, True, (1, 2, 3), 43), (50, 120, (96, 160), False, (114, 114, 7), 44)]
+    for i, (h, w, ns, auto, color, seed) in enumerate(cases):
+        img = synth.synth_image(h, w, seed)
+        o, ratio, pad = letterbox(img, ns, color=color, auto=auto)
+        out["c%d_out" % i] = o
+        out["c%d_ratio_pad" % i] = np.array([ratio[0], ratio[1], pad[0], pad[1]], np.float64)
+    out["meta"] = np.array([[h, w, (ns if isinstance(ns, int) else ns[0]), (ns if isinstance(ns, int) else ns[1]), int(a),
+                             c[0], c[1], c[2], seed] for h, w, ns, a, c, seed in cases], np.int64)
+    save("letterbox_color", **out)
+
+
+def gen_rescale_rp():
+    """scale_coords with an explicit ratio_pad (utils/general.py:379-383) -- what test.py:172 passes: the dataset's
+    shapes = (h0, w0), ((h / h0, w / w0), pad) with pad from letterbox (utils/datasets.py:590-593)."""
+    out = {}
+    rng = np.random.default_rng(15)
+    cases = [((1080, 1920), 640, False), ((480, 270), 640, False), ((2160, 3840), 1536, True), ((333, 517), 960, True),
+             ((640, 640), 640, False)]
+    meta = []
+    for i, ((h0, w0), size, auto) in enumerate(cases):
+        img0 = np.zeros((h0, w0, 3), np.uint8)
+        img, ratio, pad = letterbox(img0, size, auto=auto, scaleup=True)
+        h, w = img.shape[:2]
+        for j, rp in enumerate([(ratio, pad), ((h / h0, w / w0), pad), (ratio[0], pad)]):  # tuple gain and scalar gain
+            n = 29
+            b = rng.uniform(-40, max(h, w) + 40, (n, 4)).astype(np.float32)
+            b[:5] *= 1.5
+            k = rng.uniform(-40, max(h, w) + 40, (n, 15)).astype(np.float32)
+            out["c%d_%d_boxes" % (i, j)] = b
+            out["c%d_%d_kpts" % (i, j)] = k
+            out["c%d_%d_std_boxes" % (i, j)] = scale_coords((h, w), torch.from_numpy(b.copy()), (h0, w0), rp).numpy()
+            out["c%d_%d_std_kpts" % (i, j)] = scale_coords((h, w), torch.from_numpy(k.copy()), (h0, w0), rp,
+                                                           kpt_label=5, step=3).numpy()
+            g = rp[0][0] if isinstance(rp[0], tuple) else rp[0]
+            out["c%d_%d_rp" % (i, j)] = np.array([g, rp[1][0], rp[1][1]], np.float64)
+        meta.append([h, w, h0, w0])
+    out["meta"] = np.array(meta, np.int64)
+    save("rescale_rp", **out)
+
+
 # ------------------------------------------------------------------------------------------------
 # 5. cross-scale merge, 6. end-to-end detect_multi_scale with a stand-in backbone
 # ------------------------------------------------------------------------------------------------
@@ -533,6 +577,8 @@ if __name__ == "__main__":
     gen_head()
     gen_nms()
     gen_rescale()
+    gen_rescale_rp()
+    gen_letterbox_color()
     gen_merge()
     gen_e2e()
     gen_nms6()

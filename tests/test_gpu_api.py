@@ -45,10 +45,24 @@ def test_letterbox_scalefill_and_color_and_errors():
     out, _, _ = letterbox(img, 128, color=(0, 0, 0), auto=False)
     ref, _, _ = O.letterbox(img, 128, color=(0, 0, 0), auto=False)
     assert np.array_equal(out, ref)
-    with pytest.raises(NotImplementedError):
-        letterbox(img, 128, color=(1, 2, 3))
+    with pytest.raises(ValueError):
+        letterbox(img, 128, color=(1, 2, 300))
     with pytest.raises(ValueError):
         letterbox(img.astype(np.float32), 128)
+
+
+def test_letterbox_per_channel_colour(golden):
+    """cv2.copyMakeBorder takes one border value per channel (utils/datasets.py:902): reference outputs, host and
+    device-resident inputs."""
+    g = golden("letterbox_color")
+    for i, (h, w, ns0, ns1, auto, c0, c1, c2, seed) in enumerate(g["meta"]):
+        img = synth.synth_image(int(h), int(w), int(seed))
+        ns = int(ns0) if ns0 == ns1 else (int(ns0), int(ns1))
+        out, ratio, pad = letterbox(img, ns, color=(int(c0), int(c1), int(c2)), auto=bool(auto))
+        assert np.array_equal(out, g["c%d_out" % i])
+        assert (ratio[0], ratio[1], pad[0], pad[1]) == tuple(g["c%d_ratio_pad" % i])
+        dev, _, _ = letterbox(torch.from_numpy(img).to(DEV), ns, color=(int(c0), int(c1), int(c2)), auto=bool(auto))
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), g["c%d_out" % i])
 
 
 @pytest.mark.parametrize("i", range(len(H.API_CASES)))

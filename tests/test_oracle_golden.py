@@ -35,6 +35,16 @@ def test_letterbox_small(golden, i):
         assert np.array_equal(f32, g["small%d_f32" % i])
 
 
+def test_letterbox_per_channel_colour(golden):
+    g = golden("letterbox_color")
+    for i, (h, w, ns0, ns1, auto, c0, c1, c2, seed) in enumerate(g["meta"]):
+        img = synth.synth_image(int(h), int(w), int(seed))
+        ns = int(ns0) if ns0 == ns1 else (int(ns0), int(ns1))
+        out, ratio, pad = O.letterbox(img, ns, color=(int(c0), int(c1), int(c2)), auto=bool(auto))
+        assert np.array_equal(out, g["c%d_out" % i])
+        assert (ratio[0], ratio[1], pad[0], pad[1]) == tuple(g["c%d_ratio_pad" % i])
+
+
 @pytest.mark.parametrize("i", range(len(H.LETTERBOX_FULL)))
 def test_letterbox_full_digest(golden, i):
     g = golden("letterbox")
@@ -171,6 +181,18 @@ def test_rescale_golden(golden):
         assert np.array_equal(O.scale_coords_api((ih, iw), b.copy(), (h0, w0)), g["c%d_api_boxes" % i])
         assert np.array_equal(O.scale_coords_api((ih, iw), b.copy(), (h0, w0), do_round=True), g["c%d_api_round" % i])
 
+
+def test_rescale_ratio_pad_golden(golden):
+    """scale_coords(ratio_pad=...) (utils/general.py:379-383): tuple gain, test.py's (h/h0, w/w0) and a scalar gain."""
+    g = golden("rescale_rp")
+    for i, (ih, iw, h0, w0) in enumerate(g["meta"]):
+        for j in range(3):
+            gain, px, py = g["c%d_%d_rp" % (i, j)]
+            rp = ((gain, gain), (px, py)) if j < 2 else (gain, (px, py))
+            b = g["c%d_%d_boxes" % (i, j)]; k = g["c%d_%d_kpts" % (i, j)]
+            assert np.array_equal(O.scale_coords((ih, iw), b.copy(), (h0, w0), rp), g["c%d_%d_std_boxes" % (i, j)])
+            assert np.array_equal(O.scale_coords((ih, iw), k.copy(), (h0, w0), rp, kpt_label=5, step=3),
+                                  g["c%d_%d_std_kpts" % (i, j)])
 
 # ---------------------------------------------------------------- merge (multi_scale_face_detector.py:168-240)
 def test_merge_golden(golden):

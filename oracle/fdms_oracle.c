@@ -220,7 +220,11 @@ FO_EXPORT void fo_pack_chw(const uint8_t *hwc, int h, int w, int flip, int out_f
 /*     no) where this level's rows start at row_offset.  nc=1, nkpt=5 => no=21. */
 /* ------------------------------------------------------------------------- */
 
-static float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+/* torch.sigmoid in fp32 = 1 / (1 + exp(-x)).  ATen's vectorised expf (Sleef, 1 ulp) cannot be restated bit for bit;
+ * the exponential is taken correctly rounded here (fp64 exp rounded once) instead of libm's expf (0.502 ulp: a
+ * randomised run found one confidence in ~40 000 that differs in the last bit between the two).  The reference
+ * fixtures pin the decode within 1e-4 px either way (tests/test_oracle_golden.py). */
+static float sigmoidf_(float v) { return 1.0f / (1.0f + (float)exp(-(double)v)); }
 
 FO_EXPORT void fo_decode_level(const float *x, int bs, int na, int no, int ny, int nx, float stride,
                                const float *anchors_px /* na*2: (w,h) */, int64_t rows_total, int64_t row_offset,

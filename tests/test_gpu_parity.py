@@ -617,3 +617,104 @@ def test_letterbox_fuzz_vs_oracle(seed):
         for size, got, ref in zip(sizes, outs, refs):
             assert got.shape == ref.shape, (it, h, w, size)
             assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), (it, h, w, size, api)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_postprocess_fuzz_vs_oracle(seed):
+    """Randomised whole post-processing (decode + filter -> per-scale NMS -> rescale -> cross-scale merge, ONE
+    fdms_postprocess call) against the oracle's detect_from_heads: P5 and P6 heads, 1-3 scales of random (tiny, odd
+    nx / ny) map sizes, batch 1-3, fp16 / fp32 maps, random thresholds, both torchvision IoU flavours."""
+    rng = np.random.default_rng(500 + seed)
+    for it in range(12):
+        p6 = bool(rng.integers(0, 2))
+        strides, anchors = (synth.P6_STRIDES, synth.P6_ANCHORS) if p6 else (synth.P5_STRIDES, synth.P5_ANCHORS)
+        smax = strides[-1]
+        n_scales, bs = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        dtype = np.float16 if rng.integers(0, 2) else np.float32
+        shapes = [(int(rng.integers(1, 6)) * smax, int(rng.integers(1, 7)) * smax) for _ in range(n_scales)]
+        conf = float(rng.choice([0.05, 0.25, 0.5, 0.7]))
+        iou = float(rng.choice([0.3, 0.45, 0.5]))
+        mode = ops.IOU_TV_CPU if rng.integers(0, 2) else ops.IOU_TV_CUDA
+        h0, w0 = int(rng.integers(40, 2000)), int(rng.integers(40, 2000))
+        bias = float(rng.choice([-3.0, -1.5, 0.0]))
+        sl = []
+        for ih, iw in shapes:
+            lv = []
+            for s in strides:
+                a = (rng.standard_normal((bs, 63, ih // s, iw // s)) * 1.5).astype(np.float32)
+                a[:, 4::21] += bias  # objectness logits of the three anchors
+                lv.append(a.astype(dtype))
+            sl.append(lv)
+        rows_max = max(sum(3 * (ih // s) * (iw // s) for s in strides) for ih, iw in shapes)
+        ops.debug_poison_smem(0xFF if it & 1 else 0x7F)
+        plan = ops.PostPlan([[gpu(l) for l in lv] for lv in sl], strides, anchors, [s[0] for s in shapes], (h0, w0),
+                            conf, iou, cap=rows_max, out_cap=rows_max * n_scales, iou_mode=mode)
+        out = plan.run()
+        torch.cuda.synchronize()
+        counts = plan.cands.count.cpu().numpy()
+        nk = plan.cands.n_keep.cpu().numpy()
+        for b in range(bs):
+            heads_b = [[l[b:b + 1] for l in lv] for lv in sl]
+            ref, per_scale = O.detect_from_heads(heads_b, shapes, (h0, w0, 3), strides, anchors, conf, iou, mode)
+            tag = (seed, it, b, p6, shapes, conf, iou, mode, str(dtype))
+            for si in range(n_scales):
+                pred = O.decode_head(heads_b[si], strides, anchors)
+                assert counts[b * n_scales + si] == len(O.filter_xyxy(pred[0], conf)[1]), tag
+                assert nk[b * n_scales + si] == per_scale[si].shape[0], tag
+            n = int(out.n_out[b])
+            got = out.dets[b, :n].cpu().numpy().astype(np.float64)
+            assert got.shape[0] == (ref.shape[0] if ref.size else 0), tag
+            if ref.size:
+                assert np.array_equal(got, ref), tag
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_letterbox_fuzz_layouts_batches_and_pitches(seed):
+    """The letterbox fuzz over the remaining degrees of freedom: output type (u8 / fp16 / fp32), layout (CHW / HWC),
+    channel flip, batches of 1-3 images, sources that are views with a padded row pitch (aligned and not), border
+    values other than 114 -- bit for bit against the oracle."""
+    rng = np.random.default_rng(700 + seed)
+    for it in range(30):
+        h, w = int(rng.integers(9, 260)), int(rng.integers(9, 260))
+        if it % 5 == 0:  # exact-factor shapes
+            k = float(rng.choice([1, 2, 3, 1.5]))
+            base = int(rng.choice([32, 64]))
+            h, w = int(base * k), int(base * k * rng.choice([1, 2]))
+            sizes = [int(max(h, w) / k), int(rng.integers(24, 160))]
+        else:
+            sizes = [int(s) for s in rng.integers(16, 200, int(rng.integers(1, 4)))]
+        bs = int(rng.integers(1, 4))
+        pad = int(rng.choice([0, 0, 1, 4, 5, 16]))
+        dtype = [torch.uint8, torch.float16, torch.float32][int(rng.integers(0, 3))]
+        layout = "chw" if rng.integers(0, 2) else "hwc"
+        flip = bool(rng.integers(0, 2))
+        border = int(rng.choice([114, 0, 255, 7]))
+        api = it % 3 == 1
+        full = rng.integers(0, 256, (bs, h, w + pad, 3), dtype=np.uint8)
+        imgs = np.ascontiguousarray(full[:, :, :w])
+        src = gpu(full)[:, :, :w, :]
+        ops.debug_poison_smem(0xFF if it & 1 else 0x7F)
+        if api:
+            s_ = max(h, w)
+            geoms = [_lib.letterbox_geometry(s_, s_, size, auto=False, stride=32) for size in sizes]
+            outs = ops.pyramid(src, geoms, out_dtype=dtype, layout=layout, flip_rb=flip, border=border, virt_hw=(s_, s_))
+        else:
+            geoms = [_lib.letterbox_geometry(h, w, size, auto=bool(it & 1), stride=32) for size in sizes]
+            outs = ops.pyramid(src, geoms, out_dtype=dtype, layout=layout, flip_rb=flip, border=border)
+        torch.cuda.synchronize()
+        for size, got in zip(sizes, outs):
+            got = got.cpu().numpy()
+            for b in range(bs):
+                if api:
+                    u8 = O.letterbox(imgs[b], size, color=(border,) * 3, auto=False, stride=32, virt_hw=(s_, s_))[0]
+                else:
+                    u8 = O.letterbox(imgs[b], size, color=(border,) * 3, auto=bool(it & 1), stride=32)[0]
+                if dtype == torch.uint8:
+                    ref = u8[:, :, ::-1] if flip else u8
+                    ref = ref.transpose(2, 0, 1) if layout == "chw" else ref
+                else:
+                    ref = O.pack_chw(u8, flip, np.float16 if dtype == torch.float16 else np.float32)
+                    ref = ref if layout == "chw" else ref.transpose(1, 2, 0)
+                tag = (seed, it, b, h, w, pad, size, str(dtype), layout, flip, api)
+                assert got[b].shape == ref.shape, tag
+                assert np.array_equal(got[b], ref), tag

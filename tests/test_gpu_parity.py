@@ -718,3 +718,39 @@ def test_letterbox_fuzz_layouts_batches_and_pitches(seed):
                 tag = (seed, it, b, h, w, pad, size, str(dtype), layout, flip, api)
                 assert got[b].shape == ref.shape, tag
                 assert np.array_equal(got[b], ref), tag
+
+
+def test_letterbox_fuzz_multi_tile_shapes():
+    """The small fuzz shapes fit one 320-column tile; these do not: sources and targets of several hundred to ~1700
+    pixels (several tile columns, partial last tiles, upscales past one tile, odd pitches), fp16 CHW with the flip --
+    the detector's configuration -- bit for bit against the oracle."""
+    rng = np.random.default_rng(808)
+    for it in range(14):
+        h, w = int(rng.integers(200, 1300)), int(rng.integers(330, 1700))
+        if it % 4 == 3:
+            h, w = w, h
+        if it % 7 == 6:  # an exact 3:2 / 2:1 pyramid next to a general scale
+            h, w = 360, 960
+            sizes = [640, 480, int(rng.integers(330, 900))]
+        else:
+            sizes = [int(s) for s in rng.integers(330, 1200, 2)]
+        pad = int(rng.choice([0, 1, 4, 16]))
+        api = it % 3 == 2
+        full = rng.integers(0, 256, (1, h, w + pad, 3), dtype=np.uint8)
+        img = np.ascontiguousarray(full[0, :, :w])
+        src = gpu(full)[:, :, :w, :]
+        ops.debug_poison_smem(0xFF if it & 1 else 0x7F)
+        if api:
+            s_ = max(h, w)
+            geoms = [_lib.letterbox_geometry(s_, s_, size, auto=False, stride=32) for size in sizes]
+            outs = ops.pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=False, virt_hw=(s_, s_))
+            refs = [(O.preprocess_api(img, size).astype(np.float32) / np.float32(255)).astype(np.float16) for size in sizes]
+        else:
+            geoms = [_lib.letterbox_geometry(h, w, size, auto=True, stride=32) for size in sizes]
+            outs = ops.pyramid(src, geoms, out_dtype=torch.float16)
+            refs = [O.pack_chw(O.letterbox(img, size, auto=True, stride=32)[0], True, np.float16) for size in sizes]
+        torch.cuda.synchronize()
+        for size, got, ref in zip(sizes, outs, refs):
+            got = got[0].cpu().numpy()
+            assert got.shape == ref.shape, (it, h, w, pad, size, api)
+            assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), (it, h, w, pad, size, api)

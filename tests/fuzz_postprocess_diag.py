@@ -2,7 +2,7 @@
 """Diagnostic for tests/test_gpu_parity.py::test_postprocess_fuzz_vs_oracle: re-runs one seeded case and prints where
 the merged detections differ from the oracle's (rows, columns, values, the unrounded boxes of the oracle).
 
-    python tools/post_fuzz_diag.py SEED ITERATION
+    python tests/fuzz_postprocess_diag.py SEED ITERATION
 """
 import os
 import sys
@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from face_detection_multi_scale_b200 import ops, synth  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (diagnostic tool, not the product path)
+from oracle import oracle as O  # noqa: E402  (test infrastructure)
 
 
 def main():

@@ -392,3 +392,61 @@ def test_detect_files_pipelined_equals_per_file(tmp_path):
         ref, shape0 = one.detect_multi_scale(pth)
         assert shape0 == (h, w, 3)
         assert np.array_equal(np.asarray(got[pth]), np.asarray(ref))
+
+
+def test_compat_ops_fuzz_vs_oracle():
+    """Randomised run of the call-surface functions against the oracle: non_max_suppression (no = 21 / 6, fp16 / fp32
+    predictions, CPU and CUDA tensors, classes filter), scale_coords (boxes / keypoints, with and without ratio_pad),
+    scale_coords_api_approach, scale_img / descale_pred, bbox_overlaps."""
+    from face_detection_multi_scale_b200 import torch_utils as TU
+    from face_detection_multi_scale_b200.evaluation import bbox_overlaps
+    rng = np.random.default_rng(4242)
+    for it in range(16):
+        ops.debug_poison_smem(0xFF if it & 1 else 0x7F)
+        # --- non_max_suppression
+        bs, rows = int(rng.integers(1, 4)), int(rng.choice([1, 7, 300, 2500, 6000]))
+        no = 21 if it % 3 else 6
+        pred = np.stack([synth.synth_pred(rows, int(rng.integers(1, 12)), int(rng.integers(1, 40)), 100 * it + b)
+                         for b in range(bs)])
+        pred = np.ascontiguousarray(pred[..., :no])
+        conf, iou = float(rng.choice([0.1, 0.3, 0.5])), float(rng.choice([0.3, 0.45, 0.6]))
+        t = torch.from_numpy(pred)
+        if it & 1:
+            t = t.to(DEV)
+        got = general.non_max_suppression(t, conf, iou, kpt_label=5 if no == 21 else 0, nc=1,
+                                          iou_mode=ops.IOU_TV_CPU)
+        ref = O.non_max_suppression(pred, conf, iou, O.TV_CPU)
+        assert len(got) == bs
+        for b in range(bs):
+            assert got[b].is_cuda == bool(it & 1)
+            g_, r_ = got[b].cpu().numpy(), ref[b]
+            assert g_.shape == r_.shape, (it, b, g_.shape, r_.shape)
+            assert np.array_equal(g_, r_), (it, b)
+        # --- scale_coords / scale_coords_api_approach
+        ih, iw = int(rng.integers(2, 40)) * 32, int(rng.integers(2, 40)) * 32
+        h0, w0 = int(rng.integers(30, 3000)), int(rng.integers(30, 3000))
+        n = int(rng.choice([0, 1, 3, 4, 5, 200]))
+        boxes = rng.uniform(-50, max(ih, iw) + 50, (n, 4)).astype(np.float32)
+        kpts = rng.uniform(-50, max(ih, iw) + 50, (n, 15)).astype(np.float32)
+        rp = None if it % 2 else ((float(rng.uniform(0.1, 2.0)),) * 2, (float(rng.uniform(0, 40)), float(rng.uniform(0, 40))))
+        gb = general.scale_coords((ih, iw), torch.from_numpy(boxes.copy()).to(DEV), (h0, w0), rp)
+        assert np.array_equal(gb.cpu().numpy(), O.scale_coords((ih, iw), boxes.copy(), (h0, w0), rp))
+        gk = general.scale_coords((ih, iw), torch.from_numpy(kpts.copy()), (h0, w0), rp, kpt_label=5, step=3)
+        assert np.array_equal(gk.numpy(), O.scale_coords((ih, iw), kpts.copy(), (h0, w0), rp, kpt_label=5, step=3))
+        ga = scale_coords_api_approach((ih, iw), torch.from_numpy(boxes.copy()).to(DEV), (h0, w0, 3))
+        assert np.array_equal(ga.cpu().numpy(), O.scale_coords_api((ih, iw), boxes.copy(), (h0, w0)))
+        # --- test-time augmentation pieces
+        shape = (int(rng.integers(1, 3)), 3, int(rng.integers(1, 8)) * 32, int(rng.integers(1, 8)) * 32)
+        x = rng.random(shape, dtype=np.float32)
+        ratio, flip = float(rng.choice([1.0, 0.83, 0.67, 0.5])), [None, 2, 3][int(rng.integers(0, 3))]
+        gs_img = TU.scale_img(torch.from_numpy(x).to(DEV), ratio, gs=32, flip=flip).cpu().numpy()
+        assert np.array_equal(gs_img, O.scale_img(x, ratio, gs=32, flip=flip)), (it, shape, ratio, flip)
+        p = rng.uniform(0, 300, (shape[0], int(rng.integers(1, 500)), 21)).astype(np.float32)
+        gd = TU.descale_pred(torch.from_numpy(p.copy()).to(DEV), flip, ratio, shape[2:]).cpu().numpy()
+        assert np.array_equal(gd, O.descale_pred(p.copy(), flip, ratio, shape[2:])), (it, "descale")
+        # --- evaluation IoU matrix (float64, +1 convention)
+        a = rng.uniform(0, 800, (int(rng.integers(1, 400)), 4)); a[:, 2:] += a[:, :2]
+        q = rng.uniform(0, 800, (int(rng.integers(1, 90)), 4)); q[:, 2:] += q[:, :2]
+        if it % 4 == 0:
+            a, q = np.round(a), np.round(q)
+        assert np.array_equal(bbox_overlaps(a, q), O.bbox_overlaps(a, q))

@@ -92,6 +92,8 @@ def lib():
         with _lock:
             if _lib is None:
                 path = _build.build_lib() if os.environ.get("FDMS_NO_BUILD") != "1" else _build.LIB
+                if os.environ.get("FDMS_LIB"):  # A/B measurements: another build of the same sources
+                    path = os.environ["FDMS_LIB"]
                 if not os.path.exists(path):
                     raise RuntimeError("libfdms.so is missing (%s); there is no CPU fallback" % path)
                 h = C.CDLL(path)

@@ -23,8 +23,14 @@
 namespace {
 
 constexpr int DEC_THREADS = 128;
-constexpr int DEC_VEC = 8;                            // cells per thread
-constexpr int DEC_CELLS = DEC_THREADS * DEC_VEC;      // cells per CTA
+constexpr int DEC_VEC = 8;                            // cells per 128-bit (fp16) load
+#ifndef FDMS_DEC_UNROLL
+#define FDMS_DEC_UNROLL 4  // vectors per plane and thread, all loads issued before the first compare (1, 2 or 4)
+#endif
+constexpr int DEC_UNROLL = FDMS_DEC_UNROLL;
+constexpr int DEC_GROUP = DEC_THREADS * DEC_VEC;      // cells of one vector round of a CTA
+constexpr int DEC_CELLS = DEC_GROUP * DEC_UNROLL;     // cells per CTA
+static_assert(DEC_UNROLL >= 1 && DEC_UNROLL * DEC_VEC <= 32, "the pending-cell mask is one 32-bit word");
 constexpr int NO = 21, NA = 3;
 
 struct DecLevel {
@@ -147,23 +153,82 @@ __device__ __forceinline__ void load_vec8<float>(const float *p, long long i, in
     }
 }
 
+// One full, 16-byte aligned vector of 8 cells of a plane, kept as loaded.
+template <typename T> struct RawVec;
+template <> struct RawVec<__half> {
+    uint4 r;
+    __device__ __forceinline__ void load(const __half *p) { r = __ldg(reinterpret_cast<const uint4 *>(p)); }
+    __device__ __forceinline__ unsigned ge_mask(float lo) const {  // bit k: cell k >= lo (false for NaN)
+        const __half2 *h = reinterpret_cast<const __half2 *>(&r);
+        unsigned m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 f = __half22float2(h[k]);
+            m |= (f.x >= lo ? 1u : 0u) << (2 * k);
+            m |= (f.y >= lo ? 1u : 0u) << (2 * k + 1);
+        }
+        return m;
+    }
+};
+template <> struct RawVec<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) {
+        a = __ldg(reinterpret_cast<const float4 *>(p));
+        b = __ldg(reinterpret_cast<const float4 *>(p + 4));
+    }
+    __device__ __forceinline__ unsigned ge_mask(float lo) const {
+        return (a.x >= lo ? 1u : 0u) | (a.y >= lo ? 2u : 0u) | (a.z >= lo ? 4u : 0u) | (a.w >= lo ? 8u : 0u) |
+               (b.x >= lo ? 16u : 0u) | (b.y >= lo ? 32u : 0u) | (b.z >= lo ? 64u : 0u) | (b.w >= lo ? 128u : 0u);
+    }
+};
+
 template <typename T>
-__device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, const DecCta &C) {
+__device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, const DecCta &C, int *s_rows,
+                                                   int &s_n, int &s_base) {
     const int cells = C.cells;
-    const int cell0 = C.cell0 + (int)threadIdx.x * DEC_VEC;
-    const int n_valid = max(0, min(DEC_VEC, cells - cell0));
+    const int cell0 = C.cell0 + (int)threadIdx.x * DEC_VEC;  // first cell of this thread's vector u is cell0 + u * DEC_GROUP
     const T *base = reinterpret_cast<const T *>(L.data) + C.elem_off;
     const bool aligned = (cells % DEC_VEC == 0) && ((uintptr_t)L.data % 16 == 0);
 
-    // cheap necessary condition on the raw logits: sigmoid(obj) > thres and sigmoid(cls) > thres
-    unsigned pre = 0;
-    if (n_valid > 0) {
-        float xo[DEC_VEC], xc[DEC_VEC];
-        load_vec8<T>(base + 4LL * cells, cell0, n_valid, aligned, xo);
-        load_vec8<T>(base + 5LL * cells, cell0, n_valid, aligned, xc);
+    // cheap necessary condition on the raw logits: sigmoid(obj) > thres and sigmoid(cls) > thres.  The kernel is
+    // bound by the latency of these loads (13.5 MB in all): every thread issues its 2 * DEC_UNROLL vector loads
+    // before it looks at any of them.
+    unsigned pre = 0;  // bit u * DEC_VEC + k: cell cell0 + u * DEC_GROUP + k is pending
+    // fp32 maps take twice the registers per vector: they go in two passes of half as many vectors.  Full aligned
+    // vectors stay RAW (4 registers per fp16 vector) until their turn to be compared; ragged ones (a plane whose
+    // size is not a multiple of 8, the last vector of a plane) are rare and compared as they are read.
+    constexpr int UT = sizeof(T) == 2 ? DEC_UNROLL : (DEC_UNROLL > 1 ? DEC_UNROLL / 2 : 1);
+    const float lo = P.logit_lo;
+    const T *pobj = base + 4LL * cells, *pcls = base + 5LL * cells;
 #pragma unroll
-        for (int k = 0; k < DEC_VEC; k++)
-            if (k < n_valid && xo[k] >= P.logit_lo && xc[k] >= P.logit_lo) pre |= 1u << k;
+    for (int u0 = 0; u0 < DEC_UNROLL; u0 += UT) {
+        RawVec<T> ro[UT], rc[UT];
+        int nv[UT];
+#pragma unroll
+        for (int u = 0; u < UT; u++) {
+            const int c0 = cell0 + (u0 + u) * DEC_GROUP;
+            nv[u] = max(0, min(DEC_VEC, cells - c0));
+            if (aligned && nv[u] == DEC_VEC) {
+                ro[u].load(pobj + c0);
+                rc[u].load(pcls + c0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UT; u++) {
+            const int c0 = cell0 + (u0 + u) * DEC_GROUP;
+            unsigned m = 0;
+            if (aligned && nv[u] == DEC_VEC) {
+                m = ro[u].ge_mask(lo) & rc[u].ge_mask(lo);
+            } else if (nv[u] > 0) {
+                float xo[DEC_VEC], xc[DEC_VEC];
+                load_vec8<T>(pobj, c0, nv[u], false, xo);
+                load_vec8<T>(pcls, c0, nv[u], false, xc);
+#pragma unroll
+                for (int k = 0; k < DEC_VEC; k++)
+                    if (k < nv[u] && xo[k] >= lo && xc[k] >= lo) m |= 1u << k;
+            }
+            pre |= m << ((u0 + u) * DEC_VEC);
+        }
     }
     // The few cells that get here (~1 % of a head) are decided DENSELY: every lane with a pending cell takes its
     // lowest one, so the warp runs the exponentials once per round (1-2 rounds) instead of once per cell index
@@ -174,15 +239,14 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     // Survivors are only RECORDED (row index; the order inside a segment is irrelevant, the NMS sort key restores
     // the reference order): first in shared memory, then with ONE global atomic per CTA -- all CTAs of an image and
     // scale reserve slots in the same counter, and same-address atomics serialise in L2.
-    __shared__ int s_rows[DEC_CELLS];
-    __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const T *po = base + 4LL * cells + cell0, *pc = base + 5LL * cells + cell0;
     while (__any_sync(0xffffffffu, pre != 0)) {
         const bool have = pre != 0;
-        const int k = have ? __ffs(pre) - 1 : 0;
+        const int bit = have ? __ffs(pre) - 1 : 0;
+        const int k = (bit / DEC_VEC) * DEC_GROUP + (bit % DEC_VEC);  // cell offset from cell0
         pre &= pre - 1u;
         bool ok = false;
         if (have) {
@@ -235,10 +299,12 @@ __global__ void decode_tab_kernel(const __grid_constant__ DecParams P, DecCta *t
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
+    __shared__ int s_rows[DEC_CELLS];  // one copy for both instantiations of the body
+    __shared__ int s_n, s_base;
     const DecCta C = P.cta_tab[blockIdx.x];
     const DecLevel &L = P.lv[C.level];
-    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, C);
-    else decode_filter_body<float>(P, L, C);
+    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, C, s_rows, s_n, s_base);
+    else decode_filter_body<float>(P, L, C, s_rows, s_n, s_base);
 }
 
 // Second half of the fused decode: one thread per recorded candidate (dense warps after the compaction):

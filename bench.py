@@ -440,7 +440,7 @@ def main():
                        "l2": "inputs larger than L2 (%d MB/step) and two input sets rotated" % ((B * src_bytes + head_bytes) // 1000000),
                        "parallelism": "image-sharded, no collective" if world > 1 else "single GPU",
                        "host_cores_bound_to_gpu_numa": numa_cores},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + ops.PostPlan.LAUNCHES),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + sets[0][3].launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "streams": "pyramid and post-processing on two CUDA streams (independent data, overlapped)",
             "serial_ms_per_step": round(ms_serial / args.steps, 4),

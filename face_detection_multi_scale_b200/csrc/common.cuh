@@ -29,6 +29,8 @@ struct fdms_ctx {
     int pyr_direct = 3, pyr_th_direct = 16;  // FDMS_PYR_DIRECT (bit 0: integer factors, bit 1: the 3:2 factor) / FDMS_PYR_TH_DIRECT: unstaged tiles
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
+    int merge_fused = 1;          // FDMS_MERGE_FUSED=0: the three-kernel merge (prepare, NMS, emit) for every image
+    bool nms_small_done = false;  // set around fdms_nms_impl by the fused merge: segments <= the limit are done already
     int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)

@@ -12,14 +12,12 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "merge_rows.cuh"
 #include "nms.cuh"
 
 namespace {
 
-constexpr int NO = 21;
-constexpr int MROW = 8;  // merge row: x1 y1 x2 y2 wscore conf cls scale
-
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+constexpr int NO = MERGE_NO;
 
 // utils/general.py:374-404 (ratio_pad None or given).  gain/pad are computed in double on the host like
 // the Python floats they are, then cast to the tensor dtype by the in-place ops.
@@ -46,17 +44,6 @@ __global__ void scale_coords_kernel(float *coords, long long n, int cols, long l
     }
 }
 
-__device__ __forceinline__ float4 api_box(float4 b, float k, float w0, float h0, bool do_round) {
-    b.x = clampf(f_mul(b.x, k), 0.f, w0);
-    b.z = clampf(f_mul(b.z, k), 0.f, w0);
-    b.y = clampf(f_mul(b.y, k), 0.f, h0);
-    b.w = clampf(f_mul(b.w, k), 0.f, h0);
-    if (do_round) {  // torch.round: half to even
-        b.x = rintf(b.x); b.y = rintf(b.y); b.z = rintf(b.z); b.w = rintf(b.w);
-    }
-    return b;
-}
-
 __global__ void scale_coords_api_kernel(float *boxes, long long n, long long row_stride, float k, float w0, float h0,
                                         int do_round) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,52 +53,8 @@ __global__ void scale_coords_api_kernel(float *boxes, long long n, long long row
     r[0] = b.x; r[1] = b.y; r[2] = b.z; r[3] = b.w;
 }
 
-struct MergeParams {
-    const float *cand;
-    const int32_t *keep, *n_keep;
-    int n_scales, cap, mcap;
-    float k[FDMS_MAX_SCALES];  // max(H0, W0) / in_h per scale
-    float w0, h0;
-    float *mrows;      // (n_img, mcap, 8)
-    int32_t *msrc;     // (n_img, mcap): s * cap + item index
-    int32_t *mcount;   // (n_img)
-    int32_t *merged_in;
-};
-
 __global__ void merge_prepare_kernel(const __grid_constant__ MergeParams P) {
-    const int img = blockIdx.x;
-    int off[FDMS_MAX_SCALES + 1];
-    off[0] = 0;
-    for (int s = 0; s < P.n_scales; s++) {
-        int nk = P.n_keep[img * P.n_scales + s];
-        off[s + 1] = off[s] + max(nk, 0);
-    }
-    const int total = min(off[P.n_scales], P.mcap);
-    if (threadIdx.x == 0) {
-        P.mcount[img] = total;
-        if (P.merged_in) P.merged_in[img] = off[P.n_scales];
-    }
-    for (int pos = threadIdx.x; pos < total; pos += blockDim.x) {
-        int s = 0;
-        while (pos >= off[s + 1]) s++;
-        const int kidx = pos - off[s];
-        const long long seg = (long long)img * P.n_scales + s;
-        const int item = P.keep[seg * P.cap + kidx];
-        const float *row = P.cand + (seg * P.cap + item) * NO;
-        float4 b = api_box(make_float4(row[0], row[1], row[2], row[3]), P.k[s], P.w0, P.h0, true);  // msfd:144
-        const float conf = row[4], cls = row[5];
-        // msfd:168-201 on the rounded boxes, float64
-        double area = ((double)b.z - (double)b.x) * ((double)b.w - (double)b.y);
-        double wt = 1.0;
-        if (area < 1024.0 && s >= P.n_scales - 2) wt *= 1.2;
-        if (area >= 1024.0 && area <= 16384.0 && s == P.n_scales / 2) wt *= 1.1;
-        if (area > 16384.0 && s <= 1) wt *= 1.2;
-        float wscore = (float)__dmul_rn((double)conf, wt);  // msfd:225,229
-        float *o = P.mrows + ((long long)img * P.mcap + pos) * MROW;
-        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
-        o[4] = wscore; o[5] = conf; o[6] = cls; o[7] = (float)s;
-        P.msrc[(long long)img * P.mcap + pos] = s * P.cap + item;
-    }
+    merge_prepare_image(P, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
 // msfd:168-201 + 224-229 on an (n,7) float64 detection array (the weighted_nms drop-in):
@@ -134,43 +77,11 @@ __global__ void weighted_rows_kernel(const double *__restrict__ dets, long long 
     if (weights_out) weights_out[i] = wt;
 }
 
-struct EmitParams {
-    const float *mrows;
-    const int32_t *msrc, *keep2, *n_keep2;
-    const float *cand;
-    int n_scales, cap, mcap, out_cap;
-    float k[FDMS_MAX_SCALES];
-    float w0, h0;
-    float *dets;
-    int32_t *n_out;
-    float *kpts;
-};
-
-__global__ void merge_emit_kernel(const __grid_constant__ EmitParams P) {
+// skip_le >= 0: images with at most that many merged rows were emitted by the fused kernel already
+__global__ void merge_emit_kernel(const __grid_constant__ EmitParams P, const int32_t *__restrict__ mcount, int skip_le) {
     const int img = blockIdx.x;
-    const int nk = P.n_keep2[img];
-    if (threadIdx.x == 0) P.n_out[img] = nk;
-    const int n = min(max(nk, 0), P.out_cap);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const int pos = P.keep2[(long long)img * P.mcap + k];
-        const float *m = P.mrows + ((long long)img * P.mcap + pos) * MROW;
-        float *o = P.dets + ((long long)img * P.out_cap + k) * 7;
-        o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[3];
-        o[4] = m[5];  // original confidence (msfd:238 indexes the unweighted array)
-        o[5] = m[6];
-        o[6] = m[7];
-        if (P.kpts) {
-            const int src = P.msrc[(long long)img * P.mcap + pos];
-            const int s = src / P.cap, item = src - s * P.cap;
-            const float *row = P.cand + (((long long)img * P.n_scales + s) * P.cap + item) * NO;
-            float *ko = P.kpts + ((long long)img * P.out_cap + k) * 15;
-            for (int j = 0; j < 5; j++) {
-                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], P.k[s]), 0.f, P.w0);
-                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], P.k[s]), 0.f, P.h0);
-                ko[3 * j + 2] = row[8 + 3 * j];
-            }
-        }
-    }
+    if (skip_le >= 0 && mcount[img] <= skip_le) return;
+    merge_emit_image(P, img, P.n_keep2[img], threadIdx.x, blockDim.x);
 }
 
 }  // namespace
@@ -272,12 +183,6 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
     P.msrc = msrc;
     P.mcount = mcount;
     P.merged_in = merged_in;
-    merge_prepare_kernel<<<n_img, 256, 0, st>>>(P);
-    FDMS_LAUNCH_CHECK(ctx, "merge_prepare_kernel");
-    // torchvision.ops.nms on CPU tensors in the reference (msfd:234): TV_CPU flavour, no max_nms cut
-    if (int rc = fdms_nms_impl(ctx, mrows, MROW, 0, 4, nullptr, mcount, n_img, mcap, iou_thres, FDMS_IOU_TV_CPU, 0, keep2,
-                               n_keep2, st))
-        return rc;
     EmitParams E;
     memset(&E, 0, sizeof(E));
     E.mrows = mrows;
@@ -295,7 +200,27 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
     E.dets = dets;
     E.n_out = n_out;
     E.kpts = kpts_out;
-    merge_emit_kernel<<<n_img, 256, 0, st>>>(E);
+    // torchvision.ops.nms on CPU tensors in the reference (msfd:234): TV_CPU flavour, no max_nms cut
+    const int small_limit = fdms_merge_small_limit(ctx);
+    int skip_le = -1;
+    if (small_limit > 0 && ctx->merge_fused) {
+        // images of at most small_limit merged rows (the common case): rows -> NMS -> emit in ONE launch
+        float thr_f;
+        int inclusive;
+        fdms_fold_threshold(iou_thres, FDMS_IOU_TV_CPU, &thr_f, &inclusive);
+        if (int rc = fdms_merge_small_launch(ctx, P, E, n_img, thr_f, inclusive, st)) return rc;
+        if (mcap <= small_limit) return FDMS_OK;  // no image can have more rows
+        skip_le = small_limit;
+        ctx->nms_small_done = true;
+    } else {
+        merge_prepare_kernel<<<n_img, 256, 0, st>>>(P);
+        FDMS_LAUNCH_CHECK(ctx, "merge_prepare_kernel");
+    }
+    const int rc = fdms_nms_impl(ctx, mrows, MROW, 0, 4, nullptr, mcount, n_img, mcap, iou_thres, FDMS_IOU_TV_CPU, 0, keep2,
+                                 n_keep2, st);
+    ctx->nms_small_done = false;
+    if (rc) return rc;
+    merge_emit_kernel<<<n_img, 256, 0, st>>>(E, mcount, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "merge_emit_kernel");
     return FDMS_OK;
 }

@@ -1,0 +1,113 @@
+// Cross-scale merge rows: the per-image pieces of multi_scale_face_detector.py:138-166 (rescale, round, drop
+// landmarks, append scale_idx), :168-201,224-229 (size-aware weights) and :237-238 (detections[keep]) as device
+// functions, shared by the standalone kernels of merge.cu and the fused single-CTA merge of nms.cu.
+#pragma once
+#include "common.cuh"
+
+struct MergeParams {
+    const float *cand;
+    const int32_t *keep, *n_keep;
+    int n_scales, cap, mcap;
+    float k[FDMS_MAX_SCALES];  // max(H0, W0) / in_h per scale
+    float w0, h0;
+    float *mrows;      // (n_img, mcap, 8)
+    int32_t *msrc;     // (n_img, mcap): s * cap + item index
+    int32_t *mcount;   // (n_img)
+    int32_t *merged_in;
+};
+
+struct EmitParams {
+    const float *mrows;
+    const int32_t *msrc, *keep2, *n_keep2;
+    const float *cand;
+    int n_scales, cap, mcap, out_cap;
+    float k[FDMS_MAX_SCALES];
+    float w0, h0;
+    float *dets;
+    int32_t *n_out;
+    float *kpts;
+};
+
+namespace {
+
+constexpr int MERGE_NO = 21;
+constexpr int MROW = 8;  // merge row: x1 y1 x2 y2 wscore conf cls scale
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float4 api_box(float4 b, float k, float w0, float h0, bool do_round) {
+    b.x = clampf(f_mul(b.x, k), 0.f, w0);
+    b.z = clampf(f_mul(b.z, k), 0.f, w0);
+    b.y = clampf(f_mul(b.y, k), 0.f, h0);
+    b.w = clampf(f_mul(b.w, k), 0.f, h0);
+    if (do_round) {  // torch.round: half to even
+        b.x = rintf(b.x); b.y = rintf(b.y); b.z = rintf(b.z); b.w = rintf(b.w);
+    }
+    return b;
+}
+
+// Rows of image `img` (all threads of the CTA take part); returns the number of merged rows (CTA-uniform).
+__device__ __forceinline__ int merge_prepare_image(const MergeParams &P, int img, int tid, int n_threads) {
+    int off[FDMS_MAX_SCALES + 1];
+    off[0] = 0;
+    for (int s = 0; s < P.n_scales; s++) {
+        int nk = P.n_keep[img * P.n_scales + s];
+        off[s + 1] = off[s] + max(nk, 0);
+    }
+    const int total = min(off[P.n_scales], P.mcap);
+    if (tid == 0) {
+        P.mcount[img] = total;
+        if (P.merged_in) P.merged_in[img] = off[P.n_scales];
+    }
+    for (int pos = tid; pos < total; pos += n_threads) {
+        int s = 0;
+        while (pos >= off[s + 1]) s++;
+        const int kidx = pos - off[s];
+        const long long seg = (long long)img * P.n_scales + s;
+        const int item = P.keep[seg * P.cap + kidx];
+        const float *row = P.cand + (seg * P.cap + item) * MERGE_NO;
+        float4 b = api_box(make_float4(row[0], row[1], row[2], row[3]), P.k[s], P.w0, P.h0, true);  // msfd:144
+        const float conf = row[4], cls = row[5];
+        // msfd:168-201 on the rounded boxes, float64
+        double area = ((double)b.z - (double)b.x) * ((double)b.w - (double)b.y);
+        double wt = 1.0;
+        if (area < 1024.0 && s >= P.n_scales - 2) wt *= 1.2;
+        if (area >= 1024.0 && area <= 16384.0 && s == P.n_scales / 2) wt *= 1.1;
+        if (area > 16384.0 && s <= 1) wt *= 1.2;
+        float wscore = (float)__dmul_rn((double)conf, wt);  // msfd:225,229
+        float *o = P.mrows + ((long long)img * P.mcap + pos) * MROW;
+        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+        o[4] = wscore; o[5] = conf; o[6] = cls; o[7] = (float)s;
+        P.msrc[(long long)img * P.mcap + pos] = s * P.cap + item;
+    }
+    return total;
+}
+
+// detections[keep] of image `img` with nk kept rows (all threads of the CTA take part).  The rows and the keep list
+// may have been written by this very CTA (fused merge): plain loads, never the read-only path.
+__device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, int nk, int tid, int n_threads) {
+    if (tid == 0) P.n_out[img] = nk;
+    const int n = min(max(nk, 0), P.out_cap);
+    for (int k = tid; k < n; k += n_threads) {
+        const int pos = P.keep2[(long long)img * P.mcap + k];
+        const float *m = P.mrows + ((long long)img * P.mcap + pos) * MROW;
+        float *o = P.dets + ((long long)img * P.out_cap + k) * 7;
+        o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[3];
+        o[4] = m[5];  // original confidence (msfd:238 indexes the unweighted array)
+        o[5] = m[6];
+        o[6] = m[7];
+        if (P.kpts) {
+            const int src = P.msrc[(long long)img * P.mcap + pos];
+            const int s = src / P.cap, item = src - s * P.cap;
+            const float *row = P.cand + (((long long)img * P.n_scales + s) * P.cap + item) * MERGE_NO;
+            float *ko = P.kpts + ((long long)img * P.out_cap + k) * 15;
+            for (int j = 0; j < 5; j++) {
+                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], P.k[s]), 0.f, P.w0);
+                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], P.k[s]), 0.f, P.h0);
+                ko[3 * j + 2] = row[8 + 3 * j];
+            }
+        }
+    }
+}
+
+}  // namespace

@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "merge_rows.cuh"
 #include "nms.cuh"
 
 namespace {
@@ -465,12 +466,18 @@ __device__ __forceinline__ void greedy_block(const float4 *blk, int nb, float th
 //   suppression: the same blocked greedy sweep as nms_greedy_kernel (256 candidates per step, kept boxes
 //                compacted in place at the front of the box array).
 // No global scratch, one launch, a handful of barriers per 256 boxes.
-template <int MODE>
-__global__ void __launch_bounds__(SMALL_THREADS)
-    nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
-                     const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int cap, int max_nms,
-                     int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
-                     int32_t *__restrict__ n_keep) {
+// NC: the rows are kernel inputs (read-only path); !NC: they were written by this CTA before a barrier (the fused
+// merge below), so they are read with ld.global.cg.  n = boxes of segment g (1 .. SMALL_LIMIT); returns the number
+// of kept boxes (CTA-uniform; the keep list is in global memory behind a barrier when the function returns).
+template <bool NC>
+__device__ __forceinline__ float ld_row(const float *p) {
+    return NC ? __ldg(p) : __ldcg(p);
+}
+
+template <int MODE, bool NC>
+__device__ __forceinline__ int nms_small_body(const float *rows, int row_stride, int box_off, int score_off,
+                                              const int32_t *tie, int n, int g, int cap, int max_nms, float thr,
+                                              int inclusive, int32_t *keep) {
     __shared__ unsigned long long s_keys[SMALL_LIMIT];
     __shared__ float4 s_box[SMALL_LIMIT];
     __shared__ uint32_t s_idx[SMALL_LIMIT];
@@ -479,14 +486,8 @@ __global__ void __launch_bounds__(SMALL_THREADS)
     __shared__ unsigned long long s_rowmask[GREEDY_BS][4];
     __shared__ unsigned long long s_sup[4], s_keptbits[4];
     __shared__ int s_nkeep;
-    const int g = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
-    const int n = max(0, min(count[g], cap));
-    if (n > small_limit) return;  // the sort + greedy / bit-matrix path takes it
-    if (n == 0) {
-        if (tid == 0) n_keep[g] = 0;
-        return;
-    }
     const float *seg_rows = rows + (long long)g * cap * row_stride;
     // ---- sort: 32-key runs in registers, then rank by binary search ---------------------------------------------
     // keys are unique (tie = row index or item index; callers must not pass duplicate ties inside a segment).  Every
@@ -504,8 +505,8 @@ __global__ void __launch_bounds__(SMALL_THREADS)
         uint32_t id = (uint32_t)tid;
         if (tid < n) {
             const float *r = seg_rows + (long long)tid * row_stride;
-            const uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + tid] : (uint32_t)tid;
-            k = ((unsigned long long)score_key_desc(r[score_off]) << 32) | t;
+            const uint32_t t = tie ? (uint32_t)__ldg(tie + (long long)g * cap + tid) : (uint32_t)tid;
+            k = ((unsigned long long)score_key_desc(ld_row<NC>(r + score_off)) << 32) | t;
         }
 #pragma unroll
         for (int sz = 2; sz <= 32; sz <<= 1) {
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(SMALL_THREADS)
     if (tid < nr * 32 && s_keys[tid] != ~0ull) {
         const int item = s_item[tid], rank = s_rank[tid];
         const float *r = seg_rows + (long long)item * row_stride + box_off;
-        s_box[rank] = make_float4(r[0], r[1], r[2], r[3]);
+        s_box[rank] = make_float4(ld_row<NC>(r), ld_row<NC>(r + 1), ld_row<NC>(r + 2), ld_row<NC>(r + 3));
         s_idx[rank] = (uint32_t)item;
     }
     __syncthreads();
@@ -610,7 +611,40 @@ __global__ void __launch_bounds__(SMALL_THREADS)
                       __popcll(s_keptbits[3]);
         __syncthreads();
     }
-    if (tid == 0) n_keep[g] = s_nkeep;
+    return s_nkeep;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SMALL_THREADS)
+    nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
+                     const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int cap, int max_nms,
+                     int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
+                     int32_t *__restrict__ n_keep) {
+    const int g = blockIdx.x;
+    const int n = max(0, min(count[g], cap));
+    if (n > small_limit) return;  // the sort + greedy / bit-matrix path takes it
+    int nk = 0;
+    if (n > 0) nk = nms_small_body<MODE, true>(rows, row_stride, box_off, score_off, tie, n, g, cap, max_nms, thr, inclusive, keep);
+    if (threadIdx.x == 0) n_keep[g] = nk;
+}
+
+// The cross-scale merge of an image in ONE CTA when it has at most SMALL_LIMIT rows (the common case): merge rows
+// (rescale, round, weights; merge_rows.cuh) -> NMS with the TV_CPU arithmetic (msfd:234 runs on CPU tensors) ->
+// detections[keep].  Replaces merge_prepare_kernel + nms_small_kernel + merge_emit_kernel: two launches and two
+// kernel tails less on a chain that is pure latency.  Images with more rows only get their rows here.
+__global__ void __launch_bounds__(SMALL_THREADS)
+    merge_small_kernel(const __grid_constant__ MergeParams P, const __grid_constant__ EmitParams E, int small_limit,
+                       float thr, int inclusive) {
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int total = merge_prepare_image(P, img, tid, SMALL_THREADS);
+    if (total > small_limit) return;  // nms_sort_kernel + nms_greedy / mask + merge_emit_kernel take this image
+    __syncthreads();  // the rows above were written by other threads of this CTA
+    int nk = 0;
+    if (total > 0)
+        nk = nms_small_body<FDMS_IOU_TV_CPU, false>(P.mrows, MROW, 0, 4, nullptr, total, img, P.mcap, 0, thr, inclusive,
+                                                    const_cast<int32_t *>(E.keep2));
+    if (tid == 0) const_cast<int32_t *>(E.n_keep2)[img] = nk;
+    merge_emit_image(E, img, nk, tid, SMALL_THREADS);  // the keep list is behind the body's last barrier
 }
 
 // Blocked greedy NMS for larger segments, one CTA per segment, after nms_sort_kernel.  Boxes arrive in score
@@ -723,6 +757,17 @@ void fdms_fold_threshold(double thr, int iou_mode, float *thr_f, int *inclusive)
     }
 }
 
+int fdms_merge_small_limit(const fdms_ctx *ctx) {
+    return ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
+}
+
+int fdms_merge_small_launch(fdms_ctx *ctx, const MergeParams &P, const EmitParams &E, int n_img, float thr_f,
+                            int inclusive, cudaStream_t st) {
+    merge_small_kernel<<<n_img, SMALL_THREADS, 0, st>>>(P, E, fdms_merge_small_limit(ctx), thr_f, inclusive);
+    FDMS_LAUNCH_CHECK(ctx, "merge_small_kernel");
+    return FDMS_OK;
+}
+
 int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off, const int32_t *tie,
                   const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode, int max_nms, int32_t *keep,
                   int32_t *n_keep, cudaStream_t st) {
@@ -735,7 +780,7 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     fdms_fold_threshold(iou_thres, iou_mode, &thr_f, &inclusive);
     // ---- segments of at most small_limit boxes: one fused launch -------------------------------------------
     const int small_limit = ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
-    if (small_limit > 0) {
+    if (small_limit > 0 && !ctx->nms_small_done) {
 #define FDMS_NMS_SMALL(M)                                                                                             \
     nms_small_kernel<M><<<n_seg, SMALL_THREADS, 0, st>>>(rows, row_stride, box_off, score_off, tie, count, cap, max_nms, \
                                                          small_limit, thr_f, inclusive, keep, n_keep)
@@ -744,8 +789,8 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         else FDMS_NMS_SMALL(FDMS_IOU_TV_CPU);
 #undef FDMS_NMS_SMALL
         FDMS_LAUNCH_CHECK(ctx, "nms_small_kernel");
-        if (cap <= small_limit) return FDMS_OK;  // no segment can be larger
     }
+    if (small_limit > 0 && cap <= small_limit) return FDMS_OK;  // no segment can be larger
     const int skip_le = small_limit > 0 ? small_limit : -1;
     // ---- larger segments: sort -> mask -> sweep ----------------------------------------------------------------
     if ((cap_e + 63) / 64 > SWEEP_MAX_NBLK)

@@ -334,5 +334,11 @@ class PostPlan:
         self.ctx.check(rc, "fdms_postprocess")
         return self.out
 
-    # kernel launches of one run() for segments <= 4096 boxes: decode 2 + NMS 1 + prepare 1 + NMS 1 + emit 1 (memset excluded)
-    LAUNCHES = 6
+    @property
+    def launches(self):
+        """Kernel launches of one run() (memset excluded): decode filter + candidate decode, the per-scale NMS (one
+        fused launch when no segment can exceed 1024 boxes, else + sort + greedy sweep), the cross-scale merge (one
+        fused launch when no image can have more than 1024 merged rows, else + sort + greedy sweep + emit)."""
+        small = 1024
+        mcap = min(self.n_scales * self.cands.cap, self.out.out_cap)
+        return 2 + (1 if self.cands.cap <= small else 3) + (1 if mcap <= small else 4)

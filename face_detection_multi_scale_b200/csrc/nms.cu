@@ -39,6 +39,20 @@ constexpr int MASK_THREADS = 256;      // 64 rows x 4 column blocks
 constexpr int SWEEP_THREADS = 512;
 constexpr int SWEEP_MAX_NBLK = 4096;   // 262144 boxes per segment
 constexpr int SMALL_THREADS = 1024;
+// Register cap of the single-CTA kernels.  A resident 1024-thread CTA leaves the rest of the SM's register file to the
+// CTAs of whatever runs beside it -- in the pipelined path the HBM-bound pyramid kernel of the next batch, 7680
+// registers per CTA: at 46-48 registers (what __launch_bounds__(1024) gives) two of them fit next to an NMS CTA, at
+// 40 three, at 32 four.  Measured on cfg2 with both streams running: 263.1 / 266.8 / 270.1 k images/s for 48 / 40 / 32
+// (the pyramid launches inside the timed region 0.1224 -> 0.1198 ms); 24 registers buy nothing more (the NMS itself
+// slows from 26.6 to 28.6 us on 76 spilled bytes).  At 32 the kernels spill 4-12 bytes and take 26.6 instead of 26.3 us.
+#ifndef FDMS_NMS_SMALL_REGS
+#define FDMS_NMS_SMALL_REGS 32
+#endif
+#if FDMS_NMS_SMALL_REGS > 0
+#define FDMS_SMALL_BOUNDS __maxnreg__(FDMS_NMS_SMALL_REGS)
+#else
+#define FDMS_SMALL_BOUNDS __launch_bounds__(1024)
+#endif
 constexpr int SMALL_LIMIT = 1024;      // largest segment the fused single-CTA kernel takes (one box per thread)
 constexpr int GREEDY_THREADS = 1024;
 constexpr int GREEDY_BS = 256;         // candidates per greedy step
@@ -615,7 +629,7 @@ __device__ __forceinline__ int nms_small_body(const float *rows, int row_stride,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(SMALL_THREADS)
+__global__ void FDMS_SMALL_BOUNDS
     nms_small_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
                      const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int cap, int max_nms,
                      int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
@@ -632,7 +646,7 @@ __global__ void __launch_bounds__(SMALL_THREADS)
 // (rescale, round, weights; merge_rows.cuh) -> NMS with the TV_CPU arithmetic (msfd:234 runs on CPU tensors) ->
 // detections[keep].  Replaces merge_prepare_kernel + nms_small_kernel + merge_emit_kernel: two launches and two
 // kernel tails less on a chain that is pure latency.  Images with more rows only get their rows here.
-__global__ void __launch_bounds__(SMALL_THREADS)
+__global__ void FDMS_SMALL_BOUNDS
     merge_small_kernel(const __grid_constant__ MergeParams P, const __grid_constant__ EmitParams E, int small_limit,
                        float thr, int inclusive) {
     const int img = blockIdx.x, tid = threadIdx.x;

@@ -5,7 +5,7 @@
  * The reference (NguyendaiAI-pixta/face_detection_multi_scale) has no FFI of its own: its
  * boundary is a set of Python callables.  Each entry point below names the
  * reference callable (file:line, relative to the reference root) whose arithmetic it
- * replaces; face_detection_multi_scale_b200/*.py binds them with ctypes and re-exports the
+ * replaces; the modules of face_detection_multi_scale_b200/ bind them with ctypes and re-exports the
  * reference's Python signatures on top (INTEGRATION.md shows the binding).
  *
  * Conventions

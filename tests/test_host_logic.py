@@ -31,6 +31,27 @@ def test_header_symbols_are_exported():
     assert b"sm_100a" in h.fdms_build_info() and b"fmad=off" in h.fdms_build_info()
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/fdms.h is the drop-in boundary: it must compile as C11 (no C++ in the signatures) with warnings as
+    errors, as C++, and a C program must link against libfdms.so through it (no compute call: no GPU here)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "fdms.h"\n#include <stdio.h>\n'
+                   'int main(void) { fdms_geom g; int rc = fdms_letterbox_geometry(1080, 1920, 640, 640, 1, 0, 1, 32, &g);\n'
+                   '  printf("%d %d %d %d\\n", fdms_version(), rc, g.dst_h, g.dst_w); return rc; }\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "face_detection_multi_scale_b200")
+    _lib.lib()  # built
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe),
+                        "-L", libdir, "-l:libfdms.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["100", "0", "384", "640"], (out.stdout, out.stderr)
+
+
 def test_library_has_sm100a_code_only():
     out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "face_detection_multi_scale_b200", "libfdms.so")],
                          capture_output=True, text=True)

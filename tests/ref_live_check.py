@@ -13,6 +13,7 @@ seeded random ones, function by function:
     utils.general.scale_coords (with and without ratio_pad)   (utils/general.py:374)     bit exact
     utils.preprocess_yolo_predict.scale_coords_api_approach   (ppyp:122)                 bit exact
     MultiScaleFaceDetector.calculate_scale_weights / weighted_nms (msfd:168-240)         bit exact
+    MultiScaleFaceDetector.detect_multi_scale around a stand-in backbone (msfd:242-288)  bit exact
     utils.torch_utils.scale_img, Model._descale_pred          (torch_utils.py:247, yolo.py:402)  <= 2 ulp / bit exact
 
 Prints one JSON line {"checks": n, "failures": [...]} and exits 1 if anything differs.
@@ -176,6 +177,53 @@ def main():
         d[:, 6] = rng.integers(0, n_scales, n)
         check(np.array_equal(O.scale_weights(d, n_scales), quiet(det.calculate_scale_weights, d)), ("scale_weights", it))
         check(np.array_equal(O.weighted_nms(d, n_scales, det.iou_thres), quiet(det.weighted_nms, d)), ("weighted_nms", it))
+
+    # ---- the whole detect_multi_scale (msfd:242-288) around a stand-in backbone: an IKeypoint whose 1x1 convs copy
+    # their input, fed with synthetic raw head maps chosen by the input's (H, W); everything after the convolutions
+    # is the unmodified reference
+    from tests.helpers import e2e_heads
+
+    def identity_head():
+        with contextlib.redirect_stdout(io.StringIO()):
+            hd = IKeypoint(nc=1, anchors=synth.P5_ANCHORS.reshape(3, -1).tolist(), nkpt=5, ch=(63,) * 3)
+        eye = torch.eye(63).view(63, 63, 1, 1)
+        for i in range(3):
+            hd.ia[i].implicit.zero_()
+            hd.im[i].implicit.fill_(1.0)
+            hd.m[i].weight.copy_(eye[:18]); hd.m[i].bias.zero_()
+            hd.m_kpt[i].weight.copy_(eye[18:]); hd.m_kpt[i].bias.zero_()
+        hd.stride = torch.tensor([8., 16., 32.])
+        return hd.eval()
+
+    class StandIn(torch.nn.Module):
+        def __init__(self, heads_by_hw):
+            super().__init__()
+            self.head, self.heads_by_hw = identity_head(), heads_by_hw
+            self.stride, self.names = torch.tensor([8., 16., 32.]), ["face"]
+
+        def forward(self, img, augment=False):
+            return self.head([torch.from_numpy(l[None].copy()) for l in self.heads_by_hw[tuple(img.shape[2:])]])
+
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(5):
+            h, w = int(rng.integers(120, 500)), int(rng.integers(120, 500))
+            sizes = sorted(set(int(v) * 32 for v in rng.integers(3, 12, int(rng.integers(1, 4)))))
+            api = bool(it & 1)
+            conf, iou = float(rng.choice([0.4, 0.5, 0.6])), float(rng.choice([0.3, 0.5]))
+            n_faces = int(rng.integers(0, 30))
+            heads, shapes = e2e_heads(h, w, sizes, n_faces, api, 700 + 10 * seed + it)
+            path = os.path.join(d, "e%d.png" % it)
+            cv2.imwrite(path, synth.synth_image(h, w, it))
+            det = MultiScaleFaceDetector.__new__(MultiScaleFaceDetector)
+            det.model, det.device, det.half, det.stride = StandIn(heads), torch.device("cpu"), False, 32
+            det.img_sizes, det.names, det.conf_thres, det.iou_thres = list(sizes), ["face"], conf, iou
+            det.use_api_preprocess = api
+            ref, shape0 = quiet(det.detect_multi_scale, path)
+            ref = np.asarray(ref, np.float64)
+            got, _ = O.detect_from_heads([[l[None] for l in heads[s_]] for s_ in shapes], shapes, (h, w, 3),
+                                         synth.P5_STRIDES, synth.P5_ANCHORS, conf, iou, O.TV_CPU)
+            check(tuple(shape0) == (h, w, 3) and got.shape == ref.shape and (ref.size == 0 or np.array_equal(got, ref)),
+                  ("detect_multi_scale", it, h, w, sizes, api, conf, iou, n_faces, got.shape, ref.shape))
 
     # ---- test-time augmentation pieces
     for it in range(6):

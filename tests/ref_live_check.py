@@ -225,6 +225,21 @@ def main():
             check(tuple(shape0) == (h, w, 3) and got.shape == ref.shape and (ref.size == 0 or np.array_equal(got, ref)),
                   ("detect_multi_scale", it, h, w, sizes, api, conf, iou, n_faces, got.shape, ref.shape))
 
+    # ---- source discovery of the inference loader (utils/datasets.py:126-141): directory, glob, single file
+    from utils.datasets import LoadImages as RefLoadImages
+    from face_detection_multi_scale_b200 import datasets as D
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "sub"))
+        for name in ("b.jpg", "a.PNG", "notes.txt", "z.mp4", "c.jpeg", "sub/e.bmp", "m.avi", "k.webp"):
+            open(os.path.join(d, name), "wb").close()
+        for spec in (d, os.path.join(d, "*.jp*"), os.path.join(d, "**", "*.*"), os.path.join(d, "b.jpg")):
+            ref = quiet(RefLoadImages, spec, 64, 32)
+            found = D._expand_source(spec)
+            stills = [f for f in found if D._suffix(f) in D.IMG_FORMATS]
+            clips = [f for f in found if D._suffix(f) in D.VID_FORMATS]
+            check(stills + clips == list(ref.files) and [False] * len(stills) + [True] * len(clips) == list(ref.video_flag)
+                  and len(stills + clips) == ref.nf, ("LoadImages discovery", spec.replace(d, "<tmp>")))
+
     # ---- test-time augmentation pieces
     for it in range(6):
         shape = (int(rng.integers(1, 3)), 3, int(rng.integers(1, 8)) * 32, int(rng.integers(1, 8)) * 32)

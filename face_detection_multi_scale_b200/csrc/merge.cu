@@ -1,13 +1,16 @@
 // Rescale to original-image coordinates and cross-scale merge.
 //
 //   scale_coords_kernel / scale_coords_api_kernel : in-place drop-ins for
-//       utils/general.py:374-404 and utils/preprocess_yolo_predict.py:122-157.
-//   merge_prepare_kernel : multi_scale_face_detector.py:138-166 for every image of a batch --
-//       api rescale, clamp, round half-to-even, drop landmarks, append scale_idx -- and
-//       :168-201,224-229 (size-aware weights, weighted score in float64 then cast to float32),
-//       concatenating the scales of an image in scale order (np.vstack, :273).
-//   second NMS (nms.cu, TV_CPU flavour: the reference runs it on CPU, :234)
-//   merge_emit_kernel : detections[keep] with the ORIGINAL confidence (:237-238).
+//       utils/general.py:374-404 (ratio_pad None or given) and utils/preprocess_yolo_predict.py:122-157.
+//   The merge of an image (merge_rows.cuh holds the per-image device code):
+//     rows : multi_scale_face_detector.py:138-166 -- api rescale, clamp, round half-to-even, drop landmarks, append
+//            scale_idx -- and :168-201,224-229 (size-aware weights, weighted score in float64 then cast to
+//            float32), the scales of an image concatenated in scale order (np.vstack, :273);
+//     NMS  : TV_CPU flavour (the reference runs it on CPU, :234);
+//     emit : detections[keep] with the ORIGINAL confidence (:237-238).
+//   Images of at most 1024 merged rows do all three in one CTA (merge_small_kernel, nms.cu); larger ones use
+//   merge_prepare_kernel (here, when the fused kernel is off) / the rows written by the fused kernel, the
+//   large-segment NMS kernels and merge_emit_kernel.
 //   fdms_postprocess : decode_filter -> per-scale NMS -> merge as one host call, no host sync.
 #include <math.h>
 

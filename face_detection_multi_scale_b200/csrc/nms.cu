@@ -5,6 +5,8 @@
 //   nms_small_kernel : segments of <= 1024 boxes (the common case), one CTA per segment, everything in shared
 //                      memory: register-sorted 32-key runs + binary-search ranks, then a blocked greedy
 //                      sweep (kept-list test, balanced two-pass 256x256 pair masks, ballot resolver).
+//   merge_small_kernel: the cross-scale merge of an image of <= 1024 rows in one CTA -- merge rows
+//                      (merge_rows.cuh), the same NMS body, emit -- instead of three launches.
 //   Larger segments:
 //   nms_sort_kernel  : one CTA per segment.  64-bit key = (score descending, tie ascending),
 //                      bitonic network in shared memory (<= 8192 items, else in L2-resident

@@ -7,8 +7,10 @@ import collections
 import os
 import re
 import subprocess
+import sys
 
-from kernel_resources import kernel_name
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from kernel_resources import kernel_name  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "face_detection_multi_scale_b200", "libfdms.so")

@@ -215,3 +215,38 @@ def test_hot_pyramid_kernel_does_not_spill():
     assert m and regs
     assert (int(m.group(1)), int(m.group(2))) == (0, 0), hot[0]
     assert int(regs.group(1)) <= 48
+
+
+def test_letterbox_geometry_random_sweep_vs_oracle_and_python():
+    """fdms_letterbox_geometry (host C inside libfdms) against the oracle's geometry and a direct Python evaluation of
+    utils/datasets.py:878-901 on 5000 random shapes (Python's round() is the reference's rounding)."""
+    import numpy as np
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for _ in range(5000):
+        h, w = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+        ns = (int(rng.integers(8, 2000)), int(rng.integers(8, 2000))) if rng.random() < 0.3 else int(rng.integers(8, 2000))
+        auto, fill, up = bool(rng.integers(0, 2)), bool(rng.random() < 0.15), bool(rng.integers(0, 2))
+        stride = int(rng.choice([32, 64]))
+        nh, nw = (ns, ns) if isinstance(ns, int) else ns
+        r = min(nh / h, nw / w)
+        if not up:
+            r = min(r, 1.0)
+        uw, uh = int(round(w * r)), int(round(h * r))
+        if uw <= 0 or uh <= 0:
+            continue  # cv2.resize to an empty size fails in the reference
+        dw, dh = nw - uw, nh - uh
+        ratio = (r, r)
+        if auto:
+            dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+        elif fill:
+            dw, dh, uw, uh, ratio = 0.0, 0.0, nw, nh, (nw / w, nh / h)
+        dw, dh = dw / 2, dh / 2
+        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+        a = _lib.letterbox_geometry(h, w, ns, auto=auto, scaleFill=fill, scaleup=up, stride=stride)
+        b = O.letterbox_geometry(h, w, ns, auto, fill, up, stride)
+        want = (uh + top + bottom, uw + left + right, uh, uw, top, left, ratio[0], ratio[1], float(dw), float(dh))
+        for g in (a, b):
+            got = (g.dst_h, g.dst_w, g.unpad_h, g.unpad_w, g.top, g.left, g.ratio_w, g.ratio_h, g.dw, g.dh)
+            assert got == want, (h, w, ns, auto, fill, up, stride, got, want)

@@ -75,7 +75,7 @@ def cpu_image(oracle, synth, img, heads_s, shapes, sizes, conf, iou):
 
 def cpu_run(images, heads, shapes, wl, n_images, threads):
     """Process images[0:n_images] on `threads` host threads (the C oracle releases the GIL). Returns seconds."""
-    from face_detection_multi_scale_b200 import synth
+    from workloads import synth
     from oracle import oracle
     oracle.lib()
     per = [[[heads[s][l][b] for l in range(len(heads[s]))] for s in range(len(heads))] for b in range(n_images)]
@@ -168,7 +168,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from face_detection_multi_scale_b200 import _lib, ops, standin, synth
+    from face_detection_multi_scale_b200 import _lib, ops
+    from workloads import standin, synth
     from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
 
     if not torch.cuda.is_available():
@@ -465,7 +466,7 @@ def reference_arm(args, wl, rank, world):
     box) on all host threads, same metric/config; rank 0 only."""
     if rank != 0:
         return
-    from face_detection_multi_scale_b200 import standin
+    from workloads import standin
     thr = host_threads()
     n = args.cpu_sample or wl["batch"]  # one step = one batch, like the fdms arm
     images, heads, shapes = standin.make_batch(wl["h"], wl["w"], wl["sizes"], n, wl["faces"], seed=17, radius=wl["radius"])

@@ -12,7 +12,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from face_detection_multi_scale_b200 import ops, synth  # noqa: E402
+from face_detection_multi_scale_b200 import ops  # noqa: E402
+from workloads import synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (test infrastructure)
 
 

@@ -39,7 +39,7 @@ import cv2  # noqa: E402
 import torch  # noqa: E402
 import torchvision  # noqa: E402
 
-from face_detection_multi_scale_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 from tests.helpers import (API_CASES, CROWD_HEADS, E2E_CASES, LETTERBOX_FULL, LETTERBOX_SMALL,  # noqa: E402
                            crowd_levels, e2e_heads)
 

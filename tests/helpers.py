@@ -2,7 +2,7 @@
 container) and the parity tests (which regenerate the same inputs anywhere, GPU box included)."""
 import numpy as np
 
-from face_detection_multi_scale_b200 import synth
+from workloads import synth
 
 LETTERBOX_SMALL = [  # (h, w, new_shape, auto, scaleup, stride, seed)
     (97, 131, 64, True, True, 32, 1), (131, 97, 64, True, True, 32, 2), (37, 53, 96, True, True, 32, 3),

@@ -41,7 +41,7 @@ if not refshim.install():
 import cv2  # noqa: E402
 import torch  # noqa: E402
 
-from face_detection_multi_scale_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 
 with contextlib.redirect_stdout(io.StringIO()):
     from models.yolo import IKeypoint, Model  # noqa: E402

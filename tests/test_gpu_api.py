@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 import torch
 
-from face_detection_multi_scale_b200 import general, ops, standin, synth, yolo_head
+from face_detection_multi_scale_b200 import general, ops, yolo_head
+from workloads import standin, synth
 from face_detection_multi_scale_b200.datasets import letterbox
 from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
 from face_detection_multi_scale_b200.preprocess_yolo_predict import preprocess_api_approach, scale_coords_api_approach

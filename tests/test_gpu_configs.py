@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from face_detection_multi_scale_b200 import _lib, ops, standin, synth
+from face_detection_multi_scale_b200 import _lib, ops
+from workloads import standin, synth
 from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
 from oracle import oracle as O
 

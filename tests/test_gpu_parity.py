@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from face_detection_multi_scale_b200 import _lib, ops, synth
+from face_detection_multi_scale_b200 import _lib, ops
+from workloads import synth
 from oracle import oracle as O
 from tests import helpers as H
 

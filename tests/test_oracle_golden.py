@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from face_detection_multi_scale_b200 import synth
+from workloads import synth
 from oracle import oracle as O
 from tests import helpers as H
 

@@ -7,7 +7,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from face_detection_multi_scale_b200 import standin  # noqa: E402
+from workloads import standin  # noqa: E402
 from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector  # noqa: E402
 
 B, H, W, sizes = 32, 1080, 1920, [640, 960, 1280]

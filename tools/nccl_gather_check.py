@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from face_detection_multi_scale_b200 import dist as fdist, ops, standin  # noqa: E402
+from face_detection_multi_scale_b200 import dist as fdist, ops  # noqa: E402
+from workloads import standin  # noqa: E402
 from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector  # noqa: E402
 
 local = int(os.environ.get("LOCAL_RANK", "0"))

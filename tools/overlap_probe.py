@@ -6,7 +6,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from face_detection_multi_scale_b200 import _lib, ops, standin, synth  # noqa: E402
+from face_detection_multi_scale_b200 import _lib, ops  # noqa: E402
+from workloads import standin, synth  # noqa: E402
 
 B, H, W, sizes = 32, 1080, 1920, [640, 960, 1280]
 dev = torch.device("cuda", 0)

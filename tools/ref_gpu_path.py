@@ -25,7 +25,8 @@ import torchvision
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from face_detection_multi_scale_b200 import _lib, ops, standin, synth  # noqa: E402
+from face_detection_multi_scale_b200 import _lib, ops  # noqa: E402
+from workloads import standin, synth  # noqa: E402
 
 WORKLOADS = {
     "cfg2": dict(batch=32, h=1080, w=1920, sizes=[640, 960, 1280], faces=60, conf=0.5, iou=0.5, cap=1024, radius=1),

@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
 
-Every output array is produced by the reference's own functions, imported through oracle/refshim.py:
+Every output array is produced by the reference's own functions, imported through baseline/refshim.py:
   utils.datasets.letterbox                               (utils/datasets.py:873)
   utils.preprocess_yolo_predict.preprocess_api_approach  (utils/preprocess_yolo_predict.py:345)
   utils.preprocess_yolo_predict.scale_coords_api_approach(utils/preprocess_yolo_predict.py:122)
@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 
-from oracle import refshim  # noqa: E402
+from baseline import refshim  # noqa: E402
 
 assert refshim.install(), "reference tree not found"
 

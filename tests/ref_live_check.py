@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential check of the CPU oracle against the UNMODIFIED reference, run live.
 
-Only where the reference tree exists (the build container): the reference is imported through oracle/refshim.py in
+Only where the reference tree exists (the build container): the reference is imported through baseline/refshim.py in
 THIS process (tests/test_oracle_golden.py starts it as a subprocess, so the reference's top-level `utils` / `models`
 packages never enter the test process).  The committed fixtures pin the oracle on fixed cases; this pins it on
 seeded random ones, function by function:
@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 
 from oracle import oracle as O  # noqa: E402
-from oracle import refshim  # noqa: E402
+from baseline import refshim  # noqa: E402
 
 if not refshim.install():
     print(json.dumps({"checks": 0, "failures": [], "skipped": "no reference tree"}))

@@ -77,21 +77,25 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_the_oracle():
-    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch oracle/: not the package, not
-    the header, not the measurement tools; and bench.py / __graft_entry__ only inside those functions."""
-    for top in ("face_detection_multi_scale_b200", "include", "tools"):
+    """Only tests/, __graft_entry__.smoke() and bench.py's reference legs may touch oracle/ (the CPU restatement) or
+    baseline/ (what runs the unmodified reference): not the package, not the header, not the measurement tools; and
+    bench.py / __graft_entry__ only inside those functions."""
+    pat = r"^\s*(from|import)\s+(oracle|baseline)\b"
+    for top in ("face_detection_multi_scale_b200", "include", "tools", "workloads"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     src = open(os.path.join(dirpath, f)).read()
-                    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
-                    assert "fdms_oracle" not in src and "refshim" not in src, f
-    for name, allowed in (("bench.py", ("cpu_run", "cpu_image", "cpu_baseline", "reference_arm")), ("__graft_entry__.py", ("smoke",))):
+                    assert not re.search(pat, src, re.M), f
+                    assert "fdms_oracle" not in src and "refshim" not in src and "ref_runner" not in src, f
+    for name, allowed in (("bench.py", ("reference_block", "reference_arm")), ("__graft_entry__.py", ("smoke", "build"))):
         src = open(os.path.join(ROOT, name)).read()
-        assert not re.search(r"^(from|import)\s+oracle", src, re.M), name  # never at module level
-        for m in re.finditer(r"^(\s+)(from|import)\s+oracle", src, re.M):
+        assert not re.search(r"^(from|import)\s+(oracle|baseline)\b", src, re.M), name  # never at module level
+        for m in re.finditer(r"^(\s+)(from|import)\s+(oracle|baseline)\b", src, re.M):
             fn = re.findall(r"^def (\w+)", src[:m.start()], re.M)[-1]  # the enclosing top-level function
             assert any(a in fn for a in allowed), (name, fn)
+    # the one other place: bench.py starts baseline/backbone_bench.py as a subprocess (a real reference network on the GPU)
+    assert len(re.findall(r"backbone_bench\.py", open(os.path.join(ROOT, "bench.py")).read())) >= 1
 
 
 def test_letterbox_geometry_matches_oracle_and_reference(golden):

@@ -12,8 +12,9 @@ box), fp16 as the reference runs it on CUDA (msfd:49) -- stands between the two 
                                NMS / merge + D2H, and the same with the forward time subtracted (= the hot path's share)
   reference_gpu                the UNMODIFIED reference on the same GPU and the same network: detect_multi_scale per image
                                (msfd:242-288; image served from memory, no file decode), batch 1, sequential scales
-Prints one JSON line.  Random-init heads give no candidates at conf 0.5: the threshold is a quantile of the
-network's own confidences so that the post-processing sees about the candidate density of cfg2 (1 % of the rows).
+Prints one JSON line.  Plain random-init heads give no candidates at conf 0.5: the network's BatchNorm
+statistics are set from random batches (baseline/ref_runner.py:random_init_model), after which about 1-2 % of the rows pass
+the reference's default conf_thres 0.5 -- the candidate density of cfg2.
 """
 import argparse
 import contextlib
@@ -40,8 +41,7 @@ def main():
     ap.add_argument("--h", type=int, default=1080)
     ap.add_argument("--w", type=int, default=1920)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--gain", type=float, default=2.6)
-    ap.add_argument("--quantile", type=float, default=0.99)
+    ap.add_argument("--conf", type=float, default=0.5)
     args = ap.parse_args()
     from baseline import refshim
     if not refshim.install():
@@ -54,20 +54,14 @@ def main():
     warnings.filterwarnings("ignore", message="torch.meshgrid")
     with contextlib.redirect_stdout(io.StringIO()):
         import multi_scale_face_detector as msfd
-        from models.yolo import Model
     from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector as Mine
     from baseline.ref_runner import _Cv2Mem
     import cv2
 
     sizes = [int(v) for v in args.sizes.split(",")]
     B, dev = args.batch, torch.device("cuda", 0)
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        net = Model(os.path.join(refshim.REFERENCE_ROOT, args.cfg)).eval()
-    net.names = ["face"]
-    for m_ in net.modules():  # keep the activations of the random network alive (see tests/ref_gpu_check.py)
-        if isinstance(m_, torch.nn.Conv2d):
-            m_.weight.data.mul_(args.gain)
+    from baseline.ref_runner import random_init_model
+    net = random_init_model(args.cfg, seed=0)
     ckpt = os.path.join(tempfile.mkdtemp(prefix="fdms_bb_"), "random_init.pt")
     torch.save({"model": net}, ckpt)
     rng = np.random.default_rng(3)
@@ -81,10 +75,7 @@ def main():
     msfd.cv2 = _Cv2Mem(cv2, store)
     for b in range(B):
         store["mem:%d" % b] = images[b]
-    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-        x, _, _ = ref.preprocess_image("mem:0", sizes[len(sizes) // 2])
-        pred = ref.model(x)[0]
-    conf = float(torch.quantile((pred[0, :, 4] * pred[0, :, 5]).float(), args.quantile))
+    conf = args.conf
     ref.conf_thres = conf
 
     mine = Mine(ckpt, "", sizes, conf, 0.5, half=True, cap=16384)
@@ -127,8 +118,8 @@ def main():
     ref_run()
     t_ref = clock(ref_run, 2) / n_ref
     print(json.dumps({
-        "model": args.cfg, "weights": "random init (seed 0, conv gain %.1f), fp16" % args.gain, "batch": B, "scales": sizes,
-        "source_hw": [args.h, args.w], "conf_thres_quantile": args.quantile, "conf_thres": round(conf, 5),
+        "model": args.cfg, "weights": "random init (seed 0) + BatchNorm statistics from random batches, fp16", "batch": B, "scales": sizes,
+        "source_hw": [args.h, args.w], "conf_thres": conf,
         "candidates_per_step": stats.get("candidates"), "final_detections_per_step": stats.get("final"),
         "backbone_ms_per_step": round(bb_ms, 2), "backbone_ms_per_scale": per_scale,
         "backbone_images_per_s": round(B / (bb_ms * 1e-3), 1),

@@ -184,6 +184,38 @@ class RefHarness:
         return {k: round(1e3 * min(r[k] for r in runs), 3) for k in runs[0]}
 
 
+def random_init_model(cfg="cfg/yolov7s-face.yaml", seed=0, calib_hw=(256, 384)):
+    """A reference network without trained weights that still behaves like one: `models.yolo.Model(cfg)` with random
+    init (seeded), then its BatchNorm running statistics are set from three random batches (train-mode forwards, no
+    gradient step).  Without that, PyTorch's default conv init lets the activations of the ~100-layer stack die out and
+    every head output is its bias (no candidates); with it obj*cls spreads over (0, 1) -- about 1.5 % of the
+    rows pass the reference's default conf_thres 0.5 -- and the network is well conditioned, so a last-bit difference in
+    its input does not change its output beyond the last bits.  No checkpoint ships with the reference."""
+    from baseline import refshim
+    if not refshim.install():
+        raise RuntimeError("no reference tree")
+    import torch
+    warnings.filterwarnings("ignore", message="torch.meshgrid")
+    with _quiet():
+        from models.yolo import Model
+        torch.manual_seed(seed)
+        net = Model(os.path.join(refshim.REFERENCE_ROOT, cfg))
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = None  # cumulative average over the calibration batches
+        m.reset_running_stats()
+    net.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for _ in range(3):
+            net(torch.rand(2, 3, calib_hw[0], calib_hw[1], generator=g))
+    for m in bns:
+        m.momentum = 0.03  # utils/torch_utils.py:150
+    net.eval()
+    net.names = ["face"]
+    return net
+
+
 def maps_of(heads, shapes, b):
     """Per-image view of workloads.standin.make_batch output: {(H, W): [levels of image b]}."""
     return {tuple(int(v) for v in shapes[s]): [np.ascontiguousarray(l[b]) for l in heads[s]] for s in range(len(shapes))}

@@ -6,14 +6,20 @@ The reference tree is the byte-for-byte copy `baseline/_ref/` (or `/root/referen
 random-init `models.yolo.Model('cfg/yolov7s-face.yaml')` (seeded) is saved as a checkpoint, so the reference's own
 constructor (`MultiScaleFaceDetector(model_path, ...)`, multi_scale_face_detector.py:33-58 -> load_yolo_model ->
 attempt_load) and the unmodified `detect.py` run exactly as a user runs them.  Random-init heads give obj*cls <= ~0.25
-(SURVEY F6), so the confidence threshold is a quantile of the network's own confidences.
+(SURVEY F6), so the network's BatchNorm statistics are set from random batches (baseline/ref_runner.py:random_init_model):
+about 1.5 % of the rows then pass the reference's default conf_thres 0.5.
 
-  A  class swap (INTEGRATION route b), fp32: face_detection_multi_scale_b200.MultiScaleFaceDetector vs the reference's,
-     same checkpoint, same files, same GPU -> same (k, 7) arrays (boxes / class / scale equal, confidences to 2e-6)
-  B  monkey patch (route a), fp32: the reference's OWN class with letterbox / non_max_suppression /
-     scale_coords_api_approach rebound and the head decode patched -> same arrays as its unpatched run
-  C  the reference's default CUDA mode (half precision): reported agreement with the fp16 reference (matched boxes)
-  D  unmodified detect.py (half, --save-txt --save-conf): label files of the patched run vs the unpatched run
+  B  monkey patch (INTEGRATION route a), fp32: the reference's OWN class with letterbox / non_max_suppression /
+     scale_coords_api_approach rebound and the head decode patched -> the SAME (k, 7) arrays as its unpatched run
+     (boxes / class / scale equal, confidences to 2e-6: the network input is the reference's own pack in both runs)
+  A  class swap (route b), fp32: face_detection_multi_scale_b200.MultiScaleFaceDetector vs the reference's, same
+     checkpoint, same files, same GPU.  The fused pyramid divides by 255 (what the reference's CPU path computes and the
+     goldens pin); ATen's CUDA kernel multiplies by 1/255 for a scalar divisor, so on a CUDA device the reference's fp32
+     network input differs in the last bit of some pixels and the comparison is near-exact, not bit-exact: >= 99 % of the
+     reference's rows are reproduced exactly and the rest lies within IoU 0.95 of a row of the other run
+  C  the reference's default CUDA mode (half precision; its decode, filter and NMS run in fp16): agreement of libfdms
+     (fp32 arithmetic on the same fp16 maps) with it, boxes matched at IoU >= 0.7, counts within 3 %
+  D  unmodified detect.py (half, --save-txt --save-conf): label files of the patched run vs the unpatched run, same bar
   E  timings: backbone forward per scale, reference GPU path per image, libfdms path per image
 
 Prints one JSON line {"checks": n, "failures": [...], "report": {...}}; exit 1 on failures.
@@ -66,8 +72,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="cfg/yolov7s-face.yaml")
     ap.add_argument("--sizes", default="640,960,1280")
-    ap.add_argument("--quantile", type=float, default=0.997)
-    ap.add_argument("--gain", type=float, default=2.6)
+    ap.add_argument("--conf", type=float, default=0.5, help="the reference's default confidence threshold (msfd:33)")
     ap.add_argument("--no-detect-py", action="store_true")
     args = ap.parse_args()
     if not refshim.install():
@@ -89,15 +94,8 @@ def main():
 
     sizes = [int(v) for v in args.sizes.split(",")]
     tmp = tempfile.mkdtemp(prefix="fdms_ref_")
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        net = Model(os.path.join(ref_root, args.cfg)).eval()
-    net.names = ["face"]
-    # PyTorch's default conv init lets the activations of a ~100-layer random network die out, so every head output
-    # would be its bias; a uniform gain on the conv weights keeps them alive and the confidences spread (still random)
-    for m_ in net.modules():
-        if isinstance(m_, torch.nn.Conv2d):
-            m_.weight.data.mul_(args.gain)
+    from baseline.ref_runner import random_init_model
+    net = random_init_model(args.cfg, seed=0)  # random init + BatchNorm statistics from random batches: well conditioned
     ckpt = os.path.join(tmp, "random_init.pt")
     torch.save({"model": net}, ckpt)
     REPORT["cfg"], REPORT["params_M"] = args.cfg, round(sum(p.numel() for p in net.parameters()) / 1e6, 2)
@@ -116,37 +114,37 @@ def main():
             d.model.float()
         return d
 
-    # confidence threshold: a quantile of obj*cls of the network itself at the middle scale
+    conf = args.conf
     ref32 = ref_detector(False)
-    x, _, _ = quiet(ref32.preprocess_image, files[0], sizes[len(sizes) // 2])
-    with torch.no_grad():
-        pred = ref32.model(x)[0]
-    conf = float(torch.quantile((pred[0, :, 4] * pred[0, :, 5]).float().flatten()[:2000000], args.quantile))
-    REPORT["conf_thres"] = round(conf, 6)
     ref32.conf_thres = conf
+    REPORT["conf_thres"] = conf
 
     def rows_equal(a, b, tag):
         a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
         if a.size == 0 or b.size == 0:
             return a.size == b.size
+        a, b = a.reshape(-1, 7), b.reshape(-1, 7)
         if a.shape != b.shape:
             return False
         return bool(np.array_equal(a[:, [0, 1, 2, 3, 5, 6]], b[:, [0, 1, 2, 3, 5, 6]]) and np.max(np.abs(a[:, 4] - b[:, 4])) <= 2e-6)
 
-    # ---- A: class swap, fp32
+    # ---- A: class swap, fp32 (near-exact, see the module docstring)
     mine32 = Mine(ckpt, "", sizes, conf, 0.5, half=False)
-    ref_out = {}
+    ref_out, a_rep = {}, []
     for f in files:
         r, shape_r = quiet(ref32.detect_multi_scale, f)
         m, shape_m = mine32.detect_multi_scale(f)
-        ref_out[f] = np.asarray(r, np.float64)
-        ok = tuple(shape_r) == tuple(shape_m) and rows_equal(m, r, f)
-        if not ok:  # last-bit decode differences can flip a rounded coordinate or an NMS decision: say how far apart
-            REPORT.setdefault("A_diff", []).append({"file": os.path.basename(f), "ref": list(np.shape(r)), "mine": list(np.shape(m)),
-                                                    "matched": match_boxes(np.asarray(r).reshape(-1, 7), np.asarray(m).reshape(-1, 7), 0.95)
-                                                    if np.size(r) and np.size(m) else None})
-        check(ok, ("A class swap fp32", os.path.basename(f), np.shape(r), np.shape(m)))
-    REPORT["A_detections"] = {os.path.basename(f): int(len(v)) for f, v in ref_out.items()}
+        r, m = np.asarray(r, np.float64).reshape(-1, 7), np.asarray(m, np.float64).reshape(-1, 7)
+        ref_out[f] = r
+        rs = set(map(tuple, np.round(r[:, [0, 1, 2, 3, 5, 6]]).astype(np.int64).tolist()))
+        ms_ = set(map(tuple, np.round(m[:, [0, 1, 2, 3, 5, 6]]).astype(np.int64).tolist()))
+        exact = len(rs & ms_) / max(1, len(rs))
+        near = min(match_boxes(r, m, 0.95), match_boxes(m, r, 0.95))
+        a_rep.append({"file": os.path.basename(f), "reference": len(r), "libfdms": len(m), "rows_reproduced_exactly": round(exact, 4),
+                      "matched_iou>=0.95": round(near, 4), "bit_identical": bool(rows_equal(m, r, f))})
+        check(tuple(shape_r) == tuple(shape_m) and exact >= 0.99 and near >= 0.995 and abs(len(r) - len(m)) <= max(2, 0.01 * len(r)),
+              ("A class swap fp32", a_rep[-1]))
+    REPORT["A_class_swap_fp32"] = a_rep
 
     # ---- B: monkey patch of the reference's own class, fp32
     patched = ref_detector(False)
@@ -156,7 +154,8 @@ def main():
     try:
         for f in files:
             r, _ = quiet(patched.detect_multi_scale, f)
-            check(rows_equal(r, ref_out[f], f), ("B monkey patch fp32", os.path.basename(f), np.shape(r), ref_out[f].shape))
+            check(rows_equal(np.asarray(r, np.float64).reshape(-1, 7), ref_out[f], f),
+                  ("B monkey patch fp32", os.path.basename(f), np.shape(r), ref_out[f].shape))
     finally:
         fi.unpatch()
     REPORT["B_rebound_names"] = n_bound
@@ -171,9 +170,10 @@ def main():
         m, _ = mine16.detect_multi_scale(f)
         r, m = np.asarray(r, np.float64).reshape(-1, 7), np.asarray(m, np.float64).reshape(-1, 7)
         agree.append({"file": os.path.basename(f), "ref_fp16": len(r), "libfdms": len(m),
-                      "ref_boxes_matched_iou>=0.9": round(match_boxes(r, m), 4), "libfdms_boxes_matched": round(match_boxes(m, r), 4)})
+                      "ref_boxes_matched_iou>=0.7": round(match_boxes(r, m, 0.7), 4), "libfdms_boxes_matched": round(match_boxes(m, r, 0.7), 4)})
     REPORT["C_half_mode"] = agree
-    check(all(a["ref_boxes_matched_iou>=0.9"] >= 0.9 for a in agree if a["ref_fp16"] >= 10), ("C half agreement", agree))
+    check(all(a["ref_boxes_matched_iou>=0.7"] >= 0.95 and a["libfdms_boxes_matched"] >= 0.95 and
+              abs(a["ref_fp16"] - a["libfdms"]) <= max(3, 0.03 * a["ref_fp16"]) for a in agree), ("C half agreement", agree))
 
     # ---- D: unmodified detect.py, half precision, label files
     if not args.no_detect_py:
@@ -212,9 +212,10 @@ def main():
             # rows: cls cx cy w h conf (normalised xywh): back to corner boxes for the IoU match
             ca = np.stack([a[:, 1] - a[:, 3] / 2, a[:, 2] - a[:, 4] / 2, a[:, 1] + a[:, 3] / 2, a[:, 2] + a[:, 4] / 2], 1) if len(a) else a[:, :4]
             cb = np.stack([b[:, 1] - b[:, 3] / 2, b[:, 2] - b[:, 4] / 2, b[:, 1] + b[:, 3] / 2, b[:, 2] + b[:, 4] / 2], 1) if len(b) else b[:, :4]
-            rep.append({"file": k, "unpatched": len(a), "patched": len(b), "matched_iou>=0.9": round(match_boxes(ca, cb), 4)})
+            rep.append({"file": k, "unpatched": len(a), "patched": len(b), "matched_iou>=0.7": round(match_boxes(ca, cb, 0.7), 4)})
         REPORT["D_detect_py"] = rep
-        check(len(rep) > 0 and all(r["matched_iou>=0.9"] >= 0.9 for r in rep if r["unpatched"] >= 10), ("D detect.py", rep))
+        check(len(rep) > 0 and all(r["matched_iou>=0.7"] >= 0.95 and abs(r["unpatched"] - r["patched"]) <= max(3, 0.03 * r["unpatched"])
+                                   for r in rep), ("D detect.py", rep))
 
     # ---- E: timings on this GPU (wall clock around synchronised regions, best of 3)
     def best(fn, n=3):

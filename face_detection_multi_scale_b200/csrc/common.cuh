@@ -27,6 +27,9 @@ struct fdms_ctx {
     int pyr_special = 1;  // FDMS_PYR_SPECIAL=0 disables the integer-scale fast paths (testing)
     int pyr_smem_budget = 32 * 1024, pyr_th = 12;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
     int pyr_direct = 3, pyr_th_direct = 16;  // FDMS_PYR_DIRECT (bit 0: integer factors, bit 1: the 3:2 factor) / FDMS_PYR_TH_DIRECT: unstaged tiles
+    // FDMS_PYR_STRIP=0 disables the strip kernel (one source pass for all exact-factor scales); stage / ring size knobs
+    int pyr_strip = 1, pyr_strip_stage_bytes = 36 * 1024, pyr_strip_smem = 144 * 1024, pyr_strip_warps = 16;
+    bool pyr_strip_attr = false, pyr_cnt_ready = false;
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
     int merge_fused = 1;          // FDMS_MERGE_FUSED=0: the three-kernel merge (prepare, NMS, emit) for every image
@@ -42,6 +45,7 @@ struct fdms_ctx {
     fdms_buf merge_rows;       // merge: (n_img, mcap, 8) rows
     fdms_buf merge_cnt;        // merge: counts
     fdms_buf merge_keep;       // merge: keep + n_keep
+    fdms_buf pyr_cnt;          // strip kernel: work-item counter + finished-CTA counter (self-resetting)
     fdms_buf pyr_tab;          // pyramid tap tables of the last geometry
     unsigned long long pyr_tab_key = 0;
     fdms_buf dec_tab;          // decode filter: per-CTA table of the last head geometry

@@ -59,6 +59,10 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_PYR_SPECIAL")) c->pyr_special = atoi(e);
     if (const char *e = getenv("FDMS_PYR_SMEM_KB")) c->pyr_smem_budget = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_DIRECT")) c->pyr_direct = atoi(e);
+    if (const char *e = getenv("FDMS_PYR_STRIP")) c->pyr_strip = atoi(e);
+    if (const char *e = getenv("FDMS_PYR_STRIP_STAGE_KB")) c->pyr_strip_stage_bytes = atoi(e) * 1024;
+    if (const char *e = getenv("FDMS_PYR_STRIP_WARPS")) c->pyr_strip_warps = atoi(e);
+    if (const char *e = getenv("FDMS_PYR_STRIP_SMEM_KB")) c->pyr_strip_smem = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_TH_DIRECT")) c->pyr_th_direct = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("FDMS_PYR_TH")) c->pyr_th = atoi(e) < 1 ? 1 : (atoi(e) > 31 ? 31 : atoi(e));  // rows + sentinel are written by one warp
     if (const char *e = getenv("FDMS_NMS_SMALL_LIMIT")) c->nms_small_limit = atoi(e);
@@ -73,7 +77,7 @@ FDMS_API void fdms_destroy(fdms_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab};
+                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt};
     for (fdms_buf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete ctx;
@@ -84,7 +88,7 @@ FDMS_API const char *fdms_last_error(const fdms_ctx *ctx) { return ctx ? ctx->er
 FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx) {
     if (!ctx) return 0;
     const fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab};
+                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt};
     int64_t t = 0;
     for (const fdms_buf *b : bufs) t += (int64_t)b->bytes;
     return t;

@@ -24,6 +24,7 @@
 //     aligned words next to its neighbours' windows, so plain loads coalesce: no shared memory,
 //     no barrier, no tap prologue, several rows of loads in flight per thread.
 #include "common.cuh"
+#include "pyramid.cuh"
 
 namespace {
 
@@ -40,68 +41,6 @@ constexpr int PYR_THREADS = 160;  // 2 columns per thread: 320-column tiles divi
 constexpr int K_UNROLL32 = PYR_UNROLL32, K_UNROLL_INT = PYR_UNROLL_INT;
 constexpr int PYR_MAX_TH = 32;    // rows per tile are handled by the lanes of warp 0
 constexpr int PYR_MAX_SLOTS = 64;
-// Exact integer scale factors make OpenCV's fixed-point weights constant: an odd factor k gives
-// f == 0 on both axes (weights 2048/0: the output IS source pixel (k*d + (k-1)/2)), an even factor gives f == 0.5
-// (weights 1024/1024: (((1024*(64*(a+b)))>>16) + ... + 2) >> 2 == (a + b + c + d + 2) >> 2).  Same results as the
-// general path, fewer instructions.
-enum { PM_GENERAL = 0, PM_POINT = 1, PM_HALF = 2, PM_RATIO32 = 3 };
-
-struct PyrScale {
-    void *out;
-    long long img_stride, cs, ys, xs;  // element strides
-    int dst_h, dst_w, unpad_h, unpad_w, top, left;
-    int tile_begin, tiles_x;
-    int tw, th;        // output tile
-    int dense_rows;    // row slots cover a contiguous source-row range (scale_y <= 2)
-    int slot_bytes;    // multiple of 16
-    int vec;           // paired stores allowed
-    int mode;          // PM_GENERAL / PM_POINT / PM_HALF: strength-reduced arithmetic for exact integer scales
-    int direct;        // exact integer scale, no column padding: taps are read straight from global memory (no staging)
-    int kx, ky;        // the integer factors when mode != PM_GENERAL
-    int real_rows;     // direct tiles: interior rows whose taps are real image rows; the rest read the virtual zeros
-    double scale_x, scale_y;  // cv2: 1.0 / (dst / src) over the virtual extent
-    const int2 *xtab;         // per output column: {source column sx, a0 | a1 << 16}; sx = -1 on the border
-    const int4 *ytab;         // per output row: {r0, r1, b0 | b1 << 16, s}: clamped tap rows, weights, unclamped upper tap row; r0 = -1 on the border
-};
-
-struct PyrParams {
-    const uint8_t *src;
-    long long img_stride, pitch;
-    int src_h, src_w, virt_h, virt_w;
-    int n_scales, flip, border, vec_ok;
-    int shifted;  // !vec_ok: rows are staged with a per-slot byte shift (see TileShared::slot_shift)
-    PyrScale sc[FDMS_MAX_SCALES];
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA bulk copy global -> shared, 16 B aligned on both sides, size a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // OpenCV resize.cpp coefficient set-up for INTER_LINEAR:
 //   f = (float)((d + 0.5) * scale - 0.5); s = floor(f); f -= s
 __device__ __forceinline__ void lin_coeff(int d, double scale, int &s, float &f) {
@@ -1017,7 +956,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 // slack: tap pairs past the span and whole-word reads; shifted sources start up to 15 bytes into the slot
                 S.slot_bytes = ((span_px * 3 + 15) & ~15) + (P.shifted ? 64 : 48);
                 if (n_slots <= PYR_MAX_SLOTS && (long long)n_slots * S.slot_bytes <= ctx->pyr_smem_budget) {
-                    if (n_slots * S.slot_bytes > smem_max) smem_max = n_slots * S.slot_bytes;
+                    S.smem_need = n_slots * S.slot_bytes;
+                    if (S.smem_need > smem_max) smem_max = S.smem_need;
                     break;
                 }
                 if (th > 1) th >>= 1;
@@ -1059,6 +999,27 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                 pyramid_tables_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(P);
                 FDMS_LAUNCH_CHECK(ctx, "pyramid_tables_kernel");
                 ctx->pyr_tab_key = key;
+            }
+        }
+        // exact-factor scales of an aligned fp16 CHW pyramid: one pass over the source (pyramid_strip.cu); the tile
+        // kernel below runs whatever is left
+        if (dt == FDMS_F16) {
+            unsigned handled = 0u;
+            if (int rc = fdms_pyramid_strip(ctx, P, n_img, &handled, (cudaStream_t)stream)) return rc;
+            if (handled) {
+                int m = 0;
+                tiles = 0;
+                smem_max = 0;
+                for (int q = 0; q < n; q++) {
+                    if ((handled >> q) & 1u) continue;
+                    PyrScale S = P.sc[q];
+                    S.tile_begin = tiles;
+                    tiles += S.tiles_x * ceil_div(S.dst_h, S.th);
+                    if (S.smem_need > smem_max) smem_max = S.smem_need;
+                    P.sc[m++] = S;
+                }
+                if (m == 0) continue;
+                P.n_scales = m;
             }
         }
         int rc;

@@ -61,6 +61,7 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_PYR_DIRECT")) c->pyr_direct = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP")) c->pyr_strip = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP_STAGE_KB")) c->pyr_strip_stage_bytes = atoi(e) * 1024;
+    if (const char *e = getenv("FDMS_PYR_STRIP_REGS")) c->pyr_strip_regs = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP_WARPS")) c->pyr_strip_warps = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP_SMEM_KB")) c->pyr_strip_smem = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_TH_DIRECT")) c->pyr_th_direct = atoi(e) < 1 ? 1 : atoi(e);

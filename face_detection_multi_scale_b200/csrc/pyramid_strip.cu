@@ -30,7 +30,7 @@
 
 namespace {
 
-constexpr int ST_MAX_CONSUMER_WARPS = 16;
+constexpr int ST_MAX_CONSUMER_WARPS = 31;
 constexpr int ST_MAX_THREADS = 32 * (ST_MAX_CONSUMER_WARPS + 1);  // + the producer warp (the last warp of the CTA)
 constexpr int ST_MAX_STAGES = 8;
 constexpr int ST_MAX_SLOTS = 16;   // source rows kept in a stage
@@ -50,8 +50,11 @@ struct StripScale {
     int n_units;               // n_ru * groups
     int wu_begin;              // first warp unit of this scale in a strip's list
     int border_wu;             // warp units of this scale's border item
-    int slot0[ST_MAX_RU];      // first shared-memory slot of every row unit
+    int slot0[ST_MAX_RU];      // byte offset, inside a stage, of the first source row of every row unit
     int out_chunk_cols;        // output columns per strip
+    unsigned inv_groups;       // ceil(2^20 / groups): u / groups == (u * inv_groups) >> 20 for every unit index of a strip
+    int ru_stride;             // output elements between the first rows of consecutive row units
+    long long plane[3];        // element offset of the plane that source channel c goes to (BGR -> RGB swaps 0 and 2)
 };
 
 struct StripParams {
@@ -72,6 +75,9 @@ struct StripParams {
 struct StripShared {
     alignas(8) uint64_t full[ST_MAX_STAGES];
     alignas(8) uint64_t empty[ST_MAX_STAGES];
+    // per stage, written by the producer: the item, the hand-out counter of its work units and, per scale, the element
+    // offset of the first output row of the item (the consumers do no item arithmetic)
+    long long out_base[ST_MAX_STAGES][FDMS_MAX_SCALES];
     int item[ST_MAX_STAGES];
     int next_wu[ST_MAX_STAGES];
 };
@@ -211,7 +217,7 @@ __device__ __forceinline__ void unit_point(const uint8_t *s0, __half *const *pc)
 #undef FDMS_POINT_CH
 }
 
-__global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const __grid_constant__ StripParams P) {
+__device__ __forceinline__ void strip_body(const StripParams &P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ StripShared sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,6 +249,22 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
                 break;
             }
             const bool strip = item >= P.n_border_items;
+            int img, py = 0, cx = 0;
+            if (strip) {
+                const int q = item - P.n_border_items;
+                cx = q % P.chunks;
+                const int r = q / P.chunks;
+                py = r % P.periods;
+                img = r / P.periods;
+            } else {
+                img = item / P.n_border_scales;
+            }
+            if (lane < P.n_scales) {
+                const StripScale &S = P.sc[lane];
+                sh.out_base[s][lane] = (long long)img * S.img_stride +
+                                       (strip ? (long long)(S.top + py * S.rows_per_period) * S.dst_w + cx * S.out_chunk_cols : 0LL);
+            }
+            __syncwarp();
             if (lane == 0) {
                 sh.item[s] = item;
                 sh.next_wu[s] = 0;
@@ -251,9 +273,6 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
             }
             __syncwarp();
             if (strip && lane < P.n_slots) {
-                const int q = item - P.n_border_items;
-                const int cx = q % P.chunks, r = q / P.chunks;
-                const int py = r % P.periods, img = r / P.periods;
                 const uint8_t *g = P.src + (long long)img * P.img_stride + (long long)(py * P.L + P.slot_row[lane]) * P.pitch +
                                    (long long)cx * P.row_bytes;
                 bulk_g2s(smem + (size_t)s * P.stage_bytes + (size_t)lane * P.row_bytes, g, (uint32_t)P.row_bytes, &sh.full[s]);
@@ -279,8 +298,9 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
         if (item < 0) break;
         if (item < P.n_border_items) {
             // letterbox rows above and below the image of one (image, scale): constant rows, store only
-            const int img = item / P.n_border_scales;
-            const StripScale &S = P.sc[P.border_scale[item - img * P.n_border_scales]];
+            const int bsi = P.border_scale[item % P.n_border_scales];
+            const StripScale &S = P.sc[bsi];
+            __half *const base = S.out + sh.out_base[s][bsi];
             const int gpr = S.dst_w >> 3, n_rows = S.top + S.bottom;
             const unsigned v = pack2(border_bits, border_bits);
             const uint4 vv = make_uint4(v, v, v, v);
@@ -293,16 +313,13 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
                 if (u < n_rows * gpr) {
                     const int rr = u / gpr, g = u - rr * gpr;
                     const int y = rr < S.top ? rr : S.dst_h - (n_rows - rr);
-                    __half *p = S.out + (long long)img * S.img_stride + (long long)y * S.dst_w + 8 * g;
+                    __half *p = base + y * S.dst_w + 8 * g;
                     *reinterpret_cast<uint4 *>(p) = vv;
                     *reinterpret_cast<uint4 *>(p + S.cs) = vv;
                     *reinterpret_cast<uint4 *>(p + 2 * S.cs) = vv;
                 }
             }
         } else {
-            const int q = item - P.n_border_items;
-            const int cx = q % P.chunks, r = q / P.chunks;
-            const int py = r % P.periods, img = r / P.periods;
             const uint8_t *stage = smem + (size_t)s * P.stage_bytes;
             for (;;) {
                 int wu = 0;
@@ -316,11 +333,10 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
                 const StripScale &S = P.sc[si];
                 const int u = (wu - S.wu_begin) * 32 + lane;
                 if (u < S.n_units) {
-                    const int ru = u / S.groups, g = u - ru * S.groups;
-                    const int y = S.top + py * S.rows_per_period + (S.type == ST_R32 ? 2 * ru : ru);
-                    __half *p0 = S.out + (long long)img * S.img_stride + (long long)y * S.dst_w + cx * S.out_chunk_cols + 8 * g;
-                    __half *pc[3] = {P.flip ? p0 + 2 * S.cs : p0, p0 + S.cs, P.flip ? p0 : p0 + 2 * S.cs};
-                    const uint8_t *s0 = stage + (S.slot0[ru] * P.row_bytes + g * S.group_bytes);
+                    const int ru = (int)(((unsigned)u * S.inv_groups) >> 20), g = u - ru * S.groups;
+                    __half *p0 = S.out + sh.out_base[s][si] + (ru * S.ru_stride + 8 * g);
+                    __half *pc[3] = {p0 + S.plane[0], p0 + S.plane[1], p0 + S.plane[2]};
+                    const uint8_t *s0 = stage + (S.slot0[ru] + g * S.group_bytes);
                     if (S.type == ST_R32) unit_r32(s0, P.row_bytes, pc, S.dst_w);
                     else if (S.type == ST_HALF) {
                         if (S.k == 2) unit_half<2>(s0, P.row_bytes, pc);
@@ -339,6 +355,12 @@ __global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const 
         if (lane == 0) mbar_arrive(&sh.empty[s]);
     }
 }
+
+// Two register allocations of the same body: 64 registers (the fastest alone) and 56 (a few spilled bytes, but
+// 17 warps then leave half of the SM's register file to the 1024-thread NMS / merge CTAs of the other stream, which
+// can co-reside instead of queueing behind a persistent kernel).  FDMS_PYR_STRIP_REGS picks.
+__global__ void __launch_bounds__(ST_MAX_THREADS, 1) pyramid_strip_kernel(const __grid_constant__ StripParams P) { strip_body(P); }
+__global__ void __maxnreg__(56) pyramid_strip_kernel_r56(const __grid_constant__ StripParams P) { strip_body(P); }
 
 int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 int lcm_i(int a, int b) { return a / gcd_i(a, b) * b; }
@@ -384,7 +406,9 @@ int fdms_pyramid_strip(fdms_ctx *ctx, const PyrParams &P, int n_img, unsigned *h
         T.bottom = S.dst_h - S.top - S.unpad_h;
         idx[n++] = s;
     }
-    if (n == 0 || P.src_h % L || P.src_w % col_unit) return FDMS_OK;
+    // a launch the strip kernel covers only partly would read the source twice (strip kernel + tile kernel), which costs
+    // more than it saves (measured on 4K -> 640/960/1280/1536): all scales or none (FDMS_PYR_STRIP=2 allows the mix: tests)
+    if (n == 0 || (n != P.n_scales && ctx->pyr_strip < 2) || P.src_h % L || P.src_w % col_unit) return FDMS_OK;
     // source rows of a period that any scale reads -> shared-memory slots
     auto needed = [&](int r) {
         for (int q = 0; q < n; q++) {
@@ -448,16 +472,22 @@ int fdms_pyramid_strip(fdms_ctx *ctx, const PyrParams &P, int n_img, unsigned *h
             T.rows_per_period = 2 * L / 3;
             T.out_chunk_cols = 2 * cw / 3;
             T.group_bytes = 36;
-            for (int u = 0; u < T.n_ru; u++) T.slot0[u] = slot_of[3 * u];
+            for (int u = 0; u < T.n_ru; u++) T.slot0[u] = slot_of[3 * u] * cw * 3;
         } else {
             T.n_ru = L / T.k;
             T.rows_per_period = L / T.k;
             T.out_chunk_cols = cw / T.k;
             T.group_bytes = 24 * T.k;
-            for (int u = 0; u < T.n_ru; u++) T.slot0[u] = slot_of[T.k * u + (T.type == ST_HALF ? T.k / 2 - 1 : T.k / 2)];
+            for (int u = 0; u < T.n_ru; u++) T.slot0[u] = slot_of[T.k * u + (T.type == ST_HALF ? T.k / 2 - 1 : T.k / 2)] * cw * 3;
         }
         T.groups = T.out_chunk_cols / 8;
         T.n_units = T.n_ru * T.groups;
+        T.inv_groups = (unsigned)(((1u << 20) + T.groups - 1) / T.groups);
+        T.ru_stride = T.dst_w * (T.type == ST_R32 ? 2 : 1);
+        T.plane[0] = P.flip ? 2 * T.cs : 0;
+        T.plane[1] = T.cs;
+        T.plane[2] = P.flip ? 0 : 2 * T.cs;
+        if ((long long)T.n_units * T.inv_groups >= (1LL << 32)) { *handled = 0u; return FDMS_OK; }
         T.wu_begin = wu;
         wu += ceil_div(T.n_units, 32);
         T.border_wu = ceil_div((T.top + T.bottom) * (T.dst_w / 8), 32);
@@ -478,12 +508,14 @@ int fdms_pyramid_strip(fdms_ctx *ctx, const PyrParams &P, int n_img, unsigned *h
     const int smem = Q.n_stages * Q.stage_bytes;
     if (!ctx->pyr_strip_attr) {
         FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_strip_kernel_r56, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ctx->pyr_strip_attr = true;
     }
     int grid = ctx->sm_count;
     if (grid > Q.n_items) grid = Q.n_items;
     int warps = ctx->pyr_strip_warps < 1 ? 1 : (ctx->pyr_strip_warps > ST_MAX_CONSUMER_WARPS ? ST_MAX_CONSUMER_WARPS : ctx->pyr_strip_warps);
-    pyramid_strip_kernel<<<grid, 32 * (warps + 1), smem, st>>>(Q);
+    if (ctx->pyr_strip_regs <= 56) pyramid_strip_kernel_r56<<<grid, 32 * (warps + 1), smem, st>>>(Q);
+    else pyramid_strip_kernel<<<grid, 32 * (warps + 1), smem, st>>>(Q);
     FDMS_LAUNCH_CHECK(ctx, "pyramid_strip_kernel");
     return FDMS_OK;
 }

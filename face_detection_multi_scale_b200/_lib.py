@@ -35,7 +35,7 @@ class PostDesc(C.Structure):
                 ("in_h_host", C.POINTER(C.c_int32)), ("orig_h", C.c_int32), ("orig_w", C.c_int32),
                 ("cand", C.c_void_p), ("cand_row", C.c_void_p), ("count", C.c_void_p), ("keep", C.c_void_p),
                 ("n_keep", C.c_void_p), ("dets", C.c_void_p), ("n_out", C.c_void_p), ("out_cap", C.c_int32),
-                ("pad_", C.c_int32), ("merged_in", C.c_void_p), ("kpts_out", C.c_void_p)]
+                ("flags", C.c_int32), ("merged_in", C.c_void_p), ("kpts_out", C.c_void_p)]
 
 
 _SIGS = {
@@ -74,6 +74,7 @@ _SIGS = {
     "fdms_pack_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_postprocess": (C.c_int, [C.c_void_p, C.POINTER(PostDesc), C.c_void_p]),
+    "fdms_set_small_only": (C.c_int, [C.c_void_p, C.c_int]),
     "fdms_scale_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "fdms_descale_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
@@ -129,6 +130,10 @@ class Ctx:
             msg = lib().fdms_last_error(self._h).decode("utf-8", "replace")
             exc = ValueError if rc == -1 else FdmsError
             raise exc("%s failed (%d): %s" % (what or "libfdms call", rc, msg))
+
+    def set_small_only(self, on):
+        """fdms_set_small_only: fdms_nms / fdms_merge_scales on this context launch only the single-CTA kernels."""
+        self.check(lib().fdms_set_small_only(self._h, int(bool(on))), "fdms_set_small_only")
 
     def scratch_bytes(self):
         return int(lib().fdms_scratch_bytes(self._h))

@@ -28,11 +28,13 @@ struct fdms_ctx {
     int pyr_smem_budget = 32 * 1024, pyr_th = 12;   // FDMS_PYR_SMEM_KB / FDMS_PYR_TH (tuning knobs)
     int pyr_direct = 3, pyr_th_direct = 16;  // FDMS_PYR_DIRECT (bit 0: integer factors, bit 1: the 3:2 factor) / FDMS_PYR_TH_DIRECT: unstaged tiles
     // FDMS_PYR_STRIP=0 disables the strip kernel (one source pass for all exact-factor scales); stage / ring size knobs
-    int pyr_strip = 1, pyr_strip_stage_bytes = 36 * 1024, pyr_strip_smem = 108 * 1024, pyr_strip_warps = 16, pyr_strip_regs = 64;
+    int pyr_strip = 1, pyr_strip_stage_bytes = 36 * 1024, pyr_strip_smem = 108 * 1024, pyr_strip_warps = 14, pyr_strip_regs = 64;
     bool pyr_strip_attr = false, pyr_cnt_ready = false;
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
     int merge_fused = 1;          // FDMS_MERGE_FUSED=0: the three-kernel merge (prepare, NMS, emit) for every image
+    bool post_small_only = false; // set around fdms_postprocess(FDMS_POST_SMALL_ONLY): no large-segment launches
+    bool small_only_sticky = false;  // fdms_set_small_only: the same for fdms_nms / fdms_merge_scales called one by one
     bool nms_small_done = false;  // set around fdms_nms_impl by the fused merge: segments <= the limit are done already
     int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides

@@ -84,6 +84,12 @@ FDMS_API void fdms_destroy(fdms_ctx *ctx) {
     delete ctx;
 }
 
+FDMS_API int fdms_set_small_only(fdms_ctx *ctx, int on) {
+    if (!ctx) return FDMS_ERR_INVALID;
+    ctx->small_only_sticky = on != 0;
+    return FDMS_OK;
+}
+
 FDMS_API const char *fdms_last_error(const fdms_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
 
 FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx) {

@@ -212,7 +212,7 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
         int inclusive;
         fdms_fold_threshold(iou_thres, FDMS_IOU_TV_CPU, &thr_f, &inclusive);
         if (int rc = fdms_merge_small_launch(ctx, P, E, n_img, thr_f, inclusive, st)) return rc;
-        if (mcap <= small_limit) return FDMS_OK;  // no image can have more rows
+        if (mcap <= small_limit || ctx->post_small_only || ctx->small_only_sticky) return FDMS_OK;  // no image can have more rows / the caller checks
         skip_le = small_limit;
         ctx->nms_small_done = true;
     } else {
@@ -231,6 +231,13 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_stream stream) {
     if (int rc = fdms_bind(ctx)) return rc;
     if (!d) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_postprocess: null descriptor");
+    if ((d->flags & FDMS_POST_SMALL_ONLY) && (fdms_merge_small_limit(ctx) != FDMS_SMALL_LIMIT || !ctx->merge_fused))
+        return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_postprocess: FDMS_POST_SMALL_ONLY needs the fused single-CTA kernels");
+    struct Guard {  // the flag is per call
+        fdms_ctx *c;
+        ~Guard() { c->post_small_only = false; }
+    } guard{ctx};
+    ctx->post_small_only = (d->flags & FDMS_POST_SMALL_ONLY) != 0;
     // landmarks are decoded only when the caller asked for them in the merged output
     if (int rc = fdms_decode_filter_ex(ctx, d->levels, d->n_levels, d->n_scales, d->bs, d->conf_thres, d->cand, d->cand_row,
                                        d->count, d->cap, d->kpts_out ? 0 : FDMS_DECODE_BOXES_ONLY, stream))

@@ -638,7 +638,10 @@ __global__ void FDMS_SMALL_BOUNDS
                      int32_t *__restrict__ n_keep) {
     const int g = blockIdx.x;
     const int n = max(0, min(count[g], cap));
-    if (n > small_limit) return;  // the sort + greedy / bit-matrix path takes it
+    if (n > small_limit) {  // the sort + greedy / bit-matrix path takes it (it overwrites the marker)
+        if (threadIdx.x == 0) n_keep[g] = -2;
+        return;
+    }
     int nk = 0;
     if (n > 0) nk = nms_small_body<MODE, true>(rows, row_stride, box_off, score_off, tie, n, g, cap, max_nms, thr, inclusive, keep);
     if (threadIdx.x == 0) n_keep[g] = nk;
@@ -653,7 +656,10 @@ __global__ void FDMS_SMALL_BOUNDS
                        float thr, int inclusive) {
     const int img = blockIdx.x, tid = threadIdx.x;
     const int total = merge_prepare_image(P, img, tid, SMALL_THREADS);
-    if (total > small_limit) return;  // nms_sort_kernel + nms_greedy / mask + merge_emit_kernel take this image
+    if (total > small_limit) {  // nms_sort_kernel + nms_greedy / mask + merge_emit_kernel take this image
+        if (tid == 0) E.n_out[img] = 0;
+        return;
+    }
     __syncthreads();  // the rows above were written by other threads of this CTA
     int nk = 0;
     if (total > 0)
@@ -806,7 +812,7 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
 #undef FDMS_NMS_SMALL
         FDMS_LAUNCH_CHECK(ctx, "nms_small_kernel");
     }
-    if (small_limit > 0 && cap <= small_limit) return FDMS_OK;  // no segment can be larger
+    if (small_limit > 0 && (cap <= small_limit || ctx->post_small_only || ctx->small_only_sticky)) return FDMS_OK;  // no segment can be larger / the caller checks
     const int skip_le = small_limit > 0 ? small_limit : -1;
     // ---- larger segments: sort -> mask -> sweep ----------------------------------------------------------------
     if ((cap_e + 63) / 64 > SWEEP_MAX_NBLK)

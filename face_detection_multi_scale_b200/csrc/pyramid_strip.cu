@@ -36,6 +36,7 @@ constexpr int ST_MAX_STAGES = 8;
 constexpr int ST_MAX_SLOTS = 16;   // source rows kept in a stage
 constexpr int ST_MAX_RU = 16;      // row units of a scale per strip
 constexpr int ST_MAX_L = 48;       // source rows of a strip
+constexpr int ST_MAX_WU = 160;     // warp units of a strip
 enum { ST_POINT = 0, ST_HALF = 1, ST_R32 = 2 };
 
 struct StripScale {
@@ -52,7 +53,6 @@ struct StripScale {
     int border_wu;             // warp units of this scale's border item
     int slot0[ST_MAX_RU];      // byte offset, inside a stage, of the first source row of every row unit
     int out_chunk_cols;        // output columns per strip
-    unsigned inv_groups;       // ceil(2^20 / groups): u / groups == (u * inv_groups) >> 20 for every unit index of a strip
     int ru_stride;             // output elements between the first rows of consecutive row units
     long long plane[3];        // element offset of the plane that source channel c goes to (BGR -> RGB swaps 0 and 2)
 };
@@ -68,6 +68,7 @@ struct StripParams {
     int n_border_scales, border_scale[FDMS_MAX_SCALES];
     int n_border_items, n_items;  // border items come first
     int wu_per_strip;
+    unsigned wu_info[ST_MAX_WU];  // per warp unit of a strip: scale | row unit << 8 | first column group << 16
     int flip, border;
     unsigned *counters;  // [0] next item, [1] CTAs done
 };
@@ -77,7 +78,7 @@ struct StripShared {
     alignas(8) uint64_t empty[ST_MAX_STAGES];
     // per stage, written by the producer: the item, the hand-out counter of its work units and, per scale, the element
     // offset of the first output row of the item (the consumers do no item arithmetic)
-    long long out_base[ST_MAX_STAGES][FDMS_MAX_SCALES];
+    __half *out_ptr[ST_MAX_STAGES][FDMS_MAX_SCALES][3];  // [channel]: plane pointer at the item's first row and column
     int item[ST_MAX_STAGES];
     int next_wu[ST_MAX_STAGES];
 };
@@ -261,8 +262,11 @@ __device__ __forceinline__ void strip_body(const StripParams &P) {
             }
             if (lane < P.n_scales) {
                 const StripScale &S = P.sc[lane];
-                sh.out_base[s][lane] = (long long)img * S.img_stride +
-                                       (strip ? (long long)(S.top + py * S.rows_per_period) * S.dst_w + cx * S.out_chunk_cols : 0LL);
+                __half *base = S.out + (long long)img * S.img_stride +
+                               (strip ? (long long)(S.top + py * S.rows_per_period) * S.dst_w + cx * S.out_chunk_cols : 0LL);
+                sh.out_ptr[s][lane][0] = base + S.plane[0];
+                sh.out_ptr[s][lane][1] = base + S.plane[1];
+                sh.out_ptr[s][lane][2] = base + S.plane[2];
             }
             __syncwarp();
             if (lane == 0) {
@@ -300,7 +304,7 @@ __device__ __forceinline__ void strip_body(const StripParams &P) {
             // letterbox rows above and below the image of one (image, scale): constant rows, store only
             const int bsi = P.border_scale[item % P.n_border_scales];
             const StripScale &S = P.sc[bsi];
-            __half *const base = S.out + sh.out_base[s][bsi];
+            __half *const base = sh.out_ptr[s][bsi][P.flip ? 2 : 0];  // plane 0
             const int gpr = S.dst_w >> 3, n_rows = S.top + S.bottom;
             const unsigned v = pack2(border_bits, border_bits);
             const uint4 vv = make_uint4(v, v, v, v);
@@ -321,21 +325,19 @@ __device__ __forceinline__ void strip_body(const StripParams &P) {
             }
         } else {
             const uint8_t *stage = smem + (size_t)s * P.stage_bytes;
-            for (;;) {
-                int wu = 0;
-                if (lane == 0) wu = atomicAdd(&sh.next_wu[s], 1);
-                wu = __shfl_sync(0xffffffffu, wu, 0);
-                if (wu >= P.wu_per_strip) break;
-                int si = 0;
-#pragma unroll 1
-                for (int k = 1; k < P.n_scales; k++)
-                    if (wu >= P.sc[k].wu_begin) si = k;
+            // the next unit number is taken while the current unit runs (the shared-memory atomic's latency is hidden)
+            int wu = 0;
+            if (lane == 0) wu = atomicAdd(&sh.next_wu[s], 1);
+            wu = __shfl_sync(0xffffffffu, wu, 0);
+            while (wu < P.wu_per_strip) {
+                int nxt = 0;
+                if (lane == 0) nxt = atomicAdd(&sh.next_wu[s], 1);
+                const unsigned info = P.wu_info[wu];
+                const int si = (int)(info & 0xffu), ru = (int)((info >> 8) & 0xffu), g = (int)(info >> 16) + lane;
                 const StripScale &S = P.sc[si];
-                const int u = (wu - S.wu_begin) * 32 + lane;
-                if (u < S.n_units) {
-                    const int ru = (int)(((unsigned)u * S.inv_groups) >> 20), g = u - ru * S.groups;
-                    __half *p0 = S.out + sh.out_base[s][si] + (ru * S.ru_stride + 8 * g);
-                    __half *pc[3] = {p0 + S.plane[0], p0 + S.plane[1], p0 + S.plane[2]};
+                if (g < S.groups) {
+                    const int eo = ru * S.ru_stride + 8 * g;
+                    __half *pc[3] = {sh.out_ptr[s][si][0] + eo, sh.out_ptr[s][si][1] + eo, sh.out_ptr[s][si][2] + eo};
                     const uint8_t *s0 = stage + (S.slot0[ru] + g * S.group_bytes);
                     if (S.type == ST_R32) unit_r32(s0, P.row_bytes, pc, S.dst_w);
                     else if (S.type == ST_HALF) {
@@ -348,7 +350,7 @@ __device__ __forceinline__ void strip_body(const StripParams &P) {
                         else unit_point<5>(s0, pc);
                     }
                 }
-                __syncwarp();
+                wu = __shfl_sync(0xffffffffu, nxt, 0);
             }
         }
         __syncwarp();
@@ -482,14 +484,16 @@ int fdms_pyramid_strip(fdms_ctx *ctx, const PyrParams &P, int n_img, unsigned *h
         }
         T.groups = T.out_chunk_cols / 8;
         T.n_units = T.n_ru * T.groups;
-        T.inv_groups = (unsigned)(((1u << 20) + T.groups - 1) / T.groups);
         T.ru_stride = T.dst_w * (T.type == ST_R32 ? 2 : 1);
         T.plane[0] = P.flip ? 2 * T.cs : 0;
         T.plane[1] = T.cs;
         T.plane[2] = P.flip ? 0 : 2 * T.cs;
-        if ((long long)T.n_units * T.inv_groups >= (1LL << 32)) { *handled = 0u; return FDMS_OK; }
         T.wu_begin = wu;
-        wu += ceil_div(T.n_units, 32);
+        for (int u = 0; u < T.n_ru; u++)
+            for (int g0 = 0; g0 < T.groups; g0 += 32) {
+                if (wu >= ST_MAX_WU || T.groups >= 65536) { *handled = 0u; return FDMS_OK; }
+                Q.wu_info[wu++] = (unsigned)q | ((unsigned)u << 8) | ((unsigned)g0 << 16);
+            }
         T.border_wu = ceil_div((T.top + T.bottom) * (T.dst_w / 8), 32);
         if (T.top + T.bottom > 0) Q.border_scale[Q.n_border_scales++] = q;
         *handled |= 1u << idx2[q];

@@ -75,6 +75,7 @@ class MultiScaleFaceDetector:
         self.head = yolo_head.patch_head(yolo_head.find_head(self.model))
         self.strides, self.anchors_px = yolo_head.head_geometry(self.head)
         self._tls = threading.local()  # plan caches hold device buffers + a native ctx: one set per calling thread
+        self._speculate_small = True   # see _plan: dense batches switch it off until a sparse one is seen again
         self.last_stats = {}
 
     # ------------------------------------------------------------------ geometry / preprocessing
@@ -150,6 +151,9 @@ class MultiScaleFaceDetector:
             plans[key] = plan
         else:
             plan.rebind(scales_levels)
+        # speculate that no segment / image exceeds the single-CTA kernels' limit while the recent batches did not: the
+        # large-segment launches are then skipped and the exact counts read back with the results verify the guess
+        plan.small_only = self._speculate_small
         return plan
 
     def _stream_lanes(self, depth):
@@ -198,6 +202,7 @@ class MultiScaleFaceDetector:
             self.done = torch.cuda.Event()
             self.plan = None
             self.src = None
+            self.small_only = False
 
     def detect_stream(self, batches, depth=2):
         """Pipelined detection over an iterable of (B, H, W, 3) uint8 BGR host batches (pinned memory overlaps best):
@@ -213,8 +218,11 @@ class MultiScaleFaceDetector:
             lane.done.synchronize()
             meta = lane.h_meta.numpy()
             n_out, head = meta[:-5], meta[-5:]
-            if head[0] > lane.plan.cands.cap or head[2] > lane.plan.out.out_cap or head[1] < 0:
-                return self.detect_multi_scale_batch(lane.src)  # rare: grow capacities on the synchronous path
+            small = ops.PostPlan.small_ok(head[0], head[2])
+            missed = lane.small_only and not small
+            self._speculate_small = small
+            if head[0] > lane.plan.cands.cap or head[2] > lane.plan.out.out_cap or head[1] == -1 or missed:
+                return self.detect_multi_scale_batch(lane.src)  # rare: grow capacities / full path, synchronously
             kmax = int(n_out.max()) if n_out.size else 0
             dets = lane.h_dets[:, :kmax].numpy().astype(np.float64)
             return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
@@ -239,7 +247,7 @@ class MultiScaleFaceDetector:
                 lane.h_dets.copy_(o.dets, non_blocking=True)
                 lane.h_meta.copy_(self._meta(plan), non_blocking=True)
                 lane.done.record(lane.stream)
-            lane.plan, lane.src = plan, t
+            lane.plan, lane.src, lane.small_only = plan, t, plan.small_only
             pending.append(lane)
         for lane in pending:
             yield finish(lane)
@@ -249,9 +257,12 @@ class MultiScaleFaceDetector:
         o, c = plan.out, plan.cands
         both = self._meta(plan).cpu().numpy()
         n_out, head = both[:-5], both[-5:]  # one read, synchronises
-        if head[0] > c.cap or head[2] > o.out_cap:
+        small = ops.PostPlan.small_ok(head[0], head[2])
+        missed = plan.small_only and not small
+        self._speculate_small = small
+        if head[0] > c.cap or head[2] > o.out_cap or missed:
             return None, head
-        if head[1] < 0:
+        if head[1] == -1:
             raise _lib.FdmsError("a segment exceeded the NMS suppression-mask budget")
         kmax = int(n_out.max()) if n_out.size else 0
         dets = o.dets[:, :kmax].cpu().numpy().astype(np.float64) if kmax else np.zeros((len(n_out), 0, 7))

@@ -117,6 +117,8 @@ def decode_dense(levels, strides, anchors_px):
 
 
 DECODE_BOXES_ONLY = 1  # include/fdms.h FDMS_DECODE_BOXES_ONLY
+POST_SMALL_ONLY = 1    # include/fdms.h FDMS_POST_SMALL_ONLY
+SMALL_LIMIT = 1024     # include/fdms.h FDMS_SMALL_LIMIT
 
 
 class Candidates:
@@ -295,7 +297,10 @@ class PostPlan:
     run, so the launches go out back to back (and can be captured in a CUDA graph)."""
 
     def __init__(self, scales_levels, strides, anchors_px, in_h, orig_hw, conf_thres, iou_thres, cap, out_cap,
-                 iou_mode=IOU_TV_CUDA, with_kpts=False, ctx=None):
+                 iou_mode=IOU_TV_CUDA, with_kpts=False, ctx=None, small_only=False):
+        """small_only: launch only the single-CTA kernels (FDMS_POST_SMALL_ONLY): correct iff afterwards every
+        `cands.count` and `out.merged_in` is <= SMALL_LIMIT, which the caller must check (`small_ok`) -- otherwise run
+        the same plan again with `small_only = False`."""
         self.dev = _dev(scales_levels[0][0])
         device = scales_levels[0][0].device
         self._strides, self._anchors = list(strides), np.asarray(anchors_px, np.float32)
@@ -318,6 +323,7 @@ class PostPlan:
         d.dets, d.n_out, d.out_cap = self.out.dets.data_ptr(), self.out.n_out.data_ptr(), out_cap
         d.merged_in = self.out.merged_in.data_ptr()
         d.kpts_out = self.out.kpts.data_ptr() if with_kpts else None
+        d.flags = POST_SMALL_ONLY if small_only else 0
         self.desc = d
         self.ctx = ctx if ctx is not None else _lib.ctx(self.dev)
 
@@ -329,6 +335,19 @@ class PostPlan:
         self.arr, self._hold = arr, hold
         self.desc.levels = C.cast(self.arr, C.POINTER(_lib.Level))
 
+    @property
+    def small_only(self):
+        return bool(self.desc.flags & POST_SMALL_ONLY)
+
+    @small_only.setter
+    def small_only(self, on):
+        self.desc.flags = (self.desc.flags | POST_SMALL_ONLY) if on else (self.desc.flags & ~POST_SMALL_ONLY)
+
+    @staticmethod
+    def small_ok(max_count, max_merged_in):
+        """The check a small_only run needs: nothing exceeded the single-CTA kernels' limit."""
+        return int(max_count) <= SMALL_LIMIT and int(max_merged_in) <= SMALL_LIMIT
+
     def run(self):
         rc = _lib.lib().fdms_postprocess(self.ctx.handle, C.byref(self.desc), _stream(self.dev))
         self.ctx.check(rc, "fdms_postprocess")
@@ -339,6 +358,8 @@ class PostPlan:
         """Kernel launches of one run() (memset excluded): decode filter + candidate decode, the per-scale NMS (one
         fused launch when no segment can exceed 1024 boxes, else + sort + greedy sweep), the cross-scale merge (one
         fused launch when no image can have more than 1024 merged rows, else + sort + greedy sweep + emit)."""
-        small = 1024
+        small = SMALL_LIMIT
+        if self.small_only:
+            return 4
         mcap = min(self.n_scales * self.cands.cap, self.out.out_cap)
         return 2 + (1 if self.cands.cap <= small else 3) + (1 if mcap <= small else 4)

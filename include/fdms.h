@@ -224,6 +224,13 @@ FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, in
  * decode_filter -> per-scale NMS -> merge, back to back on `stream` without host sync.
  * cand/cand_row/count/keep/n_keep are caller-owned scratch with the shapes given above
  * (n_seg = bs*n_scales).  Counts can be read back afterwards for overflow checks. */
+/* flags of fdms_post_desc.  FDMS_POST_SMALL_ONLY: launch only the single-CTA kernels (segments / images of at most
+ * 1024 boxes -- the common case).  A segment with more candidates gets n_keep = -2 and an image with more merged rows
+ * n_out = 0: the caller MUST compare count[] and merged_in[] with FDMS_SMALL_LIMIT afterwards and redo the call
+ * without the flag when either exceeds it (the counts are exact).  Saves the launches that a capacity above 1024 would
+ * otherwise add to every call although they find nothing to do. */
+#define FDMS_POST_SMALL_ONLY 1
+#define FDMS_SMALL_LIMIT 1024
 typedef struct fdms_post_desc {
     const fdms_level *levels; /* host array */
     int32_t n_levels, n_scales, bs, cap;
@@ -233,12 +240,16 @@ typedef struct fdms_post_desc {
     const int32_t *in_h_host; /* [n_scales] */
     int32_t orig_h, orig_w;
     float *cand; int32_t *cand_row; int32_t *count; int32_t *keep; int32_t *n_keep;
-    float *dets; int32_t *n_out; int32_t out_cap; int32_t pad_;
+    float *dets; int32_t *n_out; int32_t out_cap;
+    int32_t flags; /* FDMS_POST_* */
     int32_t *merged_in; /* may be NULL */
     float *kpts_out;    /* may be NULL */
 } fdms_post_desc;
 
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_stream stream);
+/* The same contract as FDMS_POST_SMALL_ONLY for fdms_nms and fdms_merge_scales called one by one on this context
+ * (until switched off again): only the single-CTA kernels are launched, the caller checks the counts. */
+FDMS_API int fdms_set_small_only(fdms_ctx *ctx, int on);
 
 /* ---- "next" rows around the hot path ---------------------------------------------
  * widerface_evaluate/box_overlaps.pyx:15-55 bbox_overlaps: (n,4) x (k,4) float64 boxes -> (n,k) float64

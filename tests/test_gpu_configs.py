@@ -163,3 +163,43 @@ def test_repeated_runs_are_bit_identical():
         if it % 13 == 0:
             for a, b_ in zip(outs, first[2]):
                 assert torch.equal(a, b_), it
+
+
+def test_speculative_small_chain_falls_back_on_dense_batches():
+    """The detector launches only the single-CTA kernels while its batches stay sparse (FDMS_POST_SMALL_ONLY) and
+    verifies the guess from the exact counts it reads back: a dense batch (segments > 1024 candidates) between sparse
+    ones must still give the oracle's result, synchronously and streamed, and the speculation must resume afterwards."""
+    h, w, sizes, B = 540, 960, [640, 960], 2
+    sparse = standin.make_batch(h, w, sizes, B, n_faces=20, seed=41, dtype=np.float16)
+    dense = standin.make_batch(h, w, sizes, B, n_faces=700, seed=42, dtype=np.float16)
+
+    class Switch(standin.SyntheticHeadModel):
+        pass
+    model = Switch()
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, cap=4096)
+
+    def load(batch):
+        for s_, hw in enumerate(batch[2]):
+            model.set_heads(hw, batch[1][s_], pin=True)
+
+    def check(outs, batch):
+        for b in range(B):
+            ref, _ = _oracle_detect(batch[1], batch[2], b, (h, w), synth.P5_STRIDES, synth.P5_ANCHORS, 0.5, 0.5)
+            assert outs[b].shape == ref.shape and np.array_equal(outs[b], ref), (b, outs[b].shape, ref.shape)
+
+    load(sparse)
+    check(det.detect_multi_scale_batch(sparse[0]), sparse)
+    assert det._speculate_small
+    load(dense)
+    out = det.detect_multi_scale_batch(dense[0])
+    assert det.last_stats["candidates"] > 2 * 1024 * B  # some segment is beyond the single-CTA limit
+    check(out, dense)
+    assert not det._speculate_small
+    check(det.detect_multi_scale_batch(dense[0]), dense)  # no speculation now: one run
+    load(sparse)
+    check(det.detect_multi_scale_batch(sparse[0]), sparse)
+    assert det._speculate_small
+    # streamed: the dense batch arrives while the detector speculates
+    load(dense)
+    for outs in det.detect_stream([dense[0], dense[0]], depth=2):
+        check(outs, dense)

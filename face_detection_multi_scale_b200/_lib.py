@@ -75,6 +75,8 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_postprocess": (C.c_int, [C.c_void_p, C.POINTER(PostDesc), C.c_void_p]),
     "fdms_set_small_only": (C.c_int, [C.c_void_p, C.c_int]),
+    "fdms_set_numerics": (C.c_int, [C.c_void_p, C.c_int]),
+    "fdms_get_numerics": (C.c_int, [C.c_void_p]),
     "fdms_scale_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "fdms_descale_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int,
@@ -130,6 +132,16 @@ class Ctx:
             msg = lib().fdms_last_error(self._h).decode("utf-8", "replace")
             exc = ValueError if rc == -1 else FdmsError
             raise exc("%s failed (%d): %s" % (what or "libfdms call", rc, msg))
+
+    def set_numerics(self, mode):
+        """fdms_set_numerics: 'exact' (default; the CPU oracle's arithmetic) or 'aten_cuda' (bit-identical to the reference
+        running in fp32 on a CUDA device: libdevice expf in the sigmoid, x * (1 / s) for divisions by a scalar)."""
+        m = {"exact": 0, "aten_cuda": 1, 0: 0, 1: 1}[mode]
+        self.check(lib().fdms_set_numerics(self._h, m), "fdms_set_numerics")
+
+    @property
+    def numerics(self):
+        return "aten_cuda" if lib().fdms_get_numerics(self._h) == 1 else "exact"
 
     def set_small_only(self, on):
         """fdms_set_small_only: fdms_nms / fdms_merge_scales on this context launch only the single-CTA kernels."""

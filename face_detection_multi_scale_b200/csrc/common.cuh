@@ -33,6 +33,7 @@ struct fdms_ctx {
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
     int merge_fused = 1;          // FDMS_MERGE_FUSED=0: the three-kernel merge (prepare, NMS, emit) for every image
+    int numerics = FDMS_NUMERICS_EXACT;  // fdms_set_numerics / FDMS_NUMERICS
     bool post_small_only = false; // set around fdms_postprocess(FDMS_POST_SMALL_ONLY): no large-segment launches
     bool small_only_sticky = false;  // fdms_set_small_only: the same for fdms_nms / fdms_merge_scales called one by one
     bool nms_small_done = false;  // set around fdms_nms_impl by the fused merge: segments <= the limit are done already

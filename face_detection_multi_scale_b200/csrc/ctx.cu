@@ -56,6 +56,7 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (c->sm_count <= 0) c->sm_count = FDMS_SM_COUNT_FALLBACK;
+    if (const char *e = getenv("FDMS_NUMERICS")) c->numerics = (!strcmp(e, "aten_cuda") || !strcmp(e, "1")) ? FDMS_NUMERICS_ATEN_CUDA : FDMS_NUMERICS_EXACT;
     if (const char *e = getenv("FDMS_PYR_SPECIAL")) c->pyr_special = atoi(e);
     if (const char *e = getenv("FDMS_PYR_SMEM_KB")) c->pyr_smem_budget = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_DIRECT")) c->pyr_direct = atoi(e);
@@ -83,6 +84,14 @@ FDMS_API void fdms_destroy(fdms_ctx *ctx) {
         if (b->p) cudaFree(b->p);
     delete ctx;
 }
+
+FDMS_API int fdms_set_numerics(fdms_ctx *ctx, int mode) {
+    if (!ctx || (mode != FDMS_NUMERICS_EXACT && mode != FDMS_NUMERICS_ATEN_CUDA)) return FDMS_ERR_INVALID;
+    ctx->numerics = mode;
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_get_numerics(const fdms_ctx *ctx) { return ctx ? ctx->numerics : FDMS_ERR_INVALID; }
 
 FDMS_API int fdms_set_small_only(fdms_ctx *ctx, int on) {
     if (!ctx) return FDMS_ERR_INVALID;

@@ -52,6 +52,7 @@ struct DecParams {
     int32_t *cand_row;
     int32_t *count;
     const struct DecCta *cta_tab;  // per CTA of decode_filter_kernel (cached per geometry in the ctx)
+    int aten;  // FDMS_NUMERICS_ATEN_CUDA: sigmoid with libdevice's expf, like ATen's CUDA kernel (see sigmoid_ref)
 };
 
 // What a CTA of decode_filter_kernel needs to know about itself.  Deriving it in the kernel (level search, two
@@ -66,42 +67,47 @@ struct DecCta {
     int pad_;
 };
 
-__device__ __forceinline__ float sigmoid_exact(float x) {
-    float e = (float)exp(-(double)x);  // fp64 exp rounded once == correctly rounded expf
+// 1 / (1 + exp(-x)).  The reference's sigmoid is ATen's: on the CPU a vectorised expf (Sleef, <= 1 ulp), on a CUDA
+// device `one / (one + std::exp(-a))` with libdevice's expf (<= 2 ulp) -- two different roundings of the same value.
+// Default (`aten` false): exp evaluated in fp64 and rounded once, i.e. the correctly rounded expf, which the CPU oracle
+// restates bit for bit and which lies within 1 ulp of either.  `aten` true (FDMS_NUMERICS_ATEN_CUDA): the very expf
+// ATen's CUDA kernel calls, so that the decode is bit-identical to the reference running in fp32 on the same GPU.
+__device__ __forceinline__ float sigmoid_ref(float x, bool aten) {
+    const float e = aten ? expf(-x) : (float)exp(-(double)x);
     return f_div(1.0f, f_add(1.0f, e));
 }
 
 // models/yolo.py:290-295 for one cell; v[k] = raw channel k (already fp32), out = 21 floats
 // [cx, cy, w, h, obj, cls, (kx, ky, kc) x 5]
 __device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
-                                            float (&o)[NO]) {
-    float s0 = sigmoid_exact(v[0]), s1 = sigmoid_exact(v[1]), s2 = sigmoid_exact(v[2]), s3 = sigmoid_exact(v[3]);
+                                            float (&o)[NO], bool aten) {
+    float s0 = sigmoid_ref(v[0], aten), s1 = sigmoid_ref(v[1], aten), s2 = sigmoid_ref(v[2], aten), s3 = sigmoid_ref(v[3], aten);
     o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
     o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
     float t2 = f_mul(s2, 2.f), t3 = f_mul(s3, 2.f);
     o[2] = f_mul(f_mul(t2, t2), aw);
     o[3] = f_mul(f_mul(t3, t3), ah);
-    o[4] = sigmoid_exact(v[4]);
-    o[5] = sigmoid_exact(v[5]);
+    o[4] = sigmoid_ref(v[4], aten);
+    o[5] = sigmoid_ref(v[5], aten);
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         o[6 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[6 + 3 * j], 2.f), 0.5f), gx), stride);  // raw logits, no sigmoid
         o[7 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[7 + 3 * j], 2.f), 0.5f), gy), stride);
-        o[8 + 3 * j] = sigmoid_exact(v[8 + 3 * j]);
+        o[8 + 3 * j] = sigmoid_ref(v[8 + 3 * j], aten);
     }
 }
 
 // The box / objectness / class part of decode_cell alone (candidates whose landmarks nobody reads).
 __device__ __forceinline__ void decode_box(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
-                                           float (&o)[NO]) {
-    float s0 = sigmoid_exact(v[0]), s1 = sigmoid_exact(v[1]), s2 = sigmoid_exact(v[2]), s3 = sigmoid_exact(v[3]);
+                                           float (&o)[NO], bool aten) {
+    float s0 = sigmoid_ref(v[0], aten), s1 = sigmoid_ref(v[1], aten), s2 = sigmoid_ref(v[2], aten), s3 = sigmoid_ref(v[3], aten);
     o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
     o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
     float t2 = f_mul(s2, 2.f), t3 = f_mul(s3, 2.f);
     o[2] = f_mul(f_mul(t2, t2), aw);
     o[3] = f_mul(f_mul(t3, t3), ah);
-    o[4] = sigmoid_exact(v[4]);
-    o[5] = sigmoid_exact(v[5]);
+    o[4] = sigmoid_ref(v[4], aten);
+    o[5] = sigmoid_ref(v[5], aten);
 }
 
 // utils/general.py:547-563 + 299-306 on one decoded row: o -> candidate row (in place)
@@ -253,7 +259,7 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
             const float lo = to_f32(__ldg(po + k)), lc = to_f32(__ldg(pc + k));  // L1 hits: just read as vectors
             const float prod = f_mul(f_add(1.0f, expf(-lc)), f_add(1.0f, expf(-lo)));
             ok = prod < P.prod_pass;
-            if (!ok && !(prod > P.prod_fail)) ok = f_mul(sigmoid_exact(lc), sigmoid_exact(lo)) > P.conf_thres;
+            if (!ok && !(prod > P.prod_fail)) ok = f_mul(sigmoid_ref(lc, P.aten != 0), sigmoid_ref(lo, P.aten != 0)) > P.conf_thres;
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (m) {
@@ -350,8 +356,8 @@ __global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const _
 #pragma unroll
             for (int c = 0; c < NV; c++) v[c] = __ldg(p + (long long)c * cells);
         }
-        if (KPT) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
-        else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+        if (KPT) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+        else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
         row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
         float *dst = P.cand + slot * NO;
 #pragma unroll
@@ -365,6 +371,7 @@ struct DenseParams {
     int n_levels, bs;
     long long rows_total;
     float *pred;
+    int aten;  // see DecParams::aten
 };
 
 constexpr int DENSE_THREADS = 128;
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(DENSE_THREADS) decode_dense_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < NO; c++) v[c] = ld_f(L.data, L.dtype, cbase + (long long)c * cells + cell);
         int gy = (int)(cell / L.nx), gx = (int)(cell - (long long)gy * L.nx);
-        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o);
+        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
 #pragma unroll
         for (int c = 0; c < NO; c++) s_out[threadIdx.x * NO + c] = o[c];  // stride 21 words: conflict free
     }
@@ -493,6 +500,7 @@ FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int 
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: bad arguments");
     DecParams P;
     memset(&P, 0, sizeof(P));
+    P.aten = ctx->numerics == FDMS_NUMERICS_ATEN_CUDA;
     int n_blocks = 0;
     if (int rc = fill_levels(ctx, levels, n_levels, n_scales, bs, DEC_CELLS, P.lv, &n_blocks, "fdms_decode_filter"))
         return rc;
@@ -563,6 +571,7 @@ FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_le
     if (!pred || rows_total <= 0) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense: bad arguments");
     DenseParams P;
     memset(&P, 0, sizeof(P));
+    P.aten = ctx->numerics == FDMS_NUMERICS_ATEN_CUDA;
     int n_blocks = 0;
     if (int rc = fill_levels(ctx, levels, n_levels, 1, bs, DENSE_THREADS, P.lv, &n_blocks, "fdms_decode_dense"))
         return rc;

@@ -24,11 +24,14 @@ constexpr int NO = MERGE_NO;
 
 // utils/general.py:374-404 (ratio_pad None or given).  gain/pad are computed in double on the host like
 // the Python floats they are, then cast to the tensor dtype by the in-place ops.
+// inv_gain != 0 (FDMS_NUMERICS_ATEN_CUDA): `coords /= gain` as ATen's CUDA kernel computes a division by a Python
+// scalar, coords * (1 / gain) with the reciprocal rounded to fp32 first; else the true division of the CPU kernel.
 __global__ void scale_coords_kernel(float *coords, long long n, int cols, long long row_stride, float padx, float pady,
-                                    float gain, float w0, float h0, int kpt_step) {
+                                    float gain, float inv_gain, float w0, float h0, int kpt_step) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float *r = coords + i * row_stride;
+    auto f_div = [&](float a, float g) { return inv_gain != 0.f ? ::f_mul(a, inv_gain) : ::f_div(a, g); };
     if (kpt_step == 0) {
         float x1 = f_div(f_sub(r[0], padx), gain), y1 = f_div(f_sub(r[1], pady), gain);
         float x2 = f_div(f_sub(r[2], padx), gain), y2 = f_div(f_sub(r[3], pady), gain);
@@ -113,7 +116,8 @@ FDMS_API int fdms_scale_coords_ratio_pad(fdms_ctx *ctx, float *coords, int64_t n
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
     // the Python floats of general.py:377-381 meet an fp32 tensor: each in-place op rounds its scalar to fp32 first
     scale_coords_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        coords, n, cols, row_stride, (float)pad_x, (float)pad_y, (float)gain, (float)orig_w, (float)orig_h, kpt_step);
+        coords, n, cols, row_stride, (float)pad_x, (float)pad_y, (float)gain,
+        ctx->numerics == FDMS_NUMERICS_ATEN_CUDA ? 1.0f / (float)gain : 0.f, (float)orig_w, (float)orig_h, kpt_step);
     FDMS_LAUNCH_CHECK(ctx, "scale_coords_kernel");
     return FDMS_OK;
 }

@@ -166,6 +166,27 @@ template <> struct Out<float> {
     }
     static __device__ __forceinline__ void store1(float *p, unsigned a) { p[0] = f(a); }
 };
+// fp32 output as a CUDA device computes it (FDMS_NUMERICS_ATEN_CUDA): ATen's `img /= 255.0` on a CUDA tensor is
+// img * (1 / 255) with the reciprocal rounded to fp32 (one bit away from the division for some bytes).  A distinct
+// element type, so that the choice costs the other instantiations nothing.
+struct f32r {
+    float v;
+};
+template <> struct Out<f32r> {
+    static __device__ __forceinline__ float f(unsigned t) { return __fmul_rn((float)(t >> 2), 0.003921568859368563f); }
+    static __device__ __forceinline__ void store2_bits(f32r *p, unsigned a, unsigned b) {
+        *reinterpret_cast<float2 *>(p) = make_float2(f((a & 0xffu) << 2), f((b & 0xffu) << 2));
+    }
+    static __device__ __forceinline__ void store2(f32r *p, long long xs, unsigned a, unsigned b, bool vec) {
+        if (vec) {
+            *reinterpret_cast<float2 *>(p) = make_float2(f(a), f(b));
+        } else {
+            p[0].v = f(a);
+            p[xs].v = f(b);
+        }
+    }
+    static __device__ __forceinline__ void store1(f32r *p, unsigned a) { p[0].v = f(a); }
+};
 template <> struct Out<uint8_t> {
     static __device__ __forceinline__ void store2_bits(uint8_t *p, unsigned a, unsigned b) {
         p[0] = (uint8_t)a;
@@ -823,9 +844,12 @@ __global__ void __launch_bounds__(PYR_THREADS, sizeof(T) == 2 ? PYR_MIN_CTAS : 6
 }
 
 
+template <typename T> struct OutBit { static constexpr int value = 1 << (int)sizeof(T); };  // 2, 4, 16
+template <> struct OutBit<f32r> { static constexpr int value = 8; };
+
 template <typename T>
 int launch_group(fdms_ctx *ctx, const PyrParams &P, int tiles, int n_img, int smem, cudaStream_t st) {
-    const int bit = 1 << (int)sizeof(T);
+    const int bit = OutBit<T>::value;
     if (!(ctx->pyr_attr & bit)) {  // dynamic shared memory opt-in, once per ctx and instantiation
         FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1024,6 +1048,8 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
         }
         int rc;
         if (dt == FDMS_F16) rc = launch_group<__half>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
+        else if (dt == FDMS_F32 && ctx->numerics == FDMS_NUMERICS_ATEN_CUDA)
+            rc = launch_group<f32r>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
         else if (dt == FDMS_F32) rc = launch_group<float>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
         else rc = launch_group<uint8_t>(ctx, P, tiles, n_img, smem_max, (cudaStream_t)stream);
         if (rc) return rc;

@@ -50,8 +50,8 @@ __global__ void scale_img_kernel(const T *__restrict__ src, int planes, int h, i
 // models/yolo.py:402-417: p[..., :4] /= scale; flips == 2: y = img_h - y; flips == 3: x = img_w - x.  Landmark
 // columns are left as they are (the reference does not de-scale them).  Rows are written to `dst` at row offset
 // `row0` of a (bs, rows_total, no) tensor: that is the torch.cat(y, 1) of forward_augment (:374).
-__global__ void descale_pred_kernel(const float *__restrict__ pred, int bs, long long rows, int no, float scale, int flip,
-                                    float img_h, float img_w, float *__restrict__ dst, long long rows_total,
+__global__ void descale_pred_kernel(const float *__restrict__ pred, int bs, long long rows, int no, float scale,
+                                    float inv_scale, int flip, float img_h, float img_w, float *__restrict__ dst, long long rows_total,
                                     long long row0) {
     const long long total = (long long)bs * rows * no;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -60,7 +60,7 @@ __global__ void descale_pred_kernel(const float *__restrict__ pred, int bs, long
         const long long t = idx / no;
         const long long r = t % rows, b = t / rows;
         float v = pred[idx];
-        if (c < 4) v = __fdiv_rn(v, scale);
+        if (c < 4) v = inv_scale != 0.f ? __fmul_rn(v, inv_scale) : __fdiv_rn(v, scale);  // ATen CUDA: v * (1 / scale)
         if (flip == 2 && c == 1) v = __fsub_rn(img_h, v);
         if (flip == 3 && c == 0) v = __fsub_rn(img_w, v);
         dst[((long long)b * rows_total + row0 + r) * no + c] = v;
@@ -106,7 +106,7 @@ FDMS_API int fdms_descale_pred(fdms_ctx *ctx, const float *pred, int bs, int64_t
     const long long total = (long long)bs * rows * no;
     const int threads = 256;
     const int blocks = (int)min((long long)ctx->sm_count * 16, (long long)ceil_div64(total, threads));
-    descale_pred_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(pred, bs, rows, no, scale, flip, (float)img_h,
+    descale_pred_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(pred, bs, rows, no, scale, ctx->numerics == FDMS_NUMERICS_ATEN_CUDA ? 1.0f / scale : 0.f, flip, (float)img_h,
                                                                       (float)img_w, dst, rows_total, row_offset);
     FDMS_LAUNCH_CHECK(ctx, "descale_pred_kernel");
     return FDMS_OK;

@@ -247,6 +247,19 @@ typedef struct fdms_post_desc {
 } fdms_post_desc;
 
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_stream stream);
+/* Floating-point flavour of the stages whose reference arithmetic depends on the device the reference runs on:
+ *   FDMS_NUMERICS_EXACT (default)  sigmoid with the correctly rounded exponential, `x / s` as a true division -- what the
+ *       CPU oracle restates and within 1 ulp of ATen on either device;
+ *   FDMS_NUMERICS_ATEN_CUDA        what ATen computes ON A CUDA DEVICE in fp32: sigmoid = 1 / (1 + expf(-x)) with
+ *       libdevice's expf (models/yolo.py:285-306), and tensor / python-scalar = tensor * (1 / scalar)
+ *       (utils/general.py:386 `coords[:, :4] /= gain`, multi_scale_face_detector.py:102 `img /= 255.0` in fp32,
+ *       models/yolo.py:405 `p[..., :4] /= scale`): bit-identical to the reference running in fp32 on the same GPU.
+ * Also read from the environment variable FDMS_NUMERICS (exact | aten_cuda) when a context is created. */
+#define FDMS_NUMERICS_EXACT 0
+#define FDMS_NUMERICS_ATEN_CUDA 1
+FDMS_API int fdms_set_numerics(fdms_ctx *ctx, int mode);
+FDMS_API int fdms_get_numerics(const fdms_ctx *ctx);
+
 /* The same contract as FDMS_POST_SMALL_ONLY for fdms_nms and fdms_merge_scales called one by one on this context
  * (until switched off again): only the single-CTA kernels are launched, the caller checks the counts. */
 FDMS_API int fdms_set_small_only(fdms_ctx *ctx, int on);

@@ -9,21 +9,19 @@ attempt_load) and the unmodified `detect.py` run exactly as a user runs them.  R
 (SURVEY F6), so the network's BatchNorm statistics are set from random batches (baseline/ref_runner.py:random_init_model):
 about 1.5 % of the rows then pass the reference's default conf_thres 0.5.
 
-  P  stage by stage on IDENTICAL inputs, fp32, which is what BASELINE.json's tolerances are stated on:
+  Everything below runs with FDMS_NUMERICS=aten_cuda (include/fdms.h): the sigmoid uses the expf ATen's CUDA kernel
+  calls and a division by a Python scalar is a multiplication by its fp32 reciprocal, as on a CUDA device.
+  P  stage by stage on IDENTICAL inputs, fp32:
      P1 head decode: the patched head (one kernel) vs the reference's IKeypoint.forward (ATen CUDA elementwise ops) on the
-        same conv outputs -> <= 1e-4 px absolute for every value below 1024 (one fp32 ulp is 1.2e-4 above), <= 1 ulp
-        above; the ulp histogram is reported (ATen's CUDA sigmoid uses libdevice expf, libfdms the correctly rounded
-        exponential)
+        same conv outputs -> bit-identical.  Also reported (not the default any more on a GPU, but what the CPU oracle
+        pins): the same comparison with FDMS_NUMERICS=exact -- the correctly rounded exponential against libdevice's
+        expf: <= 8 ulp, ulp histogram in the report
      P2 non_max_suppression on the reference's own decoded tensor -> bit-identical lists (candidate sets, keep order, rows)
      P3 scale_coords_api_approach(...).round() and scale_coords on identical rows -> bit-identical
   B  monkey patch (INTEGRATION route a), fp32: the reference's OWN class with letterbox / non_max_suppression /
-     scale_coords_api_approach rebound and the head decode patched, against its unpatched run, whole path
-  A  class swap (route b), fp32: face_detection_multi_scale_b200.MultiScaleFaceDetector against the reference's class
-     End to end the two runs are NOT on identical inputs past the first kernel (last-bit differences of the decode; in A
-     also ATen's CUDA `x / 255` = `x * (1/255)` against the fused pyramid's true division, which is what the reference's
-     CPU path and the goldens compute), and this random network emits thousands of near-threshold, near-tied boxes, so
-     a last-bit difference flips threshold / suppression decisions: the bar is equal shapes of the per-image result up to
-     1 % of the rows; the fraction of rows reproduced exactly is reported
+     scale_coords_api_approach rebound and the head decode patched, against its unpatched run -> the same (k, 7) arrays
+  A  class swap (route b), fp32: face_detection_multi_scale_b200.MultiScaleFaceDetector against the reference's class,
+     same checkpoint, same files, same GPU -> the same (k, 7) arrays
   C  the reference's default CUDA mode (half precision; its decode, filter and NMS run in fp16) against libfdms (fp32
      arithmetic on the same fp16 maps): detection counts within 3 %, agreement reported
   D  unmodified detect.py (half, --save-txt --save-conf): label files of the patched run vs the unpatched run, same bar
@@ -46,6 +44,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+os.environ["FDMS_NUMERICS"] = "aten_cuda"  # read when a native context is created (include/fdms.h)
 
 from baseline import refshim  # noqa: E402
 
@@ -133,7 +132,7 @@ def main():
         a, b = a.reshape(-1, 7), b.reshape(-1, 7)
         if a.shape != b.shape:
             return False
-        return bool(np.array_equal(a[:, [0, 1, 2, 3, 5, 6]], b[:, [0, 1, 2, 3, 5, 6]]) and np.max(np.abs(a[:, 4] - b[:, 4])) <= 2e-6)
+        return bool(np.array_equal(a, b))
 
     # ---- P: stage by stage on identical inputs, fp32
     import utils.general as ref_general
@@ -153,11 +152,20 @@ def main():
             a_, b_ = pred_ref.float().cpu().numpy(), pred_mine.float().cpu().numpy()
             d = np.abs(a_ - b_)
             ulp = np.abs(a_.view(np.int32).astype(np.int64) - b_.view(np.int32).astype(np.int64))
-            small = np.abs(a_) < 1024
-            hist += np.bincount(np.minimum(ulp, 7).ravel(), minlength=8)
-            worst_px, worst_ulp = max(worst_px, float(d[small].max())), max(worst_ulp, int(ulp[~small].max()) if (~small).any() else 0)
-            check(a_.shape == b_.shape and float(d[small].max()) <= 1e-4 and (not (~small).any() or int(ulp[~small].max()) <= 1),
-                  ("P1 decode", os.path.basename(f), size, float(d[small].max())))
+            check(a_.shape == b_.shape and int(ulp.max()) == 0, ("P1 decode bit-identical (aten_cuda)", os.path.basename(f), size, int(ulp.max())))
+            # the oracle's flavour (correctly rounded exp) against ATen's CUDA decode, for the record
+            from face_detection_multi_scale_b200 import _lib as _L
+            cx_ = _L.ctx(torch.cuda.current_device())
+            cx_.set_numerics("exact")
+            with torch.no_grad():
+                pe = model_p(x)[0].float().cpu().numpy()
+            cx_.set_numerics("aten_cuda")
+            ue = np.abs(a_.view(np.int32).astype(np.int64) - pe.view(np.int32).astype(np.int64))
+            de = np.abs(a_ - pe)
+            hist += np.bincount(np.minimum(ue, 7).ravel(), minlength=8)
+            worst_ulp = max(worst_ulp, int(ue.max()))
+            worst_px = max(worst_px, float(de[np.abs(a_) < 256].max()))
+            check(int(ue.max()) <= 8 and float(de[np.abs(a_) < 256].max()) <= 1e-4, ("P1 decode exact-mode vs ATen CUDA", os.path.basename(f), size, int(ue.max())))
             # P2: both non_max_suppression implementations on the reference's own tensor
             r_list = quiet(ref_general.non_max_suppression, pred_ref.clone(), conf, 0.5)
             m_list = G.non_max_suppression(pred_ref.clone(), conf, 0.5)
@@ -169,9 +177,12 @@ def main():
                 m_box = PP.scale_coords_api_approach(x.shape[2:], r_list[0][:, :4].clone(), shape0).round()
                 r_sc = ref_general.scale_coords(x.shape[2:], r_list[0][:, :4].clone(), shape0)
                 m_sc = G.scale_coords(x.shape[2:], r_list[0][:, :4].clone(), shape0)
-                check(torch.equal(r_box, m_box) and torch.equal(r_sc, m_sc), ("P3 rescale", os.path.basename(f), size))
-    REPORT["P1_decode"] = {"max_abs_diff_px_below_1024": worst_px, "max_ulp_above_1024": worst_ulp,
-                           "ulp_histogram_0..7+": [int(v) for v in hist], "identical_fraction": round(float(hist[0] / hist.sum()), 5)}
+                check(torch.equal(r_box, m_box), ("P3 scale_coords_api_approach", os.path.basename(f), size))
+                check(torch.equal(r_sc, m_sc), ("P3 scale_coords", os.path.basename(f), size, float((r_sc - m_sc).abs().max())))
+    REPORT["P1_decode"] = {"aten_cuda_mode": "bit-identical to the reference's CUDA fp32 decode",
+                           "exact_mode_vs_aten_cuda": {"max_ulp": worst_ulp, "max_abs_diff_px_for_values_below_256": worst_px,
+                                                       "ulp_histogram_0..7+": [int(v) for v in hist],
+                                                       "identical_fraction": round(float(hist[0] / hist.sum()), 5)}}
     del model_p
 
     # ---- A: class swap, fp32 (near-exact, see the module docstring)
@@ -188,7 +199,7 @@ def main():
         near = min(match_boxes(r, m, 0.95), match_boxes(m, r, 0.95))
         a_rep.append({"file": os.path.basename(f), "reference": len(r), "libfdms": len(m), "rows_reproduced_exactly": round(exact, 4),
                       "matched_iou>=0.95": round(near, 4), "bit_identical": bool(rows_equal(m, r, f))})
-        check(tuple(shape_r) == tuple(shape_m) and abs(len(r) - len(m)) <= max(3, 0.01 * len(r)), ("A class swap fp32", a_rep[-1]))
+        check(tuple(shape_r) == tuple(shape_m) and bool(rows_equal(m, r, f)), ("A class swap fp32", a_rep[-1]))
     REPORT["A_class_swap_fp32"] = a_rep
 
     # ---- B: monkey patch of the reference's own class, fp32
@@ -205,7 +216,7 @@ def main():
             ms_ = set(map(tuple, np.round(r[:, [0, 1, 2, 3, 5, 6]]).astype(np.int64).tolist()))
             b_rep.append({"file": os.path.basename(f), "unpatched": len(ref_out[f]), "patched": len(r),
                           "rows_reproduced_exactly": round(len(rs & ms_) / max(1, len(rs)), 4), "bit_identical": bool(rows_equal(r, ref_out[f], f))})
-            check(abs(len(r) - len(ref_out[f])) <= max(3, 0.01 * len(ref_out[f])), ("B monkey patch fp32", b_rep[-1]))
+            check(bool(rows_equal(r, ref_out[f], f)), ("B monkey patch fp32", b_rep[-1]))
     finally:
         fi.unpatch()
     REPORT["B_monkey_patch_fp32"], REPORT["B_rebound_names"] = b_rep, n_bound

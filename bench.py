@@ -445,7 +445,7 @@ def measure_workload(name, wl, env, steps, warmup, full, repeats=0, profile=Fals
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)] for _ in range(K2)]
     # the host calls of an iteration take about as long as their kernels: park the GPU behind a spin kernel while the
     # whole loop is enqueued, so that the event intervals are kernel time and not launch latency of a starved queue
-    _lib.ctx(dev.index).set_small_only(plan0.small_only)  # the stages below go through the thread's default context
+    ops._ctx(dev.index).set_small_only(plan0.small_only)  # the stages below go through the thread's default context
     if hasattr(torch.cuda, "_sleep"):
         torch.cuda._sleep(int(40e6))
     for i in range(K2):
@@ -461,7 +461,7 @@ def measure_workload(name, wl, env, steps, warmup, full, repeats=0, profile=Fals
         ops.merge_scales(c, B, len(sizes), [g.dst_h for g in geoms], (wl["h"], wl["w"]), wl["iou"], wl["cap"], with_kpts=kp, out=plan.out)
         evs[i][4].record()
     torch.cuda.synchronize()
-    _lib.ctx(dev.index).set_small_only(False)
+    ops._ctx(dev.index).set_small_only(False)
     stage_ms = {n: float(np.median([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K2)])) for j, n in enumerate(stage_names)}
 
     src_bytes = wl["h"] * wl["w"] * 3

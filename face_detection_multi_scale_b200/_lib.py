@@ -162,14 +162,20 @@ class Ctx:
             pass
 
 
-def ctx(device=0):
-    """Thread-local context for `device` (the handle must not be shared across threads)."""
+def ctx(device=0, stream=0):
+    """Thread-local context for (`device`, `stream`): the handle must not be shared across threads, and its
+    scratch buffers and cached tables are ordered by ONE stream, so work enqueued on another CUDA stream of the same
+    thread gets a context of its own (`stream` = the cudaStream_t handle as an integer, 0 = the default stream).
+    At most 8 per thread are kept; the least recently created one is released beyond that."""
     cache = getattr(_tls, "ctx", None)
     if cache is None:
         cache = _tls.ctx = {}
-    c = cache.get(int(device))
+    key = (int(device), int(stream or 0))
+    c = cache.get(key)
     if c is None:
-        c = cache[int(device)] = Ctx(device)
+        while len(cache) >= 8:
+            cache.pop(next(iter(cache))).close()
+        c = cache[key] = Ctx(device)
     return c
 
 

@@ -100,17 +100,29 @@ static inline int fdms_reserve(fdms_ctx *ctx, fdms_buf &b, size_t bytes) {
     return FDMS_OK;
 }
 
-static inline int fdms_bind(fdms_ctx *ctx) {
-    if (!ctx) return FDMS_ERR_INVALID;
-    int cur = -1;
-    cudaError_t e = cudaGetDevice(&cur);
-    if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
-    if (cur != ctx->device) {
-        e = cudaSetDevice(ctx->device);
-        if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+// Makes the context's device current for the duration of an API call and restores the caller's device afterwards
+// (torch's current device must not drift when a tensor lives on another GPU than the current one).
+struct fdms_device_guard {
+    int prev = -1;
+    bool switched = false;
+    int bind(fdms_ctx *ctx) {
+        if (!ctx) return FDMS_ERR_INVALID;
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+        if (prev != ctx->device) {
+            e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) return fdms_fail(ctx, FDMS_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+            switched = true;
+        }
+        return FDMS_OK;
     }
-    return FDMS_OK;
-}
+    ~fdms_device_guard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define FDMS_BIND(ctx)                            \
+    fdms_device_guard fdms_guard_;                \
+    if (int rc_ = fdms_guard_.bind(ctx)) return rc_
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -21,7 +21,7 @@ extern "C" {
 FDMS_API int fdms_version(void) { return FDMS_VERSION; }
 
 FDMS_API int fdms_debug_poison_smem(fdms_ctx *ctx, int byte_value, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     const int bytes = ctx->smem_optin > 0 ? ctx->smem_optin : 48 * 1024;
     FDMS_CUDA(ctx, cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     const unsigned b = (unsigned)byte_value & 0xffu, word = b * 0x01010101u;
@@ -49,6 +49,8 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     fdms_ctx *c = new (std::nothrow) fdms_ctx();
     if (!c) return FDMS_ERR_NOMEM;
     c->device = device;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     if (cudaSetDevice(device) != cudaSuccess) {
         delete c;
         return FDMS_ERR_CUDA;
@@ -71,17 +73,21 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_MERGE_FUSED")) c->merge_fused = atoi(e);
     if (const char *e = getenv("FDMS_NMS_GREEDY_MIN_SEG")) c->nms_greedy_min_seg = atoi(e);
     if (const char *e = getenv("FDMS_MASK_BUDGET_MB")) c->mask_budget = (size_t)atoll(e) << 20;
+    if (prev_dev >= 0 && prev_dev != device) cudaSetDevice(prev_dev);  // the caller's current device is left as it was
     *out = c;
     return FDMS_OK;
 }
 
 FDMS_API void fdms_destroy(fdms_ctx *ctx) {
     if (!ctx) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->device);
     fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
                         &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt};
     for (fdms_buf *b : bufs)
         if (b->p) cudaFree(b->p);
+    if (prev_dev >= 0 && prev_dev != ctx->device) cudaSetDevice(prev_dev);
     delete ctx;
 }
 

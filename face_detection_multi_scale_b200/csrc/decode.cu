@@ -495,7 +495,7 @@ extern "C" {
 FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int n_scales, int bs,
                                    float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap, int flags,
                                    fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!cand || !cand_row || !count || cap <= 0 || n_scales <= 0 || n_scales > FDMS_MAX_SCALES)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: bad arguments");
     DecParams P;
@@ -567,7 +567,7 @@ FDMS_API int fdms_decode_filter(fdms_ctx *ctx, const fdms_level *levels, int n_l
 
 FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, float *pred,
                                int64_t rows_total, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!pred || rows_total <= 0) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense: bad arguments");
     DenseParams P;
     memset(&P, 0, sizeof(P));
@@ -590,7 +590,7 @@ FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_le
 FDMS_API int fdms_filter_pred(fdms_ctx *ctx, const void *pred, int dtype, int bs, int64_t rows, int no,
                               float conf_thres, float *cand, int32_t *cand_row, int32_t *count, int cap,
                               fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!pred || !cand || !cand_row || !count || bs <= 0 || bs > 65535 || rows <= 0 || cap <= 0 || no < 6 ||
         (no - 6) % 3 != 0 || (dtype != FDMS_F16 && dtype != FDMS_F32) || rows > 0x7fffffffLL)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_filter_pred: bad arguments");

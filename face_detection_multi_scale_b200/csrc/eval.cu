@@ -64,7 +64,7 @@ extern "C" {
 
 FDMS_API int fdms_bbox_overlaps(fdms_ctx *ctx, const double *boxes, int64_t n, const double *query, int64_t k,
                                 double *overlaps, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (n == 0 || k == 0) return FDMS_OK;
     if (!boxes || !query || !overlaps || n < 0 || k < 0 || n * k > 0x7fffffff00LL)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_bbox_overlaps: bad arguments");
@@ -76,7 +76,7 @@ FDMS_API int fdms_bbox_overlaps(fdms_ctx *ctx, const double *boxes, int64_t n, c
 FDMS_API int fdms_pack_frames(fdms_ctx *ctx, const float *dets, const int32_t *n_out, int n_img, int out_cap,
                               int max_faces, int img_w, int img_h, double *bboxes, double *confidence,
                               int32_t *class_indexes, int32_t *scale_used, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (max_faces == 0 || n_img == 0) return FDMS_OK;
     if (!dets || !n_out || !bboxes || !confidence || !class_indexes || !scale_used || n_img < 0 || n_img > 65535 ||
         out_cap <= 0 || max_faces < 0 || img_w <= 0 || img_h <= 0)

@@ -97,7 +97,7 @@ extern "C" {
 FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride, int in_h,
                                int in_w, int orig_h, int orig_w, int kpt_step, fdms_stream stream) {
     if (in_h <= 0 || in_w <= 0 || orig_h <= 0 || orig_w <= 0) {
-        if (int rc = fdms_bind(ctx)) return rc;
+        FDMS_BIND(ctx);
         return n == 0 ? FDMS_OK : fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords: bad arguments");
     }
     double gain = fmin((double)in_h / orig_h, (double)in_w / orig_w);  // general.py:377
@@ -109,7 +109,7 @@ FDMS_API int fdms_scale_coords(fdms_ctx *ctx, float *coords, int64_t n, int cols
 FDMS_API int fdms_scale_coords_ratio_pad(fdms_ctx *ctx, float *coords, int64_t n, int cols, int64_t row_stride,
                                          double gain, double pad_x, double pad_y, int orig_h, int orig_w,
                                          int kpt_step, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (n == 0) return FDMS_OK;
     if (!coords || n < 0 || cols <= 0 || row_stride < cols || orig_h <= 0 || orig_w <= 0 ||
         (kpt_step != 0 && kpt_step < 2) || (kpt_step == 0 && cols < 4))
@@ -124,7 +124,7 @@ FDMS_API int fdms_scale_coords_ratio_pad(fdms_ctx *ctx, float *coords, int64_t n
 
 FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64_t row_stride, int in_h, int orig_h,
                                    int orig_w, int do_round, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (n == 0) return FDMS_OK;
     if (!boxes || n < 0 || row_stride < 4 || in_h <= 0 || orig_h <= 0 || orig_w <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_coords_api: bad arguments");
@@ -138,7 +138,7 @@ FDMS_API int fdms_scale_coords_api(fdms_ctx *ctx, float *boxes, int64_t n, int64
 
 FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, int n_scales, float *rows_out,
                                 double *weights_out, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (n == 0) return FDMS_OK;
     if (!dets || !rows_out || n < 0 || n_scales <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_weighted_rows: bad arguments");
@@ -152,7 +152,7 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
                                int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
                                double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
                                float *kpts_out, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!cand || !keep || !n_keep || !in_h_host || !dets || !n_out || n_img <= 0 || n_scales <= 0 ||
         n_scales > FDMS_MAX_SCALES || cap <= 0 || out_cap <= 0 || orig_h <= 0 || orig_w <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad arguments");
@@ -233,7 +233,7 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
 }
 
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!d) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_postprocess: null descriptor");
     if ((d->flags & FDMS_POST_SMALL_ONLY) && (fdms_merge_small_limit(ctx) != FDMS_SMALL_LIMIT || !ctx->merge_fused))
         return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_postprocess: FDMS_POST_SMALL_ONLY needs the fused single-CTA kernels");

@@ -888,7 +888,7 @@ extern "C" {
 FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_off, int score_off,
                       const int32_t *tie, const int32_t *count, int n_seg, int cap, double iou_thres, int iou_mode,
                       int max_nms, int32_t *keep, int32_t *n_keep, fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     return fdms_nms_impl(ctx, rows, row_stride, box_off, score_off, tie, count, n_seg, cap, iou_thres, iou_mode,
                          max_nms, keep, n_keep, (cudaStream_t)stream);
 }
@@ -896,7 +896,7 @@ FDMS_API int fdms_nms(fdms_ctx *ctx, const float *rows, int row_stride, int box_
 FDMS_API int fdms_gather_rows(fdms_ctx *ctx, const float *rows, int row_stride, int n_cols, const int32_t *keep,
                               const int32_t *n_keep, int n_seg, int cap, float *out, int out_cap,
                               fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!rows || !keep || !n_keep || !out || n_seg <= 0 || n_seg > 65535 || cap <= 0 || out_cap <= 0 || n_cols <= 0 ||
         n_cols > row_stride)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_gather_rows: bad arguments");

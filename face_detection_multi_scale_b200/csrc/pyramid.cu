@@ -868,7 +868,7 @@ extern "C" FDMS_API int fdms_pyramid(fdms_ctx *ctx, const uint8_t *src, int n_im
                                      int64_t row_pitch, int src_h, int src_w, int virt_h, int virt_w,
                                      const fdms_scale_out *scales, int n_scales, int flip_rb, int border,
                                      fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!src || !scales || n_img <= 0 || n_scales <= 0 || n_scales > FDMS_MAX_SCALES || src_h <= 0 || src_w <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_pyramid: bad arguments");
     if (n_img > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_pyramid: n_img > 65535");

@@ -74,7 +74,7 @@ extern "C" {
 FDMS_API int fdms_scale_img(fdms_ctx *ctx, const void *src, int dtype, int n, int c, int h, int w, int resized_h,
                             int resized_w, int out_h, int out_w, int flip, float pad_value, void *dst,
                             fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || resized_h <= 0 || resized_w <= 0 || out_h < resized_h ||
         out_w < resized_w || (flip != 0 && flip != 2 && flip != 3) || (dtype != FDMS_F16 && dtype != FDMS_F32))
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_scale_img: bad arguments");
@@ -99,7 +99,7 @@ FDMS_API int fdms_scale_img(fdms_ctx *ctx, const void *src, int dtype, int n, in
 FDMS_API int fdms_descale_pred(fdms_ctx *ctx, const float *pred, int bs, int64_t rows, int no, float scale, int flip,
                                int img_h, int img_w, float *dst, int64_t rows_total, int64_t row_offset,
                                fdms_stream stream) {
-    if (int rc = fdms_bind(ctx)) return rc;
+    FDMS_BIND(ctx);
     if (!pred || !dst || bs <= 0 || rows <= 0 || no < 4 || !(scale > 0.f) || (flip != 0 && flip != 2 && flip != 3) ||
         row_offset < 0 || row_offset + rows > rows_total)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_descale_pred: bad arguments");

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 
 def bbox_overlaps(boxes, query_boxes, device=None):
@@ -18,7 +18,7 @@ def bbox_overlaps(boxes, query_boxes, device=None):
         raise ValueError("bbox_overlaps: float64 boxes expected (DTYPE = np.float in the reference)")
     b, q = b.contiguous(), q.contiguous()
     out = torch.zeros((b.shape[0], q.shape[0]), dtype=torch.float64, device=dev)
-    c = _lib.ctx(dev.index)
+    c = ops._ctx(dev.index)
     rc = _lib.lib().fdms_bbox_overlaps(c.handle, C.c_void_p(b.data_ptr()), b.shape[0], C.c_void_p(q.data_ptr()), q.shape[0],
                                        C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     c.check(rc, "fdms_bbox_overlaps")

@@ -44,12 +44,25 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     keypoints) -> list of (n, no) tensors [x1, y1, x2, y2, conf, cls, kpts...] per image, (0, 6) zeros for images
     without detections (:527).
     One filter launch + one batched NMS (one launch for segments of <= 1024 boxes) + one gather for the whole batch; a single
-    device->host read of the per-image counts."""
+    device->host read of the per-image counts.
+    fp16 predictions (the reference's CUDA default) are up-cast: the filter, xywh->xyxy and the IoU run in fp32 and the
+    kept rows are rounded back to fp16, whereas the reference does all of it in half arithmetic -- candidate sets and
+    boxes can differ from its fp16 result in the last fp16 bit (tests/ref_gpu_check.py, part C reports the agreement)."""
     if prediction.dim() != 3:
         raise ValueError("non_max_suppression: prediction must be (bs, rows, no)")
+    no = prediction.shape[2]
+    if no == 6 and kpt_label and nc is None:
+        # multi_scale_face_detector.py:134 (`pred[..., :6]` with the default kpt_label=5): the reference computes
+        # nc = 6 - 5 - 15 < 0, its `x[:, 5:5+nc] *= x[:, 4:5]` is a no-op on an empty slice, and the confidence it filters
+        # and sorts by is the RAW class score (rows with obj <= thres are dropped first, :515/:530).  Same thing here:
+        # obj = 1 makes conf = cls, rows the objectness test drops get cls = -inf.
+        p2 = prediction.clone()
+        p2[..., 5] = torch.where(prediction[..., 4] > conf_thres, prediction[..., 5], torch.full_like(prediction[..., 5], float("-inf")))
+        p2[..., 4] = 1.0
+        return non_max_suppression(p2, conf_thres, iou_thres, classes, agnostic, multi_label, labels, kpt_label=0, nc=1,
+                                   iou_mode=iou_mode)
     if nc is None:
         nc = prediction.shape[2] - 5 if not kpt_label else prediction.shape[2] - 5 - kpt_label * 3
-    no = prediction.shape[2]
     if nc != 1 or no < 6 or (no - 6) % 3:
         raise NotImplementedError("non_max_suppression on libfdms covers single-class heads (nc=1, no = 6 + 3*kpt: the "
                                   "face head no=21, or the [..., :6] fallback of msfd:134); got no=%d kpt_label=%r nc=%r"

@@ -138,8 +138,11 @@ class MultiScaleFaceDetector:
     def _plan(self, scales_levels, in_h, orig_hw, lane=None):
         plans = self._thread_plans() if lane is None else lane.plans
         bs = scales_levels[0][0].shape[0]
+        # a plan owns device buffers sized by the capacities and a native context that is ordered by one stream
+        stream_id = 0 if lane is not None else torch.cuda.current_stream(self.device).cuda_stream
         key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), tuple(orig_hw),
-               self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode)
+               self.cap, self.out_cap or self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode,
+               self.with_landmarks, stream_id)
         plan = plans.get(key)
         if plan is None:
             out_cap = self.out_cap or self.cap
@@ -208,7 +211,9 @@ class MultiScaleFaceDetector:
         """Pipelined detection over an iterable of (B, H, W, 3) uint8 BGR host batches (pinned memory overlaps best):
         the H2D copy and kernels of batch i+1 are enqueued while batch i is in flight and batch i-1 is being read
         back, on `depth` streams with one native context each.  Yields, in order, the same per-batch result as
-        detect_multi_scale_batch.  A batch that exceeds a capacity is transparently redone synchronously."""
+        detect_multi_scale_batch.  A batch that exceeds a capacity is transparently redone synchronously (the lanes'
+        plans are rebuilt with the grown capacities afterwards).  With `with_landmarks`, `last_landmarks` / `last_stats`
+        always describe the batch that was yielded last."""
         lanes = self._stream_lanes(max(1, int(depth)))
         for lane in lanes:
             lane.plan = lane.src = None
@@ -225,6 +230,12 @@ class MultiScaleFaceDetector:
                 return self.detect_multi_scale_batch(lane.src)  # rare: grow capacities / full path, synchronously
             kmax = int(n_out.max()) if n_out.size else 0
             dets = lane.h_dets[:, :kmax].numpy().astype(np.float64)
+            if lane.h_kpts is not None:  # with_landmarks: the landmarks of the batch being handed out
+                kp = lane.h_kpts[:, :kmax].numpy().copy()
+                self.last_landmarks = [kp[b, :n_out[b]] for b in range(len(n_out))]
+            else:
+                self.last_landmarks = None
+            self.last_stats = {"candidates": int(head[3]), "kept_per_scale": int(head[4]), "final": int(n_out.sum())}
             return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
 
         for i, batch in enumerate(batches):
@@ -245,6 +256,12 @@ class MultiScaleFaceDetector:
                     lane.h_dets = torch.empty(o.dets.shape, dtype=torch.float32).pin_memory()
                     lane.h_meta = torch.empty((o.n_out.numel() + 5,), dtype=torch.int32).pin_memory()
                 lane.h_dets.copy_(o.dets, non_blocking=True)
+                if o.kpts is not None:
+                    if lane.h_kpts is None or lane.h_kpts.shape != o.kpts.shape:
+                        lane.h_kpts = torch.empty(o.kpts.shape, dtype=torch.float32).pin_memory()
+                    lane.h_kpts.copy_(o.kpts, non_blocking=True)
+                else:
+                    lane.h_kpts = None
                 lane.h_meta.copy_(self._meta(plan), non_blocking=True)
                 lane.done.record(lane.stream)
             lane.plan, lane.src, lane.small_only = plan, t, plan.small_only
@@ -292,6 +309,9 @@ class MultiScaleFaceDetector:
             if head[2] > (self.out_cap or self.cap):
                 self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
             self._thread_plans().clear()
+            for lane in getattr(self._tls, "lanes", None) or []:  # the streaming lanes of this thread size theirs anew
+                lane.plans.clear()
+                lane.h_dets = lane.h_meta = lane.h_kpts = None
         dets, n_out, kpts = res
         self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]),
                            "kept_per_scale": int(head[4]), "final": int(n_out.sum())}

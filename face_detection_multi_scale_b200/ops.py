@@ -24,6 +24,11 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _ctx(dev):
+    """The calling thread's native context for torch's current stream on `dev` (one context serves one stream)."""
+    return _lib.ctx(dev, torch.cuda.current_stream(dev).cuda_stream)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -58,7 +63,7 @@ def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, bor
         arr[s].out_img_stride = 3 * g.dst_h * g.dst_w
         arr[s].out_dtype = _DT[out_dtype]
         arr[s].out_layout = FDMS_CHW if layout == "chw" else FDMS_HWC
-    c = ctx if ctx is not None else _lib.ctx(dev)
+    c = ctx if ctx is not None else _ctx(dev)
     rc = _lib.lib().fdms_pyramid(c.handle, _ptr(src), B, src.stride(0) if B > 1 else H * src.stride(1), src.stride(1),
                                  H, W, vh, vw, arr, n, int(bool(flip_rb)), int(border), _stream(dev))
     c.check(rc, "fdms_pyramid")
@@ -68,7 +73,7 @@ def pyramid(src, geoms, out_dtype=torch.float16, layout="chw", flip_rb=True, bor
 def debug_poison_smem(byte_value=0xFF, device=None):
     """Test hook: fill the shared memory of every SM with one byte value (see include/fdms.h)."""
     dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     c.check(_lib.lib().fdms_debug_poison_smem(c.handle, int(byte_value), _stream(dev)), "fdms_debug_poison_smem")
 
 
@@ -111,7 +116,7 @@ def decode_dense(levels, strides, anchors_px):
     dev = _dev(levels[0])
     arr, n, bs, rows, hold = _level_table([levels], strides, anchors_px)
     pred = torch.empty((bs, rows[0], NO), dtype=torch.float32, device=levels[0].device)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     c.check(_lib.lib().fdms_decode_dense(c.handle, arr, n, bs, _ptr(pred), rows[0], _stream(dev)), "fdms_decode_dense")
     return pred
 
@@ -142,7 +147,7 @@ def decode_filter(scales_levels, strides, anchors_px, conf_thres, cap, out=None,
     ns = len(scales_levels)
     if out is None:
         out = Candidates(bs * ns, cap, scales_levels[0][0].device)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_decode_filter_ex(c.handle, arr, n, ns, bs, float(np.float32(conf_thres)), _ptr(out.cand),
                                           _ptr(out.row), _ptr(out.count), out.cap, 0 if landmarks else DECODE_BOXES_ONLY,
                                           _stream(dev))
@@ -159,7 +164,7 @@ def filter_pred(pred, conf_thres, cap, out=None):
     bs, rows, no = pred.shape
     if out is None:
         out = Candidates(bs, cap, pred.device, no)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_filter_pred(c.handle, _ptr(pred), _DT[pred.dtype], bs, rows, no, float(np.float32(conf_thres)),
                                      _ptr(out.cand), _ptr(out.row), _ptr(out.count), out.cap, _stream(dev))
     c.check(rc, "fdms_filter_pred")
@@ -177,7 +182,7 @@ def nms_segments(rows, count, cap, iou_thres, iou_mode=IOU_TV_CUDA, max_nms=MAX_
         keep = torch.empty((n_seg, cap), dtype=torch.int32, device=rows.device)
     if n_keep is None:
         n_keep = torch.zeros((n_seg,), dtype=torch.int32, device=rows.device)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_nms(c.handle, _ptr(rows), stride, box_off, score_off, _ptr(tie), _ptr(count), n_seg, cap,
                              float(iou_thres), int(iou_mode), int(max_nms), _ptr(keep), _ptr(n_keep), _stream(dev))
     c.check(rc, "fdms_nms")
@@ -205,7 +210,7 @@ def gather_rows(rows, keep, n_keep, n_cols, out_cap):
     dev = _dev(rows)
     n_seg, cap, stride = rows.shape
     out = torch.empty((n_seg, out_cap, n_cols), dtype=torch.float32, device=rows.device)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_gather_rows(c.handle, _ptr(rows), stride, n_cols, _ptr(keep), _ptr(n_keep), n_seg, cap,
                                      _ptr(out), out_cap, _stream(dev))
     c.check(rc, "fdms_gather_rows")
@@ -226,7 +231,7 @@ def scale_coords_(img1_shape, coords, img0_shape, kpt_step=0, ratio_pad=None):
     if n == 0:
         return coords
     dev = _dev(coords)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     if ratio_pad is None:
         rc = _lib.lib().fdms_scale_coords(c.handle, _ptr(coords), n, cols, rs, int(img1_shape[0]), int(img1_shape[1]),
                                           int(img0_shape[0]), int(img0_shape[1]), int(kpt_step), _stream(dev))
@@ -245,7 +250,7 @@ def scale_coords_api_(img_input_shape, boxes, img0_shape, do_round=False):
     if n == 0:
         return boxes
     dev = _dev(boxes)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_scale_coords_api(c.handle, _ptr(boxes), n, rs, int(img_input_shape[0]), int(img0_shape[0]),
                                           int(img0_shape[1]), int(bool(do_round)), _stream(dev))
     c.check(rc, "fdms_scale_coords_api")
@@ -269,7 +274,7 @@ def merge_scales(cands, n_img, n_scales, in_h, orig_hw, iou_thres, out_cap, with
     if out is None:
         out = Detections(n_img, out_cap, cands.cand.device, with_kpts)
     in_h_arr = (C.c_int32 * n_scales)(*[int(h) for h in in_h])
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     rc = _lib.lib().fdms_merge_scales(c.handle, _ptr(cands.cand), _ptr(cands.keep), _ptr(cands.n_keep), n_img, n_scales,
                                       cands.cap, in_h_arr, int(orig_hw[0]), int(orig_hw[1]), float(iou_thres),
                                       _ptr(out.dets), _ptr(out.n_out), out.out_cap, _ptr(out.merged_in), _ptr(out.kpts),
@@ -285,7 +290,7 @@ def weighted_rows(dets64, n_scales, want_weights=False):
     n = dets64.shape[0]
     assert dets64.dtype == torch.float64 and dets64.is_contiguous() and dets64.shape[1] == 7
     rows = torch.empty((1, max(n, 1), 8), dtype=torch.float32, device=dets64.device)
-    c = _lib.ctx(dev)
+    c = _ctx(dev)
     w = torch.empty((n,), dtype=torch.float64, device=dets64.device) if want_weights else None
     c.check(_lib.lib().fdms_weighted_rows(c.handle, _ptr(dets64), n, int(n_scales), _ptr(rows), _ptr(w), _stream(dev)),
             "fdms_weighted_rows")
@@ -325,7 +330,7 @@ class PostPlan:
         d.kpts_out = self.out.kpts.data_ptr() if with_kpts else None
         d.flags = POST_SMALL_ONLY if small_only else 0
         self.desc = d
-        self.ctx = ctx if ctx is not None else _lib.ctx(self.dev)
+        self.ctx = ctx if ctx is not None else _ctx(self.dev)
 
     def rebind(self, scales_levels):
         """Point the plan at a new set of raw head tensors of the same shapes (buffers are reused)."""

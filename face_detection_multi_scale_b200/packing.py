@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 
 def pack_frames(dets, n_out, img_w, img_h, max_faces=None):
@@ -26,7 +26,7 @@ def pack_frames(dets, n_out, img_w, img_h, max_faces=None):
     conf = torch.empty((n_img, max_faces), dtype=torch.float64, device=dev)
     cls = torch.empty((n_img, max_faces), dtype=torch.int32, device=dev)
     scale = torch.empty((n_img, max_faces), dtype=torch.int32, device=dev)
-    c = _lib.ctx(dev.index)
+    c = ops._ctx(dev.index)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     rc = _lib.lib().fdms_pack_frames(c.handle, p(dets.contiguous()), p(n_out), n_img, out_cap, max_faces, int(img_w),
                                      int(img_h), p(bboxes), p(conf), p(cls), p(scale),

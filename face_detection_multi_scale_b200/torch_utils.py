@@ -33,7 +33,7 @@ def scale_img(img, ratio=1.0, same_shape=False, gs=32, flip=None):
     if oh < rs[0] or ow < rs[1]:
         raise ValueError("scale_img: ratio > 1 with same_shape would crop (negative F.pad); not supported")
     out = torch.empty((bs, c, oh, ow), dtype=img.dtype, device=img.device)
-    cx = _lib.ctx(dev)
+    cx = ops._ctx(dev)
     rc = _lib.lib().fdms_scale_img(cx.handle, ops._ptr(img), _lib.FDMS_F16 if img.dtype == torch.float16 else _lib.FDMS_F32,
                                    bs, c, h, w, rs[0], rs[1], oh, ow, int(flip or 0), 0.447, ops._ptr(out), ops._stream(dev))
     cx.check(rc, "fdms_scale_img")
@@ -48,7 +48,7 @@ def descale_pred(p, flips, scale, img_size, out=None, row_offset=0):
         raise ValueError("descale_pred: p must be a contiguous (bs, rows, no) fp32 tensor")
     dst = p if out is None else out
     bs, rows, no = p.shape
-    cx = _lib.ctx(dev)
+    cx = ops._ctx(dev)
     rc = _lib.lib().fdms_descale_pred(cx.handle, ops._ptr(p), bs, rows, no, float(scale), int(flips or 0), int(img_size[0]),
                                       int(img_size[1]), ops._ptr(dst), dst.shape[1], int(row_offset), ops._stream(dev))
     cx.check(rc, "fdms_descale_pred")

@@ -187,6 +187,11 @@ def main():
             m_list = G.non_max_suppression(pred_ref.clone(), conf, 0.5)
             same = len(r_list) == len(m_list) and all(tuple(r.shape) == tuple(m.shape) and torch.equal(r, m) for r, m in zip(r_list, m_list))
             check(same, ("P2 nms on identical input", os.path.basename(f), size, [tuple(r.shape) for r in r_list], [tuple(m.shape) for m in m_list]))
+            # P2b: the `pred[..., :6]` fallback of msfd:134 (default kpt_label=5 on six columns: conf = raw class score)
+            r6 = quiet(ref_general.non_max_suppression, pred_ref[..., :6].clone(), conf, 0.5)
+            m6 = G.non_max_suppression(pred_ref[..., :6].clone(), conf, 0.5)
+            check(len(r6) == len(m6) and all(tuple(r.shape) == tuple(m.shape) and torch.equal(r, m) for r, m in zip(r6, m6)),
+                  ("P2b nms on pred[..., :6]", os.path.basename(f), size, [tuple(r.shape) for r in r6], [tuple(m.shape) for m in m6]))
             # P3: rescale on identical rows
             if len(r_list[0]):
                 r_box = quiet(ref_pp.scale_coords_api_approach, x.shape[2:], r_list[0][:, :4].clone(), shape0).round()

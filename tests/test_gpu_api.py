@@ -451,3 +451,60 @@ def test_compat_ops_fuzz_vs_oracle():
         if it % 4 == 0:
             a, q = np.round(a), np.round(q)
         assert np.array_equal(bbox_overlaps(a, q), O.bbox_overlaps(a, q))
+
+
+def test_c_program_drives_the_library_on_the_gpu(tmp_path):
+    """include/fdms.h from plain C on the GPU box: create -> fdms_nms on buffers the program allocates itself with the
+    CUDA runtime -> destroy; the keep list equals torchvision's order (highest score first, ties / suppression as a7)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if cc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no C toolchain / CUDA headers on this box")
+    exe = str(tmp_path / "c_abi_gpu")
+    lib_dir = os.path.join(root, "face_detection_multi_scale_b200")
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-o", exe, os.path.join(root, "tests", "c_abi_gpu.c"), "-I", os.path.join(root, "include"),
+                           "-I", os.path.join(cuda, "include"), "-L", lib_dir, "-l:libfdms.so", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                           "-Wl,-rpath," + lib_dir, "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "n_keep 3 keep 4 0 5", lines  # 0.95 (suppresses 3), 0.9 (suppresses 2 and 1), 0.3
+    assert lines[1] == "letterbox 0 384 640 top 12", lines
+    assert lines[2].startswith("null rows -> -1"), lines
+
+
+def test_detect_stream_landmarks_and_capacity_growth():
+    """Streaming path: `last_landmarks` belongs to the batch that was yielded last (not to an earlier synchronous call),
+    and after a batch overflowed `out_cap` the lanes rebuild their plans instead of overflowing for ever."""
+    h, w, sizes, B = 270, 480, [160, 256, 320], 2
+    images, heads, shapes = standin.make_batch(h, w, sizes, B, n_faces=25, seed=14, dtype=np.float16)
+    model = standin.SyntheticHeadModel()
+    for s, hw in enumerate(shapes):
+        model.set_heads(hw, heads[s], pin=True)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, with_landmarks=True)
+    batches = [images, np.ascontiguousarray(images[::-1])]
+    want = []
+    for b in batches:  # the heads do not depend on the pixels: batch 1 is batch 0 with the images swapped
+        det.detect_multi_scale_batch(images)
+        want.append(([k.copy() for k in det.last_landmarks], dict(det.last_stats)))
+    det.last_landmarks = "stale"
+    for i, dets in enumerate(det.detect_stream(batches, depth=2)):
+        assert isinstance(det.last_landmarks, list) and len(det.last_landmarks) == B
+        for b in range(B):
+            assert det.last_landmarks[b].shape == (len(dets[b]), 15)
+            assert np.array_equal(det.last_landmarks[b], want[i][0][b])
+        assert det.last_stats["final"] == want[i][1]["final"]
+    # out_cap too small for the merged rows: the first streamed batch is redone synchronously and grows it ...
+    det2 = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, cap=256, out_cap=8)
+    ref = det.detect_multi_scale_batch(images)
+    got = list(det2.detect_stream([images, images, images], depth=2))
+    for g_ in got:
+        for a, b in zip(g_, ref):
+            assert np.array_equal(a, b)
+    assert det2.out_cap > 8
+    # ... and the lanes' plans were rebuilt with the grown capacity (no plan of the old size is left)
+    for lane in det2._tls.lanes:
+        assert lane.plans and all(p.out.out_cap == det2.out_cap for p in lane.plans.values())

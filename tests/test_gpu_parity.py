@@ -332,6 +332,33 @@ def test_nms_matches_torchvision_cuda_kernel():
             assert np.array_equal(got, ref), (n, t)
 
 
+def test_nms_ties_and_on_threshold_pairs_match_torchvision_cuda_kernel():
+    """SURVEY B7's open point, against the real sm_100 kernel: quantised scores (exact ties -> the stable sort must keep
+    the lower index first) and integer boxes whose IoU lies EXACTLY on the threshold (0.5, 1/3, 0.25, 0.3: `>` is strict
+    and the CUDA kernel's fma-based union decides the last bit)."""
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(78)
+    for n, grid in ((64, 4), (700, 8), (1500, 16), (5000, 32)):
+        # integer boxes on a coarse lattice with a few sizes: many identical boxes, many pairs with small-integer
+        # intersection / union ratios (e.g. 8x8 boxes shifted by 4 columns: inter 32, union 96 -> exactly 1/3)
+        xy = rng.integers(0, grid, (n, 2)) * 4
+        wh = rng.choice([4, 8, 12, 16], (n, 2))
+        boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        scores = (rng.integers(0, 8, n) / 8.0).astype(np.float32)  # 8 distinct scores: long runs of exact ties
+        b, sc = gpu(boxes), gpu(scores)
+        for t in (0.5, 1.0 / 3.0, 0.25, 0.3, 0.0, 1.0):
+            ref = tv.ops.nms(b, sc, t).cpu().numpy()
+            got = ops.nms(b, sc, t, ops.IOU_TV_CUDA).cpu().numpy()
+            assert np.array_equal(got, ref), (n, t, len(got), len(ref))
+    # the pairs that sit exactly on a threshold exist in the data above (otherwise the test would prove nothing)
+    a = np.array([[0, 0, 8, 8]], np.float32); c = np.array([[4, 0, 12, 8]], np.float32)
+    inter = 4 * 8; union = 64 + 64 - inter
+    assert inter / union == 1.0 / 3.0
+    pair = gpu(np.concatenate([a, c])); s2 = gpu(np.array([0.9, 0.8], np.float32))
+    for t in (1.0 / 3.0, np.nextafter(np.float32(1.0 / 3.0), np.float32(0)), np.nextafter(np.float32(1.0 / 3.0), np.float32(1))):
+        assert np.array_equal(ops.nms(pair, s2, float(t), ops.IOU_TV_CUDA).cpu().numpy(), tv.ops.nms(pair, s2, float(t)).cpu().numpy()), t
+
+
 def test_nms_batched_segments_with_ties_and_empty():
     """Many segments of different sizes (0, 1, ragged) in one call; tie order follows `tie`."""
     rng = np.random.default_rng(5)

@@ -252,7 +252,7 @@ class MultiScaleFaceDetector:
                 lane.img_dev.copy_(t, non_blocking=True)
                 plan = self.detect_batch_device(lane.img_dev, lane)
                 o = plan.out
-                if lane.h_dets is None or lane.h_dets.shape != o.dets.shape:
+                if lane.h_dets is None or lane.h_dets.shape != o.dets.shape or lane.h_meta.numel() != o.n_out.numel() + 5:
                     lane.h_dets = torch.empty(o.dets.shape, dtype=torch.float32).pin_memory()
                     lane.h_meta = torch.empty((o.n_out.numel() + 5,), dtype=torch.int32).pin_memory()
                 lane.h_dets.copy_(o.dets, non_blocking=True)
@@ -310,8 +310,7 @@ class MultiScaleFaceDetector:
                 self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
             self._thread_plans().clear()
             for lane in getattr(self._tls, "lanes", None) or []:  # the streaming lanes of this thread size theirs anew
-                lane.plans.clear()
-                lane.h_dets = lane.h_meta = lane.h_kpts = None
+                lane.plans.clear()  # (a batch in flight keeps its plan and its pinned buffers until it is read)
         dets, n_out, kpts = res
         self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]),
                            "kept_per_scale": int(head[4]), "final": int(n_out.sum())}

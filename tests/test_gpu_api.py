@@ -253,8 +253,18 @@ def test_nms_other_keypoint_counts(golden):
         res = general.non_max_suppression(pred, thr, 0.45, kpt_label=kl, iou_mode=ops.IOU_TV_CPU)
         for b in range(2):
             assert np.array_equal(res[b].cpu().numpy(), g["c%d_b%d" % (cols, b)])
-    with pytest.raises(NotImplementedError):  # kpt_label=5 on 6 columns gives nc = -14 in the reference
-        general.non_max_suppression(torch.zeros((1, 10, 6), device=DEV), kpt_label=5)
+    # kpt_label=5 on 6 columns (msfd:134) gives nc = -14 in the reference: its confidence is then the RAW class score of
+    # the rows whose objectness passes (pinned against the reference's function on the GPU box: tests/ref_gpu_check.py P2b)
+    p6 = torch.from_numpy(np.ascontiguousarray(h["tiny_pred"][..., :6])).to(DEV)
+    res = general.non_max_suppression(p6, thr, 0.45, iou_mode=ops.IOU_TV_CPU)
+    for b in range(2):
+        x = h["tiny_pred"][b][:, :6]
+        x = x[(x[:, 4] > np.float32(thr)) & (x[:, 5] > np.float32(thr))]
+        r = res[b].cpu().numpy()
+        assert len(r) <= len(x) and (len(x) == 0 or len(r) > 0)
+        assert np.all(np.isin(r[:, 4], x[:, 5]))  # conf column = one of the raw class scores
+    with pytest.raises(NotImplementedError):  # multi-class heads stay refused
+        general.non_max_suppression(torch.zeros((1, 10, 8), device=DEV), kpt_label=0)
 
 
 def test_detect_stream_matches_batch_calls():
@@ -500,7 +510,7 @@ def test_detect_stream_landmarks_and_capacity_growth():
     # out_cap too small for the merged rows: the first streamed batch is redone synchronously and grows it ...
     det2 = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, cap=256, out_cap=8)
     ref = det.detect_multi_scale_batch(images)
-    got = list(det2.detect_stream([images, images, images], depth=2))
+    got = list(det2.detect_stream([images] * 6, depth=2))
     for g_ in got:
         for a, b in zip(g_, ref):
             assert np.array_equal(a, b)

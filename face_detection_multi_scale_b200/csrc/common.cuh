@@ -32,6 +32,7 @@ struct fdms_ctx {
     bool pyr_strip_attr = false, pyr_cnt_ready = false;
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)
+    int decode_fused = 1;         // FDMS_DECODE_FUSED=0: candidates are decoded by a second kernel (decode_candidates_kernel)
     int merge_fused = 1;          // FDMS_MERGE_FUSED=0: the three-kernel merge (prepare, NMS, emit) for every image
     int numerics = FDMS_NUMERICS_EXACT;  // fdms_set_numerics / FDMS_NUMERICS
     bool post_small_only = false; // set around fdms_postprocess(FDMS_POST_SMALL_ONLY): no large-segment launches

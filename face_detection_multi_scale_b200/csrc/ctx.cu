@@ -70,6 +70,7 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_PYR_TH_DIRECT")) c->pyr_th_direct = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("FDMS_PYR_TH")) c->pyr_th = atoi(e) < 1 ? 1 : (atoi(e) > 31 ? 31 : atoi(e));  // rows + sentinel are written by one warp
     if (const char *e = getenv("FDMS_NMS_SMALL_LIMIT")) c->nms_small_limit = atoi(e);
+    if (const char *e = getenv("FDMS_DECODE_FUSED")) c->decode_fused = atoi(e);
     if (const char *e = getenv("FDMS_MERGE_FUSED")) c->merge_fused = atoi(e);
     if (const char *e = getenv("FDMS_NMS_GREEDY_MIN_SEG")) c->nms_greedy_min_seg = atoi(e);
     if (const char *e = getenv("FDMS_MASK_BUDGET_MB")) c->mask_budget = (size_t)atoll(e) << 20;

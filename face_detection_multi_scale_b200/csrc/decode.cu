@@ -188,7 +188,11 @@ template <> struct RawVec<float> {
     }
 };
 
-template <typename T>
+// FUSE: 0 = only record the survivors' rows (decode_candidates_kernel decodes them afterwards); 1 / 2 = the CTA decodes
+// the survivors it has just recorded itself, boxes only / with landmarks.  They are dense now (one per thread), belong
+// to this CTA's (image, anchor) plane group -- no level search, no row arithmetic beyond one division -- and their
+// obj / cls sectors are still in L1; the second kernel, its launch and its tail (9 us on a latency-bound chain) go away.
+template <typename T, int FUSE>
 __device__ __forceinline__ void decode_filter_body(const DecParams &P, const DecLevel &L, const DecCta &C, int *s_rows,
                                                    int &s_n, int &s_base) {
     const int cells = C.cells;
@@ -275,9 +279,33 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
     const int seg = C.seg;
     if (threadIdx.x == 0) s_base = atomicAdd(P.count + seg, n_cta);
     __syncthreads();
+    const int a = (C.row_base - L.row_offset) / cells;  // the anchor of this CTA's plane group
     for (int i = threadIdx.x; i < n_cta; i += DEC_THREADS) {
         const int pos = s_base + i;
-        if (pos < P.cap) P.cand_row[(long long)seg * P.cap + pos] = s_rows[i];
+        if (pos >= P.cap) continue;
+        const long long slot = (long long)seg * P.cap + pos;
+        const int row = s_rows[i];
+        P.cand_row[slot] = row;
+        if (FUSE) {
+            constexpr int NV = FUSE == 2 ? NO : 6;  // planes read / columns written
+            const int cell = row - C.row_base;
+            const int gy = cell / L.nx, gx = cell - gy * L.nx;
+            const T *p = base + cell;
+            float v[NO], o[NO];
+#pragma unroll
+            for (int c = NV; c < NO; c++) v[c] = 0.f;
+            T raw[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) raw[c] = __ldg(p + (long long)c * cells);  // all loads before the first conversion
+#pragma unroll
+            for (int c = 0; c < NV; c++) v[c] = to_f32(raw[c]);
+            if (FUSE == 2) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+            else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+            row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
+            float *dst = P.cand + slot * NO;
+#pragma unroll
+            for (int c = 0; c < NV; c++) dst[c] = o[c];
+        }
     }
 }
 
@@ -304,13 +332,14 @@ __global__ void decode_tab_kernel(const __grid_constant__ DecParams P, DecCta *t
     tab[blk] = c;
 }
 
+template <int FUSE>
 __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
     __shared__ int s_rows[DEC_CELLS];  // one copy for both instantiations of the body
     __shared__ int s_n, s_base;
     const DecCta C = P.cta_tab[blockIdx.x];
     const DecLevel &L = P.lv[C.level];
-    if (L.dtype == FDMS_F16) decode_filter_body<__half>(P, L, C, s_rows, s_n, s_base);
-    else decode_filter_body<float>(P, L, C, s_rows, s_n, s_base);
+    if (L.dtype == FDMS_F16) decode_filter_body<__half, FUSE>(P, L, C, s_rows, s_n, s_base);
+    else decode_filter_body<float, FUSE>(P, L, C, s_rows, s_n, s_base);
 }
 
 // Second half of the fused decode: one thread per recorded candidate (dense warps after the compaction):
@@ -547,9 +576,15 @@ FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int 
         P.cta_tab = reinterpret_cast<const DecCta *>(ctx->dec_tab.p);
     }
     FDMS_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)bs * n_scales, st));
-    decode_filter_kernel<<<n_blocks, DEC_THREADS, 0, st>>>(P);
-    FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
     const int n_seg = bs * n_scales;
+    if (ctx->decode_fused) {  // filter + candidate decode in one launch
+        if (flags & FDMS_DECODE_BOXES_ONLY) decode_filter_kernel<1><<<n_blocks, DEC_THREADS, 0, st>>>(P);
+        else decode_filter_kernel<2><<<n_blocks, DEC_THREADS, 0, st>>>(P);
+        FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
+        return FDMS_OK;
+    }
+    decode_filter_kernel<0><<<n_blocks, DEC_THREADS, 0, st>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "decode_filter_kernel");
     if (n_seg > 65535) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_filter: more than 65535 segments");
     int gx = ceil_div(cap, CAND_THREADS);
     if (gx > 8) gx = 8;

@@ -360,11 +360,13 @@ class PostPlan:
 
     @property
     def launches(self):
-        """Kernel launches of one run() (memset excluded): decode filter + candidate decode, the per-scale NMS (one
+        """Kernel launches of one run() (memset excluded): decode filter (+ candidate decode), the per-scale NMS (one
         fused launch when no segment can exceed 1024 boxes, else + sort + greedy sweep), the cross-scale merge (one
         fused launch when no image can have more than 1024 merged rows, else + sort + greedy sweep + emit)."""
+        import os
         small = SMALL_LIMIT
+        dec = 2 if os.environ.get("FDMS_DECODE_FUSED") == "0" else 1  # the filter CTAs decode their own survivors
         if self.small_only:
-            return 4
+            return dec + 2
         mcap = min(self.n_scales * self.cands.cap, self.out.out_cap)
-        return 2 + (1 if self.cands.cap <= small else 3) + (1 if mcap <= small else 4)
+        return dec + (1 if self.cands.cap <= small else 3) + (1 if mcap <= small else 4)

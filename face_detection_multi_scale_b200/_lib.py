@@ -35,7 +35,7 @@ class PostDesc(C.Structure):
                 ("in_h_host", C.POINTER(C.c_int32)), ("orig_h", C.c_int32), ("orig_w", C.c_int32),
                 ("cand", C.c_void_p), ("cand_row", C.c_void_p), ("count", C.c_void_p), ("keep", C.c_void_p),
                 ("n_keep", C.c_void_p), ("dets", C.c_void_p), ("n_out", C.c_void_p), ("out_cap", C.c_int32),
-                ("flags", C.c_int32), ("merged_in", C.c_void_p), ("kpts_out", C.c_void_p)]
+                ("flags", C.c_int32), ("merged_in", C.c_void_p), ("kpts_out", C.c_void_p), ("orig_hw_dev", C.c_void_p)]
 
 
 _SIGS = {
@@ -69,6 +69,9 @@ _SIGS = {
     "fdms_merge_scales": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdms_merge_scales_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(C.c_int32), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_weighted_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_bbox_overlaps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "fdms_pack_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

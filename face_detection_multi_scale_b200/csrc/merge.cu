@@ -148,11 +148,12 @@ FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, in
     return FDMS_OK;
 }
 
-FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
-                               int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
-                               double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
-                               float *kpts_out, fdms_stream stream) {
+static int merge_scales_impl(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep, int n_img,
+                             int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
+                             const int32_t *orig_hw_dev, double iou_thres, float *dets, int32_t *n_out, int out_cap,
+                             int32_t *merged_in, float *kpts_out, fdms_stream stream) {
     FDMS_BIND(ctx);
+    if (orig_hw_dev) orig_h = orig_w = 1;  // per-image sizes on the device; the scalars are unused
     if (!cand || !keep || !n_keep || !in_h_host || !dets || !n_out || n_img <= 0 || n_scales <= 0 ||
         n_scales > FDMS_MAX_SCALES || cap <= 0 || out_cap <= 0 || orig_h <= 0 || orig_w <= 0)
         return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad arguments");
@@ -183,7 +184,9 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
     for (int s = 0; s < n_scales; s++) {
         if (in_h_host[s] <= 0) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales: bad in_h[%d]", s);
         P.k[s] = (float)((double)sq / (double)in_h_host[s]);
+        P.in_h[s] = in_h_host[s];
     }
+    P.orig_hw = orig_hw_dev;
     P.w0 = (float)orig_w;
     P.h0 = (float)orig_h;
     P.mrows = mrows;
@@ -201,7 +204,11 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
     E.cap = cap;
     E.mcap = mcap;
     E.out_cap = out_cap;
-    for (int s = 0; s < n_scales; s++) E.k[s] = P.k[s];
+    for (int s = 0; s < n_scales; s++) {
+        E.k[s] = P.k[s];
+        E.in_h[s] = P.in_h[s];
+    }
+    E.orig_hw = orig_hw_dev;
     E.w0 = P.w0;
     E.h0 = P.h0;
     E.dets = dets;
@@ -232,6 +239,23 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
     return FDMS_OK;
 }
 
+FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
+                               int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
+                               double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
+                               float *kpts_out, fdms_stream stream) {
+    return merge_scales_impl(ctx, cand, keep, n_keep, n_img, n_scales, cap, in_h_host, orig_h, orig_w, nullptr, iou_thres, dets,
+                             n_out, out_cap, merged_in, kpts_out, stream);
+}
+
+FDMS_API int fdms_merge_scales_ragged(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
+                                      int n_img, int n_scales, int cap, const int32_t *in_h_host,
+                                      const int32_t *orig_hw_dev, double iou_thres, float *dets, int32_t *n_out,
+                                      int out_cap, int32_t *merged_in, float *kpts_out, fdms_stream stream) {
+    if (!orig_hw_dev) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_merge_scales_ragged: null orig_hw");
+    return merge_scales_impl(ctx, cand, keep, n_keep, n_img, n_scales, cap, in_h_host, 1, 1, orig_hw_dev, iou_thres, dets, n_out,
+                             out_cap, merged_in, kpts_out, stream);
+}
+
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_stream stream) {
     FDMS_BIND(ctx);
     if (!d) return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_postprocess: null descriptor");
@@ -249,8 +273,8 @@ FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_strea
     if (int rc = fdms_nms_impl(ctx, d->cand, NO, 0, 4, d->cand_row, d->count, d->bs * d->n_scales, d->cap, d->iou_thres,
                                d->iou_mode, FDMS_MAX_NMS, d->keep, d->n_keep, (cudaStream_t)stream))
         return rc;
-    return fdms_merge_scales(ctx, d->cand, d->keep, d->n_keep, d->bs, d->n_scales, d->cap, d->in_h_host, d->orig_h,
-                             d->orig_w, d->iou_thres, d->dets, d->n_out, d->out_cap, d->merged_in, d->kpts_out, stream);
+    return merge_scales_impl(ctx, d->cand, d->keep, d->n_keep, d->bs, d->n_scales, d->cap, d->in_h_host, d->orig_h, d->orig_w,
+                             d->orig_hw_dev, d->iou_thres, d->dets, d->n_out, d->out_cap, d->merged_in, d->kpts_out, stream);
 }
 
 }  // extern "C"

@@ -10,6 +10,8 @@ struct MergeParams {
     int n_scales, cap, mcap;
     float k[FDMS_MAX_SCALES];  // max(H0, W0) / in_h per scale
     float w0, h0;
+    const int32_t *orig_hw;    // ragged batches: (n_img, 2) original (H0, W0) per image on the device; k / w0 / h0 above
+    int in_h[FDMS_MAX_SCALES]; // are then derived per image from it and the scales' input heights
     float *mrows;      // (n_img, mcap, 8)
     int32_t *msrc;     // (n_img, mcap): s * cap + item index
     int32_t *mcount;   // (n_img)
@@ -23,6 +25,8 @@ struct EmitParams {
     int n_scales, cap, mcap, out_cap;
     float k[FDMS_MAX_SCALES];
     float w0, h0;
+    const int32_t *orig_hw;
+    int in_h[FDMS_MAX_SCALES];
     float *dets;
     int32_t *n_out;
     float *kpts;
@@ -46,6 +50,22 @@ __device__ __forceinline__ float4 api_box(float4 b, float k, float w0, float h0,
     return b;
 }
 
+// Rescale geometry of (image, scale): the batch-wide values, or -- ragged batches -- from the image's own size:
+// k = (float)(max(H0, W0) / in_h) computed in double like the Python float it is (ppyp:141-142).
+template <typename PT>
+__device__ __forceinline__ void merge_geom(const PT &P, int img, int s, float &k, float &w0, float &h0) {
+    if (P.orig_hw) {
+        const int H0 = P.orig_hw[2 * img], W0 = P.orig_hw[2 * img + 1];
+        k = (float)((double)max(H0, W0) / (double)P.in_h[s]);
+        w0 = (float)W0;
+        h0 = (float)H0;
+    } else {
+        k = P.k[s];
+        w0 = P.w0;
+        h0 = P.h0;
+    }
+}
+
 // Rows of image `img` (all threads of the CTA take part); returns the number of merged rows (CTA-uniform).
 __device__ __forceinline__ int merge_prepare_image(const MergeParams &P, int img, int tid, int n_threads) {
     int off[FDMS_MAX_SCALES + 1];
@@ -66,7 +86,9 @@ __device__ __forceinline__ int merge_prepare_image(const MergeParams &P, int img
         const long long seg = (long long)img * P.n_scales + s;
         const int item = P.keep[seg * P.cap + kidx];
         const float *row = P.cand + (seg * P.cap + item) * MERGE_NO;
-        float4 b = api_box(make_float4(row[0], row[1], row[2], row[3]), P.k[s], P.w0, P.h0, true);  // msfd:144
+        float gk, gw, gh;
+        merge_geom(P, img, s, gk, gw, gh);
+        float4 b = api_box(make_float4(row[0], row[1], row[2], row[3]), gk, gw, gh, true);  // msfd:144
         const float conf = row[4], cls = row[5];
         // msfd:168-201 on the rounded boxes, float64
         double area = ((double)b.z - (double)b.x) * ((double)b.w - (double)b.y);
@@ -101,9 +123,11 @@ __device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, i
             const int s = src / P.cap, item = src - s * P.cap;
             const float *row = P.cand + (((long long)img * P.n_scales + s) * P.cap + item) * MERGE_NO;
             float *ko = P.kpts + ((long long)img * P.out_cap + k) * 15;
+            float gk, gw, gh;
+            merge_geom(P, img, s, gk, gw, gh);
             for (int j = 0; j < 5; j++) {
-                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], P.k[s]), 0.f, P.w0);
-                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], P.k[s]), 0.f, P.h0);
+                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], gk), 0.f, gw);
+                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], gk), 0.f, gh);
                 ko[3 * j + 2] = row[8 + 3 * j];
             }
         }

@@ -81,13 +81,40 @@ def _expand_source(path):
     raise Exception(f'ERROR: {spec} does not exist')
 
 
+def _quit_requested():
+    """The reference polls `cv2.waitKey(1) == ord('q')` between frames (utils/datasets.py:226,319); OpenCV builds without
+    a GUI raise on that call -- nobody can press a key there."""
+    import cv2
+    try:
+        return cv2.waitKey(1) == ord('q')
+    except cv2.error:
+        return False
+
+
+def _chw_rgb(frames, img_size, stride, auto, device, device_out):
+    """letterbox(img_size, stride, auto) + BGR->RGB + HWC->CHW of a list of BGR frames: ONE libfdms launch when the
+    frames share a shape (the usual case: one camera model, one video), one per frame otherwise.  Returns the list of
+    (3, h, w) uint8 images (CUDA tensors, or ndarrays unless `device_out`)."""
+    same = all(f.shape == frames[0].shape for f in frames)
+    groups = [frames] if same else [[f] for f in frames]
+    outs = []
+    for grp in groups:
+        t = torch.stack([_to_device_u8(f, device) for f in grp]) if len(grp) > 1 else _to_device_u8(grp[0], device)[None]
+        g = _lib.letterbox_geometry(t.shape[1], t.shape[2], img_size, auto=auto, stride=stride)
+        (o,) = ops.pyramid(t, [g], out_dtype=torch.uint8, layout="chw", flip_rb=True)
+        outs.extend(o[i] for i in range(o.shape[0]))
+    return outs if device_out else [o.cpu().numpy() for o in outs]
+
+
 class LoadImages:
-    """Drop-in for utils/datasets.py:124-201 (the inference loader of detect.py:61): iterates over the images and
-    videos of a path / glob / directory and yields `(path, img, img0, cap)` with `img` = letterbox(img0, img_size,
-    stride, auto=False) flipped to RGB and transposed to CHW -- produced by ONE libfdms launch (u8 CHW output with the
-    channel flip), bit-identical to the reference's cv2 + numpy sequence.  The file is decoded once on the host
-    (cv2, like the reference).  `device_out=True` yields the CHW image as a CUDA tensor instead of an ndarray; the
-    per-file progress prints of the reference are dropped (SURVEY: no prints on the path)."""
+    """Drop-in for utils/datasets.py:124-201 (the inference loader of detect.py:61): iterates over the images and the
+    frames of the videos of a path / glob / directory and yields `(path, img, img0, cap)` with `img` =
+    letterbox(img0, img_size, stride) flipped to RGB and transposed to CHW -- produced by ONE libfdms launch (u8 CHW
+    output with the channel flip), bit-identical to the reference's cv2 + numpy sequence.  Every file is decoded once
+    on the host (cv2, like the reference).  Same public attributes as the reference's loader (`files`, `video_flag`,
+    `nf`, `mode`, `cap`, `count`, `frame`, `nframes`); the walk over the sources is a generator here.
+    `device_out=True` yields the CHW image as a CUDA tensor instead of an ndarray; the per-file progress prints of the
+    reference are dropped (SURVEY: no prints on the path)."""
 
     def __init__(self, path, img_size=640, stride=32, device=None, device_out=False):
         self.img_size, self.stride = img_size, stride
@@ -100,52 +127,209 @@ class LoadImages:
         self.video_flag = [False] * len(stills) + [True] * len(clips)
         self.nf = len(self.files)
         self.mode = 'image'
-        self.cap = None
-        if clips:
-            self.new_video(clips[0])
+        self.cap, self.frame, self.nframes, self.count = None, 0, 0, 0
+        if clips:  # like the reference (:146-147), the first clip is open from the start (stills of a mixed directory are
+            import cv2  # yielded with that capture object)
+            self.cap = cv2.VideoCapture(clips[0])
+            self.nframes = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
         assert self.nf > 0, ('No images or videos found in %s. Supported formats are:\nimages: %s\nvideos: %s'
                              % (path, list(IMG_FORMATS), list(VID_FORMATS)))
+        self._walk = None
+
+    def _sources(self):
+        """(path, BGR frame) of every still, then of every frame of every clip, in file order."""
+        import cv2
+        for idx, (path, is_clip) in enumerate(zip(self.files, self.video_flag)):
+            self.count = idx
+            if not is_clip:
+                self.mode = 'image'
+                img0 = cv2.imread(path)  # BGR
+                assert img0 is not None, 'Image Not Found ' + path
+                self.count = idx + 1  # the reference has moved on to the next file when it yields a still (:175)
+                yield path, img0
+                continue
+            self.mode = 'video'
+            if not (self.cap is not None and idx == self.video_flag.index(True) and self.frame == 0 and self.cap.isOpened()):
+                self.cap = cv2.VideoCapture(path)
+            self.frame, self.nframes = 0, int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
+            while True:
+                ok, img0 = self.cap.read()
+                if not ok:
+                    break
+                self.frame += 1
+                yield path, img0
+            self.cap.release()
+        self.count = self.nf
 
     def __iter__(self):
         self.count = 0
+        self._walk = self._sources()
+        return self
+
+    def __next__(self):
+        if self._walk is None:
+            iter(self)
+        path, img0 = next(self._walk)  # StopIteration ends the iteration
+        # letterbox + [:, :, ::-1] + transpose(2, 0, 1) + ascontiguousarray (:187-191) in one launch
+        (img,) = _chw_rgb([img0], self.img_size, self.stride, False, self.device, self.device_out)  # auto=False (:187)
+        return path, img, img0, self.cap
+
+    def __len__(self):
+        return self.nf
+
+
+def clean_str(s):
+    """utils/general.py:205-207: characters that do not belong in a window / file name become underscores."""
+    import re
+    return re.sub(pattern="[|@#!¡·$€%&()=?¿^*;:,¨´><+]", repl="_", string=s)
+
+
+class LoadStreams:
+    """Drop-in for utils/datasets.py:262-340 (`detect.py --source streams.txt | rtsp://... | 0`): one daemon thread per
+    source keeps the latest frame (every 4th grabbed frame is retrieved, a failed retrieve blanks the frame, the
+    thread sleeps 1 / fps between grabs), `next()` yields `(sources, img (bs, 3, h, w) uint8 RGB, [img0, ...], None)`
+    -- the only loader of the reference with batch > 1.  All frames of a tick go through ONE pyramid launch when the
+    streams share a shape; `rect` (all letterboxed shapes equal -> minimal padding) is decided like the reference does.
+    `device_out=True` keeps `img` on the GPU."""
+
+    def __init__(self, sources='streams.txt', img_size=640, stride=32, device=None, device_out=False):
+        import os
+        import threading
+        import cv2
+        self.mode = 'stream'
+        self.img_size, self.stride = img_size, stride
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device_out = device_out
+        if os.path.isfile(sources) and _suffix(sources) == 'txt':
+            with open(sources, 'r') as f:
+                sources = [x.strip() for x in f.read().strip().splitlines() if len(x.strip())]
+        else:
+            sources = [sources]
+        self.sources = [clean_str(x) for x in sources]
+        self.imgs = [None] * len(sources)
+        self.fps = 30.0
+        self._caps, self._threads = [], []
+        for i, src in enumerate(sources):
+            cap = cv2.VideoCapture(int(src) if src.isnumeric() else src)
+            assert cap.isOpened(), f'Failed to open {src}'
+            self.fps = cap.get(cv2.CAP_PROP_FPS) % 100 or 30.0
+            ok, self.imgs[i] = cap.read()  # guarantee first frame
+            assert ok, f'Failed to read from {src}'
+            th = threading.Thread(target=self.update, args=(i, cap), daemon=True)
+            self._caps.append(cap)
+            self._threads.append(th)
+            th.start()
+        shapes = {_lib.letterbox_geometry(x.shape[0], x.shape[1], img_size, auto=True, stride=stride).dst_h * 100000 +
+                  _lib.letterbox_geometry(x.shape[0], x.shape[1], img_size, auto=True, stride=stride).dst_w for x in self.imgs}
+        self.rect = len(shapes) == 1  # rect inference if all letterboxed shapes are equal (:300-303)
+
+    def update(self, index, cap):
+        import time
+        n = 0
+        while cap.isOpened():
+            n += 1
+            if not cap.grab():  # end of a file source / a dropped connection
+                break
+            if n == 4:  # every 4th frame is decoded (:311-315)
+                ok, im = cap.retrieve()
+                self.imgs[index] = im if ok else self.imgs[index] * 0
+                n = 0
+            time.sleep(1 / self.fps)
+
+    def __iter__(self):
+        self.count = -1
+        return self
+
+    def __next__(self):
+        self.count += 1
+        img0 = self.imgs.copy()
+        if _quit_requested():
+            raise StopIteration
+        outs = _chw_rgb(img0, self.img_size, self.stride, self.rect, self.device, True)
+        if not all(o.shape == outs[0].shape for o in outs):
+            raise ValueError("LoadStreams: the streams letterbox to different shapes %s and cannot be stacked (the "
+                             "reference's np.stack fails the same way)" % sorted({tuple(o.shape) for o in outs}))
+        img = torch.stack(outs)
+        return self.sources, (img if self.device_out else img.cpu().numpy()), img0, None
+
+    def __len__(self):
+        return 0  # endless (:339)
+
+
+class LoadWebcam:
+    """Drop-in for utils/datasets.py:204-259: one local camera (`pipe` numeric: frames are mirrored) or an IP camera
+    (every 30th grabbed frame is decoded); yields ('webcam.jpg', img, img0, None)."""
+
+    def __init__(self, pipe='0', img_size=640, stride=32, device=None, device_out=False):
+        import cv2
+        self.img_size, self.stride = img_size, stride
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device_out = device_out
+        self.pipe = int(pipe) if isinstance(pipe, str) and pipe.isnumeric() else pipe
+        self.cap = cv2.VideoCapture(self.pipe)
+        self.cap.set(cv2.CAP_PROP_BUFFERSIZE, 3)
+
+    def __iter__(self):
+        self.count = -1
         return self
 
     def __next__(self):
         import cv2
-        if self.count == self.nf:
+        self.count += 1
+        if _quit_requested():
+            self.cap.release()
             raise StopIteration
-        path = self.files[self.count]
-        if self.video_flag[self.count]:
-            self.mode = 'video'
-            ret_val, img0 = self.cap.read()
-            if not ret_val:
-                self.count += 1
-                self.cap.release()
-                if self.count == self.nf:
-                    raise StopIteration
-                path = self.files[self.count]
-                self.new_video(path)
-                ret_val, img0 = self.cap.read()
-            self.frame += 1
-        else:
-            self.count += 1
-            img0 = cv2.imread(path)  # BGR
-            assert img0 is not None, 'Image Not Found ' + path
-        # letterbox(auto=False) + [:, :, ::-1] + transpose(2, 0, 1) + ascontiguousarray (:187-191) in one launch
-        t = _to_device_u8(img0, self.device)
-        g = _lib.letterbox_geometry(t.shape[0], t.shape[1], self.img_size, auto=False, stride=self.stride)
-        (out,) = ops.pyramid(t[None], [g], out_dtype=torch.uint8, layout="chw", flip_rb=True)
-        img = out[0] if self.device_out else out[0].cpu().numpy()
-        return path, img, img0, self.cap
-
-    def new_video(self, path):
-        import cv2
-        self.frame = 0
-        self.cap = cv2.VideoCapture(path)
-        self.nframes = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        if self.pipe == 0:  # local camera
+            ok, img0 = self.cap.read()
+            if ok:
+                img0 = cv2.flip(img0, 1)
+        else:  # IP camera / file: skip to every 30th frame
+            ok, img0 = False, None
+            for _ in range(30):
+                if not self.cap.grab():
+                    break
+            else:
+                ok, img0 = self.cap.retrieve()
+        assert ok, f'Camera Error {self.pipe}'
+        (img,) = _chw_rgb([img0], self.img_size, self.stride, True, self.device, self.device_out)
+        return 'webcam.jpg', img, img0, None
 
     def __len__(self):
-        return self.nf
+        return 0
+
+
+def read_images(items, threads=None):
+    """Decode a list of image files (paths; already decoded (H, W, 3) uint8 arrays pass through) in parallel on host
+    threads with cv2.imread -- the reference's decoder (multi_scale_face_detector.py:84) -- once per image.  The images
+    may have different sizes; returns the list of BGR arrays in input order."""
+    import concurrent.futures
+    import os
+
+    import cv2
+
+    def load(it):
+        if isinstance(it, (str, bytes)) or hasattr(it, "__fspath__"):
+            img = cv2.imread(os.fsdecode(it))
+            if img is None:
+                raise ValueError(f"Could not read image: {it}")  # msfd:86
+            return img
+        img = np.asarray(it)
+        if img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:
+            raise ValueError("read_images: images must be (H, W, 3) uint8")
+        return img
+
+    items = list(items)
+    if not items:
+        raise ValueError("read_images: empty list")
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+    if len(items) == 1:
+        return [load(items[0])]
+    with concurrent.futures.ThreadPoolExecutor(max(1, min(int(threads), len(items)))) as ex:
+        return list(ex.map(load, items))
 
 
 def read_batch(items, threads=None, out=None):

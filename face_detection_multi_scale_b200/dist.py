@@ -78,11 +78,43 @@ def gather_detections(local_dets, n_total, group=None):
     return out
 
 
-def detect_sharded(detector, images, gather=True):
+def gather_device(dets, n_out, n_total, group=None):
+    """The final gather without leaving the device: `dets` (b, out_cap, C) fp32 and `n_out` (b,) int32 are this rank's
+    detections as the merge kernel left them (ops.Detections); returns (all_dets (n_total, kmax, C), all_n (n_total,))
+    in global image order on every rank, both device tensors.  Two NCCL collectives (counts, then rows cut to the
+    longest list) and one scalar read to size the second; no host copy of the rows, no float64 detour."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        k = int(n_out.max()) if n_out.numel() else 0
+        return dets[:, :k].contiguous(), n_out.clone()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    a, b = shard_range(n_total, rank, world)
+    if dets.shape[0] != b - a or n_out.shape[0] != b - a:
+        raise ValueError("rank %d holds %d results for a shard of %d images" % (rank, dets.shape[0], b - a))
+    per_img = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    counts = torch.zeros((per_img,), dtype=torch.int32, device=dets.device)
+    counts[:b - a] = n_out
+    all_counts = torch.empty((world, per_img), dtype=torch.int32, device=dets.device)
+    dist.all_gather_into_tensor(all_counts.view(-1), counts, group=group)
+    kmax = max(int(all_counts.max()), 1)  # the one host read: sizes the row exchange
+    send = torch.zeros((per_img, kmax, dets.shape[2]), dtype=dets.dtype, device=dets.device)
+    k_local = min(kmax, dets.shape[1])
+    send[:b - a, :k_local] = dets[:, :k_local]
+    recv = torch.empty((world,) + tuple(send.shape), dtype=dets.dtype, device=dets.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    keep = torch.cat([torch.arange(r * per_img, r * per_img + (shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0]),
+                                   device=dets.device) for r in range(world)])
+    return recv.view(world * per_img, kmax, -1)[keep], all_counts.view(-1)[keep]
+
+
+def detect_sharded(detector, images, gather=True, device_out=False):
     """Run `detector.detect_multi_scale_batch` on this rank's contiguous shard of `images` (B, H, W, 3) and
-    optionally gather every image's detections on every rank."""
+    optionally gather every image's detections on every rank.  `device_out`: keep everything on the device -- returns
+    (dets (n, kmax, 7) fp32, n_out (n,)) tensors (gathered over NCCL when `gather`), no per-image host arrays."""
     n = len(images)
     local = shard(images)
+    if device_out:
+        dets, n_out = detector.detect_multi_scale_batch(local, device_out=True)
+        return gather_device(dets, n_out, n) if gather else (dets, n_out)
     res = detector.detect_multi_scale_batch(local) if len(local) else []
     return gather_detections(res, n) if gather else res
 

@@ -140,7 +140,8 @@ class MultiScaleFaceDetector:
         bs = scales_levels[0][0].shape[0]
         # a plan owns device buffers sized by the capacities and a native context that is ordered by one stream
         stream_id = 0 if lane is not None else torch.cuda.current_stream(self.device).cuda_stream
-        key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), tuple(orig_hw),
+        ragged = isinstance(orig_hw, torch.Tensor)
+        key = (bs, tuple(tuple(l.shape[2:]) for lv in scales_levels for l in lv), tuple(in_h), "ragged" if ragged else tuple(orig_hw),
                self.cap, self.out_cap or self.cap, float(self.conf_thres), float(self.iou_thres), self.iou_mode,
                self.with_landmarks, stream_id)
         plan = plans.get(key)
@@ -154,6 +155,9 @@ class MultiScaleFaceDetector:
             plans[key] = plan
         else:
             plan.rebind(scales_levels)
+            if ragged:  # same shapes, other images: point the plan at this batch's sizes
+                plan._orig_hw = orig_hw
+                plan.desc.orig_hw_dev = orig_hw.data_ptr()
         # speculate that no segment / image exceeds the single-CTA kernels' limit while the recent batches did not: the
         # large-segment launches are then skipped and the exact counts read back with the results verify the guess
         plan.small_only = self._speculate_small
@@ -269,8 +273,9 @@ class MultiScaleFaceDetector:
         for lane in pending:
             yield finish(lane)
 
-    def _collect(self, plan):
-        """One device->host read of the results of `plan`; raises if a capacity was exceeded."""
+    def _collect(self, plan, device_out=False):
+        """One device->host read of the results of `plan`; raises if a capacity was exceeded.  `device_out`: only the
+        counts are read, the rows stay where they are."""
         o, c = plan.out, plan.cands
         both = self._meta(plan).cpu().numpy()
         n_out, head = both[:-5], both[-5:]  # one read, synchronises
@@ -282,17 +287,27 @@ class MultiScaleFaceDetector:
         if head[1] == -1:
             raise _lib.FdmsError("a segment exceeded the NMS suppression-mask budget")
         kmax = int(n_out.max()) if n_out.size else 0
+        if device_out:
+            return (o.dets[:, :kmax], o.n_out, o.kpts[:, :kmax] if o.kpts is not None else None), head
         dets = o.dets[:, :kmax].cpu().numpy().astype(np.float64) if kmax else np.zeros((len(n_out), 0, 7))
         kpts = o.kpts[:, :kmax].cpu().numpy() if (o.kpts is not None and kmax) else None
         return (dets, n_out, kpts), head
 
-    def detect_multi_scale_batch(self, images):
+    def detect_multi_scale_batch(self, images, device_out=False):
         """images: (B, H, W, 3) uint8 BGR ndarray / tensor (pinned host or device), or a list of same-shape
         images / paths.  Returns a list of (k, 7) float64 arrays [x1,y1,x2,y2,conf,cls,scale_idx] per image, rows
-        in weighted-score order (msfd:242-288); images without detections give np.array([]) (msfd:285)."""
+        in weighted-score order (msfd:242-288); images without detections give np.array([]) (msfd:285).
+        `device_out`: the detections stay on the GPU -- returns (dets (B, kmax, 7) fp32, n_out (B,) int32) tensors
+        that are valid until the calling thread's next call (only the counts cross PCIe)."""
         if isinstance(images, (list, tuple)):
-            from .datasets import read_batch
-            images = read_batch(images)  # parallel host decode, once per image, into a pinned batch
+            from .datasets import read_batch, read_images
+            if device_out:
+                images = read_batch(images)
+            else:
+                decoded = read_images(images)  # parallel host decode, once per image
+                if len({im.shape for im in decoded}) > 1:
+                    return self._detect_ragged(decoded)  # mixed sizes: bucketed by letterboxed shape
+                images = read_batch(decoded)  # one pinned batch
         t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
         if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
             raise ValueError("detect_multi_scale_batch: expected (B, H, W, 3) uint8 images")
@@ -300,7 +315,7 @@ class MultiScaleFaceDetector:
         t0 = time.perf_counter()
         while True:
             plan = self.detect_batch_device(batch_dev)
-            res, head = self._collect(plan)
+            res, head = self._collect(plan, device_out)
             if res is not None:
                 break
             # capacity exceeded: grow to what this batch needs and redo (counts are exact even on overflow)
@@ -312,10 +327,69 @@ class MultiScaleFaceDetector:
             for lane in getattr(self._tls, "lanes", None) or []:  # the streaming lanes of this thread size theirs anew
                 lane.plans.clear()  # (a batch in flight keeps its plan and its pinned buffers until it is read)
         dets, n_out, kpts = res
+        if device_out:
+            self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]), "kept_per_scale": int(head[4])}
+            self.last_landmarks = kpts
+            return dets, n_out
         self.last_stats = {"seconds": time.perf_counter() - t0, "candidates": int(head[3]),
                            "kept_per_scale": int(head[4]), "final": int(n_out.sum())}
         self.last_landmarks = [kpts[b, :n_out[b]] for b in range(len(n_out))] if kpts is not None else None
         return [dets[b, :n_out[b]] if n_out[b] else np.array([]) for b in range(len(n_out))]
+
+    def _detect_ragged(self, images):
+        """Images of DIFFERENT sizes in one call (the reference takes arbitrary images one at a time,
+        multi_scale_face_detector.py:242-288; autoShape batches mixed sizes, models/common.py:618-636).  They are
+        bucketed by the shapes their letterboxed inputs have at every scale, so that the backbone and the whole
+        post-processing chain still run once per bucket: inside a bucket, images of the same source size share a pyramid
+        launch that writes straight into the bucket's batch tensors, and the merge takes every image's own original size
+        (fdms_post_desc.orig_hw_dev).  Returns the per-image results in input order."""
+        n = len(images)
+        geoms = [self._geoms(im.shape[0], im.shape[1]) for im in images]
+        buckets = {}
+        for i, (g, _) in enumerate(geoms):
+            buckets.setdefault(tuple((q.dst_h, q.dst_w) for q in g), []).append(i)
+        results = [None] * n
+        landmarks = [None] * n if self.with_landmarks else None
+        stats = {"seconds": 0.0, "candidates": 0, "kept_per_scale": 0, "final": 0, "buckets": len(buckets)}
+        dtype = torch.float16 if self.half else torch.float32
+        t0 = time.perf_counter()
+        for shapes, idx in buckets.items():
+            idx = sorted(idx, key=lambda i: images[i].shape)  # same source size -> neighbours -> one launch
+            nb = len(idx)
+            outs = [torch.empty((nb, 3, h, w), dtype=dtype, device=self.device) for h, w in shapes]
+            a = 0
+            while a < nb:
+                b = a
+                while b < nb and images[idx[b]].shape == images[idx[a]].shape:
+                    b += 1
+                src = torch.from_numpy(np.stack([np.ascontiguousarray(images[i]) for i in idx[a:b]])).to(self.device, non_blocking=True)
+                g, virt = geoms[idx[a]]
+                ops.pyramid(src, g, out_dtype=dtype, layout="chw", flip_rb=True, virt_hw=virt, outs=[o[a:b] for o in outs])
+                a = b
+            hw = torch.tensor([[images[i].shape[0], images[i].shape[1]] for i in idx], dtype=torch.int32).to(self.device)
+            scales_levels = [self._raw_heads(x) for x in outs]
+            while True:
+                plan = self._plan(scales_levels, [h for h, _ in shapes], hw)
+                plan.run()
+                res, head = self._collect(plan)
+                if res is not None:
+                    break
+                if head[0] > self.cap:
+                    self.cap = max(self.cap * 2, int(head[0]))
+                if head[2] > (self.out_cap or self.cap):
+                    self.out_cap = max(2 * (self.out_cap or self.cap), int(head[2]))
+                self._thread_plans().clear()
+            dets, n_out, kpts = res
+            for j, i in enumerate(idx):
+                results[i] = dets[j, :n_out[j]] if n_out[j] else np.array([])
+                if landmarks is not None:
+                    landmarks[i] = kpts[j, :n_out[j]]
+            stats["candidates"] += int(head[3])
+            stats["kept_per_scale"] += int(head[4])
+            stats["final"] += int(n_out.sum())
+        stats["seconds"] = time.perf_counter() - t0
+        self.last_stats, self.last_landmarks = stats, landmarks
+        return results
 
     # ------------------------------------------------------------------ reference-shaped methods
     @torch.no_grad()
@@ -381,13 +455,14 @@ class MultiScaleFaceDetector:
         return out[0], img0.shape
 
     def detect_files(self, paths, batch_size=32, decode_threads=None, depth=2):
-        """Generator over image files (all of one size): yields `(path, detections (k,7) float64 or np.array([]))` in
-        input order.  The production driver of the reference builds a detector per item and decodes every file once
-        per scale (yolov7_face_multi_scale_dataframe_predict.py:607-700); here batch i+1 is decoded on host threads
-        (datasets.read_batch, cv2.imread: the reference's pixels) into a recycled pinned buffer while batch i runs
-        through detect_stream (H2D, kernels and D2H pipelined over `depth` streams)."""
+        """Generator over image files: yields `(path, detections (k,7) float64 or np.array([]))` in input order.  The
+        production driver of the reference builds a detector per item and decodes every file once per scale
+        (yolov7_face_multi_scale_dataframe_predict.py:607-700); here batch i+1 is decoded on host threads
+        (datasets.read_images, cv2.imread: the reference's pixels) while batch i runs on the GPU.  Runs of batches whose
+        images share one size go through detect_stream (pinned buffers recycled, H2D / kernels / D2H pipelined over
+        `depth` streams); a batch of mixed sizes is bucketed by letterboxed shape (_detect_ragged)."""
         import concurrent.futures
-        from .datasets import read_batch
+        from .datasets import read_batch, read_images
         paths = list(paths)
         chunks = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
         if not chunks:
@@ -395,24 +470,56 @@ class MultiScaleFaceDetector:
         bufs = {}  # pinned batch buffers, recycled per (slot, batch length); depth + 2 slots are never in flight together
 
         def load(ci):
-            key = (ci % (depth + 2), len(chunks[ci]))
-            bufs[key] = read_batch(chunks[ci], threads=decode_threads, out=bufs.get(key))
+            imgs = read_images(chunks[ci], threads=decode_threads)
+            if len({im.shape for im in imgs}) > 1:
+                return imgs  # ragged
+            key = (ci % (depth + 2), len(imgs))
+            bufs[key] = read_batch(imgs, out=bufs.get(key) if bufs.get(key) is not None and
+                                   tuple(bufs[key].shape[1:]) == imgs[0].shape else None)
             return bufs[key]
 
         with concurrent.futures.ThreadPoolExecutor(1) as ex:
-            nxt = ex.submit(load, 0)
+            state = {"next_ci": 0, "future": ex.submit(load, 0), "held": None}
 
-            def batches():
-                nonlocal nxt
-                for ci in range(len(chunks)):
-                    cur = nxt.result()
-                    if ci + 1 < len(chunks):
-                        nxt = ex.submit(load, ci + 1)
+            def take():
+                """The next decoded chunk (and start decoding the one after it)."""
+                if state["held"] is not None:
+                    cur, state["held"] = state["held"], None
+                    return cur
+                if state["next_ci"] >= len(chunks):
+                    return None
+                ci = state["next_ci"]
+                cur = state["future"].result()
+                state["next_ci"] = ci + 1
+                if ci + 1 < len(chunks):
+                    state["future"] = ex.submit(load, ci + 1)
+                return ci, cur
+
+            def uniform_run(first):
+                """`first` and the uniform batches that follow it; a ragged one is put back for the outer loop."""
+                item = first
+                while item is not None:
+                    ci, cur = item
+                    if isinstance(cur, list):
+                        state["held"] = item
+                        return
+                    order.append(ci)
                     yield cur
+                    item = take()
 
-            for ci, dets in enumerate(self.detect_stream(batches(), depth=depth)):
-                for pth, d in zip(chunks[ci], dets):
-                    yield pth, d
+            while True:
+                item = take()
+                if item is None:
+                    break
+                ci, cur = item
+                if isinstance(cur, list):
+                    for pth, d in zip(chunks[ci], self._detect_ragged(cur)):
+                        yield pth, d
+                    continue
+                order = []
+                for k, dets in enumerate(self.detect_stream(uniform_run(item), depth=depth)):
+                    for pth, d in zip(chunks[order[k]], dets):
+                        yield pth, d
 
     def get_detection_statistics(self, detections):
         """Subset of the reference's statistics helper used by detect_multi_scale's log line (msfd:281-282)."""

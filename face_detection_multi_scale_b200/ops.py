@@ -322,7 +322,15 @@ class PostPlan:
         d.iou_mode = int(iou_mode)
         d.iou_thres = float(iou_thres)
         d.in_h_host = C.cast(self._in_h, C.POINTER(C.c_int32))
-        d.orig_h, d.orig_w = int(orig_hw[0]), int(orig_hw[1])
+        # orig_hw: (H0, W0) for the whole batch, or -- ragged batch -- a (bs, 2) int32 CUDA tensor with one pair per image
+        if isinstance(orig_hw, torch.Tensor):
+            if orig_hw.dtype != torch.int32 or tuple(orig_hw.shape) != (self.bs, 2) or not orig_hw.is_cuda or not orig_hw.is_contiguous():
+                raise ValueError("PostPlan: per-image orig_hw must be a contiguous (bs, 2) int32 CUDA tensor")
+            self._orig_hw = orig_hw
+            d.orig_h, d.orig_w, d.orig_hw_dev = 1, 1, orig_hw.data_ptr()
+        else:
+            self._orig_hw = None
+            d.orig_h, d.orig_w, d.orig_hw_dev = int(orig_hw[0]), int(orig_hw[1]), None
         d.cand, d.cand_row, d.count = self.cands.cand.data_ptr(), self.cands.row.data_ptr(), self.cands.count.data_ptr()
         d.keep, d.n_keep = self.cands.keep.data_ptr(), self.cands.n_keep.data_ptr()
         d.dets, d.n_out, d.out_cap = self.out.dets.data_ptr(), self.out.n_out.data_ptr(), out_cap

@@ -211,6 +211,13 @@ FDMS_API int fdms_merge_scales(fdms_ctx *ctx, const float *cand, const int32_t *
                                int n_img, int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
                                double iou_thres, float *dets, int32_t *n_out, int out_cap, int32_t *merged_in,
                                float *kpts_out, fdms_stream stream);
+/* The same for a RAGGED batch: images of different original sizes whose letterboxed inputs share their shapes (the
+ * reference handles arbitrary images per call, multi_scale_face_detector.py:242-288; autoShape batches mixed sizes,
+ * models/common.py:618-636).  orig_hw_dev = (n_img, 2) int32 on the device, (H0, W0) per image. */
+FDMS_API int fdms_merge_scales_ragged(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep,
+                                      int n_img, int n_scales, int cap, const int32_t *in_h_host,
+                                      const int32_t *orig_hw_dev, double iou_thres, float *dets, int32_t *n_out,
+                                      int out_cap, int32_t *merged_in, float *kpts_out, fdms_stream stream);
 
 /* multi_scale_face_detector.py:168-201,224-229 for the standalone weighted_nms(detections) call:
  * dets (n,7) float64 [x1,y1,x2,y2,conf,cls,scale_idx] -> rows_out (n,8) f32
@@ -244,6 +251,8 @@ typedef struct fdms_post_desc {
     int32_t flags; /* FDMS_POST_* */
     int32_t *merged_in; /* may be NULL */
     float *kpts_out;    /* may be NULL */
+    const int32_t *orig_hw_dev; /* NULL, or (bs, 2) int32 ON THE DEVICE: (H0, W0) per image -- a batch whose images have
+                                 * different original sizes but the same letterboxed input shapes (orig_h / orig_w unused) */
 } fdms_post_desc;
 
 FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_stream stream);

@@ -240,6 +240,28 @@ def main():
             check(stills + clips == list(ref.files) and [False] * len(stills) + [True] * len(clips) == list(ref.video_flag)
                   and len(stills + clips) == ref.nf, ("LoadImages discovery", spec.replace(d, "<tmp>")))
 
+    # ---- stream loader: source list parsing, names, rect decision, first tick (utils/datasets.py:262-340), without a GPU:
+    # the drop-in's host logic against the reference's on two file "cameras"
+    from utils.datasets import LoadStreams as RefLoadStreams
+    with tempfile.TemporaryDirectory() as d:
+        for name, (hh, ww) in (("a.avi", (90, 120)), ("b.avi", (60, 120))):
+            vw = cv2.VideoWriter(os.path.join(d, name), cv2.VideoWriter_fourcc(*"MJPG"), 25, (ww, hh))
+            for i in range(20):
+                vw.write(rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8))
+            vw.release()
+        lst = os.path.join(d, "streams.txt")
+        for names in (["a.avi"], ["a.avi", "b.avi"], ["a.avi", "a.avi"]):
+            with open(lst, "w") as f:
+                f.write("\n".join(os.path.join(d, n) for n in names) + "\n")
+            try:
+                ref = quiet(RefLoadStreams, lst, 64, 32)
+            except Exception:
+                continue
+            geoms = [O.letterbox_geometry(x.shape[0], x.shape[1], 64, auto=True, stride=32) for x in ref.imgs]
+            rect = len({(g.dst_h, g.dst_w) for g in geoms}) == 1
+            check(rect == bool(ref.rect) and [D.clean_str(os.path.join(d, n)) for n in names] == list(ref.sources),
+                  ("LoadStreams rect / names", names))
+
     # ---- test-time augmentation pieces
     for it in range(6):
         shape = (int(rng.integers(1, 3)), 3, int(rng.integers(1, 8)) * 32, int(rng.integers(1, 8)) * 32)

@@ -518,3 +518,128 @@ def test_detect_stream_landmarks_and_capacity_growth():
     # ... and the lanes' plans were rebuilt with the grown capacity (no plan of the old size is left)
     for lane in det2._tls.lanes:
         assert lane.plans and all(p.out.out_cap == det2.out_cap for p in lane.plans.values())
+
+
+def _write_video(path, frames):
+    import cv2
+    h, w = frames[0].shape[:2]
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), 25, (w, h))
+    if not vw.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG/avi")
+    for f in frames:
+        vw.write(f)
+    vw.release()
+
+
+def test_load_images_video_frames_and_mixed_directory(tmp_path):
+    """utils/datasets.py:160-178: every frame of every clip after the stills, `mode` / `frame` / `nframes` / `count` as
+    the reference reports them; pixels = the oracle's letterbox(auto=False) sequence on the decoded frame."""
+    import cv2
+    from face_detection_multi_scale_b200.datasets import LoadImages
+    from oracle import oracle as O
+    frames = [np.full((90, 120, 3), 30 * i, np.uint8) + synth.synth_image(90, 120, i) // 4 for i in range(5)]
+    _write_video(tmp_path / "b.avi", frames)
+    _write_video(tmp_path / "c.avi", frames[:2])
+    assert cv2.imwrite(str(tmp_path / "a.png"), synth.synth_image(64, 100, 9))
+    ds = LoadImages(str(tmp_path), img_size=64, stride=32)
+    assert ds.nf == 3 and ds.video_flag == [False, True, True] and ds.cap is not None
+    seen = []
+    for path, img, img0, cap in ds:
+        ref, _, _ = O.letterbox(img0, 64, auto=False, stride=32)
+        assert np.array_equal(img, np.ascontiguousarray(ref[:, :, ::-1].transpose(2, 0, 1)))
+        seen.append((os.path.basename(path), ds.mode, ds.frame if ds.mode == "video" else 0))
+        if ds.mode == "video":
+            assert cap is ds.cap and ds.nframes in (5, 2)
+    assert seen == [("a.png", "image", 0)] + [("b.avi", "video", k) for k in range(1, 6)] + [("c.avi", "video", 1), ("c.avi", "video", 2)]
+    assert ds.count == ds.nf
+    # decoded frames equal what cv2 gives when the file is read directly
+    cap = cv2.VideoCapture(str(tmp_path / "b.avi"))
+    ok, f0 = cap.read()
+    first = next(iter(LoadImages(str(tmp_path / "b.avi"), img_size=64)))
+    assert ok and np.array_equal(first[2], f0)
+
+
+def test_load_streams_batches_frames_like_the_reference(tmp_path):
+    """utils/datasets.py:262-340: the stream loader (the reference's only batch > 1 loader).  File sources stand in for
+    cameras; the first tick holds the first frame of every source (`cap.read()` at :294), letterboxed with auto = rect,
+    RGB, CHW, stacked."""
+    from face_detection_multi_scale_b200.datasets import LoadStreams, clean_str
+    from oracle import oracle as O
+    fa = [synth.synth_image(90, 120, 20 + i) for i in range(40)]
+    fb = [synth.synth_image(90, 120, 70 + i) for i in range(40)]
+    _write_video(tmp_path / "cam_a.avi", fa)
+    _write_video(tmp_path / "cam_b.avi", fb)
+    lst = tmp_path / "streams.txt"
+    lst.write_text("%s\n\n%s\n" % (tmp_path / "cam_a.avi", tmp_path / "cam_b.avi"))
+    ds = LoadStreams(str(lst), img_size=64, stride=32)
+    assert ds.mode == "stream" and ds.rect and len(ds) == 0
+    assert ds.sources == [clean_str(str(tmp_path / "cam_a.avi")), clean_str(str(tmp_path / "cam_b.avi"))]
+    srcs, img, img0, cap = next(iter(ds))
+    assert cap is None and img.shape[0] == 2 and img.dtype == np.uint8 and len(img0) == 2
+    for i in range(2):
+        ref, _, _ = O.letterbox(img0[i], 64, auto=True, stride=32)
+        assert np.array_equal(img[i], np.ascontiguousarray(ref[:, :, ::-1].transpose(2, 0, 1)))
+    # a later tick still yields one frame per source with the same shape; on the device when asked for
+    ds2 = LoadStreams(str(tmp_path / "cam_a.avi"), img_size=64, device_out=True)
+    it = iter(ds2)
+    _, img_a, _, _ = next(it)
+    _, img_b, _, _ = next(it)
+    assert img_a.is_cuda and tuple(img_a.shape) == tuple(img_b.shape) == (1, 3, 64, 64) or tuple(img_a.shape)[0] == 1
+
+
+def test_ragged_batch_mixed_image_sizes(tmp_path):
+    """Images of different sizes in ONE call (msfd:242-288 takes any image; autoShape batches mixed sizes,
+    models/common.py:618-636): bucketed by letterboxed shapes, per-image original size in the merge.  Every image's
+    result equals the oracle's for that image alone; detect_files takes a directory of mixed sizes too."""
+    import cv2
+    sizes = [160, 256, 320]
+    src_shapes = [(270, 480), (260, 480), (480, 270), (270, 480), (300, 480)]  # (270,480) and (260,480) share a bucket
+    imgs = [synth.synth_image(h, w, 60 + i) for i, (h, w) in enumerate(src_shapes)]
+    det = None
+    per_img = []
+    for i, (h, w) in enumerate(src_shapes):
+        hd, shp = H.e2e_heads(h, w, sizes, 15, False, 900 + i)
+        per_img.append((hd, shp))
+    # the stand-in backbone hands out pre-generated maps per input shape: build them in the order the detector batches
+    # a bucket (images sorted by source shape inside a bucket)
+    buckets = {}
+    for i, (hd, shp) in enumerate(per_img):
+        buckets.setdefault(tuple(shp), []).append(i)
+    model = standin.SyntheticHeadModel()
+
+    class Routed(standin.SyntheticHeadModel):
+        """Delivers the maps of whichever bucket matches the input's shape AND batch size."""
+        def __init__(self):
+            super().__init__()
+            self.by_key = {}
+
+        def forward(self, x, augment=False):
+            levels = self.by_key[(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))]
+            return self.model[-1]([t.to(x.device) for t in levels])
+    model = Routed()
+    for shp, idx in buckets.items():
+        idx = sorted(idx, key=lambda i: imgs[i].shape)
+        for s_, hw in enumerate(shp):
+            levels = [torch.from_numpy(np.stack([per_img[i][0][hw][l] for i in idx]).astype(np.float16)) for l in range(3)]
+            model.by_key[(len(idx), hw[0], hw[1])] = levels
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU)
+    out = det.detect_multi_scale_batch(imgs)
+    assert det.last_stats["buckets"] == len(buckets) >= 3
+    total = 0
+    for i, (h, w) in enumerate(src_shapes):
+        hd, shp = per_img[i]
+        ref, _ = O.detect_from_heads([[hd[hw][l][None].astype(np.float16) for l in range(3)] for hw in shp], shp, (h, w, 3),
+                                     synth.P5_STRIDES, synth.P5_ANCHORS, 0.5, 0.5, O.TV_CPU)
+        assert out[i].shape == ref.shape and (ref.size == 0 or np.array_equal(out[i], ref)), (i, out[i].shape, ref.shape)
+        total += len(ref)
+    assert total > 20
+    # from files, through detect_files (chunk of mixed sizes)
+    paths = []
+    for i, im in enumerate(imgs):
+        p = tmp_path / ("r%d.png" % i)
+        assert cv2.imwrite(str(p), im)
+        paths.append(str(p))
+    got = list(det.detect_files(paths, batch_size=8))
+    assert [p for p, _ in got] == paths
+    for (p, d), o in zip(got, out):
+        assert d.shape == o.shape and np.array_equal(d, o)

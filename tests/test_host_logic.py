@@ -175,6 +175,21 @@ for a, b in zip(out, truth):
 # all-empty shard on one rank
 out = fdist.gather_detections([np.array([])] * len(local) if rank == 1 else local, n)
 assert sum(len(o) for o in out) == sum(len(t) for t in truth[:4])
+# the device-resident form of the gather (tensors in, tensors out; gloo moves CPU tensors the same way NCCL moves CUDA ones)
+import torch
+a, b = fdist.shard_range(n, rank, 2)
+cap = 12
+dets = torch.zeros((b - a, cap, 7), dtype=torch.float32)
+n_out = torch.zeros((b - a,), dtype=torch.int32)
+for i, t in enumerate(truth[a:b]):
+    t = np.asarray(t, np.float32).reshape(-1, 7) if np.size(t) else np.zeros((0, 7), np.float32)
+    dets[i, :len(t)] = torch.from_numpy(t)
+    n_out[i] = len(t)
+d_all, n_all = fdist.gather_device(dets, n_out, n)
+assert tuple(d_all.shape) == (n, 9, 7) and n_all.tolist() == [3, 0, 5, 1, 0, 0, 9]
+for i, t in enumerate(truth):
+    t = np.asarray(t, np.float32).reshape(-1, 7) if np.size(t) else np.zeros((0, 7), np.float32)
+    assert np.array_equal(d_all[i, :len(t)].numpy(), t)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """

@@ -36,6 +36,24 @@ assert len(gathered) == B
 for g, r in zip(gathered, whole):
     r = np.asarray(r).reshape(-1, 7) if np.size(r) else np.zeros((0, 7))
     assert g.shape == r.shape and np.array_equal(g, r)
+# the same without leaving the device: fp32 rows and counts gathered over NCCL, only the counts are read by the host
+d_all, n_all = fdist.detect_sharded(detector(a, b), images, gather=True, device_out=True)
+assert d_all.is_cuda and n_all.is_cuda and d_all.shape[0] == B
+for i, r in enumerate(whole):
+    r = np.asarray(r).reshape(-1, 7) if np.size(r) else np.zeros((0, 7))
+    k = int(n_all[i])
+    assert k == len(r) and np.array_equal(d_all[i, :k].cpu().numpy().astype(np.float64), r)
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+det_l = detector(a, b)
+dl, nl = det_l.detect_multi_scale_batch(images[a:b], device_out=True)
 dist.barrier()
+ev0.record()
+for _ in range(20):
+    fdist.gather_device(dl, nl, B)
+ev1.record()
+torch.cuda.synchronize()
+gather_ms = ev0.elapsed_time(ev1) / 20
+dist.barrier()
+print("rank %d/%d: device gather %.3f ms per call" % (rank, world, gather_ms))
 print("rank %d/%d: sharded + NCCL gather == single GPU for %d images (%d detections)" % (rank, world, B, sum(len(g) for g in gathered)))
 dist.destroy_process_group()

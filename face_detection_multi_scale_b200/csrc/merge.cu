@@ -84,10 +84,13 @@ __global__ void weighted_rows_kernel(const double *__restrict__ dets, long long 
 }
 
 // skip_le >= 0: images with at most that many merged rows were emitted by the fused kernel already
+// grid (parts, images): a dense image's rows (thousands, each gathering its landmarks from scattered candidate rows)
+// are spread over several CTAs -- one CTA per image left the kernel waiting on ~40 dependent loads per thread
+// (ncu: 96 % long-scoreboard stalls, 111 us for 32 CTAs on the dense-crowd workload).
 __global__ void merge_emit_kernel(const __grid_constant__ EmitParams P, const int32_t *__restrict__ mcount, int skip_le) {
-    const int img = blockIdx.x;
+    const int img = blockIdx.y;
     if (skip_le >= 0 && mcount[img] <= skip_le) return;
-    merge_emit_image(P, img, P.n_keep2[img], threadIdx.x, blockDim.x);
+    merge_emit_image(P, img, P.n_keep2[img], threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 
 }  // namespace
@@ -234,7 +237,11 @@ static int merge_scales_impl(fdms_ctx *ctx, const float *cand, const int32_t *ke
                                  n_keep2, st);
     ctx->nms_small_done = false;
     if (rc) return rc;
-    merge_emit_kernel<<<n_img, 256, 0, st>>>(E, mcount, skip_le);
+    {
+        int parts = ceil_div(mcap < out_cap ? mcap : out_cap, 256);
+        if (parts > 16) parts = 16;
+        merge_emit_kernel<<<dim3(parts, n_img), 256, 0, st>>>(E, mcount, skip_le);
+    }
     FDMS_LAUNCH_CHECK(ctx, "merge_emit_kernel");
     return FDMS_OK;
 }

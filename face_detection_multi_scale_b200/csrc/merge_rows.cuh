@@ -107,10 +107,12 @@ __device__ __forceinline__ int merge_prepare_image(const MergeParams &P, int img
 
 // detections[keep] of image `img` with nk kept rows (all threads of the CTA take part).  The rows and the keep list
 // may have been written by this very CTA (fused merge): plain loads, never the read-only path.
-__device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, int nk, int tid, int n_threads) {
-    if (tid == 0) P.n_out[img] = nk;
+// `part` / `n_parts`: the rows of an image may be split over several CTAs (the standalone emit kernel).
+__device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, int nk, int tid, int n_threads, int part = 0,
+                                                 int n_parts = 1) {
+    if (tid == 0 && part == 0) P.n_out[img] = nk;
     const int n = min(max(nk, 0), P.out_cap);
-    for (int k = tid; k < n; k += n_threads) {
+    for (int k = part * n_threads + tid; k < n; k += n_parts * n_threads) {
         const int pos = P.keep2[(long long)img * P.mcap + k];
         const float *m = P.mrows + ((long long)img * P.mcap + pos) * MROW;
         float *o = P.dets + ((long long)img * P.out_cap + k) * 7;

@@ -29,6 +29,13 @@ class Level(C.Structure):
                 ("scale", C.c_int32), ("row_offset", C.c_int32), ("stride", C.c_float), ("anchors", C.c_float * 6)]
 
 
+class JpegDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("supported", C.c_int32),
+                ("h", C.c_int32 * 3), ("v", C.c_int32 * 3), ("blocks_w", C.c_int32 * 3), ("blocks_h", C.c_int32 * 3),
+                ("down_w", C.c_int32 * 3), ("down_h", C.c_int32 * 3), ("coef_off", C.c_int64 * 3), ("coef_count", C.c_int64),
+                ("qt", (C.c_uint16 * 64) * 3), ("reason", C.c_char * 64)]
+
+
 class PostDesc(C.Structure):
     _fields_ = [("levels", C.POINTER(Level)), ("n_levels", C.c_int32), ("n_scales", C.c_int32), ("bs", C.c_int32),
                 ("cap", C.c_int32), ("conf_thres", C.c_float), ("iou_mode", C.c_int32), ("iou_thres", C.c_double),
@@ -77,6 +84,10 @@ _SIGS = {
     "fdms_pack_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdms_postprocess": (C.c_int, [C.c_void_p, C.POINTER(PostDesc), C.c_void_p]),
+    "fdms_jpeg_probe": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(JpegDesc)]),
+    "fdms_jpeg_decode_host": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),
+    "fdms_jpeg_decode_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fdms_set_small_only": (C.c_int, [C.c_void_p, C.c_int]),
     "fdms_set_numerics": (C.c_int, [C.c_void_p, C.c_int]),
     "fdms_get_numerics": (C.c_int, [C.c_void_p]),

@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfdms.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["ctx.cu", "pyramid.cu", "pyramid_strip.cu", "decode.cu", "nms.cu", "merge.cu", "eval.cu", "tta.cu"]
-HEADERS = ["common.cuh", "pyramid.cuh", "nms.cuh", "merge_rows.cuh", os.path.join("..", "..", "include", "fdms.h")]
+SOURCES = ["ctx.cu", "pyramid.cu", "pyramid_strip.cu", "decode.cu", "nms.cu", "merge.cu", "eval.cu", "tta.cu", "jpeg.cu", "jpeg_host.cu"]
+HEADERS = ["common.cuh", "pyramid.cuh", "jpeg_host.cuh", "nms.cuh", "merge_rows.cuh", os.path.join("..", "..", "include", "fdms.h")]
 
 # -fmad=false: every fp32 rounding the reference performs is kept (fused ops are explicit).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",

@@ -52,6 +52,11 @@ struct fdms_ctx {
     fdms_buf pyr_cnt;          // strip kernel: work-item counter + finished-CTA counter (self-resetting)
     fdms_buf pyr_tab;          // pyramid tap tables of the last geometry
     unsigned long long pyr_tab_key = 0;
+    fdms_buf jpg_coef, jpg_planes;  // JPEG ingest: coefficients + descriptors, component sample planes (device)
+    void *jpg_host = nullptr;       // JPEG ingest: pinned staging of the coefficients (written by the host Huffman threads)
+    size_t jpg_host_bytes = 0;
+    cudaEvent_t jpg_event = nullptr;  // the upload of the staging buffer has completed
+    bool jpg_pending = false;
     fdms_buf dec_tab;          // decode filter: per-CTA table of the last head geometry
     unsigned long long dec_tab_key = 0;
 };

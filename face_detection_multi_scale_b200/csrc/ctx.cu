@@ -85,9 +85,11 @@ FDMS_API void fdms_destroy(fdms_ctx *ctx) {
     cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->device);
     fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt};
+                        &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt, &ctx->jpg_coef, &ctx->jpg_planes};
     for (fdms_buf *b : bufs)
         if (b->p) cudaFree(b->p);
+    if (ctx->jpg_host) cudaFreeHost(ctx->jpg_host);
+    if (ctx->jpg_event) cudaEventDestroy(ctx->jpg_event);
     if (prev_dev >= 0 && prev_dev != ctx->device) cudaSetDevice(prev_dev);
     delete ctx;
 }
@@ -111,7 +113,7 @@ FDMS_API const char *fdms_last_error(const fdms_ctx *ctx) { return ctx ? ctx->er
 FDMS_API int64_t fdms_scratch_bytes(const fdms_ctx *ctx) {
     if (!ctx) return 0;
     const fdms_buf *bufs[] = {&ctx->sort_a, &ctx->idx_a, &ctx->idx_b, &ctx->boxes, &ctx->mask,
-                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt};
+                              &ctx->seginfo, &ctx->merge_rows, &ctx->merge_cnt, &ctx->merge_keep, &ctx->pyr_tab, &ctx->dec_tab, &ctx->pyr_cnt, &ctx->jpg_coef, &ctx->jpg_planes};
     int64_t t = 0;
     for (const fdms_buf *b : bufs) t += (int64_t)b->bytes;
     return t;

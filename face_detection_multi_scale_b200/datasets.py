@@ -332,6 +332,63 @@ def read_images(items, threads=None):
         return list(ex.map(load, items))
 
 
+def read_batch_device(paths, device=None, threads=0, out=None):
+    """Device-side ingest of a list of same-sized image FILES: the bytes are read on the host, JPEG streams are
+    Huffman-decoded on host threads and reconstructed on the GPU (ops.jpeg_decode_batch: IDCT, fancy chroma upsampling,
+    YCbCr -> BGR, bit-identical to cv2.imread), everything the device path does not take (PNG, progressive JPEG, EXIF
+    rotation, ...) is decoded with cv2.imread and uploaded into its slot.  Returns a (B, H, W, 3) uint8 BGR CUDA tensor whose
+    contents are complete when the call returns (the calling thread's current stream is synchronised), and the number of
+    images that went through the device path."""
+    import os
+
+    import cv2
+    paths = [os.fsdecode(p) for p in paths]
+    if not paths:
+        raise ValueError("read_batch_device: empty batch")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    blobs = []
+    for p in paths:
+        with open(p, "rb") as f:
+            blobs.append(f.read())
+    hw = None
+    d0 = ops.jpeg_probe(blobs[0])
+    if d0 is not None and d0.width > 0 and d0.height > 0:
+        hw = (int(d0.height), int(d0.width))
+    first = None
+    if hw is None:  # not a JPEG: the first image's size comes from the host decoder
+        first = cv2.imdecode(np.frombuffer(blobs[0], np.uint8), cv2.IMREAD_COLOR)
+        if first is None:
+            raise ValueError(f"Could not read image: {paths[0]}")  # msfd:86
+        hw = first.shape[:2]
+    with torch.cuda.device(dev):
+        if out is None or tuple(out.shape) != (len(paths), hw[0], hw[1], 3):
+            out = torch.empty((len(paths), hw[0], hw[1], 3), dtype=torch.uint8, device=dev)
+        is_jpeg = [b[:2] == b"\xff\xd8" for b in blobs]
+        idx = [i for i, j in enumerate(is_jpeg) if j]
+        status = np.ones((len(paths),), np.int32)
+        if idx:
+            if len(idx) == len(paths):
+                _, st = ops.jpeg_decode_batch(blobs, hw, out=out, threads=threads)
+                status = st
+            else:
+                sub, st = ops.jpeg_decode_batch([blobs[i] for i in idx], hw, threads=threads, device=dev)
+                for k, i in enumerate(idx):
+                    status[i] = st[k]
+                    if st[k] == 0:
+                        out[i].copy_(sub[k])
+        for i, s in enumerate(status):
+            if s == 0:
+                continue
+            img = first if (i == 0 and first is not None) else cv2.imread(paths[i])  # exactly the reference's decoder (EXIF etc.)
+            if img is None:
+                raise ValueError(f"Could not read image: {paths[i]}")
+            if img.shape != (hw[0], hw[1], 3):
+                raise ValueError("read_batch_device: image %d is %s, the batch is %s" % (i, img.shape, (hw[0], hw[1], 3)))
+            out[i].copy_(torch.from_numpy(img))
+        torch.cuda.current_stream(dev).synchronize()
+    return out, int((status == 0).sum())
+
+
 def read_batch(items, threads=None, out=None):
     """Decode a list of same-sized image files (paths) / already decoded (H, W, 3) uint8 arrays into ONE pinned
     (B, H, W, 3) uint8 BGR host tensor, files in parallel on `threads` host threads (cv2 releases the GIL).  The

@@ -251,10 +251,14 @@ class MultiScaleFaceDetector:
             if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
                 raise ValueError("detect_stream: expected (B, H, W, 3) uint8 batches")
             with torch.cuda.stream(lane.stream):
-                if lane.img_dev is None or lane.img_dev.shape != t.shape:
-                    lane.img_dev = torch.empty(t.shape, dtype=torch.uint8, device=self.device)
-                lane.img_dev.copy_(t, non_blocking=True)
-                plan = self.detect_batch_device(lane.img_dev, lane)
+                if t.is_cuda:  # already on the device (datasets.read_batch_device): no copy; the producer has synchronised
+                    src_dev = t
+                else:
+                    if lane.img_dev is None or lane.img_dev.shape != t.shape:
+                        lane.img_dev = torch.empty(t.shape, dtype=torch.uint8, device=self.device)
+                    lane.img_dev.copy_(t, non_blocking=True)
+                    src_dev = lane.img_dev
+                plan = self.detect_batch_device(src_dev, lane)
                 o = plan.out
                 if lane.h_dets is None or lane.h_dets.shape != o.dets.shape or lane.h_meta.numel() != o.n_out.numel() + 5:
                     lane.h_dets = torch.empty(o.dets.shape, dtype=torch.float32).pin_memory()
@@ -454,13 +458,16 @@ class MultiScaleFaceDetector:
         out = self.detect_multi_scale_batch(img0[None])
         return out[0], img0.shape
 
-    def detect_files(self, paths, batch_size=32, decode_threads=None, depth=2):
+    def detect_files(self, paths, batch_size=32, decode_threads=None, depth=2, device_decode=False):
         """Generator over image files: yields `(path, detections (k,7) float64 or np.array([]))` in input order.  The
         production driver of the reference builds a detector per item and decodes every file once per scale
         (yolov7_face_multi_scale_dataframe_predict.py:607-700); here batch i+1 is decoded on host threads
         (datasets.read_images, cv2.imread: the reference's pixels) while batch i runs on the GPU.  Runs of batches whose
         images share one size go through detect_stream (pinned buffers recycled, H2D / kernels / D2H pipelined over
-        `depth` streams); a batch of mixed sizes is bucketed by letterboxed shape (_detect_ragged)."""
+        `depth` streams); a batch of mixed sizes is bucketed by letterboxed shape (_detect_ragged).
+        `device_decode=True`: JPEG files are only Huffman-decoded on the host threads; IDCT, chroma upsampling and colour
+        conversion run on the GPU (datasets.read_batch_device, bit-identical to cv2.imread) and the batch never exists in
+        host memory as pixels.  Files the device path does not take are decoded with cv2.imread into their slot."""
         import concurrent.futures
         from .datasets import read_batch, read_images
         paths = list(paths)
@@ -469,7 +476,20 @@ class MultiScaleFaceDetector:
             return
         bufs = {}  # pinned batch buffers, recycled per (slot, batch length); depth + 2 slots are never in flight together
 
+        dev_bufs = {}
+
         def load(ci):
+            if device_decode:
+                from .datasets import read_batch_device
+                key = ci % (depth + 2)
+                try:
+                    dev_bufs[key], _ = read_batch_device(chunks[ci], device=self.device, threads=decode_threads or 0,
+                                                         out=dev_bufs.get(key))
+                    return dev_bufs[key]
+                except ValueError as e:
+                    if "the batch is" not in str(e):
+                        raise  # unreadable file: same error as the host path
+                    # mixed sizes: the host path buckets them
             imgs = read_images(chunks[ci], threads=decode_threads)
             if len({im.shape for im in imgs}) > 1:
                 return imgs  # ragged

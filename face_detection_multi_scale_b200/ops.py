@@ -77,6 +77,39 @@ def debug_poison_smem(byte_value=0xFF, device=None):
     c.check(_lib.lib().fdms_debug_poison_smem(c.handle, int(byte_value), _stream(dev)), "fdms_debug_poison_smem")
 
 
+# ---------------------------------------------------------------------------------------------- JPEG ingest
+def jpeg_probe(data):
+    """Header probe of a JPEG byte string (host only): _lib.JpegDesc with width / height / `supported` / `reason`, or None
+    when the bytes are not a JPEG stream at all."""
+    d = _lib.JpegDesc()
+    rc = _lib.lib().fdms_jpeg_probe(data, len(data), C.byref(d))
+    return d if rc == 0 else None
+
+
+def jpeg_decode_batch(datas, hw, out=None, threads=0, device=None):
+    """Device JPEG ingest: `datas` = list of JPEG byte strings of ONE image size `hw` -> ((n, h, w, 3) uint8 BGR CUDA tensor,
+    status int32 array).  The Huffman decode runs on `threads` host threads (0 = all) inside the call; IDCT, chroma
+    upsampling and colour conversion are enqueued on torch's current stream.  status[i] == 0: slot i holds cv2.imread's
+    pixels; 1: the stream needs the host decoder (progressive, 4:1:1, EXIF rotation ...) and slot i is untouched;
+    < 0: corrupt / wrong size."""
+    n = len(datas)
+    h, w = int(hw[0]), int(hw[1])
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    elif tuple(out.shape) != (n, h, w, 3) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("jpeg_decode_batch: `out` must be a contiguous (n, h, w, 3) uint8 CUDA tensor")
+    di = _dev(out)
+    ptrs = (C.c_char_p * n)(*datas)
+    lens = (C.c_size_t * n)(*[len(b) for b in datas])
+    status = np.zeros((n,), np.int32)
+    c = _ctx(di)
+    rc = _lib.lib().fdms_jpeg_decode_batch(c.handle, ptrs, lens, n, int(threads), _ptr(out), out.stride(0), out.stride(1), h, w,
+                                           C.c_void_p(status.ctypes.data), _stream(di))
+    c.check(rc, "fdms_jpeg_decode_batch")
+    return out, status
+
+
 # ---------------------------------------------------------------------------------------------- decode
 def _level_table(scales_levels, strides, anchors_px):
     """scales_levels: list over scales of list over levels of (bs, 63, ny, nx) tensors."""

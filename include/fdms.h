@@ -305,6 +305,31 @@ FDMS_API int fdms_descale_pred(fdms_ctx *ctx, const float *pred, int bs, int64_t
                                int img_h, int img_w, float *dst, int64_t rows_total, int64_t row_offset,
                                fdms_stream stream);
 
+/* ---- device JPEG ingest: multi_scale_face_detector.py:84 cv2.imread -> libjpeg-turbo -------------
+ * The entropy decode stays on the host (one image per thread), dequantisation + islow IDCT + fancy chroma upsampling +
+ * YCbCr -> BGR run on the device, bit-identical to cv2.imread.  Baseline / extended sequential 8-bit JPEG, one interleaved
+ * scan, grey or YCbCr with 4:4:4 / 4:2:2 / 4:2:0 sampling, no EXIF rotation; anything else is reported as unsupported and the
+ * caller decodes that file with the host decoder. */
+typedef struct fdms_jpeg_desc {
+    int32_t width, height, ncomp, supported;
+    int32_t h[3], v[3];                    /* sampling factors per component */
+    int32_t blocks_w[3], blocks_h[3];      /* whole 8x8 blocks per component (MCU-padded) */
+    int32_t down_w[3], down_h[3];          /* real samples per component */
+    int64_t coef_off[3], coef_count;       /* layout of the int16 coefficient buffer: (blocks_h, blocks_w, 64) per component */
+    uint16_t qt[3][64];                    /* quantisation table per component, natural (row-major) order */
+    char reason[64];                       /* why `supported` is 0 */
+} fdms_jpeg_desc;
+FDMS_API int fdms_jpeg_probe(const uint8_t *data, size_t len, fdms_jpeg_desc *out);      /* host only */
+FDMS_API int fdms_jpeg_decode_host(const uint8_t *data, size_t len, int16_t *coef);      /* host only: entropy decode */
+/* Decodes n JPEG byte streams (host pointers) of one size h x w into dst = (n, h, w, 3) uint8 BGR ON THE DEVICE (row pitch /
+ * image stride in bytes): Huffman decode on n_threads host threads (0 = all), one upload of the coefficients, two kernels on
+ * `stream`.  status[i] (host): 0 = decoded on the device; 1 = not supported by the device path (progressive, 4:1:1, EXIF
+ * rotation, ...): slot i of dst is left untouched and the caller decodes that file on the host; < 0 = corrupt stream or
+ * wrong size.  Returns after the host work; the device work is asynchronous. */
+FDMS_API int fdms_jpeg_decode_batch(fdms_ctx *ctx, const uint8_t *const *data, const size_t *len, int n, int n_threads,
+                                    uint8_t *dst, int64_t img_stride, int64_t pitch, int h, int w, int32_t *status,
+                                    fdms_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

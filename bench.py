@@ -20,6 +20,8 @@ Prints ONE JSON line (rank 0):
   roofline       algorithmic bytes of a pyramid launch / its duration (CUDA events on the kernel's own stream inside the
                  timed region; `isolated` = the kernel alone) against MEASURED_PEAKS.json
   configs        short runs of the other BASELINE.json configs (cfg1, cfg3, cfg4, cfg5): value, stages, candidates/s, roofline
+  backbone       (N=1) a real random-init reference network between the two halves: backbone ms, end to end with it
+  ingest         (N=1) from-files decode: device JPEG ingest against the host decoder (tools/ingest_bench.py)
   cpu_baseline   (N=1) the UNMODIFIED reference on the host cores of this box (baseline/ref_runner.py, kind "reference";
                  kind "port" = the same cv2 / torch / torchvision calls when no reference tree travelled), both CPU modes
 `--impl reference` prints the reference arm alone, in the same format.
@@ -703,6 +705,17 @@ def main():
         except Exception as e:
             backbone = {"error": repr(e)}
 
+    ingest = None
+    if rank == 0 and world == 1 and not args.no_backbone and not args.profile:
+        # from-files ingest: device JPEG decode against the host decoder, own process
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ingest_bench.py"), "--files", "64"], capture_output=True,
+                               text=True, timeout=600)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            ingest = json.loads(lines[-1]) if lines else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as e:
+            ingest = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -724,7 +737,7 @@ def main():
             "serial_ms_per_step": main_res["serial_ms_per_step"], "stages_ms": main_res["stages_ms"],
             "nms_candidates_per_sec": main_res["nms_candidates_per_sec"],
             "roofline_decode": main_res["roofline_decode"],
-            "configs": configs, "backbone": backbone,
+            "configs": configs, "backbone": backbone, "ingest": ingest,
         }
         print(json.dumps(line))
     if world > 1:

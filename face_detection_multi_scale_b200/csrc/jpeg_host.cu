@@ -42,6 +42,21 @@ struct HuffTable {
     int maxcode[18];   // largest code of each length, -1 if none; [17] = sentinel
     int valoffset[17]; // index of the first value of a length minus its first code
     uint8_t vals[256];
+    // AC tables only: 9-bit lookahead that also covers the magnitude bits when code + magnitude fit in 9 bits (most
+    // coefficients of a photograph): (value << 8) | (run << 4) | bits consumed, 0 = take the general path
+    int16_t fast_ac[512];
+    void build_fast_ac() {
+        for (int i = 0; i < 512; i++) {
+            fast_ac[i] = 0;
+            const unsigned e = look[i];
+            if (!e) continue;
+            const int len = (int)(e >> 8), rs = (int)(e & 0xFF), run = rs >> 4, mag = rs & 15;
+            if (mag == 0 || len + mag > 9) continue;
+            int k = ((i << len) & 511) >> (9 - mag);
+            if (k < (1 << (mag - 1))) k += (int)((~0u) << mag) + 1;  // extend
+            if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)((k * 256) + (run * 16) + (len + mag));
+        }
+    }
     bool build(const uint8_t *bits, const uint8_t *v) {
         int huffsize[257], huffcode[257];
         int p = 0;
@@ -328,6 +343,7 @@ int fdms_jpeg_decode_coefficients(const uint8_t *d, size_t len, const JpegInfo *
         }
         if (!built_ac[ta]) {
             if (!ac[ta].build(info->bits[1][ta], info->vals[1][ta])) return -1;
+            ac[ta].build_fast_ac();
             built_ac[ta] = true;
         }
     }
@@ -362,6 +378,16 @@ int fdms_jpeg_decode_coefficients(const uint8_t *d, size_t len, const JpegInfo *
                         if (s) pred[c] += extend(br.get(s), s);
                         blk[0] = (int16_t)pred[c];
                         for (int i = 1; i < 64;) {
+                            if (br.bits < 32) br.fill();  // a coefficient takes at most 16 + 11 bits
+                            const int f = tac.fast_ac[br.peek(9)];
+                            if (f) {  // code and magnitude in one look-up
+                                i += (f >> 4) & 15;
+                                if (i > 63) return -1;
+                                br.drop(f & 15);
+                                blk[kZigzag[i]] = (int16_t)(f >> 8);
+                                i++;
+                                continue;
+                            }
                             const int rs = br.decode(tac);
                             if (rs < 0) return -1;
                             const int r = rs >> 4;

@@ -516,18 +516,23 @@ def h2d_ceiling(env, nbytes=256 << 20, reps=6):
     import torch
     import torch.distributed as dist
     src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src.fill_(1)  # first touch
     dst = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
-    dst.copy_(src, non_blocking=True)
-    torch.cuda.synchronize()
-    if env.world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    for _ in range(2):
         dst.copy_(src, non_blocking=True)
-    e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = None
+    for _ in range(3):  # best of three trials: a ceiling
+        if env.world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        ms = t if ms is None else min(ms, t)
     per_rank = nbytes * reps / (ms * 1e-3) / 1e9
     if env.world > 1:
         t = torch.tensor([per_rank], device=env.dev, dtype=torch.float64)
@@ -561,14 +566,19 @@ def measure_e2e(wl, env, steps):
             return float(t.item())
         return v
 
-    def timed(fn, n):
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        x0.record()
-        fn(n)
-        x1.record()
-        barrier()
-        return allmax(x0.elapsed_time(x1) / 1e3)
+    def timed(fn, n, trials=3):
+        """Median of `trials` timed runs of n steps (host-side transients -- page placement, a neighbour's burst on the
+        shared PCIe switch -- move a single run by tens of percent)."""
+        ts = []
+        for _ in range(trials):
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            x0.record()
+            fn(n)
+            x1.record()
+            barrier()
+            ts.append(allmax(x0.elapsed_time(x1) / 1e3))
+        return float(np.median(ts))
 
     model = standin.SyntheticHeadModel(strides, anchors)
     for s, hw in enumerate(shapes):
@@ -603,7 +613,7 @@ def measure_e2e(wl, env, steps):
     stream_run(det)(4)
     model.h2d_bytes = 0
     dt3 = timed(stream_run(det), Ke)
-    h2d_step = int(pinned.numel() + model.h2d_bytes // Ke)
+    h2d_step = int(pinned.numel() + model.h2d_bytes // (3 * Ke))
     stream_run(det2)(4)
     dt2 = timed(stream_run(det2), Ke)
     ceil = h2d_ceiling(env)

@@ -63,9 +63,12 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
                                    iou_mode=iou_mode)
     if nc is None:
         nc = prediction.shape[2] - 5 if not kpt_label else prediction.shape[2] - 5 - kpt_label * 3
+    if nc > 1 and not kpt_label and no == 5 + nc:
+        return _nms_multiclass(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, nc, iou_mode)
     if nc != 1 or no < 6 or (no - 6) % 3:
-        raise NotImplementedError("non_max_suppression on libfdms covers single-class heads (nc=1, no = 6 + 3*kpt: the "
-                                  "face head no=21, or the [..., :6] fallback of msfd:134); got no=%d kpt_label=%r nc=%r"
+        raise NotImplementedError("non_max_suppression on libfdms covers single-class heads with keypoints (nc=1, no = 6 + "
+                                  "3*kpt: the face head no=21), the [..., :6] fallback of msfd:134 and multi-class heads "
+                                  "without keypoints (kpt_label=0, no = 5 + nc); got no=%d kpt_label=%r nc=%r"
                                   % (no, kpt_label, nc))
     if labels and no != 6:
         # :535-541 builds the label rows with nc + 5 columns; with keypoint columns torch.cat raises in the reference too
@@ -112,6 +115,71 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     if out.device != src_device:
         out = out.to(src_device)
     return [out[b, :int(n_keep[b])] if int(n_keep[b]) else empty for b in range(bs)]
+
+
+def _nms_multiclass(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, labels, nc, iou_mode):
+    """utils/general.py:506-600 for nc > 1 without keypoints (the Detect / IDetect heads of the YOLO family the
+    reference's code base derives from; none of its own cfg/*.yaml is multi-class): conf = obj * cls per class (:547),
+    `multi_label` = one row per (box, class) above the threshold in nonzero() order (:553-555), else the best class
+    (:558-559); `classes` filter (:566-567); boxes offset by class * 4096 unless `agnostic` (:582); one batched NMS launch
+    for all images (torchvision semantics, `iou_mode`).  The filtering is torch tensor arithmetic in the prediction's own
+    dtype, op for op as the reference writes it; the suppression is libfdms."""
+    src_device = prediction.device
+    pred = _cuda(prediction)
+    bs = pred.shape[0]
+    empty = torch.zeros((0, 6), device=src_device)
+    mode = IOU_MODE if iou_mode is None else iou_mode
+    xc = pred[..., 4] > conf_thres
+    per_image = []
+    for xi in range(bs):
+        x = pred[xi][xc[xi]]
+        if labels and len(labels[xi]):
+            lab = torch.as_tensor(labels[xi], device=x.device, dtype=x.dtype)
+            v = torch.zeros((len(lab), nc + 5), device=x.device, dtype=x.dtype)
+            v[:, :4] = lab[:, 1:5]
+            v[:, 4] = 1.0
+            v[range(len(lab)), lab[:, 0].long() + 5] = 1.0
+            x = torch.cat((x, v), 0)
+        if not x.shape[0]:
+            per_image.append(None)
+            continue
+        x = x.clone()
+        x[:, 5:] *= x[:, 4:5]
+        box = xywh2xyxy(x[:, :4])
+        if multi_label:
+            i, j = (x[:, 5:] > conf_thres).nonzero(as_tuple=False).T
+            x = torch.cat((box[i], x[i, j + 5, None], j[:, None].to(x.dtype)), 1)
+        else:
+            conf, j = x[:, 5:].max(1, keepdim=True)
+            x = torch.cat((box, conf, j.to(x.dtype)), 1)[conf.view(-1) > conf_thres]
+        if classes is not None:
+            x = x[(x[:, 5:6] == torch.tensor(classes, device=x.device)).any(1)]
+        if x.shape[0] > MAX_NMS:
+            x = x[x[:, 4].argsort(descending=True)[:MAX_NMS]]
+        per_image.append(x if x.shape[0] else None)
+    cap = max([x.shape[0] for x in per_image if x is not None], default=0)
+    if cap == 0:
+        return [empty] * bs
+    rows = torch.zeros((bs, cap, 5), dtype=torch.float32, device=pred.device)
+    count = torch.zeros((bs,), dtype=torch.int32, device=pred.device)
+    for xi, x in enumerate(per_image):
+        if x is None:
+            continue
+        c = x[:, 5:6] * (0 if agnostic else 4096)  # :582, in the prediction's dtype like the reference
+        rows[xi, :x.shape[0], :4] = (x[:, :4] + c).float()
+        rows[xi, :x.shape[0], 4] = x[:, 4].float()
+        count[xi] = x.shape[0]
+    keep, n_keep = ops.nms_segments(rows, count, cap, iou_thres, mode, max_nms=0)
+    nk = n_keep.cpu()
+    if int(nk.min()) < 0:
+        raise _lib.FdmsError("non_max_suppression: a segment exceeded the suppression-mask budget (raise FDMS_MASK_BUDGET_MB)")
+    out = []
+    for xi, x in enumerate(per_image):
+        if x is None or int(nk[xi]) == 0:
+            out.append(empty)
+            continue
+        out.append(x[keep[xi, :int(nk[xi])].long()].to(src_device))
+    return out
 
 
 def _append_labels(c, labels, n_lab, rows, conf_thres):

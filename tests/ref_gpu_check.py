@@ -200,6 +200,20 @@ def main():
                 m_sc = G.scale_coords(x.shape[2:], r_list[0][:, :4].clone(), shape0)
                 check(torch.equal(r_box, m_box), ("P3 scale_coords_api_approach", os.path.basename(f), size))
                 check(torch.equal(r_sc, m_sc), ("P3 scale_coords", os.path.basename(f), size, float((r_sc - m_sc).abs().max())))
+    # P2c: multi-class predictions without keypoints (kpt_label=0, no = 5 + nc): class offset, `classes`, `multi_label`,
+    # `agnostic` (utils/general.py:533-582) -- synthetic clustered boxes with 4 classes, both implementations on the same tensor
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n_rows, ncls = 6000, 4
+    ctr = torch.rand(40, 2, generator=g) * 600 + 20
+    pick = torch.randint(0, 40, (2, n_rows), generator=g)
+    xy = ctr[pick] + torch.randn(2, n_rows, 2, generator=g) * 6
+    wh = torch.rand(2, n_rows, 2, generator=g) * 60 + 10
+    mc = torch.cat((xy, wh, torch.rand(2, n_rows, 1, generator=g), torch.rand(2, n_rows, ncls, generator=g)), 2).to(ref32.device)
+    for kw in (dict(), dict(multi_label=True), dict(agnostic=True), dict(classes=[1, 3]), dict(multi_label=True, classes=[0], agnostic=True)):
+        r_mc = quiet(ref_general.non_max_suppression, mc.clone(), 0.3, 0.45, kpt_label=0, **kw)
+        m_mc = G.non_max_suppression(mc.clone(), 0.3, 0.45, kpt_label=0, **kw)
+        check(len(r_mc) == len(m_mc) and all(tuple(r.shape) == tuple(m.shape) and torch.equal(r, m) for r, m in zip(r_mc, m_mc))
+              and sum(len(r) for r in r_mc) > 50, ("P2c multi-class nms", kw, [tuple(r.shape) for r in r_mc], [tuple(m.shape) for m in m_mc]))
     REPORT["P0_network_input_diffs"] = p0
     del mine_p
     REPORT["P1_decode"] = {"aten_cuda_mode": "bit-identical to the reference's CUDA fp32 decode",

@@ -263,8 +263,20 @@ def test_nms_other_keypoint_counts(golden):
         r = res[b].cpu().numpy()
         assert len(r) <= len(x) and (len(x) == 0 or len(r) > 0)
         assert np.all(np.isin(r[:, 4], x[:, 5]))  # conf column = one of the raw class scores
-    with pytest.raises(NotImplementedError):  # multi-class heads stay refused
-        general.non_max_suppression(torch.zeros((1, 10, 8), device=DEV), kpt_label=0)
+    with pytest.raises(NotImplementedError):  # several classes AND keypoints: the reference itself only reads class 0 there
+        general.non_max_suppression(torch.zeros((1, 10, 5 + 3 + 15), device=DEV), kpt_label=5)
+    # multi-class heads without keypoints (kpt_label=0, no = 5 + nc): against a direct evaluation with torchvision
+    import torchvision
+    g_ = torch.Generator().manual_seed(1)
+    p = torch.cat((torch.rand(1, 500, 2, generator=g_) * 300, torch.rand(1, 500, 2, generator=g_) * 50 + 10, torch.rand(1, 500, 1, generator=g_),
+                   torch.rand(1, 500, 3, generator=g_)), 2).to(DEV)
+    out = general.non_max_suppression(p, 0.25, 0.5, kpt_label=0)[0]
+    x = p[0][p[0, :, 4] > 0.25].clone()
+    x[:, 5:] *= x[:, 4:5]
+    conf, j = x[:, 5:].max(1, keepdim=True)
+    x = torch.cat((general.xywh2xyxy(x[:, :4]), conf, j.float()), 1)[conf.view(-1) > 0.25]
+    keep = torchvision.ops.nms(x[:, :4] + x[:, 5:6] * 4096, x[:, 4], 0.5)
+    assert torch.equal(out, x[keep]) and len(out) > 20 and len(torch.unique(out[:, 5])) == 3
 
 
 def test_detect_stream_matches_batch_calls():

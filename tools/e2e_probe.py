@@ -16,7 +16,7 @@ images, heads, shapes = standin.make_batch(H, W, sizes, B, 60, seed=17, radius=1
 model = standin.SyntheticHeadModel()
 for s, hw in enumerate(shapes):
     model.set_heads(hw, heads[s], pin=True)
-det = MultiScaleFaceDetector(model, device=dev, img_sizes=sizes, conf_thres=0.5, iou_thres=0.5, cap=1024, out_cap=1024)
+det = MultiScaleFaceDetector(model, device=dev, img_sizes=sizes, conf_thres=0.5, iou_thres=0.5, cap=int(os.environ.get("PROBE_CAP", "1024")), out_cap=int(os.environ.get("PROBE_CAP", "1024")))
 pinned = torch.from_numpy(images).pin_memory()
 for _ in range(3):
     det.detect_multi_scale_batch(pinned)

@@ -21,6 +21,7 @@
 #ifndef FDMS_H_
 #define FDMS_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

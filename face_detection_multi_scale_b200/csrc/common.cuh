@@ -39,6 +39,9 @@ struct fdms_ctx {
     bool small_only_sticky = false;  // fdms_set_small_only: the same for fdms_nms / fdms_merge_scales called one by one
     bool nms_small_done = false;  // set around fdms_nms_impl by the fused merge: segments <= the limit are done already
     int nms_greedy_min_seg = 8;   // FDMS_NMS_GREEDY_MIN_SEG: fewer segments than this -> bit-matrix path
+    int nms_bin = 1;              // FDMS_NMS_BIN: 1 = nms_binned_kernel (kept boxes in a size-stratified grid), 0 = the same
+                                  // kernel without the grid, 2 = nms_greedy_kernel (the list sweep it replaced; A/B)
+    bool nms_bin_attr = false;
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
     fdms_buf sort_a;           // NMS: 64-bit keys of segments too large for shared memory

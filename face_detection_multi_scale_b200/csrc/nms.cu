@@ -750,6 +750,377 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
     if (tid == 0) n_keep[g] = s_nkeep;
 }
 
+// Large segments, one CTA per segment, after nms_sort_kernel: blocked greedy NMS in which a KEPT box marks the later
+// candidates it suppresses, found through a size-stratified grid of the segment's candidates in shared memory.  A dense
+// crowd needs ~100 pair tests per kept box instead of ~1000 per candidate against the whole kept list (ncu of the list
+// kernel on the dense-crowd workload: 81 % ALU-pipe utilisation, bound by the pair tests), and the tests of a step are
+// spread evenly over the CTA.
+//   grid      : built once per segment (counting sort, CSR).  Level l holds the candidates whose longer side m lies in
+//               (c0 2^(l-1), c0 2^l] (level 0: m <= c0) in a uniform grid of cell size c0 2^l over the segment's
+//               extent, c0 = extent / (128 x 64), 8 levels; a candidate is filed under the cell of its CENTRE.  Cells
+//               of a grid row are consecutive in the CSR order, so a row span is one contiguous run of entries.
+//   step      : the next 256 candidates that no kept box has marked (scan of the mark bits, compaction) go through the
+//               intra-block masks + ballot resolver (greedy_block); the kept ones are appended to the keep list, then
+//               every kept box is taken by a warp that walks the candidates it can suppress and marks them.
+//   which     : IoU <= min(w_small / w_large, h_small / h_large) <= m_small / m_large, so a kept box with longer side
+//               m_k can only suppress candidates with m in [t m_k, m_k / t] (t = 0.99 x threshold: the bound holds up
+//               to a few ulp in the float arithmetic of iou_gt, the margin is 1 %) -- the levels of that range; on
+//               level l (candidate extents <= c_l) the candidate's centre must lie within bin_radius() of the kept
+//               box's centre along each axis (bin_window: for a threshold of 0.5 about the kept box itself, 1-3 cells
+//               a side).  One lane per (level, row) fetches the row's run, the runs are flattened over the 32 lanes
+//               (prefix sum + shuffle search).  The cell index is a monotone function of the coordinate, so no
+//               suppressing pair is missed.  Exact: the pair test itself is unchanged.
+//   no grid   : thresholds for which disjoint or tiny boxes count (<= 0), an extent that is not finite or is tiny
+//               against the coordinates' magnitude: every kept box walks ALL later candidates (grid_on = 0).
+//   (Tried first, same workload: the KEPT boxes in a single-level grid of linked lists, candidates walking them --
+//   merge 2.6 ms instead of 0.7, the CTA waiting at barriers for the few lanes whose large candidates covered 30+
+//   cells; then kept boxes in the stratified grid -- NMS 0.99 -> 0.45 ms, merge 0.71 -> 0.49, still 53-74 % barrier
+//   stalls at 8.7 active threads per instruction: one lane per candidate walking dependent lists cannot be balanced.)
+constexpr int BIN_LEVELS = 8;
+constexpr int BIN_GX0 = 128, BIN_GY0 = 64;
+constexpr int BIN_CELLS = 10923;  // sum over levels of ceil(128 / 2^l) * ceil(64 / 2^l)
+constexpr int BIN_MAX_K = 65535;  // entries are 16-bit positions in score order
+constexpr uint32_t BIN_PER_THREAD = (BIN_CELLS + GREEDY_THREADS - 1) / GREEDY_THREADS;
+
+struct BinShared {
+    float4 blk[GREEDY_BS];
+    unsigned long long rowmask[GREEDY_BS][4];
+    unsigned long long sup[4], keptbits[4];
+    uint32_t cell_end[BIN_CELLS + 1];  // counts, then exclusive starts, then (after the scatter) the END of each cell
+    uint32_t marks[(BIN_MAX_K + 32) / 32];
+    uint16_t cpos[GREEDY_BS];  // block member -> position in score order
+    uint16_t kl[GREEDY_BS];    // kept members of this step
+    int warp_cnt[32];
+    float red[5][32];
+    int nkeep, consumed, grid_on;
+    float x0, y0, inv_c0;
+    float lvl_inv[BIN_LEVELS], lvl_c[BIN_LEVELS];
+    int lvl_gx[BIN_LEVELS], lvl_gy[BIN_LEVELS], lvl_off[BIN_LEVELS];
+    uint16_t entries[1];  // K entries (dynamic)
+};
+
+// smallest l with m <= c0 2^l, clamped to the levels there are; monotone in q = m / c0 (q > 0)
+__device__ __forceinline__ int bin_level(float q) {
+    const int l = ((__float_as_int(q) - 1) >> 23) - 126;
+    return min(max(l, 0), BIN_LEVELS - 1);
+}
+
+// longer side of a box in the kernel's own convention; 0 when the box has no extent in some dimension (or NaN): such a
+// box overlaps nothing (boxes_overlap is false for every partner), it is neither filed nor marks anything
+template <int MODE>
+__device__ __forceinline__ float box_long_side(const float4 b) {
+    const float e = MODE == FDMS_IOU_NCNN ? 1.f : 0.f;  // the ncnn flavour's extents carry +1 pixel
+    const float w = f_add(f_sub(b.z, b.x), e), h = f_add(f_sub(b.w, b.y), e);
+    return (w > 0.f && h > 0.f) ? fmaxf(w, h) : 0.f;
+}
+
+__device__ __forceinline__ int bin_cell(float v, float origin, float inv_c, int n) {
+    return __float2int_rd(fminf(fmaxf(f_mul(f_sub(v, origin), inv_c), 0.f), (float)(n - 1)));
+}
+
+// Cells of level l that can hold the centre of a candidate the kept box (centre xk yk, extent wk hk) suppresses.
+// Per axis, with w the kept extent and wc <= c_l the candidate's: IoU <= (overlap along the axis) / max(w, wc), and the
+// overlap is at most (w + wc) / 2 - |distance of the centres|, so IoU > t needs
+//     |distance| < f(wc) = (w + wc) / 2 - t max(w, wc),
+// which over wc in (0, c_l] is largest at wc = c_l or at wc = min(w, c_l) (f rises with slope 1/2 up to w and with
+// 1/2 - t after it).  + 1 % of the cell for the float arithmetic.  An empty window has cx0 > cx1 or cy0 > cy1.
+struct BinWindow {
+    int cx0, cx1, cy0, cy1, gx, off;
+};
+
+__device__ __forceinline__ float bin_radius(float w, float cl, float t) {
+    const float wa = fminf(w, cl);
+    const float f1 = f_sub(f_mul(0.5f, f_add(w, cl)), f_mul(t, fmaxf(w, cl)));
+    const float f2 = f_sub(f_mul(0.5f, f_add(w, wa)), f_mul(t, w));  // max(w, wa) = w
+    return f_add(fmaxf(f1, f2), f_mul(0.01f, cl));
+}
+
+__device__ __forceinline__ BinWindow bin_window(const BinShared &S, int l, float xk, float yk, float wk, float hk, float t,
+                                                float x0, float y0) {
+    BinWindow r;
+    const float cl = S.lvl_c[l], inv = S.lvl_inv[l];
+    const int gy = S.lvl_gy[l];
+    r.gx = S.lvl_gx[l];
+    r.off = S.lvl_off[l];
+    const float rx = bin_radius(wk, cl, t), ry = bin_radius(hk, cl, t);
+    r.cx0 = bin_cell(f_sub(xk, rx), x0, inv, r.gx);
+    r.cx1 = rx >= 0.f ? bin_cell(f_add(xk, rx), x0, inv, r.gx) : -1;
+    r.cy0 = bin_cell(f_sub(yk, ry), y0, inv, gy);
+    r.cy1 = ry >= 0.f ? bin_cell(f_add(yk, ry), y0, inv, gy) : -1;
+    return r;
+}
+
+// Every lane brings one run [b, e) of CSR entries (b == e: none); the items of all 32 runs are dealt to the lanes in
+// turn (prefix sum + shuffle search) and each is tested against the kept box: later, unmarked candidates it suppresses
+// get their mark.  Called by whole warps.
+template <int MODE>
+__device__ __forceinline__ void bin_mark_runs(BinShared &S, const float4 *__restrict__ boxes, const float4 kb, int kpos,
+                                              int base, uint32_t b, uint32_t e, float thr, bool inclusive, int lane) {
+    uint32_t incl = e - b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const int shift = (int)(b - (incl - (e - b)));  // entry = item + shift inside this lane's run
+    for (uint32_t it = lane; it < ((total + 31u) & ~31u); it += 32) {
+        int lo = 0;  // the run holding item `it`: the first lane whose inclusive count exceeds it
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+            const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + st - 1);
+            if (v <= it) lo += st;
+        }
+        const int sh = __shfl_sync(0xffffffffu, shift, lo);
+        if (it < total) {
+            const int k = S.entries[(int)it + sh];
+            if (k > kpos && k >= base && !((S.marks[k >> 5] >> (k & 31)) & 1u)) {
+                const float4 cb = boxes[k];
+                if (boxes_overlap<MODE>(kb, cb) && iou_gt<MODE>(kb, cb, thr, inclusive, false))
+                    atomicOr(&S.marks[k >> 5], 1u << (k & 31));
+            }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GREEDY_THREADS)
+    nms_binned_kernel(const SegInfo *__restrict__ seginfo, int cap_e, const float4 *__restrict__ sorted_boxes,
+                      const uint32_t *__restrict__ sorted_idx, float thr, int inclusive, int32_t *__restrict__ keep,
+                      int32_t *__restrict__ n_keep, int cap, const int32_t *__restrict__ count, int skip_le,
+                      int bin_on) {
+    extern __shared__ __align__(16) uint8_t bin_sm[];
+    BinShared &S = *reinterpret_cast<BinShared *>(bin_sm);
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (max(0, min(count[g], cap)) <= skip_le) return;  // handled by nms_small_kernel
+    const bool quick = thr > 0.f || (thr == 0.f && !inclusive);
+    const int K = seginfo[g].n;
+    const float4 *boxes = sorted_boxes + (long long)g * cap_e;
+    const uint32_t *sidx = sorted_idx + (long long)g * cap_e;
+    int32_t *kout = keep + (long long)g * cap;
+    const float ext = MODE == FDMS_IOU_NCNN ? 1.f : 0.f;
+    // ---- the segment's extent -> level grids --------------------------------------------------------------------
+    {
+        float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY, amax = 0.f;
+        for (int k = tid; k < K; k += GREEDY_THREADS) {
+            const float4 b = boxes[k];
+            mnx = fminf(mnx, b.x);
+            mny = fminf(mny, b.y);
+            mxx = fmaxf(mxx, b.z + ext);
+            mxy = fmaxf(mxy, b.w + ext);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+            if (!(fabsf(b.x) < 1e30f && fabsf(b.y) < 1e30f && fabsf(b.z) < 1e30f && fabsf(b.w) < 1e30f)) amax = INFINITY;  // NaN too
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+        }
+        if (lane == 0) {
+            S.red[0][warp] = mnx;
+            S.red[1][warp] = mny;
+            S.red[2][warp] = mxx;
+            S.red[3][warp] = mxy;
+            S.red[4][warp] = amax;
+        }
+        for (int c = tid; c <= BIN_CELLS; c += GREEDY_THREADS) S.cell_end[c] = 0u;
+        for (int w = tid; w < (K + 31) / 32; w += GREEDY_THREADS) S.marks[w] = 0u;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < GREEDY_THREADS / 32; w++) {
+                mnx = fminf(mnx, S.red[0][w]);
+                mny = fminf(mny, S.red[1][w]);
+                mxx = fmaxf(mxx, S.red[2][w]);
+                mxy = fmaxf(mxy, S.red[3][w]);
+                amax = fmaxf(amax, S.red[4][w]);
+            }
+            const float ex = mxx - mnx, ey = mxy - mny;
+            // a little more than extent / cells: the last cell index stays below the grid size without the clamp
+            const float c0 = fmaxf(ex / (float)(BIN_GX0 - 1), ey / (float)(BIN_GY0 - 1));
+            // the 2 % slack of the search window must dwarf the rounding of a coordinate (2^-23 relative)
+            const bool ok = bin_on && quick && thr < 1e30f && amax < 1e30f && c0 > 0.f && c0 > amax * 1e-4f;
+            S.grid_on = ok ? 1 : 0;
+            S.x0 = mnx;
+            S.y0 = mny;
+            S.inv_c0 = ok ? 1.f / c0 : 0.f;
+            int off = 0;
+            for (int l = 0; l < BIN_LEVELS; l++) {
+                const float cl = c0 * (float)(1 << l);
+                S.lvl_c[l] = cl;
+                S.lvl_inv[l] = ok ? 1.f / cl : 0.f;
+                S.lvl_gx[l] = ok ? min((BIN_GX0 + (1 << l) - 1) >> l, (int)(ex / cl) + 1) : 1;
+                S.lvl_gy[l] = ok ? min((BIN_GY0 + (1 << l) - 1) >> l, (int)(ey / cl) + 1) : 1;
+                S.lvl_off[l] = off;
+                off += ((BIN_GX0 + (1 << l) - 1) >> l) * ((BIN_GY0 + (1 << l) - 1) >> l);
+            }
+            S.nkeep = 0;
+        }
+        __syncthreads();
+    }
+    const bool grid_on = S.grid_on != 0;
+    const float x0 = S.x0, y0 = S.y0, inv_c0 = S.inv_c0;
+    // ---- counting sort of the candidates by cell (CSR) ------------------------------------------------------------
+    if (grid_on) {
+        for (int pass = 0; pass < 2; pass++) {
+            for (int k = tid; k < K; k += GREEDY_THREADS) {
+                const float4 b = boxes[k];
+                const float m = box_long_side<MODE>(b);
+                if (m > 0.f) {
+                    const int l = bin_level(f_mul(m, inv_c0)), gx = S.lvl_gx[l];
+                    const int cx = bin_cell(f_mul(f_add(b.x, f_add(b.z, ext)), 0.5f), x0, S.lvl_inv[l], gx);
+                    const int cy = bin_cell(f_mul(f_add(b.y, f_add(b.w, ext)), 0.5f), y0, S.lvl_inv[l], S.lvl_gy[l]);
+                    const int cell = S.lvl_off[l] + cy * gx + cx;
+                    const uint32_t at = atomicAdd(&S.cell_end[cell], 1u);
+                    if (pass) S.entries[at] = (uint16_t)k;
+                }
+            }
+            __syncthreads();
+            if (pass == 0) {  // counts -> exclusive starts
+                uint32_t v[BIN_PER_THREAD], sum = 0u;
+                const int c_first = tid * (int)BIN_PER_THREAD;
+#pragma unroll
+                for (int q = 0; q < (int)BIN_PER_THREAD; q++) {
+                    v[q] = c_first + q < BIN_CELLS ? S.cell_end[c_first + q] : 0u;
+                    sum += v[q];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) S.warp_cnt[warp] = (int)incl;
+                __syncthreads();
+                uint32_t wsum = (uint32_t)S.warp_cnt[lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, wsum, d);
+                    if (lane >= d) wsum += t;
+                }
+                const uint32_t wbefore = __shfl_sync(0xffffffffu, wsum, max(warp - 1, 0));
+                uint32_t run = (warp ? wbefore : 0u) + incl - sum;
+#pragma unroll
+                for (int q = 0; q < (int)BIN_PER_THREAD; q++) {
+                    if (c_first + q < BIN_CELLS) S.cell_end[c_first + q] = run;
+                    run += v[q];
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const float t_lo = fminf(0.99f * thr, 1.f), t_hi = 1.f / fmaxf(t_lo, 1e-30f);
+    for (int base = 0; base < K;) {
+        const int nk = S.nkeep;
+        if (tid < 4) S.sup[tid] = 0ull;
+        // ---- the next GREEDY_BS unmarked candidates, in score order ----------------------------------------------
+        int nb = 0;
+        while (nb < GREEDY_BS && base < K) {
+            const int nw = min(GREEDY_THREADS, K - base), k = base + tid;
+            const bool alive = tid < nw && !((S.marks[k >> 5] >> (k & 31)) & 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int incl = S.warp_cnt[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int before = __shfl_sync(0xffffffffu, incl, max(warp - 1, 0));
+            const int rank = nb + (warp ? before : 0) + __popc(bal & ((1u << lane) - 1u));
+            if (alive && rank < GREEDY_BS) {
+                S.blk[rank] = boxes[k];
+                S.cpos[rank] = (uint16_t)k;
+                if (rank == GREEDY_BS - 1) S.consumed = tid + 1;
+            }
+            __syncthreads();  // warp_cnt is reused by the next window; consumed is visible
+            if (nb + total >= GREEDY_BS) {
+                base += S.consumed;
+                nb = GREEDY_BS;
+            } else {
+                base += nw;
+                nb += total;
+            }
+        }
+        // (2) + (3): column masks and parallel greedy resolution over the block (begins with a barrier)
+        greedy_block<MODE>(S.blk, nb, thr, inclusive != 0, quick, S.rowmask, S.sup, S.keptbits);
+        // (4) append the kept members
+        const int k0 = __popcll(S.keptbits[0]), k1 = __popcll(S.keptbits[1]), k2 = __popcll(S.keptbits[2]),
+                  k3 = __popcll(S.keptbits[3]);
+        const int n_new = k0 + k1 + k2 + k3;
+        if (tid < nb) {
+            const int w = tid >> 6, b = tid & 63;
+            if ((S.keptbits[w] >> b) & 1ull) {
+                const int j = __popcll(S.keptbits[w] & ((1ull << b) - 1ull)) + (w > 0 ? k0 : 0) + (w > 1 ? k1 : 0) + (w > 2 ? k2 : 0);
+                kout[nk + j] = (int32_t)sidx[S.cpos[tid]];
+                S.kl[j] = (uint16_t)tid;
+            }
+        }
+        __syncthreads();
+        // (5) every kept box marks the later candidates it suppresses: one warp per kept box
+        if (base < K) {
+            for (int j = warp; j < n_new; j += GREEDY_THREADS / 32) {
+                const int member = S.kl[j];
+                const float4 kb = S.blk[member];
+                const int kpos = S.cpos[member];
+                if (!grid_on) {
+                    for (int k = max(base, kpos + 1) + lane; k < K; k += 32) {
+                        if ((S.marks[k >> 5] >> (k & 31)) & 1u) continue;
+                        const float4 cb = boxes[k];
+                        if ((!quick || boxes_overlap<MODE>(kb, cb)) && iou_gt<MODE>(kb, cb, thr, inclusive != 0, false))
+                            atomicOr(&S.marks[k >> 5], 1u << (k & 31));
+                    }
+                    continue;
+                }
+                const float m = box_long_side<MODE>(kb);
+                if (!(m > 0.f)) continue;
+                const float q = f_mul(m, inv_c0);
+                const int l_lo = bin_level(f_mul(q, t_lo)), l_hi = bin_level(f_mul(q, t_hi));
+                const float wk = f_sub(f_add(kb.z, ext), kb.x), hk = f_sub(f_add(kb.w, ext), kb.y);
+                const float xk = f_mul(f_add(kb.x, f_add(kb.z, ext)), 0.5f), yk = f_mul(f_add(kb.y, f_add(kb.w, ext)), 0.5f);
+                // the runs of one (level, row) per lane: 8 levels x 4 rows in one go; a level that needs more rows (tiny
+                // thresholds) sends the box through the row-chunk loop below instead
+                BinWindow wnd;
+                const int l_mine = l_lo + (lane >> 2);
+                wnd = bin_window(S, min(l_mine, BIN_LEVELS - 1), xk, yk, wk, hk, t_lo, x0, y0);
+                const bool l_valid = l_mine <= l_hi && wnd.cx0 <= wnd.cx1 && wnd.cy0 <= wnd.cy1;
+                if (!__any_sync(0xffffffffu, l_valid && wnd.cy1 - wnd.cy0 >= 4)) {
+                    const int cy = wnd.cy0 + (lane & 3);
+                    uint32_t b = 0u, e = 0u;
+                    if (l_valid && cy <= wnd.cy1) {
+                        const int ca = wnd.off + cy * wnd.gx + wnd.cx0, cz = wnd.off + cy * wnd.gx + wnd.cx1;
+                        b = ca ? S.cell_end[ca - 1] : 0u;
+                        e = S.cell_end[cz];
+                    }
+                    bin_mark_runs<MODE>(S, boxes, kb, kpos, base, b, e, thr, inclusive != 0, lane);
+                    continue;
+                }
+                for (int l = l_lo; l <= l_hi; l++) {
+                    wnd = bin_window(S, l, xk, yk, wk, hk, t_lo, x0, y0);
+                    if (wnd.cx0 > wnd.cx1) continue;
+                    for (int r0 = wnd.cy0; r0 <= wnd.cy1; r0 += 32) {
+                        const int cy = r0 + lane;
+                        uint32_t b = 0u, e = 0u;
+                        if (cy <= wnd.cy1) {
+                            const int ca = wnd.off + cy * wnd.gx + wnd.cx0, cz = wnd.off + cy * wnd.gx + wnd.cx1;
+                            b = ca ? S.cell_end[ca - 1] : 0u;
+                            e = S.cell_end[cz];
+                        }
+                        bin_mark_runs<MODE>(S, boxes, kb, kpos, base, b, e, thr, inclusive != 0, lane);
+                    }
+                }
+            }
+        }
+        if (tid == 0) S.nkeep = nk + n_new;
+        __syncthreads();
+    }
+    if (tid == 0) n_keep[g] = S.nkeep;
+}
+
 __global__ void gather_rows_kernel(const float *__restrict__ rows, int row_stride, int n_cols,
                                    const int32_t *__restrict__ keep, const int32_t *__restrict__ n_keep, int cap,
                                    float *__restrict__ out, int out_cap) {
@@ -857,6 +1228,26 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
         reinterpret_cast<uint32_t *>(ctx->idx_b.p), reinterpret_cast<float4 *>(ctx->boxes.p), seginfo, hdr,
         budget_words, skip_le);
     FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
+    if (greedy && ctx->nms_bin != 2 && cap_e <= BIN_MAX_K) {  // FDMS_NMS_BIN=2: the list kernel (A/B); 0: no grid
+        const size_t bin_smem = sizeof(BinShared) + (size_t)cap_e * sizeof(uint16_t);
+        if (!ctx->nms_bin_attr) {
+            const int mx = (int)(sizeof(BinShared) + (size_t)BIN_MAX_K * sizeof(uint16_t));
+            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_binned_kernel<FDMS_IOU_TV_CPU>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_binned_kernel<FDMS_IOU_TV_CUDA>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_binned_kernel<FDMS_IOU_NCNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            ctx->nms_bin_attr = true;
+        }
+#define FDMS_NMS_BINNED(M)                                                                                                \
+    nms_binned_kernel<M><<<n_seg, GREEDY_THREADS, bin_smem, st>>>(                                                            \
+        seginfo, cap_e, reinterpret_cast<const float4 *>(ctx->boxes.p), reinterpret_cast<const uint32_t *>(ctx->idx_b.p), thr_f, \
+        inclusive, keep, n_keep, cap, count, skip_le, ctx->nms_bin)
+        if (iou_mode == FDMS_IOU_TV_CUDA) FDMS_NMS_BINNED(FDMS_IOU_TV_CUDA);
+        else if (iou_mode == FDMS_IOU_NCNN) FDMS_NMS_BINNED(FDMS_IOU_NCNN);
+        else FDMS_NMS_BINNED(FDMS_IOU_TV_CPU);
+#undef FDMS_NMS_BINNED
+        FDMS_LAUNCH_CHECK(ctx, "nms_binned_kernel");
+        return FDMS_OK;
+    }
     if (greedy) {
 #define FDMS_NMS_GREEDY(M)                                                                                         \
     nms_greedy_kernel<M><<<n_seg, GREEDY_THREADS, 0, st>>>(seginfo, cap_e, reinterpret_cast<float4 *>(ctx->boxes.p),  \

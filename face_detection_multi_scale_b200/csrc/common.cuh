@@ -42,6 +42,7 @@ struct fdms_ctx {
     int nms_bin = 1;              // FDMS_NMS_BIN: 1 = nms_binned_kernel (kept boxes in a size-stratified grid), 0 = the same
                                   // kernel without the grid, 2 = nms_greedy_kernel (the list sweep it replaced; A/B)
     bool nms_bin_attr = false;
+    int nms_reg_sort = 1;         // FDMS_NMS_REG_SORT: 0 = every bitonic stage through shared memory (A/B)
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
     fdms_buf sort_a;           // NMS: 64-bit keys of segments too large for shared memory

@@ -36,7 +36,8 @@
 namespace {
 
 constexpr int SORT_THREADS = 1024;
-constexpr int SORT_SMEM_ITEMS = 8192;  // 8 B key + 4 B index each = 96 KB
+constexpr int SORT_SMEM_ITEMS = 8192;  // 8 B key + 4 B index each (+ 1/16 skew of the register-blocked sort) = 102 KB
+constexpr int SORT_SMEM_SLOTS = SORT_SMEM_ITEMS + SORT_SMEM_ITEMS / 16;
 constexpr int MASK_THREADS = 256;      // 64 rows x 4 column blocks
 constexpr int SWEEP_THREADS = 512;
 constexpr int SWEEP_MAX_NBLK = 4096;   // 262144 boxes per segment
@@ -79,12 +80,121 @@ __device__ __forceinline__ uint32_t score_key_desc(float s) {
     return ~asc;
 }
 
+// Register-blocked bitonic sort of one segment (2048 / 4096 / 8192 padded keys, E = 2 / 4 / 8 consecutive keys per thread).
+// The network is the plain one (for k = 2 .. pad, for j = k/2 .. 1: compare-exchange i with i ^ j, ascending where
+// (i & k) == 0), but only the strides that cross warps (j >= 32 E) go through shared memory: strides below E are
+// compare-exchanges between a thread's own registers, strides E .. 16 E shuffles between lanes.  8192 keys: 15 of the 91
+// stages (and 20 instead of 91 barriers) touch shared memory.  Shared-memory slots are skewed by one every 16 keys so
+// that a thread's E consecutive 64-bit keys do not fall on two banks for the whole warp.
+__device__ __forceinline__ int sort_slot(int i) { return i + (i >> 4); }
+
+template <int E>
+__device__ __forceinline__ void sort_reg_stages(unsigned long long (&key)[E], uint32_t (&idx)[E], int t, int k, int j_start) {
+    for (int j = j_start; j >= E; j >>= 1) {  // between lanes
+        const int lm = j / E;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const int i = t * E + r;
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
+            const bool take_min = ((i & j) == 0) == ((i & k) == 0);
+            // branch-free (the lanes of a warp disagree about nearly every exchange); keys are unique but for the padding,
+            // whose index is the same on both sides
+            const unsigned long long lo = ok < key[r] ? ok : key[r], hi = ok < key[r] ? key[r] : ok;
+            const unsigned long long nk = take_min ? lo : hi;
+            idx[r] = nk == ok ? oi : idx[r];
+            key[r] = nk;
+        }
+    }
+#pragma unroll
+    for (int j = E / 2; j > 0; j >>= 1) {  // inside the thread
+        if (j > j_start) continue;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            if (r & j) continue;
+            const bool up = ((t * E + r) & k) == 0;
+            if ((key[r] > key[r | j]) == up) {
+                const unsigned long long tk = key[r];
+                key[r] = key[r | j];
+                key[r | j] = tk;
+                const uint32_t ti = idx[r];
+                idx[r] = idx[r | j];
+                idx[r | j] = ti;
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_segment_regs(const float *__restrict__ seg_rows, int row_stride, int box_off, int score_off,
+                                                  const int32_t *__restrict__ seg_tie, int n, int K,
+                                                  unsigned long long *keys, uint32_t *idxs, uint32_t *__restrict__ out_idx,
+                                                  float4 *__restrict__ out_boxes) {
+    constexpr int PAD = E * SORT_THREADS;
+    const int t = threadIdx.x;
+    unsigned long long key[E];
+    uint32_t idx[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int i = t * E + r;
+        key[r] = ~0ull;
+        idx[r] = 0xffffffffu;
+        if (i < n) {
+            const float sc = seg_rows[(long long)i * row_stride + score_off];
+            const uint32_t tb = seg_tie ? (uint32_t)seg_tie[i] : (uint32_t)i;
+            key[r] = ((unsigned long long)score_key_desc(sc) << 32) | tb;
+            idx[r] = (uint32_t)i;
+        }
+    }
+    for (int k = 2; k <= PAD; k <<= 1) {
+        int j = k >> 1;
+        if (j >= 32 * E) {
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                keys[sort_slot(t * E + r)] = key[r];
+                idxs[sort_slot(t * E + r)] = idx[r];
+            }
+            __syncthreads();
+            for (; j >= 32 * E; j >>= 1) {
+                for (int c = t; c < PAD / 2; c += SORT_THREADS) {
+                    const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1)), p = i + j;
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = keys[sort_slot(i)], b = keys[sort_slot(p)];
+                    if ((a > b) == up) {
+                        keys[sort_slot(i)] = b;
+                        keys[sort_slot(p)] = a;
+                        const uint32_t ia = idxs[sort_slot(i)], ib = idxs[sort_slot(p)];
+                        idxs[sort_slot(i)] = ib;
+                        idxs[sort_slot(p)] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                key[r] = keys[sort_slot(t * E + r)];
+                idx[r] = idxs[sort_slot(t * E + r)];
+            }
+        }
+        sort_reg_stages<E>(key, idx, t, k, j);
+    }
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int kk = t * E + r;
+        if (kk < K) {
+            const float *rw = seg_rows + (long long)idx[r] * row_stride + box_off;
+            out_idx[kk] = idx[r];
+            out_boxes[kk] = make_float4(rw[0], rw[1], rw[2], rw[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
     nms_sort_kernel(const float *__restrict__ rows, int row_stride, int box_off, int score_off,
                     const int32_t *__restrict__ tie, const int32_t *__restrict__ count, int n_seg, int cap, int cap_e,
                     int max_nms, unsigned long long *gkeys, uint32_t *gidx, long long gpad,
                     uint32_t *__restrict__ sorted_idx, float4 *__restrict__ sorted_boxes, SegInfo *seginfo,
-                    PlanHeader *hdr, long long mask_budget_words, int skip_le) {
+                    PlanHeader *hdr, long long mask_budget_words, int skip_le, int reg_sort) {
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ int s_last;
     __shared__ long long s_carry[2];
@@ -99,50 +209,60 @@ __global__ void __launch_bounds__(SORT_THREADS)
     uint32_t *idx;
     if (pad <= SORT_SMEM_ITEMS) {
         keys = reinterpret_cast<unsigned long long *>(sm);
-        idx = reinterpret_cast<uint32_t *>(sm + (size_t)SORT_SMEM_ITEMS * 8);
+        idx = reinterpret_cast<uint32_t *>(sm + (size_t)SORT_SMEM_SLOTS * 8);
     } else {
         keys = gkeys + (long long)g * gpad;
         idx = gidx + (long long)g * gpad;
     }
     const float *seg_rows = rows + (long long)g * cap * row_stride;
-    for (int i = tid; i < pad; i += SORT_THREADS) {
-        if (i < n) {
-            float s = seg_rows[(long long)i * row_stride + score_off];
-            uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + i] : (uint32_t)i;
-            keys[i] = ((unsigned long long)score_key_desc(s) << 32) | t;
-            idx[i] = (uint32_t)i;
-        } else {
-            keys[i] = ~0ull;
-            idx[i] = 0xffffffffu;
-        }
-    }
-    __syncthreads();
-    if (n > 1) {
-        for (int k = 2; k <= pad; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (pad >> 1); t += SORT_THREADS) {
-                    int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    int p = i + j;
-                    bool up = (i & k) == 0;
-                    unsigned long long a = keys[i], b = keys[p];
-                    if ((a > b) == up) {
-                        keys[i] = b;
-                        keys[p] = a;
-                        uint32_t ia = idx[i], ib = idx[p];
-                        idx[i] = ib;
-                        idx[p] = ia;
-                    }
-                }
-                __syncthreads();
+    const int K = (max_nms > 0) ? min(n, max_nms) : n;  // utils/general.py:578-579
+    if (reg_sort && pad >= 2 * SORT_THREADS && pad <= SORT_SMEM_ITEMS) {
+        const int32_t *seg_tie = tie ? tie + (long long)g * cap : nullptr;
+        uint32_t *o_idx = sorted_idx + (long long)g * cap_e;
+        float4 *o_box = sorted_boxes + (long long)g * cap_e;
+        uint32_t *idxs = reinterpret_cast<uint32_t *>(sm + (size_t)SORT_SMEM_SLOTS * 8);
+        if (pad == 2 * SORT_THREADS) sort_segment_regs<2>(seg_rows, row_stride, box_off, score_off, seg_tie, n, K, keys, idxs, o_idx, o_box);
+        else if (pad == 4 * SORT_THREADS) sort_segment_regs<4>(seg_rows, row_stride, box_off, score_off, seg_tie, n, K, keys, idxs, o_idx, o_box);
+        else sort_segment_regs<8>(seg_rows, row_stride, box_off, score_off, seg_tie, n, K, keys, idxs, o_idx, o_box);
+    } else {
+        for (int i = tid; i < pad; i += SORT_THREADS) {
+            if (i < n) {
+                float s = seg_rows[(long long)i * row_stride + score_off];
+                uint32_t t = tie ? (uint32_t)tie[(long long)g * cap + i] : (uint32_t)i;
+                keys[i] = ((unsigned long long)score_key_desc(s) << 32) | t;
+                idx[i] = (uint32_t)i;
+            } else {
+                keys[i] = ~0ull;
+                idx[i] = 0xffffffffu;
             }
         }
-    }
-    const int K = (max_nms > 0) ? min(n, max_nms) : n;  // utils/general.py:578-579
-    for (int k = tid; k < K; k += SORT_THREADS) {
-        uint32_t ii = idx[k];
-        const float *r = seg_rows + (long long)ii * row_stride + box_off;
-        sorted_idx[(long long)g * cap_e + k] = ii;
-        sorted_boxes[(long long)g * cap_e + k] = make_float4(r[0], r[1], r[2], r[3]);
+        __syncthreads();
+        if (n > 1) {
+            for (int k = 2; k <= pad; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (pad >> 1); t += SORT_THREADS) {
+                        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        int p = i + j;
+                        bool up = (i & k) == 0;
+                        unsigned long long a = keys[i], b = keys[p];
+                        if ((a > b) == up) {
+                            keys[i] = b;
+                            keys[p] = a;
+                            uint32_t ia = idx[i], ib = idx[p];
+                            idx[i] = ib;
+                            idx[p] = ia;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        for (int k = tid; k < K; k += SORT_THREADS) {
+            uint32_t ii = idx[k];
+            const float *r = seg_rows + (long long)ii * row_stride + box_off;
+            sorted_idx[(long long)g * cap_e + k] = ii;
+            sorted_boxes[(long long)g * cap_e + k] = make_float4(r[0], r[1], r[2], r[3]);
+        }
     }
     if (tid == 0) {
         seginfo[g].n = K;
@@ -1219,14 +1339,14 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     SegInfo *seginfo = reinterpret_cast<SegInfo *>(hdr + 1);
     if (!ctx->nms_attr) {
         FDMS_CUDA(ctx, cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SORT_SMEM_ITEMS * 12));
+                                            SORT_SMEM_SLOTS * 12));
         ctx->nms_attr = true;
     }
-    nms_sort_kernel<<<n_seg, SORT_THREADS, SORT_SMEM_ITEMS * 12, st>>>(
+    nms_sort_kernel<<<n_seg, SORT_THREADS, SORT_SMEM_SLOTS * 12, st>>>(
         rows, row_stride, box_off, score_off, tie, count, n_seg, cap, cap_e, max_nms,
         reinterpret_cast<unsigned long long *>(ctx->sort_a.p), reinterpret_cast<uint32_t *>(ctx->idx_a.p), pad,
         reinterpret_cast<uint32_t *>(ctx->idx_b.p), reinterpret_cast<float4 *>(ctx->boxes.p), seginfo, hdr,
-        budget_words, skip_le);
+        budget_words, skip_le, ctx->nms_reg_sort);
     FDMS_LAUNCH_CHECK(ctx, "nms_sort_kernel");
     if (greedy && ctx->nms_bin != 2 && cap_e <= BIN_MAX_K) {  // FDMS_NMS_BIN=2: the list kernel (A/B); 0: no grid
         const size_t bin_smem = sizeof(BinShared) + (size_t)cap_e * sizeof(uint16_t);

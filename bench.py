@@ -703,7 +703,7 @@ def main():
                               "repeats": r["repeats"], "stages_ms": r["stages_ms"], "candidates_per_step": r["candidates_per_step"],
                               "nms_candidates_per_sec": r["nms_candidates_per_sec"], "cap": r["cap"],
                               "roofline": {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "launch_ms",
-                                                                          "algorithmic_bytes_per_launch", "isolated")}}
+                                                                          "algorithmic_bytes_per_launch", "source_rows_touched", "isolated")}}
             except SystemExit as e:
                 configs[c] = {"error": str(e)}
 

@@ -29,6 +29,7 @@ struct fdms_ctx {
     int pyr_direct = 3, pyr_th_direct = 16;  // FDMS_PYR_DIRECT (bit 0: integer factors, bit 1: the 3:2 factor) / FDMS_PYR_TH_DIRECT: unstaged tiles
     // FDMS_PYR_STRIP=0 disables the strip kernel (one source pass for all exact-factor scales); stage / ring size knobs
     int pyr_strip = 1, pyr_strip_stage_bytes = 36 * 1024, pyr_strip_smem = 108 * 1024, pyr_strip_warps = 14, pyr_strip_regs = 64;
+    int pyr_strip_ctas = 0, pyr_strip_reserve = 0;  // FDMS_PYR_STRIP_CTAS (0 = one per SM), FDMS_PYR_STRIP_RESERVE_KB: shared memory claimed per CTA beyond the stages (keeps other kernels' CTAs off its SM)
     bool pyr_strip_attr = false, pyr_cnt_ready = false;
     bool nms_attr = false, nms_small_attr = false;
     int nms_small_limit = 1024;   // FDMS_NMS_SMALL_LIMIT: largest segment of the fused kernel (0 disables it)

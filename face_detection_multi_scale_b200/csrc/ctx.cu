@@ -67,6 +67,8 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_PYR_STRIP_REGS")) c->pyr_strip_regs = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP_WARPS")) c->pyr_strip_warps = atoi(e);
     if (const char *e = getenv("FDMS_PYR_STRIP_SMEM_KB")) c->pyr_strip_smem = atoi(e) * 1024;
+    if (const char *e = getenv("FDMS_PYR_STRIP_CTAS")) c->pyr_strip_ctas = atoi(e);
+    if (const char *e = getenv("FDMS_PYR_STRIP_RESERVE_KB")) c->pyr_strip_reserve = atoi(e) * 1024;
     if (const char *e = getenv("FDMS_PYR_TH_DIRECT")) c->pyr_th_direct = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("FDMS_PYR_TH")) c->pyr_th = atoi(e) < 1 ? 1 : (atoi(e) > 31 ? 31 : atoi(e));  // rows + sentinel are written by one warp
     if (const char *e = getenv("FDMS_NMS_SMALL_LIMIT")) c->nms_small_limit = atoi(e);

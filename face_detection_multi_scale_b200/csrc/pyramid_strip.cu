@@ -509,13 +509,14 @@ int fdms_pyramid_strip(fdms_ctx *ctx, const PyrParams &P, int n_img, unsigned *h
         ctx->pyr_cnt_ready = true;
     }
     Q.counters = reinterpret_cast<unsigned *>(ctx->pyr_cnt.p);
-    const int smem = Q.n_stages * Q.stage_bytes;
+    int smem = Q.n_stages * Q.stage_bytes;
+    if (ctx->pyr_strip_reserve > smem) smem = ctx->pyr_strip_reserve > 200 * 1024 ? 200 * 1024 : ctx->pyr_strip_reserve;
     if (!ctx->pyr_strip_attr) {
         FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         FDMS_CUDA(ctx, cudaFuncSetAttribute(pyramid_strip_kernel_r56, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ctx->pyr_strip_attr = true;
     }
-    int grid = ctx->sm_count;
+    int grid = ctx->pyr_strip_ctas > 0 && ctx->pyr_strip_ctas < ctx->sm_count ? ctx->pyr_strip_ctas : ctx->sm_count;
     if (grid > Q.n_items) grid = Q.n_items;
     int warps = ctx->pyr_strip_warps < 1 ? 1 : (ctx->pyr_strip_warps > ST_MAX_CONSUMER_WARPS ? ST_MAX_CONSUMER_WARPS : ctx->pyr_strip_warps);
     if (ctx->pyr_strip_regs <= 56) pyramid_strip_kernel_r56<<<grid, 32 * (warps + 1), smem, st>>>(Q);

@@ -729,7 +729,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_backbone and not args.profile:
         # from-files ingest: device JPEG decode against the host decoder, own process
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ingest_bench.py"), "--files", "64"], capture_output=True,
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ingest_bench.py"), "--files", "128"], capture_output=True,
                                text=True, timeout=600)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
             ingest = json.loads(lines[-1]) if lines else {"error": (r.stderr or r.stdout)[-400:]}

@@ -43,6 +43,7 @@ struct fdms_ctx {
     int nms_bin = 1;              // FDMS_NMS_BIN: 1 = nms_binned_kernel (kept boxes in a size-stratified grid), 0 = the same
                                   // kernel without the grid, 2 = nms_greedy_kernel (the list sweep it replaced; A/B)
     bool nms_bin_attr = false;
+    int pdl = 0;                  // FDMS_PDL: 1 = the per-scale NMS and the merge are launched as programmatic dependents of the kernel before them
     int nms_reg_sort = 1;         // FDMS_NMS_REG_SORT: 0 = every bitonic stage through shared memory (A/B)
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
     // scratch (grow-only)
@@ -113,6 +114,14 @@ static inline int fdms_reserve(fdms_ctx *ctx, fdms_buf &b, size_t bytes) {
 
 // Makes the context's device current for the duration of an API call and restores the caller's device afterwards
 // (torch's current device must not drift when a tensor lives on another GPU than the current one).
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while the kernel before it
+// in the stream still runs; fdms_pdl_wait() blocks until that kernel has completed and its writes are visible (a no-op for
+// a normal launch), fdms_pdl_trigger() lets the dependents of THIS kernel be scheduled from now on.
+#ifdef __CUDACC__
+__device__ __forceinline__ void fdms_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void fdms_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 struct fdms_device_guard {
     int prev = -1;
     bool switched = false;

@@ -336,6 +336,7 @@ template <int FUSE>
 __global__ void __launch_bounds__(DEC_THREADS) decode_filter_kernel(const __grid_constant__ DecParams P) {
     __shared__ int s_rows[DEC_CELLS];  // one copy for both instantiations of the body
     __shared__ int s_n, s_base;
+    fdms_pdl_trigger();  // the NMS launched behind this kernel may be scheduled; it waits for this grid to complete
     const DecCta C = P.cta_tab[blockIdx.x];
     const DecLevel &L = P.lv[C.level];
     if (L.dtype == FDMS_F16) decode_filter_body<__half, FUSE>(P, L, C, s_rows, s_n, s_base);

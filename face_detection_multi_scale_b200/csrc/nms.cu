@@ -757,6 +757,8 @@ __global__ void FDMS_SMALL_BOUNDS
                      int small_limit, float thr, int inclusive, int32_t *__restrict__ keep,
                      int32_t *__restrict__ n_keep) {
     const int g = blockIdx.x;
+    fdms_pdl_trigger();
+    fdms_pdl_wait();  // the candidates come from the kernel before this one
     const int n = max(0, min(count[g], cap));
     if (n > small_limit) {  // the sort + greedy / bit-matrix path takes it (it overwrites the marker)
         if (threadIdx.x == 0) n_keep[g] = -2;
@@ -775,6 +777,7 @@ __global__ void FDMS_SMALL_BOUNDS
     merge_small_kernel(const __grid_constant__ MergeParams P, const __grid_constant__ EmitParams E, int small_limit,
                        float thr, int inclusive) {
     const int img = blockIdx.x, tid = threadIdx.x;
+    fdms_pdl_wait();  // the keep lists come from the kernel before this one
     const int total = merge_prepare_image(P, img, tid, SMALL_THREADS);
     if (total > small_limit) {  // nms_sort_kernel + nms_greedy / mask + merge_emit_kernel take this image
         if (tid == 0) E.n_out[img] = 0;
@@ -1279,7 +1282,20 @@ int fdms_merge_small_limit(const fdms_ctx *ctx) {
 
 int fdms_merge_small_launch(fdms_ctx *ctx, const MergeParams &P, const EmitParams &E, int n_img, float thr_f,
                             int inclusive, cudaStream_t st) {
-    merge_small_kernel<<<n_img, SMALL_THREADS, 0, st>>>(P, E, fdms_merge_small_limit(ctx), thr_f, inclusive);
+    if (ctx->pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(n_img);
+        cfg.blockDim = dim3(SMALL_THREADS);
+        cfg.stream = st;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        FDMS_CUDA(ctx, cudaLaunchKernelEx(&cfg, merge_small_kernel, P, E, fdms_merge_small_limit(ctx), thr_f, inclusive));
+    } else {
+        merge_small_kernel<<<n_img, SMALL_THREADS, 0, st>>>(P, E, fdms_merge_small_limit(ctx), thr_f, inclusive);
+    }
     FDMS_LAUNCH_CHECK(ctx, "merge_small_kernel");
     return FDMS_OK;
 }
@@ -1297,9 +1313,18 @@ int fdms_nms_impl(fdms_ctx *ctx, const float *rows, int row_stride, int box_off,
     // ---- segments of at most small_limit boxes: one fused launch -------------------------------------------
     const int small_limit = ctx->nms_small_limit < SMALL_LIMIT ? ctx->nms_small_limit : SMALL_LIMIT;
     if (small_limit > 0 && !ctx->nms_small_done) {
-#define FDMS_NMS_SMALL(M)                                                                                             \
-    nms_small_kernel<M><<<n_seg, SMALL_THREADS, 0, st>>>(rows, row_stride, box_off, score_off, tie, count, cap, max_nms, \
-                                                         small_limit, thr_f, inclusive, keep, n_keep)
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(n_seg);
+        cfg.blockDim = dim3(SMALL_THREADS);
+        cfg.stream = st;
+        cfg.attrs = at;
+        cfg.numAttrs = ctx->pdl ? 1 : 0;
+#define FDMS_NMS_SMALL(M)                                                                                                    \
+    FDMS_CUDA(ctx, cudaLaunchKernelEx(&cfg, nms_small_kernel<M>, rows, row_stride, box_off, score_off, tie, count, cap, max_nms, \
+                                      small_limit, thr_f, inclusive, keep, n_keep))
         if (iou_mode == FDMS_IOU_TV_CUDA) FDMS_NMS_SMALL(FDMS_IOU_TV_CUDA);
         else if (iou_mode == FDMS_IOU_NCNN) FDMS_NMS_SMALL(FDMS_IOU_NCNN);
         else FDMS_NMS_SMALL(FDMS_IOU_TV_CPU);

@@ -88,7 +88,11 @@ __device__ __forceinline__ uint32_t score_key_desc(float s) {
 // that a thread's E consecutive 64-bit keys do not fall on two banks for the whole warp.
 __device__ __forceinline__ int sort_slot(int i) { return i + (i >> 4); }
 
-template <int E>
+// PACKED: the item index rides in the low bits of the key (score << 32 | tie << log2(PAD) | index), possible when every
+// tie of the segment is below 2^(32 - log2(PAD)) -- head row numbers and merge rows always are: two shuffles per key and
+// stage instead of three, no index select, shared-memory stages on the keys alone.  The order is the same: ties are
+// unique inside a segment, so the index bits never decide.
+template <int E, bool PACKED>
 __device__ __forceinline__ void sort_reg_stages(unsigned long long (&key)[E], uint32_t (&idx)[E], int t, int k, int j_start) {
     for (int j = j_start; j >= E; j >>= 1) {  // between lanes
         const int lm = j / E;
@@ -96,13 +100,15 @@ __device__ __forceinline__ void sort_reg_stages(unsigned long long (&key)[E], ui
         for (int r = 0; r < E; r++) {
             const int i = t * E + r;
             const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key[r], lm);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
             const bool take_min = ((i & j) == 0) == ((i & k) == 0);
             // branch-free (the lanes of a warp disagree about nearly every exchange); keys are unique but for the padding,
             // whose index is the same on both sides
             const unsigned long long lo = ok < key[r] ? ok : key[r], hi = ok < key[r] ? key[r] : ok;
             const unsigned long long nk = take_min ? lo : hi;
-            idx[r] = nk == ok ? oi : idx[r];
+            if (!PACKED) {
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx[r], lm);
+                idx[r] = nk == ok ? oi : idx[r];
+            }
             key[r] = nk;
         }
     }
@@ -113,46 +119,31 @@ __device__ __forceinline__ void sort_reg_stages(unsigned long long (&key)[E], ui
         for (int r = 0; r < E; r++) {
             if (r & j) continue;
             const bool up = ((t * E + r) & k) == 0;
-            if ((key[r] > key[r | j]) == up) {
-                const unsigned long long tk = key[r];
-                key[r] = key[r | j];
-                key[r | j] = tk;
-                const uint32_t ti = idx[r];
-                idx[r] = idx[r | j];
-                idx[r | j] = ti;
+            const bool sw = (key[r] > key[r | j]) == up;
+            const unsigned long long ka = key[r], kb = key[r | j];
+            key[r] = sw ? kb : ka;
+            key[r | j] = sw ? ka : kb;
+            if (!PACKED) {
+                const uint32_t ia = idx[r], ib = idx[r | j];
+                idx[r] = sw ? ib : ia;
+                idx[r | j] = sw ? ia : ib;
             }
         }
     }
 }
 
-template <int E>
-__device__ __forceinline__ void sort_segment_regs(const float *__restrict__ seg_rows, int row_stride, int box_off, int score_off,
-                                                  const int32_t *__restrict__ seg_tie, int n, int K,
-                                                  unsigned long long *keys, uint32_t *idxs, uint32_t *__restrict__ out_idx,
-                                                  float4 *__restrict__ out_boxes) {
+template <int E, bool PACKED>
+__device__ __forceinline__ void sort_segment_body(unsigned long long (&key)[E], uint32_t (&idx)[E], unsigned long long *keys,
+                                                  uint32_t *idxs) {
     constexpr int PAD = E * SORT_THREADS;
     const int t = threadIdx.x;
-    unsigned long long key[E];
-    uint32_t idx[E];
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-        const int i = t * E + r;
-        key[r] = ~0ull;
-        idx[r] = 0xffffffffu;
-        if (i < n) {
-            const float sc = seg_rows[(long long)i * row_stride + score_off];
-            const uint32_t tb = seg_tie ? (uint32_t)seg_tie[i] : (uint32_t)i;
-            key[r] = ((unsigned long long)score_key_desc(sc) << 32) | tb;
-            idx[r] = (uint32_t)i;
-        }
-    }
     for (int k = 2; k <= PAD; k <<= 1) {
         int j = k >> 1;
         if (j >= 32 * E) {
 #pragma unroll
             for (int r = 0; r < E; r++) {
                 keys[sort_slot(t * E + r)] = key[r];
-                idxs[sort_slot(t * E + r)] = idx[r];
+                if (!PACKED) idxs[sort_slot(t * E + r)] = idx[r];
             }
             __syncthreads();
             for (; j >= 32 * E; j >>= 1) {
@@ -163,9 +154,11 @@ __device__ __forceinline__ void sort_segment_regs(const float *__restrict__ seg_
                     if ((a > b) == up) {
                         keys[sort_slot(i)] = b;
                         keys[sort_slot(p)] = a;
-                        const uint32_t ia = idxs[sort_slot(i)], ib = idxs[sort_slot(p)];
-                        idxs[sort_slot(i)] = ib;
-                        idxs[sort_slot(p)] = ia;
+                        if (!PACKED) {
+                            const uint32_t ia = idxs[sort_slot(i)], ib = idxs[sort_slot(p)];
+                            idxs[sort_slot(i)] = ib;
+                            idxs[sort_slot(p)] = ia;
+                        }
                     }
                 }
                 __syncthreads();
@@ -173,10 +166,53 @@ __device__ __forceinline__ void sort_segment_regs(const float *__restrict__ seg_
 #pragma unroll
             for (int r = 0; r < E; r++) {
                 key[r] = keys[sort_slot(t * E + r)];
-                idx[r] = idxs[sort_slot(t * E + r)];
+                if (!PACKED) idx[r] = idxs[sort_slot(t * E + r)];
             }
         }
-        sort_reg_stages<E>(key, idx, t, k, j);
+        sort_reg_stages<E, PACKED>(key, idx, t, k, j);
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_segment_regs(const float *__restrict__ seg_rows, int row_stride, int box_off, int score_off,
+                                                  const int32_t *__restrict__ seg_tie, int n, int K,
+                                                  unsigned long long *keys, uint32_t *idxs, uint32_t *__restrict__ out_idx,
+                                                  float4 *__restrict__ out_boxes) {
+    constexpr int PAD = E * SORT_THREADS;
+    constexpr int IDX_BITS = E == 2 ? 11 : (E == 4 ? 12 : 13);
+    static_assert((1 << IDX_BITS) == PAD, "index bits");
+    const int t = threadIdx.x;
+    unsigned long long key[E];
+    uint32_t idx[E], tie_v[E];
+    uint32_t sk[E];
+    bool wide = false;  // a tie that does not leave room for the index bits
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int i = t * E + r;
+        sk[r] = 0xffffffffu;
+        tie_v[r] = 0u;
+        idx[r] = 0xffffffffu;
+        if (i < n) {
+            const float sc = seg_rows[(long long)i * row_stride + score_off];
+            tie_v[r] = seg_tie ? (uint32_t)seg_tie[i] : (uint32_t)i;
+            sk[r] = score_key_desc(sc);
+            idx[r] = (uint32_t)i;
+            wide |= tie_v[r] >= (1u << (32 - IDX_BITS));
+        }
+    }
+    const bool packed = !__syncthreads_or(wide ? 1 : 0);
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int i = t * E + r;
+        if (i < n) key[r] = ((unsigned long long)sk[r] << 32) | (packed ? ((tie_v[r] << IDX_BITS) | (uint32_t)i) : tie_v[r]);
+        else key[r] = ~0ull;
+    }
+    if (packed) {
+        sort_segment_body<E, true>(key, idx, keys, idxs);
+#pragma unroll
+        for (int r = 0; r < E; r++) idx[r] = (uint32_t)key[r] & (uint32_t)(PAD - 1);
+    } else {
+        sort_segment_body<E, false>(key, idx, keys, idxs);
     }
 #pragma unroll
     for (int r = 0; r < E; r++) {

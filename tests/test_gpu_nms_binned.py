@@ -175,3 +175,30 @@ def test_grid_and_list_kernels_agree_on_the_bench_distribution(monkeypatch):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1] == outs[2], outs
+
+
+@pytest.mark.parametrize("n", [1500, 3000, 7000])
+def test_sort_tie_order_packed_and_wide_keys(n):
+    """The register-blocked sort packs the item index under the tie when the ties are small (head row numbers) and
+    carries it separately when they are not; exact score ties must resolve by ASCENDING TIE in both cases, whatever
+    the order of the rows."""
+    rng = np.random.default_rng(70 + n)
+    n_seg = 8
+    rows = np.zeros((n_seg, n, 6), np.float32)
+    for g in range(n_seg):
+        rows[g, :, :4] = np.round(crowd(rng, n, 300))
+        rows[g, :, 4] = np.round(rng.uniform(0.5, 1.0, n), 2)  # ~50 distinct scores: ties everywhere
+    counts = np.full((n_seg,), n, np.int32)
+    idx = np.arange(n, dtype=np.int64)
+    for name, tie_of in (("small ascending", idx * 3 + 5), ("small descending", (n - 1 - idx) * 7),
+                         ("wide ascending", idx * 1000 + (1 << 21)), ("wide descending", (n - 1 - idx) * 4099 + (1 << 20))):
+        tie = np.tile(tie_of.astype(np.int32), (n_seg, 1))
+        keep, n_keep = ops.nms_segments(gpu(rows), gpu(counts), n, 0.5, ops.IOU_TV_CUDA, max_nms=0, tie=gpu(tie))
+        torch.cuda.synchronize()
+        for g in range(n_seg):
+            if "ascending" in name:
+                ref = O.nms(rows[g, :, :4], rows[g, :, 4], 0.5, ops.IOU_TV_CUDA)
+            else:  # the oracle breaks ties by position: feed it the rows in reverse
+                ref = n - 1 - O.nms(rows[g, ::-1, :4], rows[g, ::-1, 4], 0.5, ops.IOU_TV_CUDA)
+            got = keep[g, :int(n_keep[g])].cpu().numpy()
+            assert np.array_equal(got, ref), (name, g, n)

@@ -43,6 +43,7 @@ struct fdms_ctx {
     int nms_bin = 1;              // FDMS_NMS_BIN: 1 = nms_binned_kernel (kept boxes in a size-stratified grid), 0 = the same
                                   // kernel without the grid, 2 = nms_greedy_kernel (the list sweep it replaced; A/B)
     bool nms_bin_attr = false;
+    int lazy_kpts = 1;            // FDMS_LAZY_KPTS: fdms_postprocess decodes landmarks at emit time, for the final detections only
     int pdl = 0;                  // FDMS_PDL: 1 = the per-scale NMS and the merge are launched as programmatic dependents of the kernel before them
     int nms_reg_sort = 1;         // FDMS_NMS_REG_SORT: 0 = every bitonic stage through shared memory (A/B)
     size_t mask_budget = (size_t)8 << 30;  // bytes; FDMS_MASK_BUDGET_MB overrides
@@ -154,6 +155,17 @@ __device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b
 __device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// 1 / (1 + exp(-x)).  The reference's sigmoid is ATen's: on the CPU a vectorised expf (Sleef, <= 1 ulp), on a CUDA
+// device `one / (one + std::exp(-a))` with libdevice's expf (<= 2 ulp) -- two different roundings of the same value.
+// Default (`aten` false): exp evaluated in fp64 and rounded once, i.e. the correctly rounded expf, which the CPU oracle
+// restates bit for bit and which lies within 1 ulp of either.  `aten` true (FDMS_NUMERICS_ATEN_CUDA): the very expf
+// ATen's CUDA kernel calls, so that the decode is bit-identical to the reference running in fp32 on the same GPU.
+__device__ __forceinline__ float sigmoid_ref(float x, bool aten) {
+    const float e = aten ? expf(-x) : (float)exp(-(double)x);
+    return f_div(1.0f, f_add(1.0f, e));
+}
+
 
 __device__ __forceinline__ float ld_f(const void *p, int dtype, int64_t i) {
     return dtype == FDMS_F16 ? __half2float(__ldg(reinterpret_cast<const __half *>(p) + i))

@@ -76,6 +76,7 @@ FDMS_API int fdms_create(fdms_ctx **out, int device) {
     if (const char *e = getenv("FDMS_MERGE_FUSED")) c->merge_fused = atoi(e);
     if (const char *e = getenv("FDMS_NMS_GREEDY_MIN_SEG")) c->nms_greedy_min_seg = atoi(e);
     if (const char *e = getenv("FDMS_PDL")) c->pdl = atoi(e);
+    if (const char *e = getenv("FDMS_LAZY_KPTS")) c->lazy_kpts = atoi(e);
     if (const char *e = getenv("FDMS_NMS_BIN")) c->nms_bin = atoi(e);
     if (const char *e = getenv("FDMS_NMS_REG_SORT")) c->nms_reg_sort = atoi(e);
     if (const char *e = getenv("FDMS_MASK_BUDGET_MB")) c->mask_budget = (size_t)atoll(e) << 20;

@@ -67,16 +67,6 @@ struct DecCta {
     int pad_;
 };
 
-// 1 / (1 + exp(-x)).  The reference's sigmoid is ATen's: on the CPU a vectorised expf (Sleef, <= 1 ulp), on a CUDA
-// device `one / (one + std::exp(-a))` with libdevice's expf (<= 2 ulp) -- two different roundings of the same value.
-// Default (`aten` false): exp evaluated in fp64 and rounded once, i.e. the correctly rounded expf, which the CPU oracle
-// restates bit for bit and which lies within 1 ulp of either.  `aten` true (FDMS_NUMERICS_ATEN_CUDA): the very expf
-// ATen's CUDA kernel calls, so that the decode is bit-identical to the reference running in fp32 on the same GPU.
-__device__ __forceinline__ float sigmoid_ref(float x, bool aten) {
-    const float e = aten ? expf(-x) : (float)exp(-(double)x);
-    return f_div(1.0f, f_add(1.0f, e));
-}
-
 // models/yolo.py:290-295 for one cell; v[k] = raw channel k (already fp32), out = 21 floats
 // [cx, cy, w, h, obj, cls, (kx, ky, kc) x 5]
 __device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,

@@ -154,7 +154,8 @@ FDMS_API int fdms_weighted_rows(fdms_ctx *ctx, const double *dets, int64_t n, in
 static int merge_scales_impl(fdms_ctx *ctx, const float *cand, const int32_t *keep, const int32_t *n_keep, int n_img,
                              int n_scales, int cap, const int32_t *in_h_host, int orig_h, int orig_w,
                              const int32_t *orig_hw_dev, double iou_thres, float *dets, int32_t *n_out, int out_cap,
-                             int32_t *merged_in, float *kpts_out, fdms_stream stream) {
+                             int32_t *merged_in, float *kpts_out, fdms_stream stream, const fdms_level *lazy_levels = nullptr,
+                             int n_lazy_levels = 0, const int32_t *cand_row = nullptr) {
     FDMS_BIND(ctx);
     if (orig_hw_dev) orig_h = orig_w = 1;  // per-image sizes on the device; the scalars are unused
     if (!cand || !keep || !n_keep || !in_h_host || !dets || !n_out || n_img <= 0 || n_scales <= 0 ||
@@ -217,6 +218,20 @@ static int merge_scales_impl(fdms_ctx *ctx, const float *cand, const int32_t *ke
     E.dets = dets;
     E.n_out = n_out;
     E.kpts = kpts_out;
+    if (kpts_out && lazy_levels && cand_row && n_lazy_levels > 0 && n_lazy_levels <= FDMS_MAX_LEVELS) {
+        E.n_levels = n_lazy_levels;
+        E.aten = ctx->numerics == FDMS_NUMERICS_ATEN_CUDA;
+        E.cand_row = cand_row;
+        for (int l = 0; l < n_lazy_levels; l++) {
+            E.lv[l].data = lazy_levels[l].data;
+            E.lv[l].dtype = lazy_levels[l].dtype;
+            E.lv[l].ny = lazy_levels[l].ny;
+            E.lv[l].nx = lazy_levels[l].nx;
+            E.lv[l].scale = lazy_levels[l].scale;
+            E.lv[l].row_offset = lazy_levels[l].row_offset;
+            E.lv[l].stride = lazy_levels[l].stride;
+        }
+    }
     // torchvision.ops.nms on CPU tensors in the reference (msfd:234): TV_CPU flavour, no max_nms cut
     const int small_limit = fdms_merge_small_limit(ctx);
     int skip_le = -1;
@@ -273,15 +288,18 @@ FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *d, fdms_strea
         ~Guard() { c->post_small_only = false; }
     } guard{ctx};
     ctx->post_small_only = (d->flags & FDMS_POST_SMALL_ONLY) != 0;
-    // landmarks are decoded only when the caller asked for them in the merged output
+    // landmarks: never for every candidate.  When the caller wants them in the merged output they are decoded by the emit
+    // step from the raw head maps, for the final detections only (ctx->lazy_kpts, FDMS_LAZY_KPTS=0: decoded with the boxes)
+    const bool lazy = d->kpts_out && ctx->lazy_kpts;
     if (int rc = fdms_decode_filter_ex(ctx, d->levels, d->n_levels, d->n_scales, d->bs, d->conf_thres, d->cand, d->cand_row,
-                                       d->count, d->cap, d->kpts_out ? 0 : FDMS_DECODE_BOXES_ONLY, stream))
+                                       d->count, d->cap, (d->kpts_out && !lazy) ? 0 : FDMS_DECODE_BOXES_ONLY, stream))
         return rc;
     if (int rc = fdms_nms_impl(ctx, d->cand, NO, 0, 4, d->cand_row, d->count, d->bs * d->n_scales, d->cap, d->iou_thres,
                                d->iou_mode, FDMS_MAX_NMS, d->keep, d->n_keep, (cudaStream_t)stream))
         return rc;
     return merge_scales_impl(ctx, d->cand, d->keep, d->n_keep, d->bs, d->n_scales, d->cap, d->in_h_host, d->orig_h, d->orig_w,
-                             d->orig_hw_dev, d->iou_thres, d->dets, d->n_out, d->out_cap, d->merged_in, d->kpts_out, stream);
+                             d->orig_hw_dev, d->iou_thres, d->dets, d->n_out, d->out_cap, d->merged_in, d->kpts_out, stream,
+                             lazy ? d->levels : nullptr, lazy ? d->n_levels : 0, lazy ? d->cand_row : nullptr);
 }
 
 }  // extern "C"

@@ -2,6 +2,8 @@
 // landmarks, append scale_idx), :168-201,224-229 (size-aware weights) and :237-238 (detections[keep]) as device
 // functions, shared by the standalone kernels of merge.cu and the fused single-CTA merge of nms.cu.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 struct MergeParams {
@@ -30,6 +32,16 @@ struct EmitParams {
     float *dets;
     int32_t *n_out;
     float *kpts;
+    // landmarks decoded HERE, for the final detections only, from the raw head maps (fdms_postprocess): the candidates
+    // then carry boxes only -- 6 instead of 21 gathered sectors per candidate in the filter, and a dense crowd has ~15
+    // candidates per final detection.  n_levels == 0: the candidate rows hold decoded landmarks (fdms_merge_scales).
+    int n_levels, aten;
+    const int32_t *cand_row;  // head row of every candidate (fdms_decode_filter)
+    struct Lv {
+        const void *data;
+        int dtype, ny, nx, scale, row_offset;
+        float stride;
+    } lv[FDMS_MAX_LEVELS];
 };
 
 namespace {
@@ -123,14 +135,48 @@ __device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, i
         if (P.kpts) {
             const int src = P.msrc[(long long)img * P.mcap + pos];
             const int s = src / P.cap, item = src - s * P.cap;
-            const float *row = P.cand + (((long long)img * P.n_scales + s) * P.cap + item) * MERGE_NO;
+            const long long slot = ((long long)img * P.n_scales + s) * P.cap + item;
             float *ko = P.kpts + ((long long)img * P.out_cap + k) * 15;
             float gk, gw, gh;
             merge_geom(P, img, s, gk, gw, gh);
+            float kp[15];
+            if (P.n_levels > 0) {
+                // models/yolo.py:296-301 on the raw channels 6..20 of this detection's head cell (same operations, same
+                // order as decode_cell in decode.cu)
+                const int hrow = P.cand_row[slot];
+                int li = -1;
+                for (int l = 0; l < P.n_levels; l++)
+                    if (P.lv[l].scale == s && hrow >= P.lv[l].row_offset) li = l;  // levels of a scale ascend in row_offset
+                const EmitParams::Lv &L = P.lv[li];
+                const int cells = L.ny * L.nx, rel = hrow - L.row_offset;
+                const int a = rel / cells, cell = rel - a * cells;
+                const int gy = cell / L.nx, gx = cell - gy * L.nx;
+                const long long e0 = (((long long)img * 3 + a) * MERGE_NO + 6) * cells + cell;
+                float v[15];
+                if (L.dtype == FDMS_F16) {
+                    const __half *p = reinterpret_cast<const __half *>(L.data) + e0;
+#pragma unroll
+                    for (int c = 0; c < 15; c++) v[c] = __half2float(__ldg(p + (long long)c * cells));
+                } else {
+                    const float *p = reinterpret_cast<const float *>(L.data) + e0;
+#pragma unroll
+                    for (int c = 0; c < 15; c++) v[c] = __ldg(p + (long long)c * cells);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    kp[3 * j] = f_mul(f_add(f_sub(f_mul(v[3 * j], 2.f), 0.5f), (float)gx), L.stride);
+                    kp[3 * j + 1] = f_mul(f_add(f_sub(f_mul(v[3 * j + 1], 2.f), 0.5f), (float)gy), L.stride);
+                    kp[3 * j + 2] = sigmoid_ref(v[3 * j + 2], P.aten != 0);
+                }
+            } else {
+                const float *row = P.cand + slot * MERGE_NO;
+#pragma unroll
+                for (int c = 0; c < 15; c++) kp[c] = row[6 + c];
+            }
             for (int j = 0; j < 5; j++) {
-                ko[3 * j] = clampf(f_mul(row[6 + 3 * j], gk), 0.f, gw);
-                ko[3 * j + 1] = clampf(f_mul(row[7 + 3 * j], gk), 0.f, gh);
-                ko[3 * j + 2] = row[8 + 3 * j];
+                ko[3 * j] = clampf(f_mul(kp[3 * j], gk), 0.f, gw);
+                ko[3 * j + 1] = clampf(f_mul(kp[3 * j + 1], gk), 0.f, gh);
+                ko[3 * j + 2] = kp[3 * j + 2];
             }
         }
     }

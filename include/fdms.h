@@ -251,7 +251,9 @@ typedef struct fdms_post_desc {
     float *dets; int32_t *n_out; int32_t out_cap;
     int32_t flags; /* FDMS_POST_* */
     int32_t *merged_in; /* may be NULL */
-    float *kpts_out;    /* may be NULL */
+    float *kpts_out;    /* may be NULL; (bs, out_cap, 15) landmarks of the final detections.  cand[..., 6:21] is NOT filled by
+                         * fdms_postprocess in either case: the landmarks are decoded from the head maps for the final
+                         * detections only (the standalone fdms_decode_filter fills all 21 columns) */
     const int32_t *orig_hw_dev; /* NULL, or (bs, 2) int32 ON THE DEVICE: (H0, W0) per image -- a batch whose images have
                                  * different original sizes but the same letterboxed input shapes (orig_h / orig_w unused) */
 } fdms_post_desc;

@@ -474,9 +474,18 @@ class MultiScaleFaceDetector:
         chunks = [paths[i:i + batch_size] for i in range(0, len(paths), batch_size)]
         if not chunks:
             return
-        bufs = {}  # pinned batch buffers, recycled per (slot, batch length); depth + 2 slots are never in flight together
-
-        dev_bufs = {}
+        # pinned / device batch buffers, recycled per (slot, batch length); depth + 2 slots are never in flight together.
+        # They and the loader thread (whose libfdms context owns the pinned staging of the device JPEG path) outlive the
+        # call: a new thread per call re-allocated ~400 MB of pinned and device memory every time.
+        if not hasattr(self, "_file_bufs"):
+            self._file_bufs, self._file_dev_bufs, self._file_active = {}, {}, False
+            self._file_loader = concurrent.futures.ThreadPoolExecutor(1, thread_name_prefix="fdms-loader")
+        shared = not self._file_active  # a second generator running on the same detector gets buffers of its own
+        if shared:
+            self._file_active = True
+            bufs, dev_bufs, ex = self._file_bufs, self._file_dev_bufs, self._file_loader
+        else:
+            bufs, dev_bufs, ex = {}, {}, concurrent.futures.ThreadPoolExecutor(1)
 
         def load(ci):
             if device_decode:
@@ -498,7 +507,7 @@ class MultiScaleFaceDetector:
                                    tuple(bufs[key].shape[1:]) == imgs[0].shape else None)
             return bufs[key]
 
-        with concurrent.futures.ThreadPoolExecutor(1) as ex:
+        try:
             state = {"next_ci": 0, "future": ex.submit(load, 0), "held": None}
 
             def take():
@@ -540,6 +549,11 @@ class MultiScaleFaceDetector:
                 for k, dets in enumerate(self.detect_stream(uniform_run(item), depth=depth)):
                     for pth, d in zip(chunks[order[k]], dets):
                         yield pth, d
+        finally:
+            if shared:
+                self._file_active = False
+            else:
+                ex.shutdown(wait=False)
 
     def get_detection_statistics(self, detections):
         """Subset of the reference's statistics helper used by detect_multi_scale's log line (msfd:281-282)."""

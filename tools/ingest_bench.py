@@ -91,7 +91,7 @@ def main():
         gpu_side = n_files / (time.perf_counter() - t0)
         res = {}
         for mode in (False, True):
-            list(det.detect_files(paths[:2 * B], batch_size=B, device_decode=mode))
+            list(det.detect_files(paths[:4 * B], batch_size=B, device_decode=mode))  # warm-up: every buffer slot (depth + 2) exists
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             got = list(det.detect_files(paths, batch_size=B, device_decode=mode))

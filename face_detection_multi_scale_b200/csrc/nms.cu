@@ -951,7 +951,7 @@ struct BinShared {
     uint16_t kl[GREEDY_BS];    // kept members of this step
     int warp_cnt[32];
     float red[5][32];
-    int nkeep, consumed, grid_on;
+    int nkeep, consumed, grid_on, next_kept;
     float x0, y0, inv_c0;
     float lvl_inv[BIN_LEVELS], lvl_c[BIN_LEVELS];
     int lvl_gx[BIN_LEVELS], lvl_gy[BIN_LEVELS], lvl_off[BIN_LEVELS];
@@ -1174,6 +1174,7 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
     for (int base = 0; base < K;) {
         const int nk = S.nkeep;
         if (tid < 4) S.sup[tid] = 0ull;
+        if (tid == 4) S.next_kept = 0;
         // ---- the next GREEDY_BS unmarked candidates, in score order ----------------------------------------------
         int nb = 0;
         while (nb < GREEDY_BS && base < K) {
@@ -1222,7 +1223,12 @@ __global__ void __launch_bounds__(GREEDY_THREADS)
         __syncthreads();
         // (5) every kept box marks the later candidates it suppresses: one warp per kept box
         if (base < K) {
-            for (int j = warp; j < n_new; j += GREEDY_THREADS / 32) {
+            // kept boxes are handed to the warps one at a time (their neighbourhoods differ in size by an order of magnitude)
+            for (;;) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&S.next_kept, 1);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                if (j >= n_new) break;
                 const int member = S.kl[j];
                 const float4 kb = S.blk[member];
                 const int kpos = S.cpos[member];

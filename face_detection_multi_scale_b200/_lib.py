@@ -10,6 +10,7 @@ FDMS_U8, FDMS_F16, FDMS_F32 = 0, 1, 2
 FDMS_CHW, FDMS_HWC = 0, 1
 IOU_TV_CPU, IOU_TV_CUDA, IOU_NCNN = 0, 1, 2  # include/fdms.h fdms_iou_mode
 MAX_SCALES, MAX_LEVELS, MAX_NMS = 8, 32, 30000
+MAX_ANCHORS, MAX_HEAD_NO = 8, 383
 
 
 class Geom(C.Structure):
@@ -56,6 +57,8 @@ _SIGS = {
     "fdms_pyramid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.POINTER(ScaleOut), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fdms_decode_dense": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fdms_decode_dense_head": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "fdms_decode_filter": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fdms_decode_filter_ex": (C.c_int, [C.c_void_p, C.POINTER(Level), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,

@@ -427,6 +427,80 @@ __global__ void __launch_bounds__(DENSE_THREADS) decode_dense_kernel(const __gri
     for (int i = threadIdx.x; i < n_rows * NO; i += DENSE_THREADS) dst[i] = s_out[i];
 }
 
+// ---- dense decode of any detection head of models/yolo.py ------------------------------------
+// Detect (:59-106), IDetect (:152-207) and IKeypoint (:267-308) share one inference branch; what differs between
+// the head variants the reference can actually run is the column semantics:
+//   nkpt > 0 (inplace branch, nc == 1, no == 6 + 3 nkpt): columns 0..5 sigmoid -> xy / wh / obj / cls, then per
+//            keypoint (raw*2 - 0.5 + gx) * stride, (raw*2 - 0.5 + gy) * stride, sigmoid(conf);
+//   nkpt == 0: every column through the sigmoid, xy / wh decoded, the rest (obj, nc classes) as they are -- the plain
+//            YOLO head (the non-inplace branch :95-99 for nc > 1; the inplace branch for nc == 1, where x_kpt is empty).
+// A CTA takes `blockDim.x` cells of one (image, anchor) plane group: channel planes are read coalesced (thread = cell),
+// the (cells x no) block of pred is staged in shared memory with an odd pitch and written out contiguously.
+struct HeadLevel {
+    const void *data;
+    int dtype, ny, nx, row_offset;
+    int block_begin, chunks;
+    float stride;
+    float anchors[2 * FDMS_MAX_ANCHORS];
+};
+
+struct HeadParams {
+    HeadLevel lv[FDMS_MAX_LEVELS];
+    int n_levels, bs, na, no, nkpt, pitch;
+    long long rows_total;
+    float *pred;
+    int aten;
+};
+
+__global__ void __launch_bounds__(128) decode_head_kernel(const __grid_constant__ HeadParams P) {
+    extern __shared__ float s_rows[];  // [blockDim.x][pitch]
+    int li = 0;
+#pragma unroll 1
+    for (int l = 1; l < P.n_levels; l++)
+        if ((int)blockIdx.x >= P.lv[l].block_begin) li = l;
+    const HeadLevel &L = P.lv[li];
+    const int T = blockDim.x, tid = threadIdx.x, no = P.no, na = P.na;
+    const int local_block = blockIdx.x - L.block_begin;
+    const int planes = P.bs * na;
+    const int chunk = local_block / planes, plane = local_block - chunk * planes;
+    const int b = plane / na, a = plane - b * na;
+    const long long cells = (long long)L.ny * L.nx;
+    const long long cell_first = (long long)chunk * T, cell = cell_first + tid;
+    const long long cbase = ((long long)b * na + a) * no * cells;
+    const bool aten = P.aten != 0;
+    if (cell < cells) {
+        const int gyi = (int)(cell / L.nx), gxi = (int)(cell - (long long)gyi * L.nx);
+        const float gx = (float)gxi, gy = (float)gyi, stride = L.stride;
+        const int n_sig = P.nkpt > 0 ? 6 : no;  // leading columns that go through the sigmoid
+        float *row = s_rows + tid * P.pitch;
+#pragma unroll 1
+        for (int c = 0; c < no; c++) {
+            const float v = ld_f(L.data, L.dtype, cbase + (long long)c * cells + cell);
+            float o;
+            if (c < n_sig) {
+                const float sg = sigmoid_ref(v, aten);
+                if (c < 2) o = f_mul(f_add(f_sub(f_mul(sg, 2.f), 0.5f), c == 0 ? gx : gy), stride);  // :73 / :166 / :290
+                else if (c < 4) {
+                    const float t = f_mul(sg, 2.f);
+                    o = f_mul(f_mul(t, t), L.anchors[2 * a + (c - 2)]);  // :74 / :167 / :291
+                } else o = sg;
+            } else {
+                const int k = (c - 6) % 3;
+                if (k == 2) o = sigmoid_ref(v, aten);  // :81 / :183 / :295
+                else o = f_mul(f_add(f_sub(f_mul(v, 2.f), 0.5f), k == 0 ? gx : gy), stride);  // raw logits, :76-77
+            }
+            row[c] = o;
+        }
+    }
+    __syncthreads();
+    const int n_rows = (int)min((long long)T, cells - cell_first);
+    float *dst = P.pred + ((long long)b * P.rows_total + L.row_offset + (long long)a * cells + cell_first) * no;
+    for (int i = tid; i < n_rows * no; i += T) {
+        const int r = i / no, c = i - r * no;
+        dst[i] = s_rows[r * P.pitch + c];
+    }
+}
+
 // ---- filter on decoded pred -------------------------------------------------------------------
 constexpr int FLT_THREADS = 256;
 
@@ -610,6 +684,56 @@ FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_le
     P.pred = pred;
     decode_dense_kernel<<<n_blocks, DENSE_THREADS, 0, (cudaStream_t)stream>>>(P);
     FDMS_LAUNCH_CHECK(ctx, "decode_dense_kernel");
+    return FDMS_OK;
+}
+
+FDMS_API int fdms_decode_dense_head(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, int na, int no, int nkpt,
+                                    const float *anchors_px, float *pred, int64_t rows_total, fdms_stream stream) {
+    FDMS_BIND(ctx);
+    if (!pred || rows_total <= 0 || !anchors_px || !levels || n_levels <= 0 || n_levels > FDMS_MAX_LEVELS || bs <= 0)
+        return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense_head: bad arguments");
+    if (na <= 0 || na > FDMS_MAX_ANCHORS || no < 6 || no > FDMS_MAX_HEAD_NO)
+        return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_dense_head: na must be 1..%d and no 6..%d (got na=%d no=%d)",
+                         FDMS_MAX_ANCHORS, FDMS_MAX_HEAD_NO, na, no);
+    if (nkpt < 0 || (nkpt > 0 && no != 6 + 3 * nkpt))
+        return fdms_fail(ctx, FDMS_ERR_INVALID,
+                         "fdms_decode_dense_head: a keypoint head has no = 6 + 3 * nkpt columns (nc = 1); got no=%d nkpt=%d", no,
+                         nkpt);
+    HeadParams P;
+    memset(&P, 0, sizeof(P));
+    P.aten = ctx->numerics == FDMS_NUMERICS_ATEN_CUDA;
+    P.pitch = no | 1;  // odd: the staging rows never share a bank pattern
+    int T = 128;       // cells per CTA: as many as 48 KB of staging allow
+    while (T > 32 && (size_t)T * P.pitch * sizeof(float) > 48 * 1024) T >>= 1;
+    long long blocks = 0;
+    for (int l = 0; l < n_levels; l++) {
+        const fdms_level &in = levels[l];
+        if (!in.data || in.ny <= 0 || in.nx <= 0 || (in.dtype != FDMS_F16 && in.dtype != FDMS_F32) || in.row_offset < 0)
+            return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense_head: bad level %d", l);
+        if ((int64_t)in.row_offset + (int64_t)na * in.ny * in.nx > rows_total || rows_total > 0x7fffffffLL)
+            return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_dense_head: level %d exceeds rows_total", l);
+        HeadLevel &L = P.lv[l];
+        L.data = in.data;
+        L.dtype = in.dtype;
+        L.ny = in.ny;
+        L.nx = in.nx;
+        L.row_offset = in.row_offset;
+        L.stride = in.stride;
+        for (int k = 0; k < 2 * na; k++) L.anchors[k] = anchors_px[(size_t)l * 2 * na + k];
+        L.chunks = (int)ceil_div64((long long)in.ny * in.nx, T);
+        L.block_begin = (int)blocks;
+        blocks += (long long)L.chunks * bs * na;
+        if (blocks > 0x7fffffffLL) return fdms_fail(ctx, FDMS_ERR_UNSUPPORTED, "fdms_decode_dense_head: grid too large");
+    }
+    P.n_levels = n_levels;
+    P.bs = bs;
+    P.na = na;
+    P.no = no;
+    P.nkpt = nkpt;
+    P.rows_total = rows_total;
+    P.pred = pred;
+    decode_head_kernel<<<(unsigned)blocks, T, (size_t)T * P.pitch * sizeof(float), (cudaStream_t)stream>>>(P);
+    FDMS_LAUNCH_CHECK(ctx, "decode_head_kernel");
     return FDMS_OK;
 }
 

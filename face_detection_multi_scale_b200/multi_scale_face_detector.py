@@ -73,6 +73,10 @@ class MultiScaleFaceDetector:
         self.iou_mode = iou_mode               # per-scale NMS flavour; the merge NMS is always TV_CPU (msfd:234)
         self.with_landmarks = bool(with_landmarks)
         self.head = yolo_head.patch_head(yolo_head.find_head(self.model))
+        if not yolo_head.is_face_head(self.head):  # the reference's class is a face detector too: it reads det[:, :6] of a
+            # 21-column row (msfd:151); other heads go through patch_head + general.non_max_suppression (compat level)
+            raise NotImplementedError("MultiScaleFaceDetector runs the face head (na=3, no=21); got na=%d no=%d"
+                                      % (self.head.na, self.head.no))
         self.strides, self.anchors_px = yolo_head.head_geometry(self.head)
         self._tls = threading.local()  # plan caches hold device buffers + a native ctx: one set per calling thread
         self._speculate_small = True   # see _plan: dense batches switch it off until a sparse one is seen again

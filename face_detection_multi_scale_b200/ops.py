@@ -154,6 +154,46 @@ def decode_dense(levels, strides, anchors_px):
     return pred
 
 
+def decode_dense_head(levels, strides, anchors_px, na, no, nkpt):
+    """The inference branch of ANY reference head (models/yolo.py Detect :59-106, IDetect :152-207, IKeypoint :267-308):
+    list of raw (bs, na*no, ny, nx) fp16/fp32 CUDA tensors -> pred (bs, rows, no) fp32.  nkpt > 0: keypoint head
+    (no == 6 + 3*nkpt, nc = 1); nkpt == 0: plain head (no == 5 + nc).  anchors_px: (nl, na, 2) pixels."""
+    na, no, nkpt = int(na), int(no), int(nkpt)
+    n = len(levels)
+    if n == 0 or n > _lib.MAX_LEVELS:
+        raise ValueError("decode_dense_head: 1..%d levels" % _lib.MAX_LEVELS)
+    if not (1 <= na <= _lib.MAX_ANCHORS) or not (6 <= no <= _lib.MAX_HEAD_NO):
+        raise NotImplementedError("decode_dense_head: na in 1..%d and no in 6..%d (got na=%d no=%d)"
+                                  % (_lib.MAX_ANCHORS, _lib.MAX_HEAD_NO, na, no))
+    if nkpt < 0 or (nkpt > 0 and no != 6 + 3 * nkpt):
+        raise ValueError("decode_dense_head: a keypoint head has no = 6 + 3*nkpt columns (got no=%d nkpt=%d)" % (no, nkpt))
+    anchors = np.ascontiguousarray(np.asarray(anchors_px, np.float32).reshape(n, na, 2))
+    bs = levels[0].shape[0]
+    arr = (_lib.Level * n)()
+    hold, off = [], 0
+    for i, t in enumerate(levels):
+        if t.dim() != 4 or t.shape[1] != na * no or t.shape[0] != bs or t.dtype not in (torch.float16, torch.float32):
+            raise ValueError("head level must be (bs, %d, ny, nx) fp16/fp32, got %r %s" % (na * no, tuple(t.shape), t.dtype))
+        if not t.is_cuda:
+            raise ValueError("decode_dense_head: CUDA tensors only (libfdms has no CPU path)")
+        if not t.is_contiguous():
+            t = t.contiguous()
+        hold.append(t)
+        arr[i].data = t.data_ptr()
+        arr[i].dtype = _DT[t.dtype]
+        arr[i].ny, arr[i].nx = t.shape[2], t.shape[3]
+        arr[i].scale = 0
+        arr[i].row_offset = off
+        arr[i].stride = float(strides[i])
+        off += na * t.shape[2] * t.shape[3]
+    dev = _dev(levels[0])
+    pred = torch.empty((bs, off, no), dtype=torch.float32, device=levels[0].device)
+    c = _ctx(dev)
+    c.check(_lib.lib().fdms_decode_dense_head(c.handle, arr, n, bs, na, no, nkpt, C.c_void_p(anchors.ctypes.data),
+                                              _ptr(pred), off, _stream(dev)), "fdms_decode_dense_head")
+    return pred
+
+
 DECODE_BOXES_ONLY = 1  # include/fdms.h FDMS_DECODE_BOXES_ONLY
 POST_SMALL_ONLY = 1    # include/fdms.h FDMS_POST_SMALL_ONLY
 SMALL_LIMIT = 1024     # include/fdms.h FDMS_SMALL_LIMIT

@@ -53,6 +53,8 @@ typedef enum fdms_iou_mode {
 
 #define FDMS_MAX_SCALES 8
 #define FDMS_MAX_LEVELS 32
+#define FDMS_MAX_ANCHORS 8   /* anchors per level of fdms_decode_dense_head */
+#define FDMS_MAX_HEAD_NO 383 /* columns per row of fdms_decode_dense_head (5 + nc, or 6 + 3 * nkpt) */
 #define FDMS_MAX_NMS 30000 /* utils/general.py:520 */
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -129,6 +131,17 @@ typedef struct fdms_level {
  * (all levels must have scale == 0).  models/yolo.py:308 `cat(z, 1)`. */
 FDMS_API int fdms_decode_dense(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, float *pred,
                                int64_t rows_total, fdms_stream stream);
+
+/* The same full decode for ANY detection head the reference can run in eval mode -- Detect (models/yolo.py:59-106),
+ * IDetect (:152-207), IKeypoint (:267-308) with na anchors per level and no columns per row:
+ *   nkpt > 0  : the keypoint heads (inplace branch; the reference slices `[..., :6]`, i.e. nc = 1, so no must equal
+ *               6 + 3 * nkpt): columns 0..5 as in fdms_decode_dense, then (x, y, conf) per keypoint;
+ *   nkpt == 0 : every column through the sigmoid, xy / wh decoded, obj and the nc = no - 5 class columns as they are (the
+ *               plain YOLO head: `inplace=False` branch :95-99 for nc > 1; nc = 1 also through the inplace branch).
+ * levels[l].anchors is ignored; anchors_px is a HOST array (n_levels, na, 2) in pixels (`anchor_grid`).  All levels
+ * must have scale == 0.  pred: (bs, rows_total, no) f32, rows level-major then anchor, y, x (:308 `cat(z, 1)`). */
+FDMS_API int fdms_decode_dense_head(fdms_ctx *ctx, const fdms_level *levels, int n_levels, int bs, int na, int no, int nkpt,
+                                    const float *anchors_px, float *pred, int64_t rows_total, fdms_stream stream);
 
 /* Fused decode + confidence filter + xywh2xyxy + stream compaction ("fused level"):
  * models/yolo.py:267-308 then utils/general.py:515,531,547-563 and :299-306.

@@ -254,6 +254,33 @@ FO_EXPORT void fo_decode_level(const float *x, int bs, int na, int no, int ny, i
                 }
 }
 
+/* The same inference branch for every head variant the reference can run (Detect models/yolo.py:59-106, IDetect
+ * :152-207, IKeypoint :267-308): nkpt > 0 -> 6 detection columns (nc = 1) + (x, y, conf) per keypoint, inplace
+ * branch; nkpt == 0 -> all columns through the sigmoid, xy / wh decoded (the plain head: :95-99 for nc > 1). */
+FO_EXPORT void fo_decode_level_head(const float *x, int bs, int na, int no, int nkpt, int ny, int nx, float stride,
+                                    const float *anchors_px /* na*2: (w,h) */, int64_t rows_total, int64_t row_offset,
+                                    float *pred) {
+    int64_t P = (int64_t)ny * nx;
+    int n_sig = nkpt > 0 ? 6 : no;
+    for (int b = 0; b < bs; b++)
+        for (int a = 0; a < na; a++)
+            for (int gy = 0; gy < ny; gy++)
+                for (int gx = 0; gx < nx; gx++) {
+                    const float *in = x + ((int64_t)b * na * no + (int64_t)a * no) * P + (int64_t)gy * nx + gx;
+                    float *o = pred + ((int64_t)b * rows_total + row_offset + a * P + (int64_t)gy * nx + gx) * no;
+                    for (int c = 0; c < no; c++) {
+                        float v = in[c * P], t;
+                        if (c < n_sig) {
+                            float sg = sigmoidf_(v);
+                            if (c < 2) { t = sg * 2.f; t = t - 0.5f; t = t + (float)(c == 0 ? gx : gy); o[c] = t * stride; }
+                            else if (c < 4) { t = sg * 2.f; t = t * t; o[c] = t * anchors_px[a * 2 + (c - 2)]; }
+                            else o[c] = sg;
+                        } else if ((c - 6) % 3 == 2) o[c] = sigmoidf_(v);
+                        else { t = v * 2.f; t = t - 0.5f; t = t + (float)((c - 6) % 3 == 0 ? gx : gy); o[c] = t * stride; }
+                    }
+                }
+}
+
 /* ------------------------------------------------------------------------- */
 /* B6  confidence filter + xywh2xyxy -- utils/general.py:515,531,547-563,299-306 */
 /*     nc == 1, kpt_label == 5.  Output rows: [x1,y1,x2,y2,conf,0,15 kpt] (21), */

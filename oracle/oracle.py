@@ -126,6 +126,26 @@ def decode_head(levels, strides, anchors_px, no=21, na=3):
     return pred
 
 
+def decode_head_general(levels, strides, anchors_px, na, no, nkpt):
+    """Any head variant of models/yolo.py (Detect :59-106, IDetect :152-207, IKeypoint :267-308): levels = list of
+    (bs, na*no, ny, nx); nkpt > 0 -> keypoint head (no == 6 + 3*nkpt), nkpt == 0 -> plain head (no == 5 + nc)."""
+    levels = [np.ascontiguousarray(np.asarray(l, dtype=np.float32)) for l in levels]
+    assert nkpt == 0 or no == 6 + 3 * nkpt
+    bs = levels[0].shape[0]
+    rows = sum(na * l.shape[2] * l.shape[3] for l in levels)
+    pred = np.empty((bs, rows, no), np.float32)
+    anchors_px = np.asarray(anchors_px, np.float32).reshape(len(levels), na, 2)
+    off = 0
+    for i, l in enumerate(levels):
+        _, ch, ny, nx = l.shape
+        assert ch == na * no
+        a = np.ascontiguousarray(anchors_px[i])
+        lib().fo_decode_level_head(_p(l), bs, na, no, nkpt, ny, nx, C.c_float(float(strides[i])), _p(a), C.c_int64(rows),
+                                   C.c_int64(off), _p(pred))
+        off += na * ny * nx
+    return pred
+
+
 # ---- B6 filter: utils/general.py:515-563 -------------------------------------------------------
 def filter_xyxy(pred_img, conf_thres):
     """pred_img: (rows, 21) fp32 for ONE image.  Returns (cand (n,21), src_row (n,))."""

@@ -569,6 +569,62 @@ def gen_ikeypoint():
     save("ikeypoint", **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# 16. every head variant the reference can run in eval mode (Detect / IDetect / IKeypoint, any na / nc / nkpt)
+# ------------------------------------------------------------------------------------------------
+HEAD_VARIANTS = {
+    # name: (class, nc, nkpt, na, inplace)
+    "detect_nc3": ("Detect", 3, 0, 3, False),       # plain multi-class head, non-inplace branch (models/yolo.py:95-99)
+    "detect_nc80": ("Detect", 80, 0, 3, False),     # COCO-sized rows (no = 85)
+    "idetect_nc1": ("IDetect", 1, 0, 2, True),      # no = 6 through the inplace branch, two anchors per level
+    "idetect_pose": ("IDetect", 1, 17, 3, True),    # 17 keypoints (no = 57): the keypoint columns of x are decoded in place
+    "detect_face": ("Detect", 1, 5, 3, True),       # the face layout on a Detect head (x mutated, :76-81)
+    "ikeypoint_k3": ("IKeypoint", 1, 3, 4, True),   # three keypoints, four anchors per level (no = 15)
+}
+
+
+def gen_heads():
+    import models.yolo as Y
+    out = {}
+    ch, strides, hw = (8, 16, 32), (8., 16., 32.), (32, 64)
+    for vi, (name, (cls, nc, nkpt, na, inplace)) in enumerate(sorted(HEAD_VARIANTS.items())):
+        torch.manual_seed(100 + vi)
+        rng = np.random.default_rng(100 + vi)
+        anchors = (rng.uniform(4, 200, size=(3, na * 2))).round(1).tolist()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = getattr(Y, cls)(nc=nc, anchors=anchors, nkpt=nkpt, ch=ch, inplace=inplace)
+        m.stride = torch.tensor(strides)
+        m.eval()
+        for p_ in m.parameters():
+            p_.data.mul_(3.0)
+        with_module = name != "detect_nc80"  # weights + conv inputs for the patched-module test (kept small)
+        if with_module:
+            for k, v in m.state_dict().items():
+                out["%s__w_%s" % (name, k.replace(".", "__"))] = v.numpy()
+        xs = [torch.randn(2, c, int(hw[0] // s), int(hw[1] // s)) for c, s in zip(ch, strides)]
+        # the decode's input: the conv outputs exactly as the head's forward computes them (:62-65, :155-158, :270-273)
+        for i, x in enumerate(xs):
+            det = m.im[i](m.m[i](m.ia[i](x))) if hasattr(m, "ia") else m.m[i](x)
+            raw = det if not nkpt else torch.cat((det, m.m_kpt[i](x)), 1)
+            if with_module:
+                out["%s__x%d" % (name, i)] = x.numpy()
+            out["%s__raw%d" % (name, i)] = raw.numpy()
+        pred, xo = m([x.clone() for x in xs])
+        assert pred.shape[-1] == m.no
+        out[name + "__pred"] = pred.numpy()
+        for i, r in enumerate(xo):  # second return value: (bs, na, ny, nx, no); Detect / IDetect decode its keypoint columns
+            bs, na_, ny, nx, no = r.shape
+            raw_view = torch.from_numpy(out["%s__raw%d" % (name, i)]).view(bs, na_, no, ny, nx).permute(0, 1, 3, 4, 2)
+            if cls == "IKeypoint" or not nkpt:
+                assert torch.equal(r, raw_view)  # un-mutated
+            else:
+                assert torch.equal(r[..., :6], raw_view[..., :6]) and not torch.equal(r[..., 6:], raw_view[..., 6:])
+                out["%s__xo%d" % (name, i)] = r.numpy()
+        out[name + "__meta"] = np.array([nc, nkpt, na, int(inplace)])
+        out[name + "__anchors_px"] = m.anchor_grid.view(m.nl, m.na, 2).numpy()
+    save("heads", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()["gen_" + sys.argv[1]]()
@@ -588,3 +644,4 @@ if __name__ == "__main__":
     gen_tta()
     gen_pack()
     gen_ikeypoint()
+    gen_heads()

@@ -15,6 +15,7 @@ seeded random ones, function by function:
     MultiScaleFaceDetector.calculate_scale_weights / weighted_nms (msfd:168-240)         bit exact
     MultiScaleFaceDetector.detect_multi_scale around a stand-in backbone (msfd:242-288)  bit exact
     utils.torch_utils.scale_img, Model._descale_pred          (torch_utils.py:247, yolo.py:402)  <= 2 ulp / bit exact
+    models.yolo.Detect / IDetect / IKeypoint, any na / nc / nkpt (models/yolo.py:59-308)  <= 1e-4 px or 4 ulp; refusals
 
 Prints one JSON line {"checks": n, "failures": [...]} and exits 1 if anything differs.
 """
@@ -275,6 +276,46 @@ def main():
         ref = Model._descale_pred(type("M", (), {"inplace": True})(), torch.from_numpy(p.copy()), flips, ratio,
                                   shape[2:]).numpy()
         check(np.array_equal(O.descale_pred(p.copy(), flips, ratio, shape[2:]), ref), ("descale_pred", it))
+
+    # ---- every head class of models/yolo.py, random geometry: the oracle's general decode against the live modules, and the
+    # combinations face_detection_multi_scale_b200.yolo_head.head_columns refuses really fail (or scramble) in the reference
+    import models.yolo as Y
+    for it in range(12):
+        cls = ("Detect", "IDetect", "IKeypoint")[it % 3]
+        nkpt = int(rng.choice([0, 1, 5, 17]))
+        nc, inplace = (1, True) if nkpt else (int(rng.choice([1, 2, 20])), False)
+        if nkpt == 0 and it % 2:
+            nc, inplace = 1, True  # no = 6 through the inplace branch
+        na, nl = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        anchors = rng.uniform(4, 150, size=(nl, na * 2)).round(1).tolist()
+        ch = tuple(int(c) for c in rng.integers(2, 9, nl))
+        m = quiet(getattr(Y, cls), nc=nc, anchors=anchors, nkpt=nkpt, ch=ch, inplace=inplace)
+        strides = [8.0 * 2 ** i for i in range(nl)]
+        m.stride = torch.tensor(strides)
+        m.eval()
+        for p_ in m.parameters():
+            p_.data.mul_(3.0)
+        hw = (int(rng.integers(1, 4)) * 8 * 2 ** (nl - 1), int(rng.integers(1, 4)) * 8 * 2 ** (nl - 1))
+        xs = [torch.from_numpy(rng.normal(size=(2, c, int(hw[0] // s), int(hw[1] // s))).astype(np.float32))
+              for c, s in zip(ch, strides)]
+        raws = []
+        for i, x in enumerate(xs):
+            det = m.im[i](m.m[i](m.ia[i](x))) if hasattr(m, "ia") else m.m[i](x)
+            raws.append((det if not nkpt else torch.cat((det, m.m_kpt[i](x)), 1)).numpy())
+        ref = m([x.clone() for x in xs])[0].numpy()
+        got = O.decode_head_general(raws, strides, m.anchor_grid.view(nl, na, 2).numpy(), na, m.no, nkpt)
+        check(got.shape == ref.shape and bool(np.all(np.abs(got - ref) <= np.maximum(1e-4, 4 * np.spacing(np.abs(ref))))),
+              ("head variant", cls, nc, nkpt, na, nl, inplace))
+    for cls, nc, nkpt, inplace in (("Detect", 2, 5, True), ("IDetect", 1, 5, False), ("IKeypoint", 1, 5, False),
+                                   ("IKeypoint", 2, 5, True), ("Detect", 80, 0, True), ("IDetect", 3, 0, True)):
+        m = quiet(getattr(Y, cls), nc=nc, anchors=[[10, 13, 16, 30, 33, 23]], nkpt=nkpt, ch=(8,), inplace=inplace)
+        m.stride = torch.tensor([8.])
+        m.eval()
+        try:
+            rows = m([torch.zeros(1, 8, 4, 6)])[0].shape[1]
+            check(rows != 3 * 4 * 6, ("the reference runs a head that head_columns refuses", cls, nc, nkpt, inplace))
+        except RuntimeError:
+            check(True, "refused combination raises in the reference")
 
     print(json.dumps({"checks": N[0], "failures": [repr(f) for f in FAIL[:20]]}))
     sys.exit(1 if FAIL else 0)

@@ -85,3 +85,156 @@ def test_reference_pred_through_nms(golden):
     res = general.non_max_suppression(pred, float(g["thr"]), 0.45, iou_mode=ops.IOU_TV_CPU)
     for b in range(2):
         assert np.array_equal(res[b].cpu().numpy(), g["nms_b%d" % b])
+
+
+# ---- every other head variant the reference can run (tests/golden/heads.npz, make_golden.py::gen_heads) ------------
+HEAD_VARIANTS = {  # name: class of the reference module
+    "detect_nc3": "Detect", "detect_nc80": "Detect", "idetect_nc1": "IDetect", "idetect_pose": "IDetect",
+    "detect_face": "Detect", "ikeypoint_k3": "IKeypoint",
+}
+
+
+def _variant(golden, name):
+    g = golden("heads")
+    nc, nkpt, na, inplace = (int(v) for v in g[name + "__meta"])
+    return g, nc, nkpt, na, bool(inplace), 5 + nc + 3 * nkpt
+
+
+@pytest.mark.parametrize("name", list(HEAD_VARIANTS))
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_decode_dense_head_vs_oracle_and_reference(golden, name, dtype):
+    from oracle import oracle as O
+    g, nc, nkpt, na, _, no = _variant(golden, name)
+    raw = [g["%s__raw%d" % (name, i)].astype(dtype) for i in range(3)]
+    anchors = g[name + "__anchors_px"]
+    pred = ops.decode_dense_head([torch.from_numpy(r).to(DEV) for r in raw], (8, 16, 32), anchors, na, no, nkpt).cpu().numpy()
+    ref = O.decode_head_general(raw, (8, 16, 32), anchors, na, no, nkpt)
+    assert pred.shape == ref.shape == g[name + "__pred"].shape
+    assert np.array_equal(pred, ref)  # same correctly rounded sigmoid, every operation rounded separately: bit identical
+    if dtype is np.float32:  # the reference module's own output (ATen CPU exp: <= 1 ulp in the sigmoid, see test_oracle_golden)
+        gp = g[name + "__pred"]
+        assert np.all(np.abs(pred - gp) <= np.maximum(1e-4, 4 * np.spacing(np.abs(gp))))
+
+
+def test_decode_dense_head_equals_face_kernel(golden):
+    """On the face layout (na=3, no=21, nkpt=5) the general kernel and the specialised one are the same function."""
+    g = golden("heads")
+    raw = [torch.from_numpy(g["detect_face__raw%d" % i]).to(DEV) for i in range(3)]
+    a = ops.decode_dense(raw, (8, 16, 32), g["detect_face__anchors_px"])
+    b = ops.decode_dense_head(raw, (8, 16, 32), g["detect_face__anchors_px"], 3, 21, 5)
+    assert torch.equal(a, b)
+
+
+def test_decode_dense_head_ragged_tail_and_wide_rows():
+    """Cell counts that are no multiple of the CTA size, one anchor, the widest supported row (staging in 32-cell CTAs)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    for na, no, nkpt, hw in ((1, 6, 0, (7, 13)), (8, 9, 1, (5, 3)), (2, 383, 0, (3, 11)), (3, 96, 30, (9, 17)), (5, 200, 0, (6, 7))):
+        raw = [rng.normal(0, 2, size=(2, na * no, hw[0] * k, hw[1] * k)).astype(np.float32) for k in (2, 1)]
+        anchors = rng.uniform(4, 300, size=(2, na, 2)).astype(np.float32)
+        pred = ops.decode_dense_head([torch.from_numpy(r).to(DEV) for r in raw], (8, 16), anchors, na, no, nkpt).cpu().numpy()
+        assert np.array_equal(pred, O.decode_head_general(raw, (8, 16), anchors, na, no, nkpt)), (na, no, nkpt)
+
+
+def test_decode_dense_head_rejects_bad_arguments():
+    x = [torch.zeros((1, 3 * 22, 4, 4), device=DEV)]
+    with pytest.raises(ValueError):
+        ops.decode_dense_head(x, [8], np.ones((1, 3, 2)), 3, 22, 5)  # a keypoint head has 6 + 3*nkpt columns
+    with pytest.raises(NotImplementedError):
+        ops.decode_dense_head(x, [8], np.ones((1, 9, 2)), 9, 22, 0)  # more anchors than FDMS_MAX_ANCHORS
+    with pytest.raises(ValueError):
+        ops.decode_dense_head(x, [8], np.ones((1, 3, 2)), 3, 21, 5)  # channel count does not match na * no
+
+
+class _AnyHead(torch.nn.Module):
+    """Attribute layout of models/yolo.py::Detect / IDetect / IKeypoint for any nc / nkpt / na (single-conv keypoint branch)."""
+
+    def __init__(self, kind, ch, nc, nkpt, na, inplace, anchors_px, strides):
+        super().__init__()
+        self.nc, self.nkpt, self.no_det, self.no_kpt, self.nl, self.na = nc, nkpt, nc + 5, 3 * nkpt, len(ch), na
+        self.no, self.inplace = self.no_det + self.no_kpt, inplace
+        a = torch.as_tensor(np.asarray(anchors_px, np.float32)).view(self.nl, -1, 2)
+        self.register_buffer("anchors", a.clone())
+        self.register_buffer("anchor_grid", a.clone().view(self.nl, 1, -1, 1, 1, 2))
+        self.m = torch.nn.ModuleList(torch.nn.Conv2d(c, self.no_det * na, 1) for c in ch)
+        if kind != "Detect":
+            self.ia = torch.nn.ModuleList(_ImplicitA(c) for c in ch)
+            self.im = torch.nn.ModuleList(_ImplicitM(self.no_det * na) for _ in ch)
+        self.m_kpt = torch.nn.ModuleList(torch.nn.Conv2d(c, self.no_kpt * na, 1) for c in ch)
+        self.stride = torch.tensor([float(s) for s in strides])
+
+
+# the test classes carry the reference's class names: patch_head keys the in-place keypoint write-back on them
+class Detect(_AnyHead):
+    pass
+
+
+class IDetect(_AnyHead):
+    pass
+
+
+class IKeypoint(_AnyHead):
+    pass
+
+
+@pytest.mark.parametrize("name", [n for n in HEAD_VARIANTS if n != "detect_nc80"])
+def test_patched_head_variants_equal_reference_modules(golden, name):
+    g, nc, nkpt, na, inplace, no = _variant(golden, name)
+    kind = HEAD_VARIANTS[name]
+    head = {"Detect": Detect, "IDetect": IDetect, "IKeypoint": IKeypoint}[kind](
+        kind, (8, 16, 32), nc, nkpt, na, inplace, g[name + "__anchors_px"], (8, 16, 32))
+    pre = name + "__w_"
+    sd = {k[len(pre):].replace("__", "."): torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}
+    head.load_state_dict(sd, strict=True)
+    head.to(DEV).eval()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yolo_head.patch_head(head)
+    xs = [torch.from_numpy(g["%s__x%d" % (name, i)]).to(DEV) for i in range(3)]
+    with torch.no_grad():
+        pred, xo = head([x.clone() for x in xs])
+    gp = g[name + "__pred"]
+    assert pred.shape == gp.shape
+    # the convolutions run in cuDNN (other summation order than the CPU reference); their error is amplified by the
+    # stride / the anchors, so the module-level comparison is loose and the decode itself is pinned above
+    d = np.abs(pred.cpu().numpy() - gp)
+    assert np.max(d / np.maximum(1.0, np.abs(gp))) <= 2e-3
+    assert np.mean(d <= 1e-3 * np.maximum(1.0, np.abs(gp))) > 0.999
+    mutated = nkpt > 0 and kind in ("Detect", "IDetect")
+    off = 0
+    for i, r in enumerate(xo):
+        bs, na_, ny, nx, no_ = r.shape
+        assert (na_, no_) == (na, no)
+        raw_view = head.fdms_raw[i].view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2)
+        if mutated:  # models/yolo.py:76-81 / :169-183: the keypoint columns of the returned tensor hold decoded values
+            assert torch.equal(r[..., :6], raw_view[..., :6])
+            assert torch.equal(r[..., 6:], pred[:, off:off + na * ny * nx].view(bs, na, ny, nx, no)[..., 6:])
+            gx = g["%s__xo%d" % (name, i)]
+            assert np.max(np.abs(r.cpu().numpy() - gx) / np.maximum(1.0, np.abs(gx))) <= 2e-3
+        else:
+            assert torch.equal(r, raw_view)
+        off += na * ny * nx
+
+
+def test_patch_head_refuses_what_the_reference_cannot_run():
+    mk = lambda kind, nc, nkpt, inplace: {"Detect": Detect, "IDetect": IDetect}[kind](  # noqa: E731
+        kind, (8,), nc, nkpt, 3, inplace, np.ones((1, 3, 2)), (8,))
+    for args in (("Detect", 2, 5, True), ("IDetect", 1, 5, False), ("Detect", 80, 0, True)):
+        with pytest.raises(NotImplementedError):
+            yolo_head.patch_head(mk(*args))
+
+
+def test_plain_head_through_multiclass_nms(golden):
+    """A multi-class head end to end at the compat level: libfdms decode -> general.non_max_suppression (class offsets,
+    utils/general.py:533-582) against the oracle's decode pushed through the same function."""
+    from oracle import oracle as O
+    g, nc, nkpt, na, _, no = _variant(golden, "detect_nc3")
+    raw = [g["detect_nc3__raw%d" % i] for i in range(3)]
+    anchors = g["detect_nc3__anchors_px"]
+    pred = ops.decode_dense_head([torch.from_numpy(r).to(DEV) for r in raw], (8, 16, 32), anchors, na, no, nkpt)
+    ref = torch.from_numpy(O.decode_head_general(raw, (8, 16, 32), anchors, na, no, nkpt)).to(DEV)
+    a = general.non_max_suppression(pred, 0.05, 0.45, kpt_label=0)
+    b = general.non_max_suppression(ref, 0.05, 0.45, kpt_label=0)
+    assert sum(len(r) for r in a) > 10
+    for ra, rb in zip(a, b):
+        assert ra.shape[1] == 6 and torch.equal(ra, rb)

@@ -71,6 +71,8 @@ def test_no_cpu_fallback():
     from face_detection_multi_scale_b200 import ops
     with pytest.raises(ValueError):
         ops.decode_dense([torch.zeros((1, 63, 4, 4))], [8], np.ones((1, 3, 2)))
+    with pytest.raises(ValueError):
+        ops.decode_dense_head([torch.zeros((1, 24, 4, 4))], [8], np.ones((1, 3, 2)), 3, 8, 0)
     from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
     with pytest.raises(RuntimeError):
         MultiScaleFaceDetector(torch.nn.Identity(), device="")
@@ -269,3 +271,20 @@ def test_letterbox_geometry_random_sweep_vs_oracle_and_python():
         for g in (a, b):
             got = (g.dst_h, g.dst_w, g.unpad_h, g.unpad_w, g.top, g.left, g.ratio_w, g.ratio_h, g.dw, g.dh)
             assert got == want, (h, w, ns, auto, fill, up, stride, got, want)
+
+
+def test_head_columns_accepts_what_the_reference_runs():
+    """yolo_head.head_columns: the (class, nc, nkpt, inplace) combinations of models/yolo.py:59-106 / :152-207 / :267-308
+    that run in eval mode, and refusals for those where the reference itself raises or scrambles its rows."""
+    from types import SimpleNamespace as NS
+    from face_detection_multi_scale_b200 import yolo_head
+    ok = [(3, 1, 5, True), (3, 1, 17, True), (2, 1, 0, True), (3, 80, 0, False), (4, 1, 3, True), (3, 1, 0, False)]
+    for na, nc, nkpt, inplace in ok:
+        h = NS(na=na, nc=nc, nkpt=nkpt, no=5 + nc + 3 * nkpt, inplace=inplace)
+        assert yolo_head.head_columns(h) == (na, 5 + nc + 3 * nkpt, nkpt)
+    for na, nc, nkpt, inplace in [(3, 2, 5, True), (3, 1, 5, False), (3, 80, 0, True)]:
+        with pytest.raises(NotImplementedError):
+            yolo_head.head_columns(NS(na=na, nc=nc, nkpt=nkpt, no=5 + nc + 3 * nkpt, inplace=inplace))
+    with pytest.raises(ValueError):
+        yolo_head.head_columns(NS(na=3, nc=1, nkpt=5, no=22, inplace=True))
+    assert yolo_head.is_face_head(NS(na=3, no=21, nkpt=5)) and not yolo_head.is_face_head(NS(na=3, no=85, nkpt=0))

@@ -114,6 +114,29 @@ def test_decode_and_nms_crowd(golden, name):
             assert np.max(np.abs(res[b] - ref)) <= 1e-4 if ref.size else True
 
 
+HEAD_VARIANTS = ("detect_nc3", "detect_nc80", "idetect_nc1", "idetect_pose", "detect_face", "ikeypoint_k3")
+
+
+@pytest.mark.parametrize("name", HEAD_VARIANTS)
+def test_decode_head_variants(golden, name):
+    """Detect / IDetect / IKeypoint of models/yolo.py with other na / nc / nkpt than the face head: the oracle's general
+    decode against the reference modules' own eval-mode output (tests/golden/make_golden.py::gen_heads)."""
+    g = golden("heads")
+    nc, nkpt, na, _ = (int(v) for v in g[name + "__meta"])
+    no = 5 + nc + 3 * nkpt
+    raw = [g["%s__raw%d" % (name, i)] for i in range(3)]
+    pred = O.decode_head_general(raw, (8, 16, 32), g[name + "__anchors_px"], na, no, nkpt)
+    ref = g[name + "__pred"]
+    assert pred.shape == ref.shape
+    # 1e-4 px (north_star), or 4 ulp where a box is so large (anchors up to 200 px x 4) that 1e-4 px is less than that:
+    # ATen's vectorised CPU exp (Sleef) and the correctly rounded one differ by <= 1 ulp in the sigmoid, (2s)^2 doubles
+    # the relative error and the product with the anchor rounds once more (seen: 1.2e-4 at 379 px)
+    assert np.all(np.abs(pred - ref) <= np.maximum(1e-4, 4 * np.spacing(np.abs(ref))))
+    assert np.mean(pred == ref) > 0.9
+    if nkpt == 5 and na == 3:  # the face layout: the specialised restatement agrees bit for bit
+        assert np.array_equal(O.decode_head(raw, (8, 16, 32), g[name + "__anchors_px"]), pred)
+
+
 def test_nms_on_reference_pred(golden):
     """filter + NMS from the reference's own decoded pred: bit-exact rows."""
     g = golden("head")

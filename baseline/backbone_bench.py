@@ -9,7 +9,8 @@ A REAL reference network -- random-init `models.yolo.Model(cfg)` from the refere
 box), fp16 as the reference runs it on CUDA (msfd:49) -- stands between the two halves of the hot path:
   backbone_ms_per_step         the PyTorch forward of the unchanged network, all scales, batch B (CUDA events)
   libfdms                      MultiScaleFaceDetector.detect_multi_scale_batch(pinned host batch): H2D + pyramid + backbone + decode /
-                               NMS / merge + D2H, and the same with the forward time subtracted (= the hot path's share)
+                               NMS / merge + D2H, and the same with the forward time subtracted (= the hot path's share);
+                               detect_stream over the same batches (copies of neighbouring batches overlap the backbone)
   reference_gpu                the UNMODIFIED reference on the same GPU and the same network: detect_multi_scale per image
                                (msfd:242-288; image served from memory, no file decode), batch 1, sequential scales
 Prints one JSON line.  Plain random-init heads give no candidates at conf 0.5: the network's BatchNorm
@@ -92,6 +93,15 @@ def main():
         return (time.perf_counter() - t0) / n
 
     t_mine = clock(lambda: mine.detect_multi_scale_batch(pinned), args.steps)
+    # the same through the pipelined entry: the H2D copy of batch i+1 and the D2H of batch i-1 overlap the backbone of batch i
+    pinned2 = torch.from_numpy(rng.integers(0, 256, images.shape, dtype=np.uint8)).pin_memory()
+    n_stream = max(4, args.steps)
+
+    def stream_run():
+        for _ in mine.detect_stream((pinned if i % 2 == 0 else pinned2 for i in range(n_stream)), depth=2):
+            pass
+    stream_run()
+    t_stream = clock(stream_run, 1) / n_stream
     # backbone alone: the forward of the unchanged network on the pyramid's tensors, all scales (CUDA events)
     xs, _ = mine._pyramid(pinned.to(dev))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -125,6 +135,9 @@ def main():
         "backbone_images_per_s": round(B / (bb_ms * 1e-3), 1),
         "libfdms": {"e2e_with_backbone_images_per_s": round(B / t_mine, 1), "ms_per_step": round(1e3 * t_mine, 2),
                     "hot_path_ms_per_step": round(1e3 * t_mine - bb_ms, 2),
+                    "detect_stream_images_per_s": round(B / t_stream, 1), "detect_stream_ms_per_step": round(1e3 * t_stream, 2),
+                    "detect_stream_api": "MultiScaleFaceDetector.detect_stream(pinned host batches, depth=2): copies overlapped with the "
+                                         "backbone of the neighbouring batches",
                     "api": "MultiScaleFaceDetector.detect_multi_scale_batch(pinned host batch): H2D + pyramid + backbone + post + D2H"},
         "reference_gpu": {"e2e_with_backbone_images_per_s": round(1.0 / t_ref, 2), "ms_per_image": round(1e3 * t_ref, 2),
                           "images_timed": n_ref,

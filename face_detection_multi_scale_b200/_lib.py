@@ -152,7 +152,8 @@ class Ctx:
 
     def set_numerics(self, mode):
         """fdms_set_numerics: 'exact' (default; the CPU oracle's arithmetic) or 'aten_cuda' (bit-identical to the reference
-        running in fp32 on a CUDA device: libdevice expf in the sigmoid, x * (1 / s) for divisions by a scalar)."""
+        running on a CUDA device: libdevice expf in the sigmoid, x * (1 / s) for divisions by a scalar, and -- on fp16 head
+        maps, i.e. a half model -- the half roundings of ATen's elementwise kernels in the head decode)."""
         m = {"exact": 0, "aten_cuda": 1, 0: 0, 1: 1}[mode]
         self.check(lib().fdms_set_numerics(self._h, m), "fdms_set_numerics")
 

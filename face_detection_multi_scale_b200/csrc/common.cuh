@@ -166,6 +166,23 @@ __device__ __forceinline__ float sigmoid_ref(float x, bool aten) {
     return f_div(1.0f, f_add(1.0f, e));
 }
 
+// Round to half precision and back: one ATen operation on a half tensor (opmath float, the result stored as c10::Half).
+__device__ __forceinline__ float h_rn(float x) { return __half2float(__float2half_rn(x)); }
+
+// The head decode as ATen computes it ON A CUDA DEVICE FOR A HALF MODEL (the reference's default, msfd:49 `model.half()`):
+// the conv outputs, the sigmoid, `y * 2.`, `- 0.5`, `** 2` and `* anchor_grid` are half tensors (every operation rounds to
+// half), `self.grid[i]` is created float32 (models/yolo.py:310-313), so `+ grid` promotes to float32 and `* stride` stays
+// there; the keypoint coordinates are written back into the half tensor x_kpt (rounded once more) and `torch.cat` promotes
+// the row to float32 -- pred is a float32 tensor of half-valued columns 2..20 and float32 xy.  Verified op by op against the
+// reference module on half tensors (tests/ref_live_check.py) and on the GPU (tests/ref_gpu_check.py, part C).
+__device__ __forceinline__ float h_sigmoid(float x) { return h_rn(f_div(1.0f, f_add(1.0f, expf(-x)))); }
+__device__ __forceinline__ float h_xy(float s, float g, float stride) {  // (s * 2. - 0.5 + grid) * stride, s a half value
+    return f_mul(f_add(h_rn(f_sub(h_rn(f_mul(s, 2.f)), 0.5f)), g), stride);
+}
+__device__ __forceinline__ float h_wh(float s, float anchor) {  // (s * 2) ** 2 * anchor_grid, all half tensors
+    const float t = h_rn(f_mul(s, 2.f));
+    return h_rn(f_mul(h_rn(f_mul(t, t)), h_rn(anchor)));
+}
 
 __device__ __forceinline__ float ld_f(const void *p, int dtype, int64_t i) {
     return dtype == FDMS_F16 ? __half2float(__ldg(reinterpret_cast<const __half *>(p) + i))

@@ -68,9 +68,19 @@ struct DecCta {
 };
 
 // models/yolo.py:290-295 for one cell; v[k] = raw channel k (already fp32), out = 21 floats
-// [cx, cy, w, h, obj, cls, (kx, ky, kc) x 5]
-__device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
-                                            float (&o)[NO], bool aten) {
+// [cx, cy, w, h, obj, cls, (kx, ky, kc) x 5].  hf: the half-model arithmetic of ATen's CUDA kernels (common.cuh).
+__device__ __forceinline__ void decode_box(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
+                                           float (&o)[NO], bool aten, bool hf) {
+    if (hf) {
+        const float s0 = h_sigmoid(v[0]), s1 = h_sigmoid(v[1]), s2 = h_sigmoid(v[2]), s3 = h_sigmoid(v[3]);
+        o[0] = h_xy(s0, gx, stride);
+        o[1] = h_xy(s1, gy, stride);
+        o[2] = h_wh(s2, aw);
+        o[3] = h_wh(s3, ah);
+        o[4] = h_sigmoid(v[4]);
+        o[5] = h_sigmoid(v[5]);
+        return;
+    }
     float s0 = sigmoid_ref(v[0], aten), s1 = sigmoid_ref(v[1], aten), s2 = sigmoid_ref(v[2], aten), s3 = sigmoid_ref(v[3], aten);
     o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
     o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
@@ -79,25 +89,23 @@ __device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, floa
     o[3] = f_mul(f_mul(t3, t3), ah);
     o[4] = sigmoid_ref(v[4], aten);
     o[5] = sigmoid_ref(v[5], aten);
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        o[6 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[6 + 3 * j], 2.f), 0.5f), gx), stride);  // raw logits, no sigmoid
-        o[7 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[7 + 3 * j], 2.f), 0.5f), gy), stride);
-        o[8 + 3 * j] = sigmoid_ref(v[8 + 3 * j], aten);
-    }
 }
 
-// The box / objectness / class part of decode_cell alone (candidates whose landmarks nobody reads).
-__device__ __forceinline__ void decode_box(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
-                                           float (&o)[NO], bool aten) {
-    float s0 = sigmoid_ref(v[0], aten), s1 = sigmoid_ref(v[1], aten), s2 = sigmoid_ref(v[2], aten), s3 = sigmoid_ref(v[3], aten);
-    o[0] = f_mul(f_add(f_sub(f_mul(s0, 2.f), 0.5f), gx), stride);
-    o[1] = f_mul(f_add(f_sub(f_mul(s1, 2.f), 0.5f), gy), stride);
-    float t2 = f_mul(s2, 2.f), t3 = f_mul(s3, 2.f);
-    o[2] = f_mul(f_mul(t2, t2), aw);
-    o[3] = f_mul(f_mul(t3, t3), ah);
-    o[4] = sigmoid_ref(v[4], aten);
-    o[5] = sigmoid_ref(v[5], aten);
+__device__ __forceinline__ void decode_cell(const float (&v)[NO], float gx, float gy, float stride, float aw, float ah,
+                                            float (&o)[NO], bool aten, bool hf) {
+    decode_box(v, gx, gy, stride, aw, ah, o, aten, hf);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        if (hf) {  // the float32 product is stored into the half tensor x_kpt (models/yolo.py:293-295)
+            o[6 + 3 * j] = h_rn(h_xy(v[6 + 3 * j], gx, stride));
+            o[7 + 3 * j] = h_rn(h_xy(v[7 + 3 * j], gy, stride));
+            o[8 + 3 * j] = h_sigmoid(v[8 + 3 * j]);
+        } else {
+            o[6 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[6 + 3 * j], 2.f), 0.5f), gx), stride);  // raw logits, no sigmoid
+            o[7 + 3 * j] = f_mul(f_add(f_sub(f_mul(v[7 + 3 * j], 2.f), 0.5f), gy), stride);
+            o[8 + 3 * j] = sigmoid_ref(v[8 + 3 * j], aten);
+        }
+    }
 }
 
 // utils/general.py:547-563 + 299-306 on one decoded row: o -> candidate row (in place)
@@ -253,7 +261,11 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
             const float lo = to_f32(__ldg(po + k)), lc = to_f32(__ldg(pc + k));  // L1 hits: just read as vectors
             const float prod = f_mul(f_add(1.0f, expf(-lc)), f_add(1.0f, expf(-lo)));
             ok = prod < P.prod_pass;
-            if (!ok && !(prod > P.prod_fail)) ok = f_mul(sigmoid_ref(lc, P.aten != 0), sigmoid_ref(lo, P.aten != 0)) > P.conf_thres;
+            if (!ok && !(prod > P.prod_fail)) {
+                const bool hf = P.aten != 0 && sizeof(T) == 2;
+                const float sc = hf ? h_sigmoid(lc) : sigmoid_ref(lc, P.aten != 0), so = hf ? h_sigmoid(lo) : sigmoid_ref(lo, P.aten != 0);
+                ok = f_mul(sc, so) > P.conf_thres;
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (m) {
@@ -289,8 +301,9 @@ __device__ __forceinline__ void decode_filter_body(const DecParams &P, const Dec
             for (int c = 0; c < NV; c++) raw[c] = __ldg(p + (long long)c * cells);  // all loads before the first conversion
 #pragma unroll
             for (int c = 0; c < NV; c++) v[c] = to_f32(raw[c]);
-            if (FUSE == 2) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
-            else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+            const bool hf = P.aten != 0 && sizeof(T) == 2;
+            if (FUSE == 2) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0, hf);
+            else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0, hf);
             row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
             float *dst = P.cand + slot * NO;
 #pragma unroll
@@ -376,8 +389,9 @@ __global__ void __launch_bounds__(CAND_THREADS) decode_candidates_kernel(const _
 #pragma unroll
             for (int c = 0; c < NV; c++) v[c] = __ldg(p + (long long)c * cells);
         }
-        if (KPT) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
-        else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+        const bool hf = P.aten != 0 && L.dtype == FDMS_F16;
+        if (KPT) decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0, hf);
+        else decode_box(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0, hf);
         row_to_candidate(o, f_mul(o[5], o[4]));  // general.py:547: cls *= obj
         float *dst = P.cand + slot * NO;
 #pragma unroll
@@ -415,7 +429,8 @@ __global__ void __launch_bounds__(DENSE_THREADS) decode_dense_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < NO; c++) v[c] = ld_f(L.data, L.dtype, cbase + (long long)c * cells + cell);
         int gy = (int)(cell / L.nx), gx = (int)(cell - (long long)gy * L.nx);
-        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0);
+        decode_cell(v, (float)gx, (float)gy, L.stride, L.anchors[2 * a], L.anchors[2 * a + 1], o, P.aten != 0,
+                    P.aten != 0 && L.dtype == FDMS_F16);
 #pragma unroll
         for (int c = 0; c < NO; c++) s_out[threadIdx.x * NO + c] = o[c];  // stride 21 words: conflict free
     }
@@ -467,7 +482,7 @@ __global__ void __launch_bounds__(128) decode_head_kernel(const __grid_constant_
     const long long cells = (long long)L.ny * L.nx;
     const long long cell_first = (long long)chunk * T, cell = cell_first + tid;
     const long long cbase = ((long long)b * na + a) * no * cells;
-    const bool aten = P.aten != 0;
+    const bool aten = P.aten != 0, hf = aten && L.dtype == FDMS_F16;  // hf: ATen's CUDA arithmetic for a half model (common.cuh)
     if (cell < cells) {
         const int gyi = (int)(cell / L.nx), gxi = (int)(cell - (long long)gyi * L.nx);
         const float gx = (float)gxi, gy = (float)gyi, stride = L.stride;
@@ -478,15 +493,17 @@ __global__ void __launch_bounds__(128) decode_head_kernel(const __grid_constant_
             const float v = ld_f(L.data, L.dtype, cbase + (long long)c * cells + cell);
             float o;
             if (c < n_sig) {
-                const float sg = sigmoid_ref(v, aten);
-                if (c < 2) o = f_mul(f_add(f_sub(f_mul(sg, 2.f), 0.5f), c == 0 ? gx : gy), stride);  // :73 / :166 / :290
-                else if (c < 4) {
+                const float sg = hf ? h_sigmoid(v) : sigmoid_ref(v, aten);
+                if (c < 2) {  // :73 / :166 / :290
+                    o = hf ? h_xy(sg, c == 0 ? gx : gy, stride) : f_mul(f_add(f_sub(f_mul(sg, 2.f), 0.5f), c == 0 ? gx : gy), stride);
+                } else if (c < 4) {  // :74 / :167 / :291
                     const float t = f_mul(sg, 2.f);
-                    o = f_mul(f_mul(t, t), L.anchors[2 * a + (c - 2)]);  // :74 / :167 / :291
+                    o = hf ? h_wh(sg, L.anchors[2 * a + (c - 2)]) : f_mul(f_mul(t, t), L.anchors[2 * a + (c - 2)]);
                 } else o = sg;
             } else {
                 const int k = (c - 6) % 3;
-                if (k == 2) o = sigmoid_ref(v, aten);  // :81 / :183 / :295
+                if (k == 2) o = hf ? h_sigmoid(v) : sigmoid_ref(v, aten);  // :81 / :183 / :295
+                else if (hf) o = h_rn(h_xy(v, k == 0 ? gx : gy, stride));  // stored back into the half tensor x_kpt
                 else o = f_mul(f_add(f_sub(f_mul(v, 2.f), 0.5f), k == 0 ? gx : gy), stride);  // raw logits, :76-77
             }
             row[c] = o;
@@ -612,11 +629,16 @@ FDMS_API int fdms_decode_filter_ex(fdms_ctx *ctx, const fdms_level *levels, int 
         if (levels[l].scale < levels[l - 1].scale ||
             (levels[l].scale == levels[l - 1].scale && levels[l].row_offset <= levels[l - 1].row_offset))
             return fdms_fail(ctx, FDMS_ERR_INVALID, "fdms_decode_filter: levels must be sorted by (scale, row_offset)");
-    P.logit_lo = logit_lower_bound(conf_thres);
-    {   // conf > thres * (1 + 4e-6) certainly passes, conf < thres * (1 - 4e-6) certainly fails (the fast product is
+    // half-model arithmetic (aten_cuda numerics on fp16 maps): both sigmoids are rounded to half (2^-11 relative each)
+    // before the product, so the fast decisions keep a 2e-3 band instead of 4e-6 and the logit bound moves accordingly
+    bool hf = false;
+    for (int l = 0; l < n_levels; l++) hf = hf || (P.aten && levels[l].dtype == FDMS_F16);
+    const double band = hf ? 2e-3 : 4e-6;
+    P.logit_lo = logit_lower_bound(hf && conf_thres > 0.f ? conf_thres * (1.0f - 2e-3f) : conf_thres);
+    {   // conf > thres * (1 + band) certainly passes, conf < thres * (1 - band) certainly fails (the fast product is
         // good to ~3e-7 relative); non-positive thresholds have no fast "fail" side
-        const double hi = (double)conf_thres + 4e-6 * fabs((double)conf_thres) + 1e-37;
-        const double lo = (double)conf_thres - 4e-6 * fabs((double)conf_thres) - 1e-37;
+        const double hi = (double)conf_thres + band * fabs((double)conf_thres) + 1e-37;
+        const double lo = (double)conf_thres - band * fabs((double)conf_thres) - 1e-37;
         P.prod_pass = hi > 0.0 ? (float)(1.0 / hi) : INFINITY;
         P.prod_fail = lo > 0.0 ? (float)(1.0 / lo) : INFINITY;
     }

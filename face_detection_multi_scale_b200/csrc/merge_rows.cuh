@@ -162,11 +162,18 @@ __device__ __forceinline__ void merge_emit_image(const EmitParams &P, int img, i
 #pragma unroll
                     for (int c = 0; c < 15; c++) v[c] = __ldg(p + (long long)c * cells);
                 }
+                const bool hf = P.aten != 0 && L.dtype == FDMS_F16;  // ATen's CUDA arithmetic for a half model (common.cuh)
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    kp[3 * j] = f_mul(f_add(f_sub(f_mul(v[3 * j], 2.f), 0.5f), (float)gx), L.stride);
-                    kp[3 * j + 1] = f_mul(f_add(f_sub(f_mul(v[3 * j + 1], 2.f), 0.5f), (float)gy), L.stride);
-                    kp[3 * j + 2] = sigmoid_ref(v[3 * j + 2], P.aten != 0);
+                    if (hf) {
+                        kp[3 * j] = h_rn(h_xy(v[3 * j], (float)gx, L.stride));
+                        kp[3 * j + 1] = h_rn(h_xy(v[3 * j + 1], (float)gy, L.stride));
+                        kp[3 * j + 2] = h_sigmoid(v[3 * j + 2]);
+                    } else {
+                        kp[3 * j] = f_mul(f_add(f_sub(f_mul(v[3 * j], 2.f), 0.5f), (float)gx), L.stride);
+                        kp[3 * j + 1] = f_mul(f_add(f_sub(f_mul(v[3 * j + 1], 2.f), 0.5f), (float)gy), L.stride);
+                        kp[3 * j + 2] = sigmoid_ref(v[3 * j + 2], P.aten != 0);
+                    }
                 }
             } else {
                 const float *row = P.cand + slot * MERGE_NO;

@@ -84,16 +84,16 @@ def _forward(self, x):
         return raw
     strides, anchors = self._fdms_geom
     na, no, nkpt = self._fdms_cols
+    # float32 whatever the model's precision: the reference's own pred is a float32 tensor for a half model too --
+    # `self.grid[i]` is created float32 (models/yolo.py:310-313), so the xy columns and then `torch.cat` promote the row
     pred = decode_head(raw, strides, anchors, na, no, nkpt)
-    if raw[0].dtype != torch.float32:
-        pred = pred.to(raw[0].dtype)
     xs, off = [], 0
     for r in raw:  # second element of the reference's return value: (bs, na, ny, nx, no) raw maps
         bs, _, ny, nx = r.shape
         xi = r.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2)
         if self._fdms_mutates_kpt:  # Detect / IDetect decode the keypoint columns IN the returned tensor (:76-81, :169-183)
             xi = xi.contiguous()
-            xi[..., 6:] = pred[:, off:off + na * ny * nx].view(bs, na, ny, nx, no)[..., 6:]
+            xi[..., 6:] = pred[:, off:off + na * ny * nx].view(bs, na, ny, nx, no)[..., 6:].to(xi.dtype)
         xs.append(xi)
         off += na * ny * nx
     return pred, xs

@@ -275,10 +275,15 @@ FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_st
 /* Floating-point flavour of the stages whose reference arithmetic depends on the device the reference runs on:
  *   FDMS_NUMERICS_EXACT (default)  sigmoid with the correctly rounded exponential, `x / s` as a true division -- what the
  *       CPU oracle restates and within 1 ulp of ATen on either device;
- *   FDMS_NUMERICS_ATEN_CUDA        what ATen computes ON A CUDA DEVICE in fp32: sigmoid = 1 / (1 + expf(-x)) with
+ *   FDMS_NUMERICS_ATEN_CUDA        what ATen computes ON A CUDA DEVICE: sigmoid = 1 / (1 + expf(-x)) with
  *       libdevice's expf (models/yolo.py:285-306), and tensor / python-scalar = tensor * (1 / scalar)
  *       (utils/general.py:386 `coords[:, :4] /= gain`, multi_scale_face_detector.py:102 `img /= 255.0` in fp32,
- *       models/yolo.py:405 `p[..., :4] /= scale`): bit-identical to the reference running in fp32 on the same GPU.
+ *       models/yolo.py:405 `p[..., :4] /= scale`): bit-identical to the reference running on the same GPU --
+ *       in fp32 for f32 head maps, and for F16 head maps (a half model, the reference's default on a GPU, msfd:49) with
+ *       the roundings of ATen's half tensors: sigmoid, `* 2.`, `- 0.5`, `** 2`, `* anchor_grid` round to half, `+ grid`
+ *       and `* stride` are float32 (the grid is created float32, models/yolo.py:310-313), the keypoint coordinates are
+ *       stored back into the half tensor; pred is float32 in the reference too (torch.cat promotes), and everything
+ *       after the head is float32 arithmetic in both.
  * Also read from the environment variable FDMS_NUMERICS (exact | aten_cuda) when a context is created. */
 #define FDMS_NUMERICS_EXACT 0
 #define FDMS_NUMERICS_ATEN_CUDA 1

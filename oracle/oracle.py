@@ -146,6 +146,45 @@ def decode_head_general(levels, strides, anchors_px, na, no, nkpt):
     return pred
 
 
+def decode_head_half(levels, strides, anchors_px, na=3, no=21, nkpt=5):
+    """The same decode as ATen computes it for a HALF model (the reference's default on a GPU, msfd:49 `model.half()`):
+    the conv outputs, the sigmoid, `* 2.`, `- 0.5`, `** 2`, `* anchor_grid` are half tensors (each operation computes in
+    float32 and rounds to half), `self.grid[i]` is float32 (models/yolo.py:310-313), so `+ grid` and `* stride` are float32;
+    the keypoint coordinates are stored back into the half tensor `x_kpt` (:293-295) and `torch.cat` (:297) promotes the
+    row: pred is FLOAT32 with half-valued columns 2.. and float32 xy.  levels: list of (bs, na*no, ny, nx) float16 arrays.
+    Pinned op by op against the reference modules on half tensors (tests/ref_live_check.py); numpy, small cases."""
+    f32, f16 = np.float32, np.float16
+    h = lambda a: np.asarray(a, f32).astype(f16).astype(f32)  # noqa: E731  one half rounding
+    sig = lambda a: h(f32(1.0) / (f32(1.0) + np.exp(-np.asarray(a, f32))))  # noqa: E731
+    anchors_px = np.asarray(anchors_px, f32).reshape(len(levels), na, 2)
+    n_sig = 6 if nkpt > 0 else no
+    outs = []
+    for i, l in enumerate(levels):
+        l = np.asarray(l)
+        assert l.dtype == f16, "decode_head_half takes the half conv outputs"
+        bs, ch, ny, nx = l.shape
+        assert ch == na * no
+        v = l.reshape(bs, na, no, ny, nx).transpose(0, 1, 3, 4, 2).astype(f32)
+        gy, gx = np.meshgrid(np.arange(ny, dtype=f32), np.arange(nx, dtype=f32), indexing="ij")
+        st = f32(strides[i])
+        o = np.empty_like(v)
+        s = sig(v[..., :n_sig])
+        o[..., 0] = (h(h(s[..., 0] * f32(2)) - f32(0.5)) + gx) * st
+        o[..., 1] = (h(h(s[..., 1] * f32(2)) - f32(0.5)) + gy) * st
+        anc = h(anchors_px[i])  # the anchor_grid buffer of a half model
+        for c in (2, 3):
+            t = h(s[..., c] * f32(2))
+            o[..., c] = h(h(t * t) * anc[:, c - 2][None, :, None, None])
+        o[..., 4:n_sig] = s[..., 4:]
+        for j in range(nkpt):
+            for k, g in ((0, gx), (1, gy)):
+                t = h(h(v[..., 6 + 3 * j + k] * f32(2)) - f32(0.5))
+                o[..., 6 + 3 * j + k] = h((t + g) * st)
+            o[..., 8 + 3 * j] = sig(v[..., 8 + 3 * j])
+        outs.append(o.reshape(bs, -1, no))
+    return np.concatenate(outs, 1)
+
+
 # ---- B6 filter: utils/general.py:515-563 -------------------------------------------------------
 def filter_xyxy(pred_img, conf_thres):
     """pred_img: (rows, 21) fp32 for ONE image.  Returns (cand (n,21), src_row (n,))."""

@@ -16,6 +16,7 @@ seeded random ones, function by function:
     MultiScaleFaceDetector.detect_multi_scale around a stand-in backbone (msfd:242-288)  bit exact
     utils.torch_utils.scale_img, Model._descale_pred          (torch_utils.py:247, yolo.py:402)  <= 2 ulp / bit exact
     models.yolo.Detect / IDetect / IKeypoint, any na / nc / nkpt (models/yolo.py:59-308)  <= 1e-4 px or 4 ulp; refusals
+    the same heads as HALF models (msfd:49): float32 pred with half-rounded columns        bit exact
 
 Prints one JSON line {"checks": n, "failures": [...]} and exits 1 if anything differs.
 """
@@ -316,6 +317,33 @@ def main():
             check(rows != 3 * 4 * 6, ("the reference runs a head that head_columns refuses", cls, nc, nkpt, inplace))
         except RuntimeError:
             check(True, "refused combination raises in the reference")
+
+    # ---- a HALF model (the reference's default on a GPU): pred is float32 with half-rounded columns; the oracle's
+    # restatement of where ATen rounds against the live modules on half tensors
+    for it in range(6):
+        cls = ("Detect", "IDetect", "IKeypoint")[it % 3]
+        nkpt = [5, 5, 5, 0, 17, 1][it]
+        na, nl = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        anchors = rng.uniform(4, 300, size=(nl, na * 2)).round(2).tolist()
+        ch = tuple(int(c) for c in rng.integers(2, 9, nl))
+        m = quiet(getattr(Y, cls), nc=1, anchors=anchors, nkpt=nkpt, ch=ch, inplace=True)
+        strides = [8.0 * 2 ** i for i in range(nl)]
+        m.stride = torch.tensor(strides)
+        m.eval()
+        for p_ in m.parameters():
+            p_.data.mul_(3.0)
+        m.half()
+        hw = (int(rng.integers(1, 4)) * 8 * 2 ** (nl - 1), int(rng.integers(1, 4)) * 8 * 2 ** (nl - 1))
+        xs = [torch.from_numpy(rng.normal(size=(2, c, int(hw[0] // s), int(hw[1] // s))).astype(np.float16))
+              for c, s in zip(ch, strides)]
+        raws = []
+        for i, x in enumerate(xs):
+            det = m.im[i](m.m[i](m.ia[i](x))) if hasattr(m, "ia") else m.m[i](x)
+            raws.append((det if not nkpt else torch.cat((det, m.m_kpt[i](x)), 1)).numpy())
+        ref = m([x.clone() for x in xs])[0]
+        got = O.decode_head_half(raws, strides, m.anchor_grid.view(nl, na, 2).float().numpy(), na, m.no, nkpt)
+        check(ref.dtype == torch.float32 and got.shape == tuple(ref.shape) and np.array_equal(got, ref.numpy()),
+              ("half-model head", cls, nkpt, na, nl, float(np.max(np.abs(got - ref.numpy()))) if got.shape == tuple(ref.shape) else None))
 
     print(json.dumps({"checks": N[0], "failures": [repr(f) for f in FAIL[:20]]}))
     sys.exit(1 if FAIL else 0)

@@ -238,3 +238,75 @@ def test_plain_head_through_multiclass_nms(golden):
     assert sum(len(r) for r in a) > 10
     for ra, rb in zip(a, b):
         assert ra.shape[1] == 6 and torch.equal(ra, rb)
+
+
+# ---- the half-model arithmetic of FDMS_NUMERICS=aten_cuda on fp16 maps (the reference's default mode on a GPU) --------------
+def _aten_cuda(fn):
+    from face_detection_multi_scale_b200 import _lib
+    c = _lib.ctx(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    c.set_numerics("aten_cuda")
+    try:
+        return fn()
+    finally:
+        c.set_numerics("exact")
+
+
+def _half_close(got, ref, stride_max=32.0):
+    """Equal except where libdevice's expf and numpy's differ in the last float bit AND that flips a half rounding:
+    such an element moves by one half ulp (xy: one half ulp of the sigmoid times 2 * stride)."""
+    same = got == ref
+    assert same.mean() > 0.999, float(same.mean())
+    d = np.abs(got - ref)[~same]
+    r = np.abs(ref)[~same]
+    assert np.all(d <= np.maximum(2.0 ** -10 * r, 2.0 ** -10 * stride_max)), float(d.max()) if d.size else 0.0
+
+
+@pytest.mark.parametrize("name", ["detect_face", "idetect_pose", "ikeypoint_k3", "idetect_nc1"])
+def test_half_model_decode_matches_oracle(golden, name):
+    """The dense decode kernels with aten_cuda numerics on fp16 maps round where ATen rounds for a half model
+    (oracle.decode_head_half, pinned bit for bit against the reference modules on half tensors by tests/ref_live_check.py;
+    the GPU pin against the real reference is tests/ref_gpu_check.py P1h / C / D)."""
+    from oracle import oracle as O
+    g, nc, nkpt, na, _, no = _variant(golden, name)
+    raw = [g["%s__raw%d" % (name, i)].astype(np.float16) for i in range(3)]
+    anchors = g[name + "__anchors_px"]
+    ref = O.decode_head_half(raw, (8, 16, 32), anchors, na, no, nkpt)
+    dev = [torch.from_numpy(r).to(DEV) for r in raw]
+    got = _aten_cuda(lambda: ops.decode_dense_head(dev, (8, 16, 32), anchors, na, no, nkpt)).cpu().numpy()
+    _half_close(got, ref)
+    if na == 3 and no == 21:  # the specialised face kernel runs the same arithmetic
+        got2 = _aten_cuda(lambda: ops.decode_dense(dev, (8, 16, 32), anchors)).cpu().numpy()
+        assert np.array_equal(got, got2)
+    # fp32 maps under aten_cuda keep the fp32 arithmetic (a float model): no half rounding
+    raw32 = [torch.from_numpy(r.astype(np.float32)).to(DEV) for r in raw]
+    a = _aten_cuda(lambda: ops.decode_dense_head(raw32, (8, 16, 32), anchors, na, no, nkpt)).cpu().numpy()
+    assert np.max(np.abs(a - O.decode_head_general([r.astype(np.float32) for r in raw], (8, 16, 32), anchors, na, no, nkpt))) <= 1e-3
+    assert not np.array_equal(a, got)
+
+
+def test_half_model_fused_filter_matches_dense_decode(golden):
+    """The fused decode + filter under the half-model arithmetic keeps exactly the rows the dense half decode passes through
+    the confidence test (conf = cls * obj on the half-rounded columns, float32 product), with identical candidate rows."""
+    g = golden("heads")
+    raw = [torch.from_numpy(g["detect_face__raw%d" % i].astype(np.float16)).to(DEV) for i in range(3)]
+    anchors = g["detect_face__anchors_px"]
+    for thr in (0.05, 0.25, 0.5):
+        def run():
+            pred = ops.decode_dense(raw, (8, 16, 32), anchors)
+            c = ops.decode_filter([raw], (8, 16, 32), anchors, thr, cap=4096)
+            return pred, c
+        pred, c = _aten_cuda(run)
+        pred = pred.cpu().numpy()
+        for b in range(pred.shape[0]):
+            p = pred[b]
+            conf = (p[:, 5] * p[:, 4]).astype(np.float32)
+            want = np.nonzero((p[:, 4] > np.float32(thr)) & (conf > np.float32(thr)))[0]
+            n = int(c.count[b].item())
+            rows = c.row[b, :n].cpu().numpy()
+            order = np.argsort(rows)
+            assert np.array_equal(rows[order], want), (thr, b, n, len(want))
+            cand = c.cand[b, :n].cpu().numpy()[order]
+            q = p[want]
+            box = np.stack([q[:, 0] - q[:, 2] / 2, q[:, 1] - q[:, 3] / 2, q[:, 0] + q[:, 2] / 2, q[:, 1] + q[:, 3] / 2], 1)
+            assert np.array_equal(cand[:, :4], box.astype(np.float32)) and np.array_equal(cand[:, 4], conf[want])
+            assert np.array_equal(cand[:, 6:], q[:, 6:])

@@ -49,5 +49,5 @@ def unpatch():
 
 
 def patch_model(model):
-    """Replace the decode of the model's detection head (IKeypoint / IDetect / Detect with na=3, no=21)."""
+    """Replace the decode of the model's detection head (IKeypoint / IDetect / Detect: yolo_head.head_columns)."""
     return yolo_head.patch_head(yolo_head.find_head(model))

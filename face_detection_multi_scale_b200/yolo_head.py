@@ -37,7 +37,7 @@ def head_convs(head, x):
             det = head.im[i](head.m[i](head.ia[i](xi)))
         else:
             det = head.m[i](xi)
-        if getattr(head, "nkpt", None):
+        if getattr(head, "nkpt", None) and hasattr(head, "m_kpt"):  # (a head whose `m` delivers all na*no channels has none)
             det = torch.cat((det, head.m_kpt[i](xi)), 1)
         out.append(det)
     return out

@@ -433,17 +433,23 @@ def test_compat_ops_fuzz_vs_oracle():
                          for b in range(bs)])
         pred = np.ascontiguousarray(pred[..., :no])
         conf, iou = float(rng.choice([0.1, 0.3, 0.5])), float(rng.choice([0.3, 0.45, 0.6]))
+        half = it % 4 >= 2  # fp16 predictions: up-cast, filtered / converted / suppressed in fp32, kept rows rounded back
+        if half:
+            pred = pred.astype(np.float16)
         t = torch.from_numpy(pred)
         if it & 1:
             t = t.to(DEV)
         got = general.non_max_suppression(t, conf, iou, kpt_label=5 if no == 21 else 0, nc=1,
                                           iou_mode=ops.IOU_TV_CPU)
-        ref = O.non_max_suppression(pred, conf, iou, O.TV_CPU)
+        ref = O.non_max_suppression(pred.astype(np.float32), conf, iou, O.TV_CPU)
         assert len(got) == bs
         for b in range(bs):
             assert got[b].is_cuda == bool(it & 1)
             g_, r_ = got[b].cpu().numpy(), ref[b]
             assert g_.shape == r_.shape, (it, b, g_.shape, r_.shape)
+            if half and len(r_):
+                assert got[b].dtype == torch.float16
+                r_ = r_.astype(np.float16)
             assert np.array_equal(g_, r_), (it, b)
         # --- scale_coords / scale_coords_api_approach
         ih, iw = int(rng.integers(2, 40)) * 32, int(rng.integers(2, 40)) * 32

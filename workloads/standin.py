@@ -23,7 +23,7 @@ class _Head(torch.nn.Module):
         self.na = 3
         self.no = synth.NO
         self.nc = 1
-        self.nkpt = 0  # the synthetic maps already hold all 63 channels: no m_kpt branch
+        self.nkpt = 5  # no m_kpt branch: the synthetic maps already hold all 63 channels (yolo_head.head_convs)
         self.stride = torch.tensor([float(s) for s in strides])
         a = torch.as_tensor(np.asarray(anchors_px, np.float32)).view(self.nl, -1, 2)
         self.register_buffer("anchor_grid", a.clone().view(self.nl, 1, -1, 1, 1, 2))

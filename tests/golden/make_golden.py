@@ -625,6 +625,40 @@ def gen_heads():
     save("heads", **out)
 
 
+def gen_heads_half():
+    """The same head classes as HALF models (the reference's default on a GPU, msfd:49), run here on CPU half tensors: ATen
+    rounds every half operation the same way on either device (opmath float32, result stored as half); only the exponential
+    inside the sigmoid differs in the last float32 bit, which the GPU check (tests/ref_gpu_check.py P1h) pins.  Stored: the
+    half conv outputs and the reference's float32 pred."""
+    import models.yolo as Y
+    out = {}
+    ch, strides, hw = (8, 16, 32), (8., 16., 32.), (32, 64)
+    for vi, name in enumerate(("detect_face", "idetect_pose", "ikeypoint_k3", "idetect_nc1")):
+        cls, nc, nkpt, na, inplace = HEAD_VARIANTS[name]
+        torch.manual_seed(200 + vi)
+        rng = np.random.default_rng(200 + vi)
+        anchors = (rng.uniform(4, 300, size=(3, na * 2))).round(2).tolist()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = getattr(Y, cls)(nc=nc, anchors=anchors, nkpt=nkpt, ch=ch, inplace=inplace)
+        m.stride = torch.tensor(strides)
+        m.eval()
+        for p_ in m.parameters():
+            p_.data.mul_(3.0)
+        m.half()
+        xs = [torch.randn(2, c, int(hw[0] // s), int(hw[1] // s)).half() for c, s in zip(ch, strides)]
+        for i, x in enumerate(xs):
+            det = m.im[i](m.m[i](m.ia[i](x))) if hasattr(m, "ia") else m.m[i](x)
+            raw = det if not nkpt else torch.cat((det, m.m_kpt[i](x)), 1)
+            assert raw.dtype == torch.float16
+            out["%s__raw%d" % (name, i)] = raw.numpy()
+        pred, _ = m([x.clone() for x in xs])
+        assert pred.dtype == torch.float32  # the grid is float32: `+ grid` and torch.cat promote (models/yolo.py:290-297)
+        out[name + "__pred"] = pred.numpy()
+        out[name + "__meta"] = np.array([nc, nkpt, na, int(inplace)])
+        out[name + "__anchors_px"] = m.anchor_grid.view(m.nl, m.na, 2).float().numpy()
+    save("heads_half", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()["gen_" + sys.argv[1]]()
@@ -645,3 +679,4 @@ if __name__ == "__main__":
     gen_pack()
     gen_ikeypoint()
     gen_heads()
+    gen_heads_half()

@@ -310,3 +310,14 @@ def test_half_model_fused_filter_matches_dense_decode(golden):
             box = np.stack([q[:, 0] - q[:, 2] / 2, q[:, 1] - q[:, 3] / 2, q[:, 0] + q[:, 2] / 2, q[:, 1] + q[:, 3] / 2], 1)
             assert np.array_equal(cand[:, :4], box.astype(np.float32)) and np.array_equal(cand[:, 4], conf[want])
             assert np.array_equal(cand[:, 6:], q[:, 6:])
+
+
+@pytest.mark.parametrize("name", ("detect_face", "idetect_pose", "ikeypoint_k3", "idetect_nc1"))
+def test_half_model_decode_matches_reference_fixture(golden, name):
+    """The same kernels against what the reference's own modules return for a half model (tests/golden/heads_half.npz)."""
+    g = golden("heads_half")
+    nc, nkpt, na, _ = (int(v) for v in g[name + "__meta"])
+    raw = [torch.from_numpy(g["%s__raw%d" % (name, i)]).to(DEV) for i in range(3)]
+    got = _aten_cuda(lambda: ops.decode_dense_head(raw, (8, 16, 32), g[name + "__anchors_px"], na, 5 + nc + 3 * nkpt, nkpt))
+    assert got.dtype == torch.float32
+    _half_close(got.cpu().numpy(), g[name + "__pred"])

@@ -137,6 +137,18 @@ def test_decode_head_variants(golden, name):
         assert np.array_equal(O.decode_head(raw, (8, 16, 32), g[name + "__anchors_px"]), pred)
 
 
+@pytest.mark.parametrize("name", ("detect_face", "idetect_pose", "ikeypoint_k3", "idetect_nc1"))
+def test_decode_head_half_model(golden, name):
+    """A HALF model (the reference's default on a GPU): float32 pred with half-rounded columns, bit for bit against the
+    reference modules run on half tensors (tests/golden/make_golden.py::gen_heads_half)."""
+    g = golden("heads_half")
+    nc, nkpt, na, _ = (int(v) for v in g[name + "__meta"])
+    raw = [g["%s__raw%d" % (name, i)] for i in range(3)]
+    assert raw[0].dtype == np.float16 and g[name + "__pred"].dtype == np.float32
+    pred = O.decode_head_half(raw, (8, 16, 32), g[name + "__anchors_px"], na, 5 + nc + 3 * nkpt, nkpt)
+    assert np.array_equal(pred, g[name + "__pred"])
+
+
 def test_nms_on_reference_pred(golden):
     """filter + NMS from the reference's own decoded pred: bit-exact rows."""
     g = golden("head")

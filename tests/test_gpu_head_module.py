@@ -253,12 +253,13 @@ def _aten_cuda(fn):
 
 def _half_close(got, ref, stride_max=32.0):
     """Equal except where libdevice's expf and numpy's differ in the last float bit AND that flips a half rounding:
-    such an element moves by one half ulp (xy: one half ulp of the sigmoid times 2 * stride)."""
+    such an element moves by one half ulp (xy: one half ulp of the sigmoid times 2 * stride; wh = (2 s)^2 * anchor doubles
+    the relative step, so two half ulps are allowed)."""
     same = got == ref
     assert same.mean() > 0.999, float(same.mean())
     d = np.abs(got - ref)[~same]
     r = np.abs(ref)[~same]
-    assert np.all(d <= np.maximum(2.0 ** -10 * r, 2.0 ** -10 * stride_max)), float(d.max()) if d.size else 0.0
+    assert np.all(d <= np.maximum(2.0 ** -9 * r, 2.0 ** -9 * stride_max)), float(d.max()) if d.size else 0.0  # <= 2 half ulps
 
 
 @pytest.mark.parametrize("name", ["detect_face", "idetect_pose", "ikeypoint_k3", "idetect_nc1"])

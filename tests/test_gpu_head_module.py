@@ -322,3 +322,36 @@ def test_half_model_decode_matches_reference_fixture(golden, name):
     got = _aten_cuda(lambda: ops.decode_dense_head(raw, (8, 16, 32), g[name + "__anchors_px"], na, 5 + nc + 3 * nkpt, nkpt))
     assert got.dtype == torch.float32
     _half_close(got.cpu().numpy(), g[name + "__pred"])
+
+
+def test_half_model_landmarks_at_emit_equal_the_staged_path():
+    """fdms_postprocess decodes the landmarks of the FINAL detections straight from the head maps (merge_rows.cuh); under the
+    half-model arithmetic that must equal the staged path -- decode_filter with all 21 columns, NMS, merge taking the
+    landmark columns from the candidate rows -- bit for bit, detections included."""
+    from workloads import standin, synth
+    h, w, sizes, B = 270, 480, [160, 256, 320], 2
+    _, heads, shapes = standin.make_batch(h, w, sizes, B, n_faces=25, seed=9, dtype=np.float16)
+    sl = [[torch.from_numpy(l).to(DEV) for l in heads[s]] for s in range(len(sizes))]
+    in_h = [s[0] for s in shapes]
+
+    def run():
+        plan = ops.PostPlan(sl, synth.P5_STRIDES, synth.P5_ANCHORS, in_h, (h, w), 0.4, 0.5, cap=2048, out_cap=2048,
+                            iou_mode=ops.IOU_TV_CPU, with_kpts=True)
+        a = plan.run()
+        c = ops.decode_filter(sl, synth.P5_STRIDES, synth.P5_ANCHORS, 0.4, cap=2048, landmarks=True)
+        ops.nms_segments(c.cand, c.count, c.cap, 0.5, ops.IOU_TV_CPU, tie=c.row, keep=c.keep, n_keep=c.n_keep)
+        b = ops.merge_scales(c, B, len(sizes), in_h, (h, w), 0.5, 2048, with_kpts=True)
+        torch.cuda.synchronize()
+        return a, b
+    a, b = _aten_cuda(run)
+    assert torch.equal(a.n_out, b.n_out) and int(a.n_out.sum()) > 10
+    for i in range(B):
+        n = int(a.n_out[i])
+        assert torch.equal(a.dets[i, :n], b.dets[i, :n])
+        assert torch.equal(a.kpts[i, :n], b.kpts[i, :n])
+    # and the half-model landmarks differ from the fp32 arithmetic on the same maps (the mode is really on)
+    a32 = ops.PostPlan(sl, synth.P5_STRIDES, synth.P5_ANCHORS, in_h, (h, w), 0.4, 0.5, cap=2048, out_cap=2048,
+                       iou_mode=ops.IOU_TV_CPU, with_kpts=True).run()
+    torch.cuda.synchronize()
+    n0 = min(int(a.n_out[0]), int(a32.n_out[0]))
+    assert not torch.equal(a.kpts[0, :n0], a32.kpts[0, :n0])

@@ -319,7 +319,7 @@ def test_nms_with_apriori_labels_golden(golden):
 @pytest.mark.parametrize("seed", [0, 1])
 def test_oracle_matches_live_reference_on_random_inputs(seed):
     """Only where the reference tree exists (the build container): tests/ref_live_check.py imports the UNMODIFIED
-    reference in a subprocess and compares ~170 seeded random calls of its functions (letterbox, api preprocessing,
+    reference in a subprocess and compares ~200 seeded random calls of its functions (letterbox, api preprocessing, every head class incl. half models,
     IKeypoint decode, non_max_suppression, scale_coords*, weighted_nms, scale_img, _descale_pred) with the oracle."""
     import json
     import subprocess

@@ -26,6 +26,7 @@ about 1.5 % of the rows then pass the reference's default conf_thres 0.5.
         `** 2`, `* anchor_grid` are half tensors, `+ grid` / `* stride` promote to float32, pred is float32 -- the kernels
         round where ATen rounds (csrc/common.cuh h_sigmoid / h_xy / h_wh) -> bit-identical pred
   C  class swap against the reference's default CUDA mode (half precision) -> the same (k, 7) arrays
+  C2 class swap with the production preprocessing (use_api_preprocess=True), fp32 and half -> the same (k, 7) arrays
   D  unmodified detect.py (half, --save-txt --save-conf): label files of the patched run vs the unpatched run -> identical
   E  timings: backbone forward per scale, reference GPU path per image, libfdms path per image
 
@@ -116,8 +117,8 @@ def main():
     files.append(syn)
     REPORT["files"] = [os.path.basename(f) for f in files]
 
-    def ref_detector(half):
-        d = quiet(msfd.MultiScaleFaceDetector, ckpt, "", sizes, 0.5, 0.5)  # the reference's own constructor
+    def ref_detector(half, api=False):
+        d = quiet(msfd.MultiScaleFaceDetector, ckpt, "", sizes, 0.5, 0.5, api)  # the reference's own constructor
         if not half:
             # load_yolo_model has already rounded the weights to fp16 (ppyp:395): the fp32 mode needs the checkpoint's own
             # weights, as its loader returns them
@@ -301,6 +302,23 @@ def main():
                       "ref_boxes_matched_iou>=0.7": round(match_boxes(r, m, 0.7), 4), "libfdms_boxes_matched": round(match_boxes(m, r, 0.7), 4)})
         check(bool(rows_equal(m, r, f)), ("C class swap, half model", agree[-1]))
     REPORT["C_half_mode"] = agree
+
+    # ---- C2: the production preprocessing (`use_api_preprocess=True`, what yolov7_face_multi_scale_dataframe_predict.py:109
+    # constructs: PIL decode, zero-padded square, letterbox(auto=False); ppyp:345-378), class swap in both precisions
+    api_rep = []
+    for half in (False, True):
+        ref_api = ref_detector(half, api=True)
+        ref_api.conf_thres = conf
+        mine_api = Mine(ckpt, "", sizes, conf, 0.5, use_api_preprocess=True, half=half)
+        for f in files:
+            r, shape_r = quiet(ref_api.detect_multi_scale, f)
+            m, shape_m = mine_api.detect_multi_scale(f)
+            r, m = np.asarray(r, np.float64).reshape(-1, 7), np.asarray(m, np.float64).reshape(-1, 7)
+            api_rep.append({"file": os.path.basename(f), "half": half, "reference": len(r), "libfdms": len(m),
+                            "bit_identical": bool(rows_equal(m, r, f))})
+            check(tuple(shape_r) == tuple(shape_m) and bool(rows_equal(m, r, f)), ("C2 class swap, api preprocessing", api_rep[-1]))
+        del ref_api, mine_api
+    REPORT["C2_api_preprocess"] = api_rep
 
     # ---- D: unmodified detect.py, half precision, label files
     if not args.no_detect_py:

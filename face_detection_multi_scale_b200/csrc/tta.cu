@@ -19,7 +19,7 @@ template <> __device__ __forceinline__ void tta_st<__half>(__half *p, long long 
 // F.pad(value=0.447) of scale_img.  One thread per output element, x fastest.
 template <typename T>
 __global__ void scale_img_kernel(const T *__restrict__ src, int planes, int h, int w, int rh, int rw, int oh, int ow,
-                                 int flip, float pad_value, float sy, float sx, T *__restrict__ dst) {
+                                 int flip, float pad_value, float sy, float sx, int aten, T *__restrict__ dst) {
     const long long total = (long long)planes * oh * ow;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -40,8 +40,12 @@ __global__ void scale_img_kernel(const T *__restrict__ src, int planes, int h, i
             const long long base = p * h * w;
             const float v00 = tta_ld<T>(src, base + (long long)ya * w + xa), v01 = tta_ld<T>(src, base + (long long)ya * w + xb);
             const float v10 = tta_ld<T>(src, base + (long long)yb * w + xa), v11 = tta_ld<T>(src, base + (long long)yb * w + xb);
-            v = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01))),
-                          __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11))));
+            if (aten)  // upsample_bilinear2d_out_frame as nvcc contracted it in torch's sm_100 build (read from its SASS):
+                       // h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d) = fma(h0, fma(w0, a, w1 * b), h1 * fma(w0, c, w1 * d))
+                v = __fmaf_rn(hy, __fmaf_rn(hx, v00, __fmul_rn(lx, v01)), __fmul_rn(ly, __fmaf_rn(hx, v10, __fmul_rn(lx, v11))));
+            else  // every product and sum rounded (the CPU oracle's statement; <= 2 ulp from ATen on either device)
+                v = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01))),
+                              __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11))));
         }
         tta_st<T>(dst, idx, v);
     }
@@ -84,13 +88,14 @@ FDMS_API int fdms_scale_img(fdms_ctx *ctx, const void *src, int dtype, int n, in
     // ATen: area_pixel_compute_scale<float>(in, out, align_corners=false, scales=nullopt) = (float)in / out
     const float sy = (float)h / (float)resized_h, sx = (float)w / (float)resized_w;
     cudaStream_t st = (cudaStream_t)stream;
+    const int aten = ctx->numerics == FDMS_NUMERICS_ATEN_CUDA;
     if (dtype == FDMS_F16)
         scale_img_kernel<__half><<<blocks, threads, 0, st>>>(reinterpret_cast<const __half *>(src), n * c, h, w, resized_h,
-                                                            resized_w, out_h, out_w, flip, pad_value, sy, sx,
+                                                            resized_w, out_h, out_w, flip, pad_value, sy, sx, aten,
                                                             reinterpret_cast<__half *>(dst));
     else
         scale_img_kernel<float><<<blocks, threads, 0, st>>>(reinterpret_cast<const float *>(src), n * c, h, w, resized_h,
-                                                           resized_w, out_h, out_w, flip, pad_value, sy, sx,
+                                                           resized_w, out_h, out_w, flip, pad_value, sy, sx, aten,
                                                            reinterpret_cast<float *>(dst));
     FDMS_LAUNCH_CHECK(ctx, "scale_img_kernel");
     return FDMS_OK;

@@ -278,7 +278,8 @@ FDMS_API int fdms_postprocess(fdms_ctx *ctx, const fdms_post_desc *desc, fdms_st
  *   FDMS_NUMERICS_ATEN_CUDA        what ATen computes ON A CUDA DEVICE: sigmoid = 1 / (1 + expf(-x)) with
  *       libdevice's expf (models/yolo.py:285-306), and tensor / python-scalar = tensor * (1 / scalar)
  *       (utils/general.py:386 `coords[:, :4] /= gain`, multi_scale_face_detector.py:102 `img /= 255.0` in fp32,
- *       models/yolo.py:405 `p[..., :4] /= scale`): bit-identical to the reference running on the same GPU --
+ *       models/yolo.py:405 `p[..., :4] /= scale`), and fdms_scale_img with the FMA contraction of ATen's CUDA bilinear
+ *       kernel (utils/torch_utils.py:254 F.interpolate): bit-identical to the reference running on the same GPU --
  *       in fp32 for f32 head maps, and for F16 head maps (a half model, the reference's default on a GPU, msfd:49) with
  *       the roundings of ATen's half tensors: sigmoid, `* 2.`, `- 0.5`, `** 2`, `* anchor_grid` round to half, `+ grid`
  *       and `* stride` are float32 (the grid is created float32, models/yolo.py:310-313), the keypoint coordinates are

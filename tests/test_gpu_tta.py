@@ -44,6 +44,18 @@ def test_scale_img_vs_oracle_and_torch(shape, ratio, flip):
     ref = torch.nn.functional.interpolate(xt, size=rs, mode="bilinear", align_corners=False)
     assert torch.max(torch.abs(got[:, :, :rs[0], :rs[1]] - ref)).item() <= TOL
     assert torch.all(got[:, :, rs[0]:, :] == 0.447) and torch.all(got[:, :, :, rs[1]:] == 0.447)
+    # FDMS_NUMERICS=aten_cuda: the FMA contraction of ATen's CUDA kernel (csrc/tta.cu) -> bit-identical to F.interpolate here
+    from face_detection_multi_scale_b200 import _lib
+    c = _lib.ctx(torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    c.set_numerics("aten_cuda")
+    try:
+        got_a = TU.scale_img(gpu(x), ratio, gs=32, flip=flip)
+        got_h = TU.scale_img(gpu(x).half(), ratio, gs=32, flip=flip)
+    finally:
+        c.set_numerics("exact")
+    assert torch.equal(got_a[:, :, :rs[0], :rs[1]], ref)
+    ref_h = torch.nn.functional.interpolate(xt.half(), size=rs, mode="bilinear", align_corners=False)
+    assert torch.equal(got_h[:, :, :rs[0], :rs[1]], ref_h)
 
 
 def test_scale_img_fp16():

@@ -25,6 +25,7 @@ about 1.5 % of the rows then pass the reference's default conf_thres 0.5.
      P1h the same for the reference's DEFAULT CUDA mode, a half model (msfd:49): its conv outputs, sigmoid, `* 2.`, `- 0.5`,
         `** 2`, `* anchor_grid` are half tensors, `+ grid` / `* stride` promote to float32, pred is float32 -- the kernels
         round where ATen rounds (csrc/common.cuh h_sigmoid / h_xy / h_wh) -> bit-identical pred
+  T  test-time augmentation: Model.forward(x, augment=True) against torch_utils.forward_augment, fp32 and half model -> identical
   C  class swap against the reference's default CUDA mode (half precision) -> the same (k, 7) arrays
   C2 class swap with the production preprocessing (use_api_preprocess=True), fp32 and half -> the same (k, 7) arrays
   D  unmodified detect.py (half, --save-txt --save-conf): label files of the patched run vs the unpatched run -> identical
@@ -203,6 +204,21 @@ def main():
                 m_sc = G.scale_coords(x.shape[2:], r_list[0][:, :4].clone(), shape0)
                 check(torch.equal(r_box, m_box), ("P3 scale_coords_api_approach", os.path.basename(f), size))
                 check(torch.equal(r_sc, m_sc), ("P3 scale_coords", os.path.basename(f), size, float((r_sc - m_sc).abs().max())))
+    # T: test-time augmentation (models/yolo.py:363-374: scale_img -> forward_once -> _descale_pred, three passes, cat) around
+    # the same network: the reference's Model.forward(x, augment=True) against torch_utils.forward_augment on libfdms
+    # (fdms_scale_img with ATen's CUDA contraction, the patched head, fdms_descale_pred)
+    from face_detection_multi_scale_b200 import torch_utils as TU
+    t_rep = []
+    for f in (files[0], files[-1]):
+        x, _, _ = quiet(ref32.preprocess_image, f, sizes[0])
+        with torch.no_grad():
+            tr = ref32.model(x, augment=True)[0]
+            tm = TU.forward_augment(model_p.forward_once, x, gs=int(ref32.model.stride.max()))[0]
+        same = tuple(tr.shape) == tuple(tm.shape) and torch.equal(tr, tm)
+        t_rep.append({"file": os.path.basename(f), "rows": int(tr.shape[1]), "bit_identical": bool(same),
+                      "max_abs": float((tr - tm).abs().max()) if tuple(tr.shape) == tuple(tm.shape) else None})
+        check(same, ("T forward_augment fp32", t_rep[-1]))
+    REPORT["T_forward_augment_fp32"] = t_rep
     # P1h: the head decode of a HALF model on identical half conv outputs (the reference's default mode on a GPU)
     ref16_model = _copy.deepcopy(ref32.model).half()
     model_ph = _copy.deepcopy(ref16_model)
@@ -225,6 +241,17 @@ def main():
             check(len(r_list) == len(m_list) and all(tuple(r.shape) == tuple(m.shape) and torch.equal(r, m) for r, m in zip(r_list, m_list)),
                   ("P2h nms after the half-model decode", os.path.basename(f), size))
     REPORT["P1h_half_model_decode_diffs"] = p1h
+    th_rep = []
+    for f in (files[0], files[-1]):  # the same augmentation with the half model (half images through scale_img, float32 pred)
+        x, _, _ = quiet(ref32.preprocess_image, f, sizes[0])
+        with torch.no_grad():
+            tr = ref16_model(x.half(), augment=True)[0]
+            tm = TU.forward_augment(model_ph.forward_once, x.half(), gs=int(ref32.model.stride.max()))[0]
+        same = tr.dtype == tm.dtype and tuple(tr.shape) == tuple(tm.shape) and torch.equal(tr, tm)
+        th_rep.append({"file": os.path.basename(f), "rows": int(tr.shape[1]), "bit_identical": bool(same), "dtype_ref": str(tr.dtype),
+                       "max_abs": float((tr.float() - tm.float()).abs().max()) if tuple(tr.shape) == tuple(tm.shape) else None})
+        check(same, ("T forward_augment half model", th_rep[-1]))
+    REPORT["T_forward_augment_half"] = th_rep
     del ref16_model, model_ph
     # P2c: multi-class predictions without keypoints (kpt_label=0, no = 5 + nc): class offset, `classes`, `multi_label`,
     # `agnostic` (utils/general.py:533-582) -- synthetic clustered boxes with 4 classes, both implementations on the same tensor

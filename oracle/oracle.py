@@ -280,13 +280,15 @@ def weighted_nms(dets, n_scales, iou_thres):
 
 
 def detect_from_heads(heads_per_scale, in_hw_per_scale, img0_shape, strides, anchors_px, conf_thres, iou_thres,
-                      mode=TV_CPU):
+                      mode=TV_CPU, half_model=False):
     """multi_scale_face_detector.py:109-166,242-288 for ONE image, starting from the raw head
     tensors of each scale (the backbone is outside the hot path).  heads_per_scale[s] is a list of
-    (1, 63, ny, nx) arrays.  Returns ((k,7) float64, per-scale (n,7) list)."""
+    (1, 63, ny, nx) arrays.  Returns ((k,7) float64, per-scale (n,7) list).
+    half_model: the levels are the float16 conv outputs of a half model (msfd:48-49) and the head decode rounds where
+    ATen's half tensors round (decode_head_half); pred is float32 and everything after it is unchanged, as in the reference."""
     per_scale = []
     for s, levels in enumerate(heads_per_scale):
-        pred = decode_head(levels, strides, anchors_px)
+        pred = decode_head_half(levels, strides, anchors_px) if half_model else decode_head(levels, strides, anchors_px)
         det = non_max_suppression(pred, conf_thres, iou_thres, mode)[0]
         if det.shape[0] == 0:
             per_scale.append(np.zeros((0, 7)))

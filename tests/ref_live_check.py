@@ -226,6 +226,15 @@ def main():
                                          synth.P5_STRIDES, synth.P5_ANCHORS, conf, iou, O.TV_CPU)
             check(tuple(shape0) == (h, w, 3) and got.shape == ref.shape and (ref.size == 0 or np.array_equal(got, ref)),
                   ("detect_multi_scale", it, h, w, sizes, api, conf, iou, n_faces, got.shape, ref.shape))
+            # the same call as the reference makes it on a GPU: a half model fed half images (msfd:48-49,101); float32 pred
+            heads16 = {k: [l.astype(np.float16) for l in v] for k, v in heads.items()}
+            det.model, det.half = StandIn(heads16).half(), True
+            ref, _ = quiet(det.detect_multi_scale, path)
+            ref = np.asarray(ref, np.float64)
+            got, _ = O.detect_from_heads([[l[None] for l in heads16[s_]] for s_ in shapes], shapes, (h, w, 3),
+                                         synth.P5_STRIDES, synth.P5_ANCHORS, conf, iou, O.TV_CPU, half_model=True)
+            check(got.shape == ref.shape and (ref.size == 0 or np.array_equal(got, ref)),
+                  ("detect_multi_scale, half model", it, h, w, sizes, api, conf, iou, n_faces, got.shape, ref.shape))
 
     # ---- source discovery of the inference loader (utils/datasets.py:126-141): directory, glob, single file
     from utils.datasets import LoadImages as RefLoadImages

@@ -355,3 +355,26 @@ def test_half_model_landmarks_at_emit_equal_the_staged_path():
     torch.cuda.synchronize()
     n0 = min(int(a.n_out[0]), int(a32.n_out[0]))
     assert not torch.equal(a.kpts[0, :n0], a32.kpts[0, :n0])
+
+
+def test_half_model_detector_matches_oracle_pipeline():
+    """The whole fused path (decode + filter, NMS, rescale, cross-scale merge) of a half model under aten_cuda numerics
+    against the oracle's half-model pipeline (oracle.detect_from_heads(half_model=True), pinned against the live reference's
+    detect_multi_scale on half tensors by tests/ref_live_check.py): the same (k, 7) arrays."""
+    from oracle import oracle as O
+    from workloads import standin, synth
+    from face_detection_multi_scale_b200.multi_scale_face_detector import MultiScaleFaceDetector
+    h, w, sizes, B = 270, 480, [160, 256, 320], 3
+    images, heads, shapes = standin.make_batch(h, w, sizes, B, n_faces=25, seed=3, dtype=np.float16)
+    model = standin.SyntheticHeadModel()
+    for s, hw in enumerate(shapes):
+        model.set_heads(hw, heads[s], pin=True)
+    det = MultiScaleFaceDetector(model, device=DEV, img_sizes=sizes, iou_mode=ops.IOU_TV_CPU, half=True)
+    out = _aten_cuda(lambda: det.detect_multi_scale_batch(images))
+    n_total = 0
+    for b in range(B):
+        ref, _ = O.detect_from_heads([[l[b:b + 1] for l in heads[s]] for s in range(len(sizes))], shapes, (h, w, 3),
+                                     synth.P5_STRIDES, synth.P5_ANCHORS, 0.5, 0.5, O.TV_CPU, half_model=True)
+        assert out[b].shape == ref.shape and np.array_equal(out[b], ref), b
+        n_total += len(ref)
+    assert n_total > 20

@@ -10,7 +10,7 @@
  * Parity pinning: every function here is checked by tests/test_oracle_golden.py
  * against golden vectors produced by the reference's OWN functions run in the
  * build container (tests/golden/make_golden.py imports /root/reference through
- * oracle/refshim.py) and, where the arithmetic lives in a third-party library
+ * baseline/refshim.py) and, where the arithmetic lives in a third-party library
  * that the reference merely calls (cv2.resize, torchvision.ops.nms, torch
  * elementwise ops), against that library directly.
  *

@@ -31,6 +31,43 @@ def test_header_symbols_are_exported():
     assert b"sm_100a" in h.fdms_build_info() and b"fmad=off" in h.fdms_build_info()
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Binding drift check: every prototype of include/fdms.h against its ctypes signature in _lib._SIGS -- the number of
+    parameters, and per parameter whether the header passes a pointer / a 64-bit integer / a double (a mismatch there
+    corrupts the call silently on x86-64)."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "fdms.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"FDMS_API\s+([\w\s\*]+?)\b(fdms_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 30
+    ptr_types = (C.c_void_p, C.c_char_p)
+    for ret, name, args in protos:
+        res, argtypes = _lib._SIGS[name]
+        params = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for prm, at in zip(params, argtypes):
+            is_ptr_h = "*" in prm or prm.startswith("fdms_stream")
+            is_ptr_c = at in ptr_types or hasattr(at, "_type_") and not isinstance(at._type_, str) or getattr(at, "__name__", "").startswith("LP_")
+            assert is_ptr_h == bool(is_ptr_c), (name, prm, at)
+            if not is_ptr_h:
+                if re.match(r"(const\s+)?(int64_t|size_t)\b", prm):
+                    assert C.sizeof(at) == 8 and at not in (C.c_double,), (name, prm, at)
+                elif re.match(r"(const\s+)?double\b", prm):
+                    assert at is C.c_double, (name, prm, at)
+                elif re.match(r"(const\s+)?float\b", prm):
+                    assert at is C.c_float, (name, prm, at)
+                else:
+                    assert C.sizeof(at) == 4 and at not in (C.c_float,), (name, prm, at)
+        if "*" in ret:
+            assert res in ptr_types, (name, ret, res)
+        elif ret.strip() == "void":
+            assert res is None, (name, res)
+        elif ret.strip() in ("int64_t", "size_t"):
+            assert res is not None and C.sizeof(res) == 8, (name, ret, res)
+        else:
+            assert res is C.c_int, (name, ret, res)
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/fdms.h is the drop-in boundary: it must compile as C11 (no C++ in the signatures) with warnings as
     errors, as C++, and a C program must link against libfdms.so through it (no compute call: no GPU here)."""

@@ -68,6 +68,29 @@ def test_ctypes_signatures_match_the_header_prototypes():
             assert res is C.c_int, (name, ret, res)
 
 
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """sizeof and every field offset of the five structures that cross the C ABI, as gcc lays them out from include/fdms.h,
+    against the ctypes mirrors in _lib.py (field names are the header's)."""
+    import subprocess
+    pairs = (("fdms_geom", _lib.Geom), ("fdms_scale_out", _lib.ScaleOut), ("fdms_level", _lib.Level),
+             ("fdms_post_desc", _lib.PostDesc), ("fdms_jpeg_desc", _lib.JpegDesc))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fdms.h"', "int main(void) {"]
+    for cname, st in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in st._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for cname, st in pairs:
+        assert int(got[cname]) == ctypes.sizeof(st), (cname, got[cname], ctypes.sizeof(st))
+        for fname, _ in st._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(st, fname).offset, (cname, fname)
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/fdms.h is the drop-in boundary: it must compile as C11 (no C++ in the signatures) with warnings as
     errors, as C++, and a C program must link against libfdms.so through it (no compute call: no GPU here)."""

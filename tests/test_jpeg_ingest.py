@@ -168,3 +168,39 @@ def test_unsupported_streams_are_reported_not_guessed():
     rc, d = probe(rot)
     assert rc == 0 and d.supported == 0 and "EXIF" in d.reason.decode()
     assert cv2.imdecode(np.frombuffer(rot, np.uint8), cv2.IMREAD_COLOR).shape == (96, 64, 3)  # cv2 does rotate it
+
+
+def test_host_decoder_survives_mutated_streams(tmp_path):
+    """The marker parser and the Huffman decoder under AddressSanitizer + UBSan on 20 000 mutated streams (tests/fuzz_jpeg_host.cpp):
+    a production ingest must answer a corrupt file with a status, not with an out-of-bounds access."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "face_detection_multi_scale_b200", "csrc")
+    exe = str(tmp_path / "fuzz")
+    r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-I", csrc,
+                        "-x", "c++", os.path.join(csrc, "jpeg_host.cu"), os.path.join(here, "fuzz_jpeg_host.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available here: %s" % r.stderr[-300:])
+    rng = np.random.default_rng(1)
+    img = cv2.GaussianBlur((rng.random((67, 93, 3)) * 255).astype(np.uint8), (0, 0), 2)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    seeds = []
+    for name, params in (("s420", [cv2.IMWRITE_JPEG_QUALITY, 85]),
+                         ("s444", [cv2.IMWRITE_JPEG_QUALITY, 90, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]),
+                         ("s422", [cv2.IMWRITE_JPEG_QUALITY, 75, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]),
+                         ("rst", [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 3]),
+                         ("opt", [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_OPTIMIZE, 1])):
+        path = str(tmp_path / ("%s.jpg" % name))
+        assert cv2.imwrite(path, img, params)
+        seeds.append(path)
+    gray = str(tmp_path / "gray.jpg")
+    assert cv2.imwrite(gray, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 80])
+    seeds.append(gray)
+    r = subprocess.run([exe, "20000"] + seeds, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "decoded" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    n_ok = int(r.stdout.split("decoded")[1].split(",")[0])
+    assert n_ok > 5000  # most mutations of the entropy-coded bytes still decode (to garbage), as in any JPEG decoder
